@@ -1,0 +1,210 @@
+/*
+ * pycontact_b200.h -- C ABI of the B200 contact-analysis library
+ * (libpycontact_b200.so, CUDA sm_100a).
+ *
+ * This is the drop-in boundary for the per-frame hot path of PyContact.  Each entry
+ * point names the reference interface it replaces (paths relative to the
+ * reference root).  Plain pointers and sizes only; no torch / numpy types.
+ *
+ * Conventions
+ *   - every function returns 0 on success, a negative PC_ERR_* code otherwise;
+ *     pc_last_error() gives a message for the calling thread's last failure;
+ *   - one pc_ctx per GPU; a context is not thread-safe, different contexts are;
+ *   - "local index" = position of an atom inside its selection (the idx1 / idx2
+ *     that cy_find_contacts returns); the Python layer converts to global indices;
+ *   - pointers named h_* are host memory, d_* device memory of the context's GPU;
+ *   - `stream` is a cudaStream_t passed as void* (NULL = the legacy default
+ *     stream); all work is enqueued on it and nothing synchronises unless stated.
+ */
+#ifndef PYCONTACT_B200_H
+#define PYCONTACT_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PC_OK                 0
+#define PC_ERR_INVALID       -1   /* bad argument / call order */
+#define PC_ERR_CUDA          -2   /* CUDA runtime error (message has the detail) */
+#define PC_ERR_CAPACITY      -3   /* an output buffer was too small; see pc_scan_status */
+#define PC_ERR_MISSING_H     -4   /* a hydrogen bonded to a selected N/O/S atom is not in that
+                                     selection: the reference raises here too
+                                     (core/ContactAnalyzer.py:432, core/multi_trajectory.py:158) */
+#define PC_ERR_NOMEM         -5
+
+/* per-atom flag bits (pc_set_topology) */
+#define PC_ATOM_HYDROGEN   1u   /* name starts with "H"   (core/ContactAnalyzer.py:360)      */
+#define PC_ATOM_HBCLASS    2u   /* name[0] in {O,N,S}     (core/Biochemistry.py:32-33)       */
+#define PC_ATOM_BACKBONE   4u   /* index in MDAnalysis "backbone" (core/ContactAnalyzer.py:287) */
+
+/* coordinate layouts of a frame batch in device / host memory */
+#define PC_LAYOUT_XYZ   3   /* packed float32 x,y,z   (numpy (F,n,3), what sel.positions gives) */
+#define PC_LAYOUT_XYZW  4   /* float4 per atom, w ignored                                       */
+
+/* One AtomContact (core/Biochemistry.py:299-312) without the Python object:
+ * i, j are local indices into selection 1 / selection 2. */
+typedef struct { int32_t i, j; float distance, weight; } pc_contact;
+
+/* One HydrogenBond (core/Biochemistry.py:315-331).  (i, j) is the contact it belongs
+ * to; `hyd` is the hydrogen's local index in the donor's selection; bit 31 of `hyd`
+ * set => the donor is atom j (selection 2), clear => the donor is atom i. */
+typedef struct { int32_t i, j; uint32_t hyd; float distance, angle; } pc_hbond;
+
+/* One (frame, key) cell of the accumulation
+ * (TempContactAccumulate, core/Biochemistry.py:283-296): key = gid1*G2 + gid2. */
+typedef struct {
+    uint64_t key;
+    double   score;        /* fscore: sum of weights                                   */
+    double   bb1, bb2;     /* backbone part of the score for atom 1 / atom 2 (sc = score - bb) */
+    uint32_t ncontacts;    /* len(contributingAtomContacts)                            */
+    uint32_t nhbonds;      /* sum of len(hbondinfo) -> AccumulatedContact.hbondFramesScan */
+    uint64_t first;        /* smallest order key of a contributing contact (first appearance) */
+} pc_row;
+
+typedef struct pc_ctx pc_ctx;
+
+const char *pc_last_error(void);
+int pc_version(void);
+int pc_device_count(void);   /* CUDA devices visible to this process (0 when there is none) */
+
+/* Analyzer(psf, dcd, cutoff, hbondcutoff, hbondcutangle, sel1text, sel2text)
+ * (core/ContactAnalyzer.py:23-46): the numeric part of the constructor.
+ * self_mode != 0  <=>  sel2text == "self" (core/ContactAnalyzer.py:304-307). */
+int pc_create(int device, double cutoff, double hb_cutoff, double hb_angle_deg, int self_mode,
+              pc_ctx **out);
+void pc_destroy(pc_ctx *ctx);
+
+/* Static per-selection data that the reference re-derives per raw pair in its Python loop
+ * (core/multi_trajectory.py:83-155): flags, residue ids / segment ids (self-interaction
+ * filter, :93-95) and the bonded-hydrogen CSR (:115-155, local indices; -1 marks a hydrogen
+ * outside the selection).  In self mode the *2 arrays are ignored.  Host pointers, copied. */
+int pc_set_topology(pc_ctx *ctx, int32_t n1, int32_t n2,
+                    const uint8_t *h_flags1, const uint8_t *h_flags2,
+                    const int32_t *h_resid1, const int32_t *h_segid1,
+                    const int32_t *h_resid2, const int32_t *h_segid2,
+                    const int32_t *h_hptr1, const int32_t *h_hidx1,
+                    const int32_t *h_hptr2, const int32_t *h_hidx2);
+
+/* Accumulation maps (Analyzer.runContactAnalysis(map1, map2), core/ContactAnalyzer.py:64-70,
+ * makeKeyArraysFromMaps :107-158): group id of every selection atom under map1 / map2. */
+int pc_set_maps(pc_ctx *ctx, const int32_t *h_gid1, const int32_t *h_gid2, int64_t n_groups2);
+
+/* Optional per-frame limits of the kernels' on-chip staging (0 = automatic): contacts and H-bonds
+ * one frame may produce on the small-frame path, grid cells, accumulation-table slots. */
+int pc_set_limits(pc_ctx *ctx, int32_t hits_per_frame, int32_t hbonds_per_frame, int32_t cells,
+                  int32_t table_slots);
+
+/* Kernel path: 0 = automatic (by selection size), 1 = one CTA per frame out of shared memory,
+ * 2 = tiled large-frame path.  Both give the same records; tests use this to cover both. */
+int pc_set_path(pc_ctx *ctx, int path);
+
+/* Output capacities for one batch (totals over the batch, not per frame). */
+int pc_reserve(pc_ctx *ctx, int32_t max_frames, int64_t cap_contacts, int64_t cap_hbonds, int64_t cap_rows);
+
+/* The frame loop body for a batch of frames resident in HBM
+ * (loop_trajectory_grid, core/multi_trajectory.py:50-222; serial twin
+ * core/ContactAnalyzer.py:319-493): neighbour search + heavy-atom / self filters +
+ * distance + weight + H-bond test for `nframes` frames.  d_xyz2 is ignored in self mode.
+ * pitch* = floats between consecutive frames.  order_keys != 0 additionally computes the
+ * reference's in-frame order key per contact. */
+int pc_scan_device(pc_ctx *ctx, const float *d_xyz1, const float *d_xyz2, int32_t nframes,
+                   int32_t layout, int64_t pitch1, int64_t pitch2, int32_t order_keys, void *stream);
+
+/* analyze_contactResultsWithMaps (core/ContactAnalyzer.py:502-597), per-frame part:
+ * groups the contacts of the last scan by key into pc_row's. */
+int pc_accumulate(pc_ctx *ctx, void *stream);
+
+/* Time-aggregated maps for the end-of-run reduction over ranks: adds the rows of the last
+ * accumulated batch into d_totals[n_keys][4] = (sum score, sum bb1, sum bb2, frames with an
+ * H-bond), key = gid1 * n_groups2 + gid2 < n_keys (the sums behind mean_score, bb/sc and
+ * hbond_percentage, core/Biochemistry.py:150-186, core/ContactAnalyzer.py:588-591). */
+int pc_fold_rows(pc_ctx *ctx, double *d_totals, int64_t n_keys, void *stream);
+
+/* Analyzer.runContactAnalysis(map1, map2) may be called again with other maps on the SAME
+ * contactResults (core/ContactAnalyzer.py:64-70): loads previously fetched records of `nframes`
+ * frames back into the context so that pc_accumulate can regroup them.  Synchronous. */
+int pc_load_records(pc_ctx *ctx, const pc_contact *h_contacts, const uint64_t *h_order_keys,
+                    const pc_hbond *h_hbonds, int32_t nframes,
+                    const uint32_t *h_frame_cstart, const uint32_t *h_frame_ccount,
+                    const uint32_t *h_frame_hstart, const uint32_t *h_frame_hcount, void *stream);
+
+/* Same two steps for frames in HOST memory (pinned or pageable): H2D copy, scan,
+ * accumulate if maps are set; all asynchronous on `stream`. */
+int pc_scan_host(pc_ctx *ctx, const float *h_xyz1, const float *h_xyz2, int32_t nframes,
+                 int32_t layout, int32_t order_keys, int32_t accumulate, void *stream);
+
+/* Synchronises `stream` and reports the totals of the last batch and its status
+ * (0, PC_ERR_CAPACITY or PC_ERR_MISSING_H). */
+int pc_batch_totals(pc_ctx *ctx, void *stream, int64_t *n_contacts, int64_t *n_hbonds, int64_t *n_rows,
+                    int64_t *n_pair_evals);
+
+/* Raw status of the last pc_batch_totals: PC_ST_* bits, the record counts the batch NEEDED (for
+ * re-reserving after PC_ERR_CAPACITY) and which kernel path ran (1 = one CTA per frame,
+ * 2 = tiled large-frame path). */
+int pc_last_status(pc_ctx *ctx, uint64_t *status, int64_t *need_contacts, int64_t *need_hbonds,
+                   int64_t *need_rows, int32_t *path);
+
+/* Device pointers of the last batch's outputs (valid until the next scan / reserve). */
+int pc_device_outputs(pc_ctx *ctx, pc_contact **d_contacts, pc_hbond **d_hbonds, pc_row **d_rows,
+                      uint64_t **d_order_keys,
+                      uint32_t **d_frame_cstart, uint32_t **d_frame_ccount,
+                      uint32_t **d_frame_hstart, uint32_t **d_frame_hcount,
+                      uint32_t **d_frame_rstart, uint32_t **d_frame_rcount);
+
+/* D2H of the last batch's outputs into caller buffers sized from pc_batch_totals
+ * (any pointer may be NULL to skip it).  frame_* arrays have nframes entries.
+ * Asynchronous on `stream`; synchronise before reading. */
+int pc_fetch(pc_ctx *ctx, void *stream,
+             pc_contact *h_contacts, pc_hbond *h_hbonds, pc_row *h_rows, uint64_t *h_order_keys,
+             uint32_t *h_frame_cstart, uint32_t *h_frame_ccount,
+             uint32_t *h_frame_hstart, uint32_t *h_frame_hcount,
+             uint32_t *h_frame_rstart, uint32_t *h_frame_rcount);
+
+/* cy_find_contacts(xyz1, natoms1, xyz2, natoms2, r)  (cy_modules/cy_gridsearch.pyx:31-35 ->
+ * find_contacts, cy_modules/src/gridsearch.C:408-427): ALL atoms, no filters.  Returns a CSR:
+ * h_row_ptr[n1+1] (caller allocated); *h_cols is allocated by the library (pc_free_host) with
+ * h_row_ptr[n1] entries, each row in the reference's order (stencil rank, then index).
+ * Host pointers; synchronous. */
+int pc_find_contacts(int device, const float *h_xyz1, int32_t n1, const float *h_xyz2, int32_t n2,
+                     double cutoff, int64_t *h_row_ptr, int32_t **h_cols);
+void pc_free_host(void *p);
+
+/* Synthetic trajectory generator used by bench.py: frame f =
+ * base + amp[res]*sin(2*pi*f/period[res] + phase[res]) + N(0, sigma) jitter from a
+ * counter-based generator keyed (seed, frame, atom).  Writes nframes frames in `layout`. */
+int pc_synth_frames(int device, const float *d_base_xyz, const int32_t *d_residue_of,
+                    const float *d_amp, const float *d_period, const float *d_phase,
+                    int32_t natoms, float sigma, uint64_t seed, int32_t frame0, int32_t nframes,
+                    int32_t layout, int64_t pitch, float *d_out, void *stream);
+
+/* Streams for the frame-batch scheduler (the Pool of core/multi_trajectory.py:357, 434-445 becomes
+ * batches in flight on CUDA streams): cudaStreamCreateWithFlags(non-blocking) / synchronize / destroy. */
+int pc_stream_create(int device, void **out_stream);
+int pc_stream_sync(void *stream);
+void pc_stream_destroy(void *stream);
+
+/* Device memory helpers for callers without a CUDA binding of their own (bench.py, tests):
+ * cudaMalloc / cudaFree / cudaMemcpyAsync (kind 1 = H2D, 2 = D2H, 3 = D2D) / cudaDeviceSynchronize. */
+int pc_device_alloc(int device, int64_t bytes, void **out);
+void pc_device_free(int device, void *p);
+int pc_memcpy(int device, void *dst, const void *src, int64_t bytes, int kind, void *stream);
+int pc_device_sync(int device);
+
+/* Measurement helpers (bench.py): kernels launched by this library so far, and CUDA events so that
+ * the caller can time work on the stream it was enqueued on. */
+int64_t pc_launch_count(void);
+int pc_event_create(int device, void **out_event);
+int pc_event_record(void *event, void *stream);
+int pc_event_elapsed_ms(void *start_event, void *end_event, float *ms);   /* synchronises on end_event */
+void pc_event_destroy(void *event);
+
+/* Pinned host memory helpers for the Python layer (cudaHostAlloc / cudaFreeHost). */
+int pc_host_alloc(void **out, int64_t bytes);
+void pc_host_free(void *p);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PYCONTACT_B200_H */

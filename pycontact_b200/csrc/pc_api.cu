@@ -1,0 +1,621 @@
+// pc_api.cu -- C ABI of libpycontact_b200.so (see include/pycontact_b200.h).
+//
+// Host-side glue only: context, device buffers, kernel selection and launches.  All
+// numerical work is in the kernels (pc_scan_small.cuh, pc_scan_large.cuh, pc_accumulate.cuh).
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+#include <algorithm>
+
+#include "pc_common.cuh"
+#include "pc_scan_small.cuh"
+#include "pc_scan_large.cuh"
+#include "pc_accumulate.cuh"
+#include "pc_order.cuh"
+#include "pc_search.cuh"
+#include "pc_synth.cuh"
+
+static thread_local std::string g_err;
+static unsigned long long g_launches = 0;      // kernels launched by this library (bench.py's gpu_launches)
+
+static int fail(int code, const std::string &msg) { g_err = msg; return code; }
+
+#define CUDA_TRY(expr)                                                                     \
+    do {                                                                                   \
+        cudaError_t _e = (expr);                                                           \
+        if (_e != cudaSuccess)                                                             \
+            return fail(PC_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(_e)); \
+    } while (0)
+
+template <typename T>
+struct DevBuf {
+    T *p = nullptr;
+    size_t n = 0;
+    ~DevBuf() { release(); }
+    void release() { if (p) cudaFree(p); p = nullptr; n = 0; }
+    cudaError_t ensure(size_t count) {
+        if (count <= n && p) return cudaSuccess;
+        release();
+        cudaError_t e = cudaMalloc(&p, std::max<size_t>(count, 1) * sizeof(T));
+        if (e == cudaSuccess) n = count;
+        return e;
+    }
+    cudaError_t upload(const std::vector<T> &v, cudaStream_t s = 0) {
+        cudaError_t e = ensure(v.size());
+        if (e != cudaSuccess || v.empty()) return e;
+        return cudaMemcpyAsync(p, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice, s);
+    }
+};
+
+struct pc_ctx {
+    int device = 0;
+    double cutoff = 0, hb_cutoff = 0, hb_angle = 0;
+    int self_mode = 0;
+    int num_sms = 148;
+    size_t smem_optin = 0;
+    bool have_topology = false, have_maps = false;
+    int n1 = 0, n2 = 0, n1h = 0, n2h = 0;
+    DevBuf<int> heavy1, heavy2, hres1, hseg1, hres2, hseg2, hhptr1, hidx1, hhptr2, hidx2, lgid1, lgid2;
+    DevBuf<uint8_t> hflag1, hflag2, lflag1, lflag2;
+    unsigned long long ngroups2 = 0;
+    // limits (0 = automatic)
+    int lim_hits = 0, lim_hb = 0, lim_cells = 0, lim_table = 0;
+    int force_path = 0;               // 0 = automatic, 1 = small-frame kernel, 2 = large-frame path
+    // batch outputs
+    int max_frames = 0;
+    long long cap_contacts = 0, cap_hbonds = 0, cap_rows = 0;
+    DevBuf<pc_contact> contacts;
+    DevBuf<pc_hbond> hbonds;
+    DevBuf<pc_row> rows;
+    DevBuf<unsigned long long> order_keys;
+    DevBuf<unsigned long long> counters;
+    DevBuf<uint32_t> frame_meta;      // 6 arrays of max_frames
+    DevBuf<float> stage1, stage2;     // H2D staging for pc_scan_host
+    PcLargeWork large;                // work buffers of the large-frame path
+    int last_nframes = 0;
+    bool last_order_keys = false;
+    unsigned long long *h_counters = nullptr;   // pinned mirror
+    int last_path = 0;                // 1 = small, 2 = large
+    std::vector<uint32_t> h_meta;     // host copy of the scan's 4 frame arrays (large path: sliced outputs)
+};
+
+extern "C" const char *pc_last_error(void) { return g_err.c_str(); }
+extern "C" int pc_version(void) { return 100; }
+extern "C" int pc_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+
+extern "C" int pc_create(int device, double cutoff, double hb_cutoff, double hb_angle_deg, int self_mode,
+                         pc_ctx **out) {
+    if (!out) return fail(PC_ERR_INVALID, "pc_create: out is NULL");
+    if (!(cutoff > 0)) return fail(PC_ERR_INVALID, "pc_create: cutoff must be positive");
+    int ndev = 0;
+    CUDA_TRY(cudaGetDeviceCount(&ndev));
+    if (device < 0 || device >= ndev) return fail(PC_ERR_INVALID, "pc_create: no such CUDA device");
+    CUDA_TRY(cudaSetDevice(device));
+    pc_ctx *c = new pc_ctx();
+    c->device = device; c->cutoff = cutoff; c->hb_cutoff = hb_cutoff; c->hb_angle = hb_angle_deg;
+    c->self_mode = self_mode ? 1 : 0;
+    cudaDeviceProp prop;
+    CUDA_TRY(cudaGetDeviceProperties(&prop, device));
+    c->num_sms = prop.multiProcessorCount;
+    c->smem_optin = prop.sharedMemPerBlockOptin;
+    CUDA_TRY(c->counters.ensure(PC_CNT_COUNT));
+    CUDA_TRY(cudaMemset(c->counters.p, 0, PC_CNT_COUNT * sizeof(unsigned long long)));
+    CUDA_TRY(cudaHostAlloc(&c->h_counters, PC_CNT_COUNT * sizeof(unsigned long long), cudaHostAllocDefault));
+    *out = c;
+    return PC_OK;
+}
+
+extern "C" void pc_destroy(pc_ctx *c) {
+    if (!c) return;
+    cudaSetDevice(c->device);
+    if (c->h_counters) cudaFreeHost(c->h_counters);
+    delete c;
+}
+
+extern "C" int pc_set_path(pc_ctx *c, int path) {
+    if (!c || path < 0 || path > 2) return fail(PC_ERR_INVALID, "pc_set_path: path must be 0, 1 or 2");
+    c->force_path = path;
+    return PC_OK;
+}
+
+extern "C" int pc_set_limits(pc_ctx *c, int hits_per_frame, int hbonds_per_frame, int cells, int table_slots) {
+    if (!c) return fail(PC_ERR_INVALID, "pc_set_limits: ctx is NULL");
+    c->lim_hits = hits_per_frame; c->lim_hb = hbonds_per_frame; c->lim_cells = cells; c->lim_table = table_slots;
+    return PC_OK;
+}
+
+// Re-index the per-atom topology by "heavy ordinal" (position among the non-hydrogen atoms of the
+// selection) so kernels never touch hydrogens except inside the H-bond test.
+static int build_side(int n, const uint8_t *flags, const int32_t *resid, const int32_t *segid,
+                      const int32_t *hptr, const int32_t *hidx, std::vector<int> &heavy,
+                      std::vector<uint8_t> &hflag, std::vector<int> &hres, std::vector<int> &hseg,
+                      std::vector<int> &hhptr, std::vector<int> &hh) {
+    heavy.clear(); hflag.clear(); hres.clear(); hseg.clear(); hhptr.clear(); hh.clear();
+    hhptr.push_back(0);
+    for (int i = 0; i < n; i++) {
+        if (flags[i] & PC_ATOM_HYDROGEN) continue;
+        heavy.push_back(i);
+        hflag.push_back(flags[i]);
+        hres.push_back(resid ? resid[i] : 0);
+        hseg.push_back(segid ? segid[i] : 0);
+        if (hptr && (flags[i] & PC_ATOM_HBCLASS))
+            for (int p = hptr[i]; p < hptr[i + 1]; p++) hh.push_back(hidx[p]);
+        hhptr.push_back((int)hh.size());
+    }
+    return (int)heavy.size();
+}
+
+extern "C" int pc_set_topology(pc_ctx *c, int32_t n1, int32_t n2, const uint8_t *f1, const uint8_t *f2,
+                               const int32_t *resid1, const int32_t *segid1, const int32_t *resid2,
+                               const int32_t *segid2, const int32_t *hptr1, const int32_t *hidx1,
+                               const int32_t *hptr2, const int32_t *hidx2) {
+    if (!c) return fail(PC_ERR_INVALID, "pc_set_topology: ctx is NULL");
+    if (n1 <= 0 || !f1) return fail(PC_ERR_INVALID, "pc_set_topology: selection 1 is empty");
+    if (!c->self_mode && (n2 <= 0 || !f2)) return fail(PC_ERR_INVALID, "pc_set_topology: selection 2 is empty");
+    CUDA_TRY(cudaSetDevice(c->device));
+    std::vector<int> heavy, hres, hseg, hhptr, hh;
+    std::vector<uint8_t> hflag;
+    c->n1 = n1;
+    c->n1h = build_side(n1, f1, resid1, segid1, hptr1, hidx1, heavy, hflag, hres, hseg, hhptr, hh);
+    CUDA_TRY(c->heavy1.upload(heavy)); CUDA_TRY(c->hflag1.upload(hflag)); CUDA_TRY(c->hres1.upload(hres));
+    CUDA_TRY(c->hseg1.upload(hseg)); CUDA_TRY(c->hhptr1.upload(hhptr)); CUDA_TRY(c->hidx1.upload(hh));
+    CUDA_TRY(c->lflag1.upload(std::vector<uint8_t>(f1, f1 + n1)));
+    CUDA_TRY(cudaDeviceSynchronize());
+    if (c->self_mode) {
+        c->n2 = n1; c->n2h = c->n1h;
+    } else {
+        c->n2 = n2;
+        c->n2h = build_side(n2, f2, resid2, segid2, hptr2, hidx2, heavy, hflag, hres, hseg, hhptr, hh);
+        CUDA_TRY(c->heavy2.upload(heavy)); CUDA_TRY(c->hflag2.upload(hflag)); CUDA_TRY(c->hres2.upload(hres));
+        CUDA_TRY(c->hseg2.upload(hseg)); CUDA_TRY(c->hhptr2.upload(hhptr)); CUDA_TRY(c->hidx2.upload(hh));
+        CUDA_TRY(c->lflag2.upload(std::vector<uint8_t>(f2, f2 + n2)));
+        CUDA_TRY(cudaDeviceSynchronize());
+    }
+    c->have_topology = true;
+    c->have_maps = false;
+    return PC_OK;
+}
+
+extern "C" int pc_set_maps(pc_ctx *c, const int32_t *gid1, const int32_t *gid2, int64_t ngroups2) {
+    if (!c || !c->have_topology) return fail(PC_ERR_INVALID, "pc_set_maps: set the topology first");
+    if (!gid1 || !gid2 || ngroups2 <= 0) return fail(PC_ERR_INVALID, "pc_set_maps: bad arguments");
+    CUDA_TRY(cudaSetDevice(c->device));
+    CUDA_TRY(c->lgid1.upload(std::vector<int>(gid1, gid1 + c->n1)));
+    CUDA_TRY(c->lgid2.upload(std::vector<int>(gid2, gid2 + c->n2)));
+    CUDA_TRY(cudaDeviceSynchronize());
+    c->ngroups2 = (unsigned long long)ngroups2;
+    c->have_maps = true;
+    return PC_OK;
+}
+
+extern "C" int pc_reserve(pc_ctx *c, int32_t max_frames, int64_t cap_contacts, int64_t cap_hbonds, int64_t cap_rows) {
+    if (!c) return fail(PC_ERR_INVALID, "pc_reserve: ctx is NULL");
+    if (max_frames <= 0 || cap_contacts <= 0 || cap_hbonds <= 0 || cap_rows <= 0)
+        return fail(PC_ERR_INVALID, "pc_reserve: capacities must be positive");
+    if (cap_contacts > 0xffffffffll || cap_hbonds > 0xffffffffll || cap_rows > 0xffffffffll)
+        return fail(PC_ERR_INVALID, "pc_reserve: per-batch capacities are limited to 2^32-1 records");
+    CUDA_TRY(cudaSetDevice(c->device));
+    CUDA_TRY(c->contacts.ensure((size_t)cap_contacts));
+    CUDA_TRY(c->order_keys.ensure((size_t)cap_contacts));
+    CUDA_TRY(c->hbonds.ensure((size_t)cap_hbonds));
+    CUDA_TRY(c->rows.ensure((size_t)cap_rows));
+    CUDA_TRY(c->frame_meta.ensure((size_t)max_frames * 6));
+    c->max_frames = max_frames;
+    c->cap_contacts = cap_contacts; c->cap_hbonds = cap_hbonds; c->cap_rows = cap_rows;
+    return PC_OK;
+}
+
+static PcTopoDev topo_dev(const pc_ctx *c) {
+    PcTopoDev t;
+    t.n1 = c->n1; t.n2 = c->n2; t.n1h = c->n1h; t.n2h = c->n2h;
+    t.heavy1 = c->heavy1.p; t.heavy2 = c->self_mode ? c->heavy1.p : c->heavy2.p;
+    t.hflag1 = c->hflag1.p; t.hflag2 = c->self_mode ? c->hflag1.p : c->hflag2.p;
+    t.hres1 = c->hres1.p; t.hseg1 = c->hseg1.p;
+    t.hres2 = c->self_mode ? c->hres1.p : c->hres2.p; t.hseg2 = c->self_mode ? c->hseg1.p : c->hseg2.p;
+    t.hhptr1 = c->hhptr1.p; t.hidx1 = c->hidx1.p;
+    t.hhptr2 = c->self_mode ? c->hhptr1.p : c->hhptr2.p; t.hidx2 = c->self_mode ? c->hidx1.p : c->hidx2.p;
+    t.hgid1 = nullptr; t.hgid2 = nullptr;
+    t.lgid1 = c->lgid1.p; t.lgid2 = c->lgid2.p;
+    t.lflag1 = c->lflag1.p; t.lflag2 = c->self_mode ? c->lflag1.p : c->lflag2.p;
+    t.ngroups2 = c->ngroups2;
+    return t;
+}
+
+static uint32_t *meta(pc_ctx *c, int which) { return c->frame_meta.p + (size_t)which * c->max_frames; }
+
+// Pick shared-memory capacities and CTAs/SM for the small-frame kernel.  Returns false when the
+// frame does not fit one CTA's shared memory (-> large-frame path).
+static bool plan_small(const pc_ctx *c, int order_keys, int &capCells, int &capHits, int &capHb,
+                       PcSmallSmem &L, int &ctas_per_sm) {
+    const int NT = 512;
+    if (c->n1h > 65535 || c->n2h > 65535) return false;
+    capHits = c->lim_hits > 0 ? c->lim_hits : 4096;
+    capHb = c->lim_hb > 0 ? c->lim_hb : 256;
+    const size_t sm_total = 233472, static_smem = 2048;
+    const size_t optin = c->smem_optin ? c->smem_optin : 232448;
+    const int max_by_threads = 2048 / NT;
+    const int cell_arrays = c->self_mode ? 1 : 2;
+    for (int k = max_by_threads; k >= 1; k--) {
+        size_t budget = std::min(optin, sm_total / k - 1024) - static_smem;
+        PcSmallSmem base = pc_small_layout(c->n1h, c->n2h, c->self_mode, 0, capHits, capHb, order_keys);
+        if ((size_t)base.total + cell_arrays * 4 * 513 > budget) continue;
+        int cells = (int)((budget - base.total) / (4 * cell_arrays)) - 8;
+        cells = std::min(cells, 16384);
+        if (c->lim_cells > 0) cells = std::min(cells, c->lim_cells);
+        // prefer more co-resident CTAs unless that would squeeze the grid below 1024 cells
+        if (cells < 1024 && k > 1) {
+            size_t budget_lo = std::min(optin, sm_total / (k - 1) - 1024) - static_smem;
+            if ((size_t)base.total + cell_arrays * 4 * 1025 <= budget_lo) continue;
+        }
+        capCells = cells;
+        L = pc_small_layout(c->n1h, c->n2h, c->self_mode, capCells, capHits, capHb, order_keys);
+        ctas_per_sm = k;
+        return true;
+    }
+    return false;
+}
+
+extern "C" int pc_scan_device(pc_ctx *c, const float *d_xyz1, const float *d_xyz2, int32_t nframes,
+                              int32_t layout, int64_t pitch1, int64_t pitch2, int32_t order_keys, void *stream) {
+    if (!c || !c->have_topology) return fail(PC_ERR_INVALID, "pc_scan_device: set the topology first");
+    if (nframes <= 0) return fail(PC_ERR_INVALID, "pc_scan_device: nframes must be positive");
+    if (layout != PC_LAYOUT_XYZ && layout != PC_LAYOUT_XYZW) return fail(PC_ERR_INVALID, "pc_scan_device: bad layout");
+    if (!d_xyz1 || (!c->self_mode && !d_xyz2)) return fail(PC_ERR_INVALID, "pc_scan_device: NULL coordinates");
+    if (nframes > c->max_frames || c->cap_contacts <= 0)
+        return fail(PC_ERR_INVALID, "pc_scan_device: call pc_reserve with max_frames >= nframes first");
+    if (layout == PC_LAYOUT_XYZW && (((uintptr_t)d_xyz1 | (uintptr_t)d_xyz2) & 15 || (pitch1 & 3) || (pitch2 & 3)))
+        return fail(PC_ERR_INVALID, "pc_scan_device: float4 layout needs 16-byte aligned frames");
+    CUDA_TRY(cudaSetDevice(c->device));
+    cudaStream_t s = (cudaStream_t)stream;
+
+    PcScanArgs a;
+    memset(&a, 0, sizeof(a));
+    a.xyz1 = d_xyz1; a.xyz2 = c->self_mode ? d_xyz1 : d_xyz2;
+    a.pitch1 = pitch1; a.pitch2 = c->self_mode ? pitch1 : pitch2;
+    a.stride = layout; a.nframes = nframes; a.self_mode = c->self_mode; a.order_keys = order_keys;
+    a.t = topo_dev(c);
+    a.cutoff_f = (float)c->cutoff;                       // gridsearch.C:417 -> :904 (double -> float)
+    a.sqdist = a.cutoff_f * a.cutoff_f;                  // gridsearch.C:936
+    a.edge = a.cutoff_f * PC_EDGE_SCALE;
+    a.hb_cutoff = c->hb_cutoff; a.hb_angle = c->hb_angle;
+    a.contacts = c->contacts.p; a.hbonds = c->hbonds.p; a.order_out = order_keys ? c->order_keys.p : nullptr;
+    a.counters = c->counters.p;
+    a.cap_contacts = c->cap_contacts; a.cap_hbonds = c->cap_hbonds;
+    a.frame_cstart = meta(c, 0); a.frame_ccount = meta(c, 1); a.frame_hstart = meta(c, 2); a.frame_hcount = meta(c, 3);
+    CUDA_TRY(cudaMemsetAsync(c->counters.p, 0, PC_CNT_COUNT * sizeof(unsigned long long), s));
+
+    PcSmallSmem L;
+    int ctas = 1;
+    const bool fits_small = c->force_path != 2 && plan_small(c, order_keys, a.capCells, a.capHits, a.capHb, L, ctas);
+    if (c->force_path == 1 && !fits_small)
+        return fail(PC_ERR_INVALID, "pc_scan_device: the frame does not fit the small-frame kernel");
+    if (fits_small) {
+        auto kern = pc_scan_small_kernel<512>;
+        CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L.total));
+        const int grid = std::min(nframes, ctas * c->num_sms);
+        kern<<<grid, 512, L.total, s>>>(a, L);
+        CUDA_TRY(cudaGetLastError());
+        g_launches += 1;
+        c->last_path = 1;
+    } else {
+        int rc = pc_large_scan(c->large, a, c->num_sms, s, g_err, &g_launches);
+        if (rc != PC_OK) return rc;
+        c->last_path = 2;
+    }
+    if (order_keys) {
+        if (c->n1 >= (1 << 27)) return fail(PC_ERR_INVALID, "pc_scan_device: order keys need n1 < 2^27");
+        pc_order_kernel<256><<<std::min(nframes, 8 * c->num_sms), 256, 0, s>>>(a);
+        CUDA_TRY(cudaGetLastError());
+        g_launches += 1;
+    }
+    c->last_nframes = nframes;
+    c->last_order_keys = order_keys != 0;
+    return PC_OK;
+}
+
+extern "C" int pc_accumulate(pc_ctx *c, void *stream) {
+    if (!c || !c->have_maps) return fail(PC_ERR_INVALID, "pc_accumulate: set the maps first");
+    if (c->last_nframes <= 0) return fail(PC_ERR_INVALID, "pc_accumulate: no scanned batch");
+    CUDA_TRY(cudaSetDevice(c->device));
+    cudaStream_t s = (cudaStream_t)stream;
+    PcAccArgs a;
+    a.contacts = c->contacts.p; a.hbonds = c->hbonds.p;
+    a.order_keys = c->last_order_keys ? c->order_keys.p : nullptr;
+    a.frame_cstart = meta(c, 0); a.frame_ccount = meta(c, 1); a.frame_hstart = meta(c, 2); a.frame_hcount = meta(c, 3);
+    a.lgid1 = c->lgid1.p; a.lgid2 = c->lgid2.p;
+    a.lflag1 = c->lflag1.p; a.lflag2 = c->self_mode ? c->lflag1.p : c->lflag2.p;
+    a.ngroups2 = c->ngroups2;
+    a.nframes = c->last_nframes;
+    int cap = c->lim_table > 0 ? c->lim_table : 1024;
+    int p2 = 64; while (p2 < cap) p2 <<= 1;
+    a.cap = p2;
+    a.rows = c->rows.p; a.cap_rows = c->cap_rows; a.counters = c->counters.p;
+    a.frame_rstart = meta(c, 4); a.frame_rcount = meta(c, 5);
+    const size_t smem = (size_t)a.cap * 48;
+    if (smem > (c->smem_optin ? c->smem_optin : 232448) - 1024)
+        return fail(PC_ERR_INVALID, "pc_accumulate: table does not fit shared memory");
+    auto kern = pc_accumulate_kernel<256>;
+    CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int per_sm = (int)std::max<size_t>(1, std::min<size_t>(8, 233472 / (smem + 2048)));
+    const int grid = std::min(a.nframes, per_sm * c->num_sms);
+    kern<<<grid, 256, smem, s>>>(a);
+    CUDA_TRY(cudaGetLastError());
+    g_launches += 1;
+    return PC_OK;
+}
+
+extern "C" int pc_fold_rows(pc_ctx *c, double *d_totals, int64_t n_keys, void *stream) {
+    if (!c || !c->have_maps || !d_totals || n_keys <= 0) return fail(PC_ERR_INVALID, "pc_fold_rows: bad arguments");
+    CUDA_TRY(cudaSetDevice(c->device));
+    pc_fold_rows_kernel<<<2 * c->num_sms, 256, 0, (cudaStream_t)stream>>>(c->rows.p, c->counters.p, c->cap_rows, d_totals,
+                                                                         (unsigned long long)n_keys);
+    CUDA_TRY(cudaGetLastError());
+    g_launches += 1;
+    return PC_OK;
+}
+
+extern "C" int pc_load_records(pc_ctx *c, const pc_contact *h_contacts, const uint64_t *h_order_keys,
+                               const pc_hbond *h_hbonds, int32_t nframes, const uint32_t *cs, const uint32_t *cc,
+                               const uint32_t *hs, const uint32_t *hc, void *stream) {
+    if (!c || !c->have_topology) return fail(PC_ERR_INVALID, "pc_load_records: set the topology first");
+    if (nframes <= 0 || !cs || !cc || !hs || !hc) return fail(PC_ERR_INVALID, "pc_load_records: bad arguments");
+    if (nframes > c->max_frames) return fail(PC_ERR_INVALID, "pc_load_records: call pc_reserve with max_frames >= nframes first");
+    unsigned long long nc = 0, nh = 0;
+    for (int f = 0; f < nframes; f++) {
+        nc = std::max<unsigned long long>(nc, (unsigned long long)cs[f] + cc[f]);
+        nh = std::max<unsigned long long>(nh, (unsigned long long)hs[f] + hc[f]);
+    }
+    if ((long long)nc > c->cap_contacts || (long long)nh > c->cap_hbonds)
+        return fail(PC_ERR_CAPACITY, "pc_load_records: records exceed the reserved capacities");
+    if ((nc && !h_contacts) || (nh && !h_hbonds)) return fail(PC_ERR_INVALID, "pc_load_records: NULL records");
+    CUDA_TRY(cudaSetDevice(c->device));
+    cudaStream_t s = (cudaStream_t)stream;
+    if (nc) CUDA_TRY(cudaMemcpyAsync(c->contacts.p, h_contacts, nc * sizeof(pc_contact), cudaMemcpyHostToDevice, s));
+    if (nc && h_order_keys)
+        CUDA_TRY(cudaMemcpyAsync(c->order_keys.p, h_order_keys, nc * sizeof(uint64_t), cudaMemcpyHostToDevice, s));
+    if (nh) CUDA_TRY(cudaMemcpyAsync(c->hbonds.p, h_hbonds, nh * sizeof(pc_hbond), cudaMemcpyHostToDevice, s));
+    const uint32_t *src[4] = {cs, cc, hs, hc};
+    for (int k = 0; k < 4; k++)
+        CUDA_TRY(cudaMemcpyAsync(meta(c, k), src[k], (size_t)nframes * sizeof(uint32_t), cudaMemcpyHostToDevice, s));
+    unsigned long long cnt[PC_CNT_COUNT] = {0};
+    cnt[PC_CNT_CONTACTS] = nc; cnt[PC_CNT_HBONDS] = nh;
+    // the copies above read pageable or pinned caller memory: finish them before returning
+    CUDA_TRY(cudaMemcpyAsync(c->counters.p, cnt, sizeof cnt, cudaMemcpyHostToDevice, s));
+    CUDA_TRY(cudaStreamSynchronize(s));
+    c->last_nframes = nframes;
+    c->last_order_keys = h_order_keys != nullptr;
+    c->last_path = 1;
+    return PC_OK;
+}
+
+extern "C" int pc_scan_host(pc_ctx *c, const float *h_xyz1, const float *h_xyz2, int32_t nframes,
+                            int32_t layout, int32_t order_keys, int32_t accumulate, void *stream) {
+    if (!c || !c->have_topology) return fail(PC_ERR_INVALID, "pc_scan_host: set the topology first");
+    if (!h_xyz1 || (!c->self_mode && !h_xyz2)) return fail(PC_ERR_INVALID, "pc_scan_host: NULL coordinates");
+    if (layout != PC_LAYOUT_XYZ && layout != PC_LAYOUT_XYZW) return fail(PC_ERR_INVALID, "pc_scan_host: bad layout");
+    CUDA_TRY(cudaSetDevice(c->device));
+    cudaStream_t s = (cudaStream_t)stream;
+    const size_t f1 = (size_t)c->n1 * layout, f2 = (size_t)c->n2 * layout;
+    CUDA_TRY(c->stage1.ensure(f1 * nframes + 4));
+    CUDA_TRY(cudaMemcpyAsync(c->stage1.p, h_xyz1, f1 * nframes * sizeof(float), cudaMemcpyHostToDevice, s));
+    if (!c->self_mode) {
+        CUDA_TRY(c->stage2.ensure(f2 * nframes + 4));
+        CUDA_TRY(cudaMemcpyAsync(c->stage2.p, h_xyz2, f2 * nframes * sizeof(float), cudaMemcpyHostToDevice, s));
+    }
+    int rc = pc_scan_device(c, c->stage1.p, c->stage2.p, nframes, layout, (int64_t)f1, (int64_t)f2, order_keys, stream);
+    if (rc != PC_OK) return rc;
+    if (accumulate) return pc_accumulate(c, stream);
+    return PC_OK;
+}
+
+extern "C" int pc_batch_totals(pc_ctx *c, void *stream, int64_t *n_contacts, int64_t *n_hbonds, int64_t *n_rows,
+                               int64_t *n_pair_evals) {
+    if (!c) return fail(PC_ERR_INVALID, "pc_batch_totals: ctx is NULL");
+    CUDA_TRY(cudaSetDevice(c->device));
+    cudaStream_t s = (cudaStream_t)stream;
+    CUDA_TRY(cudaMemcpyAsync(c->h_counters, c->counters.p, PC_CNT_COUNT * sizeof(unsigned long long),
+                             cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(cudaStreamSynchronize(s));
+    if (c->last_path == 2 && c->last_nframes > 0) {
+        // large path: every frame owns a slice of the buffers; keep the slice table for pc_fetch
+        c->h_meta.resize((size_t)4 * c->last_nframes);
+        for (int k = 0; k < 4; k++)
+            CUDA_TRY(cudaMemcpy(c->h_meta.data() + (size_t)k * c->last_nframes, meta(c, k),
+                                (size_t)c->last_nframes * sizeof(uint32_t), cudaMemcpyDeviceToHost));
+    }
+    const unsigned long long st = c->h_counters[PC_CNT_STATUS];
+    if (n_contacts) *n_contacts = (int64_t)std::min<unsigned long long>(c->h_counters[PC_CNT_CONTACTS], c->cap_contacts);
+    if (n_hbonds) *n_hbonds = (int64_t)std::min<unsigned long long>(c->h_counters[PC_CNT_HBONDS], c->cap_hbonds);
+    if (n_rows) *n_rows = (int64_t)std::min<unsigned long long>(c->h_counters[PC_CNT_ROWS], c->cap_rows);
+    if (n_pair_evals) *n_pair_evals = (int64_t)c->h_counters[PC_CNT_EVALS];
+    if (st & PC_ST_BAD_COORDS) return fail(PC_ERR_INVALID, "non-finite coordinates in a frame");
+    if (st & PC_ST_MISSING_H)
+        return fail(PC_ERR_MISSING_H, "a hydrogen bonded to a selected N/O/S atom is not part of that selection");
+    if (st & (PC_ST_HITS_OVERFLOW | PC_ST_HB_OVERFLOW | PC_ST_OUT_OVERFLOW | PC_ST_TABLE_OVERFLOW)) {
+        char buf[256];
+        snprintf(buf, sizeof buf,
+                 "capacity exceeded (status 0x%llx: 1=hits/frame 2=hbonds/frame 4=batch buffers 32=accumulation table); "
+                 "needed contacts=%llu hbonds=%llu rows=%llu",
+                 st, c->h_counters[PC_CNT_CONTACTS], c->h_counters[PC_CNT_HBONDS], c->h_counters[PC_CNT_ROWS]);
+        g_err = buf;
+        return PC_ERR_CAPACITY;
+    }
+    return PC_OK;
+}
+
+extern "C" int pc_last_status(pc_ctx *c, uint64_t *status, int64_t *need_contacts, int64_t *need_hbonds,
+                              int64_t *need_rows, int32_t *path) {
+    if (!c) return fail(PC_ERR_INVALID, "pc_last_status: ctx is NULL");
+    if (status) *status = c->h_counters[PC_CNT_STATUS];
+    if (need_contacts) *need_contacts = (int64_t)c->h_counters[PC_CNT_CONTACTS];
+    if (need_hbonds) *need_hbonds = (int64_t)c->h_counters[PC_CNT_HBONDS];
+    if (need_rows) *need_rows = (int64_t)c->h_counters[PC_CNT_ROWS];
+    if (path) *path = c->last_path;
+    return PC_OK;
+}
+
+extern "C" int pc_device_outputs(pc_ctx *c, pc_contact **d_contacts, pc_hbond **d_hbonds, pc_row **d_rows,
+                                 uint64_t **d_order_keys, uint32_t **cs, uint32_t **cc, uint32_t **hs,
+                                 uint32_t **hc, uint32_t **rs, uint32_t **rc) {
+    if (!c) return fail(PC_ERR_INVALID, "pc_device_outputs: ctx is NULL");
+    if (d_contacts) *d_contacts = c->contacts.p;
+    if (d_hbonds) *d_hbonds = c->hbonds.p;
+    if (d_rows) *d_rows = c->rows.p;
+    if (d_order_keys) *d_order_keys = (uint64_t *)c->order_keys.p;
+    uint32_t **outs[6] = {cs, cc, hs, hc, rs, rc};
+    for (int k = 0; k < 6; k++) if (outs[k]) *outs[k] = meta(c, k);
+    return PC_OK;
+}
+
+extern "C" int pc_fetch(pc_ctx *c, void *stream, pc_contact *h_contacts, pc_hbond *h_hbonds, pc_row *h_rows,
+                        uint64_t *h_order_keys, uint32_t *cs, uint32_t *cc, uint32_t *hs, uint32_t *hc,
+                        uint32_t *rs, uint32_t *rc) {
+    if (!c) return fail(PC_ERR_INVALID, "pc_fetch: ctx is NULL");
+    CUDA_TRY(cudaSetDevice(c->device));
+    cudaStream_t s = (cudaStream_t)stream;
+    const size_t nc = std::min<unsigned long long>(c->h_counters[PC_CNT_CONTACTS], c->cap_contacts);
+    const size_t nh = std::min<unsigned long long>(c->h_counters[PC_CNT_HBONDS], c->cap_hbonds);
+    const size_t nr = std::min<unsigned long long>(c->h_counters[PC_CNT_ROWS], c->cap_rows);
+    if (c->last_path == 2) {
+        // sliced outputs -> dense host arrays; the start arrays handed back are the dense offsets
+        const int nf = c->last_nframes;
+        if ((int)c->h_meta.size() != 4 * nf) return fail(PC_ERR_INVALID, "pc_fetch: call pc_batch_totals first");
+        const uint32_t *ms = c->h_meta.data();
+        size_t oc = 0, oh = 0;
+        for (int f = 0; f < nf; f++) {
+            const uint32_t s0 = ms[f], n0 = ms[nf + f], s1 = ms[2 * nf + f], n1 = ms[3 * nf + f];
+            if (h_contacts && n0)
+                CUDA_TRY(cudaMemcpyAsync(h_contacts + oc, c->contacts.p + s0, n0 * sizeof(pc_contact), cudaMemcpyDeviceToHost, s));
+            if (h_order_keys && n0 && c->last_order_keys)
+                CUDA_TRY(cudaMemcpyAsync(h_order_keys + oc, c->order_keys.p + s0, n0 * sizeof(uint64_t), cudaMemcpyDeviceToHost, s));
+            if (h_hbonds && n1)
+                CUDA_TRY(cudaMemcpyAsync(h_hbonds + oh, c->hbonds.p + s1, n1 * sizeof(pc_hbond), cudaMemcpyDeviceToHost, s));
+            if (cs) cs[f] = (uint32_t)oc;
+            if (cc) cc[f] = n0;
+            if (hs) hs[f] = (uint32_t)oh;
+            if (hc) hc[f] = n1;
+            oc += n0; oh += n1;
+        }
+        if (h_rows && nr)
+            CUDA_TRY(cudaMemcpyAsync(h_rows, c->rows.p, nr * sizeof(pc_row), cudaMemcpyDeviceToHost, s));
+        if (rs) CUDA_TRY(cudaMemcpyAsync(rs, meta(c, 4), (size_t)nf * sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
+        if (rc) CUDA_TRY(cudaMemcpyAsync(rc, meta(c, 5), (size_t)nf * sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
+        return PC_OK;
+    }
+    if (h_contacts && nc)
+        CUDA_TRY(cudaMemcpyAsync(h_contacts, c->contacts.p, nc * sizeof(pc_contact), cudaMemcpyDeviceToHost, s));
+    if (h_order_keys && nc && c->last_order_keys)
+        CUDA_TRY(cudaMemcpyAsync(h_order_keys, c->order_keys.p, nc * sizeof(uint64_t), cudaMemcpyDeviceToHost, s));
+    if (h_hbonds && nh)
+        CUDA_TRY(cudaMemcpyAsync(h_hbonds, c->hbonds.p, nh * sizeof(pc_hbond), cudaMemcpyDeviceToHost, s));
+    if (h_rows && nr)
+        CUDA_TRY(cudaMemcpyAsync(h_rows, c->rows.p, nr * sizeof(pc_row), cudaMemcpyDeviceToHost, s));
+    uint32_t *outs[6] = {cs, cc, hs, hc, rs, rc};
+    for (int k = 0; k < 6; k++)
+        if (outs[k])
+            CUDA_TRY(cudaMemcpyAsync(outs[k], meta(c, k), (size_t)c->last_nframes * sizeof(uint32_t),
+                                     cudaMemcpyDeviceToHost, s));
+    return PC_OK;
+}
+
+extern "C" int pc_find_contacts(int device, const float *h_xyz1, int32_t n1, const float *h_xyz2, int32_t n2,
+                                double cutoff, int64_t *h_row_ptr, int32_t **h_cols) {
+    if (!h_row_ptr || !h_cols) return fail(PC_ERR_INVALID, "pc_find_contacts: NULL output");
+    *h_cols = nullptr;
+    for (int i = 0; i <= std::max(n1, 0); i++) h_row_ptr[i] = 0;
+    if (n1 <= 0 || n2 <= 0) return PC_OK;            // gridsearch.C:906
+    if (!h_xyz1 || !h_xyz2) return fail(PC_ERR_INVALID, "pc_find_contacts: NULL coordinates");
+    if (!(cutoff > 0)) return fail(PC_ERR_INVALID, "pc_find_contacts: cutoff must be positive");
+    CUDA_TRY(cudaSetDevice(device));
+    return pc_search_all(h_xyz1, n1, h_xyz2, n2, cutoff, h_row_ptr, h_cols, g_err);
+}
+
+extern "C" void pc_free_host(void *p) { free(p); }
+
+extern "C" int pc_synth_frames(int device, const float *d_base, const int32_t *d_res, const float *d_amp,
+                               const float *d_period, const float *d_phase, int32_t natoms, float sigma,
+                               uint64_t seed, int32_t frame0, int32_t nframes, int32_t layout, int64_t pitch,
+                               float *d_out, void *stream) {
+    if (!d_base || !d_res || !d_amp || !d_period || !d_phase || !d_out || natoms <= 0 || nframes <= 0)
+        return fail(PC_ERR_INVALID, "pc_synth_frames: bad arguments");
+    if (layout != PC_LAYOUT_XYZ && layout != PC_LAYOUT_XYZW) return fail(PC_ERR_INVALID, "pc_synth_frames: bad layout");
+    CUDA_TRY(cudaSetDevice(device));
+    pc_synth_launch(d_base, d_res, d_amp, d_period, d_phase, natoms, sigma, seed, frame0, nframes, layout, pitch,
+                    d_out, (cudaStream_t)stream);
+    CUDA_TRY(cudaGetLastError());
+    g_launches += (unsigned long long)((nframes + 32767) / 32768);
+    return PC_OK;
+}
+
+extern "C" int pc_stream_create(int device, void **out) {
+    if (!out) return fail(PC_ERR_INVALID, "pc_stream_create: out is NULL");
+    CUDA_TRY(cudaSetDevice(device));
+    cudaStream_t s;
+    CUDA_TRY(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
+    *out = (void *)s;
+    return PC_OK;
+}
+extern "C" int pc_stream_sync(void *stream) {
+    CUDA_TRY(cudaStreamSynchronize((cudaStream_t)stream));
+    return PC_OK;
+}
+extern "C" void pc_stream_destroy(void *stream) { if (stream) cudaStreamDestroy((cudaStream_t)stream); }
+
+extern "C" int pc_device_alloc(int device, int64_t bytes, void **out) {
+    if (!out || bytes <= 0) return fail(PC_ERR_INVALID, "pc_device_alloc: bad arguments");
+    CUDA_TRY(cudaSetDevice(device));
+    CUDA_TRY(cudaMalloc(out, (size_t)bytes));
+    return PC_OK;
+}
+extern "C" void pc_device_free(int device, void *p) {
+    if (!p) return;
+    cudaSetDevice(device);
+    cudaFree(p);
+}
+extern "C" int pc_memcpy(int device, void *dst, const void *src, int64_t bytes, int kind, void *stream) {
+    if (!dst || !src || bytes < 0 || kind < 1 || kind > 3) return fail(PC_ERR_INVALID, "pc_memcpy: bad arguments");
+    CUDA_TRY(cudaSetDevice(device));
+    const cudaMemcpyKind k = kind == 1 ? cudaMemcpyHostToDevice : kind == 2 ? cudaMemcpyDeviceToHost : cudaMemcpyDeviceToDevice;
+    CUDA_TRY(cudaMemcpyAsync(dst, src, (size_t)bytes, k, (cudaStream_t)stream));
+    return PC_OK;
+}
+extern "C" int pc_device_sync(int device) {
+    CUDA_TRY(cudaSetDevice(device));
+    CUDA_TRY(cudaDeviceSynchronize());
+    return PC_OK;
+}
+
+extern "C" int64_t pc_launch_count(void) { return (int64_t)g_launches; }
+
+extern "C" int pc_event_create(int device, void **out) {
+    if (!out) return fail(PC_ERR_INVALID, "pc_event_create: out is NULL");
+    CUDA_TRY(cudaSetDevice(device));
+    cudaEvent_t e;
+    CUDA_TRY(cudaEventCreate(&e));
+    *out = (void *)e;
+    return PC_OK;
+}
+extern "C" int pc_event_record(void *event, void *stream) {
+    CUDA_TRY(cudaEventRecord((cudaEvent_t)event, (cudaStream_t)stream));
+    return PC_OK;
+}
+extern "C" int pc_event_elapsed_ms(void *start, void *end, float *ms) {
+    if (!ms) return fail(PC_ERR_INVALID, "pc_event_elapsed_ms: ms is NULL");
+    CUDA_TRY(cudaEventSynchronize((cudaEvent_t)end));
+    CUDA_TRY(cudaEventElapsedTime(ms, (cudaEvent_t)start, (cudaEvent_t)end));
+    return PC_OK;
+}
+extern "C" void pc_event_destroy(void *event) { if (event) cudaEventDestroy((cudaEvent_t)event); }
+
+extern "C" int pc_host_alloc(void **out, int64_t bytes) {
+    if (!out || bytes <= 0) return fail(PC_ERR_INVALID, "pc_host_alloc: bad arguments");
+    CUDA_TRY(cudaHostAlloc(out, (size_t)bytes, cudaHostAllocDefault));
+    return PC_OK;
+}
+extern "C" void pc_host_free(void *p) { if (p) cudaFreeHost(p); }

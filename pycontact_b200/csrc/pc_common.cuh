@@ -1,0 +1,117 @@
+// pc_common.cuh -- shared device helpers and argument blocks (sm_100a).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <math.h>
+#include "../../include/pycontact_b200.h"
+
+#define PC_FULL_MASK 0xffffffffu
+
+// status bits written by kernels into counters[PC_CNT_STATUS]
+#define PC_ST_HITS_OVERFLOW   1ull   // per-frame shared hit queue too small
+#define PC_ST_HB_OVERFLOW     2ull   // per-frame shared H-bond staging too small
+#define PC_ST_OUT_OVERFLOW    4ull   // batch-wide contact / hbond / row buffer too small
+#define PC_ST_MISSING_H       8ull   // bonded hydrogen not in the selection (reference raises)
+#define PC_ST_BAD_COORDS     16ull   // non-finite coordinates
+#define PC_ST_TABLE_OVERFLOW 32ull   // accumulation hash table too small
+
+enum { PC_CNT_CONTACTS = 0, PC_CNT_HBONDS = 1, PC_CNT_STATUS = 2, PC_CNT_EVALS = 3, PC_CNT_ROWS = 4,
+       PC_CNT_WORK = 5, PC_CNT_COUNT = 8 };
+
+// cell edge = cutoff * PC_EDGE_SCALE.  A pair accepted by the reference's float32 test has a
+// true separation <= cutoff*(1+3e-7); cell coordinates computed in float32 carry an error
+// below 3e-5 cells for extents up to 1000 A, so with 2e-4 of slack two such atoms always
+// land in the same or adjacent cells (DESIGN.md "grid exactness").
+#define PC_EDGE_SCALE 1.0002f
+
+struct PcTopoDev {
+    int n1, n2, n1h, n2h;
+    const int *heavy1, *heavy2;        // heavy ordinal -> local index
+    const uint8_t *hflag1, *hflag2;    // per heavy ordinal: PC_ATOM_* bits
+    const int *hres1, *hseg1, *hres2, *hseg2;   // per heavy ordinal
+    const int *hhptr1, *hidx1, *hhptr2, *hidx2; // bonded-H CSR per heavy ordinal -> local H index
+    const int *hgid1, *hgid2;          // per heavy ordinal group ids (maps)
+    const int *lgid1, *lgid2;          // per LOCAL index group ids (maps)
+    const uint8_t *lflag1, *lflag2;    // per LOCAL index flags
+    unsigned long long ngroups2;
+};
+
+struct PcScanArgs {
+    const float *xyz1, *xyz2;
+    long long pitch1, pitch2;          // floats per frame
+    int stride;                        // floats per atom (3 or 4)
+    int nframes, self_mode, order_keys;
+    PcTopoDev t;
+    float edge, sqdist, cutoff_f;
+    double hb_cutoff, hb_angle;
+    int capCells, capHits, capHb;      // shared-memory capacities (small-frame path)
+    pc_contact *contacts;
+    pc_hbond *hbonds;
+    unsigned long long *order_out;
+    unsigned long long *counters;
+    long long cap_contacts, cap_hbonds;
+    uint32_t *frame_cstart, *frame_ccount, *frame_hstart, *frame_hcount;
+};
+
+__device__ __forceinline__ float warp_min(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fminf(v, __shfl_xor_sync(PC_FULL_MASK, v, o));
+    return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(PC_FULL_MASK, v, o));
+    return v;
+}
+__device__ __forceinline__ uint32_t warp_incl_scan(uint32_t v, int lane) {
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        uint32_t n = __shfl_up_sync(PC_FULL_MASK, v, o);
+        if (lane >= o) v += n;
+    }
+    return v;
+}
+
+// The reference's pair test (gridsearch.C:48-55, :1126): float32, ((dx*dx + dy*dy) + dz*dz),
+// every operation rounded separately -- the _rn intrinsics are never contracted into FMAs.
+__device__ __forceinline__ float dist2_exact(float ax, float ay, float az, float bx, float by, float bz) {
+    const float dx = __fsub_rn(ax, bx), dy = __fsub_rn(ay, by), dz = __fsub_rn(az, bz);
+    return __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
+}
+
+// weight_function (core/multi_trajectory.py:15-17), float64 like the reference
+__device__ __forceinline__ double contact_weight(double d) { return 1.0 / (1.0 + exp(5.0 * (d - 4.0))); }
+
+__device__ __forceinline__ void load_xyz(const float *frame, int idx, int stride, float &x, float &y, float &z) {
+    if (stride == 4) {
+        const float4 v = __ldg(reinterpret_cast<const float4 *>(frame) + idx);
+        x = v.x; y = v.y; z = v.z;
+    } else {
+        const float *p = frame + 3ll * idx;
+        x = __ldg(p); y = __ldg(p + 1); z = __ldg(p + 2);
+    }
+}
+
+// One donor-H...acceptor test (core/multi_trajectory.py:157-181 / :183-205), float64 on the
+// exactly promoted float32 coordinates.  Returns true and fills dist/angle when it is an H-bond.
+__device__ __forceinline__ bool hbond_test(double hx, double hy, double hz, double dx_, double dy_, double dz_,
+                                           double ax, double ay, double az, double hb_cutoff, double hb_angle,
+                                           double &dist, double &angle) {
+    const double v1x = hx - ax, v1y = hy - ay, v1z = hz - az;   // H - acceptor
+    const double n1 = sqrt(v1x * v1x + v1y * v1y + v1z * v1z);
+    if (!(n1 <= hb_cutoff)) return false;
+    const double v2x = hx - dx_, v2y = hy - dy_, v2z = hz - dz_; // H - donor
+    const double n2 = sqrt(v2x * v2x + v2y * v2y + v2z * v2z);
+    const double dot = v1x * v2x + v1y * v2y + v1z * v2z;
+    const double ang = acos(dot / (n1 * n2)) * 57.29577951308232;   // np.degrees
+    if (!(ang >= hb_angle)) return false;
+    dist = n1; angle = ang;
+    return true;
+}
+
+// stencil rank of a box offset in make_neighborlist_sym order (gridsearch.C:858-885, App. A.3);
+// index = (dx+1) + 3*(dy+1) + 9*(dz+1)
+__constant__ unsigned char PC_STENCIL_RANK[27] = {
+    /* dz=-1 */ 23, 19, 24,  18, 16, 21,  25, 22, 26,
+    /* dz= 0 */ 17, 15,  7,  14,  0,  1,  20,  2,  4,
+    /* dz=+1 */ 13,  9, 12,   8,  3,  5,  11,  6, 10};

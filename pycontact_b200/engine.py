@@ -1,0 +1,378 @@
+"""Frame-batch engine: the host side of the CUDA hot path.
+
+``ContactEngine`` owns one GPU's contexts of libpycontact_b200.so and runs batches of
+frames through it: H2D copy -> scan (search + filters + score + H-bond test) ->
+[order keys] -> [accumulate] -> D2H of the records.  It replaces the reference's
+frame-chunking scheduler (``run_load_parallel``'s ``chunks`` + ``Pool.apply_async`` +
+``loop_trajectory_grid`` per chunk, PyContact/core/multi_trajectory.py:423-451): chunks
+become frame batches, pool workers become batches in flight on CUDA streams (two slots:
+while one batch computes, the next is uploaded and the previous is read back).
+
+There is no CPU fallback: every number returned was produced by the CUDA library.
+"""
+from __future__ import annotations
+
+import ctypes
+from dataclasses import dataclass
+from typing import Iterable, Iterator, Optional, Tuple
+
+import numpy as np
+
+from . import _lib
+from ._lib import PcError, check, ptr
+from .prepare import SelectionTopology
+
+
+@dataclass
+class BatchResult:
+    """Records of one frame batch as flat arrays (frames are contiguous ranges)."""
+    frame0: int
+    nframes: int
+    contacts: Optional[np.ndarray]       # _lib.contact_dtype, local indices i / j
+    order_keys: Optional[np.ndarray]     # uint64 per contact (reference order key) or None
+    hbonds: Optional[np.ndarray]         # _lib.hbond_dtype
+    rows: Optional[np.ndarray]           # _lib.row_dtype ((frame, key) cells) or None
+    cstart: np.ndarray
+    ccount: np.ndarray
+    hstart: np.ndarray
+    hcount: np.ndarray
+    rstart: Optional[np.ndarray]
+    rcount: Optional[np.ndarray]
+    n_pair_evals: int
+    path: int                            # 1 = one CTA per frame, 2 = tiled large-frame path
+
+
+class _Slot:
+    """One batch in flight: a library context, a stream and pinned staging buffers."""
+
+    def __init__(self, eng: "ContactEngine"):
+        lib = eng.lib
+        self.eng = eng
+        self.ctx = ctypes.c_void_p()
+        check(lib.pc_create(eng.device, eng.cutoff, eng.hbondcutoff, eng.hbondcutangle, int(eng.self_mode),
+                            ctypes.byref(self.ctx)))
+        self.stream = ctypes.c_void_p()
+        check(lib.pc_stream_create(eng.device, ctypes.byref(self.stream)))
+        s1, s2 = eng.sel1, eng.sel2
+        check(lib.pc_set_topology(
+            self.ctx, s1.n, 0 if eng.self_mode else s2.n,
+            ptr(s1.flags), None if eng.self_mode else ptr(s2.flags),
+            ptr(s1.resid), ptr(s1.segid),
+            None if eng.self_mode else ptr(s2.resid), None if eng.self_mode else ptr(s2.segid),
+            ptr(s1.hptr), ptr(s1.hidx),
+            None if eng.self_mode else ptr(s2.hptr), None if eng.self_mode else ptr(s2.hidx)))
+        self.max_frames = 0
+        self.cap = [0, 0, 0]
+        self.pin_in = [None, None]
+        self.pin_out = {}
+        self.pending = None
+
+    def close(self):
+        lib = self.eng.lib
+        if self.ctx:
+            lib.pc_stream_sync(self.stream)
+            lib.pc_destroy(self.ctx)
+            lib.pc_stream_destroy(self.stream)
+            self.ctx = None
+        self.pin_in = [None, None]
+        self.pin_out = {}
+
+    def reserve(self, nframes, cap_c, cap_h, cap_r):
+        if nframes > self.max_frames or cap_c > self.cap[0] or cap_h > self.cap[1] or cap_r > self.cap[2]:
+            self.max_frames = max(self.max_frames, nframes)
+            self.cap = [max(self.cap[0], cap_c), max(self.cap[1], cap_h), max(self.cap[2], cap_r)]
+            check(self.eng.lib.pc_reserve(self.ctx, self.max_frames, *self.cap))
+
+    def staging(self, which, nfloats):
+        buf = self.pin_in[which]
+        if buf is None or buf.array.size < nfloats:
+            buf = _lib.PinnedArray((nfloats,), np.float32)
+            self.pin_in[which] = buf
+        return buf.array
+
+    def out(self, name, count, dtype):
+        buf = self.pin_out.get(name)
+        if buf is None or buf.array.size < count:
+            buf = _lib.PinnedArray((max(int(count * 1.25), 1024),), dtype)
+            self.pin_out[name] = buf
+        return buf.array
+
+
+class ContactEngine:
+    def __init__(self, sel1: SelectionTopology, sel2: Optional[SelectionTopology], cutoff, hbondcutoff,
+                 hbondcutangle, device: int = 0, slots: int = 2):
+        self.lib = _lib.load()
+        self.device = int(device)
+        self.cutoff, self.hbondcutoff, self.hbondcutangle = float(cutoff), float(hbondcutoff), float(hbondcutangle)
+        self.self_mode = sel2 is None
+        self.sel1 = sel1
+        self.sel2 = sel1 if sel2 is None else sel2
+        if self.sel1.n == 0 or self.sel2.n == 0:
+            raise Exception("empty atom selection")       # core/ContactAnalyzer.py:312-313
+        self.n1, self.n2 = self.sel1.n, self.sel2.n
+        self.slots = [_Slot(self) for _ in range(max(1, slots))]
+        self.maps_set = False
+        self.n_groups2 = 0
+        # per-frame guesses, grown on PC_ERR_CAPACITY
+        heavy = int(min((~(self.sel1.flags & 1).astype(bool)).sum(), (~(self.sel2.flags & 1).astype(bool)).sum()))
+        self.guess = [max(256, 2 * heavy), max(64, heavy // 4), 256]
+        self.lim = [0, 0, 0, 0]          # hits/frame, hbonds/frame, cells, table slots (0 = automatic)
+        self.launches = 0
+
+    # ------------------------------------------------------------------------------------------
+    def close(self):
+        for s in self.slots:
+            s.close()
+        self.slots = []
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def set_maps(self, gid1: np.ndarray, gid2: np.ndarray, n_groups2: int):
+        g1 = np.ascontiguousarray(gid1, np.int32)
+        g2 = np.ascontiguousarray(gid2, np.int32)
+        if g1.size != self.n1 or g2.size != self.n2:
+            raise ValueError("group id arrays must cover the selections")
+        for s in self.slots:
+            check(self.lib.pc_set_maps(s.ctx, ptr(g1), ptr(g2), int(n_groups2)))
+        self.maps_set = True
+        self.n_groups2 = int(n_groups2)
+
+    def set_limits(self, hits=0, hbonds=0, cells=0, table=0):
+        self.lim = [int(hits), int(hbonds), int(cells), int(table)]
+        for s in self.slots:
+            check(self.lib.pc_set_limits(s.ctx, *self.lim))
+
+    def set_path(self, path: int):
+        """0 = automatic, 1 = small-frame kernel, 2 = large-frame path (tests cover both)."""
+        for s in self.slots:
+            check(self.lib.pc_set_path(s.ctx, int(path)))
+
+    # ------------------------------------------------------------------------------------------
+    def _grow(self, slot: _Slot, nframes: int):
+        """After PC_ERR_CAPACITY: enlarge whatever overflowed."""
+        st = ctypes.c_uint64()
+        need = [ctypes.c_int64(), ctypes.c_int64(), ctypes.c_int64()]
+        path = ctypes.c_int32()
+        check(self.lib.pc_last_status(slot.ctx, ctypes.byref(st), ctypes.byref(need[0]), ctypes.byref(need[1]),
+                                      ctypes.byref(need[2]), ctypes.byref(path)))
+        st = st.value
+        if st & _lib.ST_HITS_OVERFLOW:
+            self.lim[0] = max(8192, 2 * (self.lim[0] or 4096))
+        if st & _lib.ST_HB_OVERFLOW:
+            self.lim[1] = max(1024, 2 * (self.lim[1] or 256))
+        if st & _lib.ST_TABLE_OVERFLOW:
+            self.lim[3] = max(2048, 2 * (self.lim[3] or 1024))
+            if self.lim[3] > 4096:
+                raise PcError(_lib.PC_ERR_CAPACITY, "more than 4096 accumulation keys in one frame")
+        if self.lim[0] > 32768 or self.lim[1] > 8192:
+            raise PcError(_lib.PC_ERR_CAPACITY, "frame produces more records than the small-frame path can stage")
+        for s in self.slots:
+            check(self.lib.pc_set_limits(s.ctx, *self.lim))
+        if st & _lib.ST_OUT_OVERFLOW:
+            # the large-frame path slices the buffers per frame: size by the worst frame seen
+            per = [max(1, -(-n.value // nframes)) for n in need]
+            grow = 4 if path.value == 2 else 1.5
+            self.guess = [max(g, int(p * grow) + 64) for g, p in zip(self.guess, per)]
+
+    def submit(self, slot_id: int, xyz1, xyz2, *, frame0=0, order_keys=False, accumulate=False,
+               pinned=False):
+        """Enqueue one batch on a slot (asynchronous).  xyz*: float32 (nf, n, 3) host arrays."""
+        slot = self.slots[slot_id]
+        xyz1 = np.asarray(xyz1)
+        nf = int(xyz1.shape[0])
+        if xyz1.dtype != np.float32 or xyz1.shape[1:] != (self.n1, 3):
+            raise ValueError("xyz1 must be float32 with shape (nframes, %d, 3)" % self.n1)
+        if not self.self_mode:
+            xyz2 = np.asarray(xyz2)
+            if xyz2.dtype != np.float32 or xyz2.shape != (nf, self.n2, 3):
+                raise ValueError("xyz2 must be float32 with shape (%d, %d, 3)" % (nf, self.n2))
+        if accumulate and not self.maps_set:
+            raise ValueError("set_maps() before accumulating")
+        if pinned:
+            h1 = np.ascontiguousarray(xyz1)
+            h2 = None if self.self_mode else np.ascontiguousarray(xyz2)
+        else:
+            h1 = slot.staging(0, nf * self.n1 * 3)[: nf * self.n1 * 3]
+            h1[:] = xyz1.reshape(-1)
+            h2 = None
+            if not self.self_mode:
+                h2 = slot.staging(1, nf * self.n2 * 3)[: nf * self.n2 * 3]
+                h2[:] = xyz2.reshape(-1)
+        slot.pending = dict(h1=h1, h2=h2, nf=nf, frame0=frame0, order_keys=bool(order_keys),
+                            accumulate=bool(accumulate))
+        self._launch(slot)
+
+    def _launch(self, slot: _Slot):
+        p = slot.pending
+        nf = p["nf"]
+        slot.reserve(nf, nf * self.guess[0], nf * self.guess[1], nf * self.guess[2])
+        check(self.lib.pc_scan_host(slot.ctx, ptr(p["h1"]), ptr(p["h2"]), nf, _lib.PC_LAYOUT_XYZ,
+                                    int(p["order_keys"]), int(p["accumulate"]), slot.stream))
+        self.launches += 1
+
+    def collect(self, slot_id: int, *, want_contacts=True, want_hbonds=True, copy=True) -> BatchResult:
+        """Wait for the slot's batch and read its records back (retrying after growing any
+        buffer that overflowed)."""
+        slot = self.slots[slot_id]
+        p = slot.pending
+        if p is None:
+            raise RuntimeError("nothing submitted on this slot")
+        lib = self.lib
+        nf = p["nf"]
+        tot = [ctypes.c_int64() for _ in range(4)]
+        for attempt in range(12):
+            rc = lib.pc_batch_totals(slot.ctx, slot.stream, *[ctypes.byref(t) for t in tot])
+            if rc == _lib.PC_ERR_CAPACITY:
+                self._grow(slot, nf)
+                self._launch(slot)
+                continue
+            check(rc)
+            break
+        else:
+            raise PcError(_lib.PC_ERR_CAPACITY, "batch still does not fit after growing the buffers")
+        nc, nh, nr, ne = (int(t.value) for t in tot)
+        path = ctypes.c_int32()
+        check(lib.pc_last_status(slot.ctx, None, None, None, None, ctypes.byref(path)))
+        acc = p["accumulate"]
+        meta = slot.out("meta", 6 * nf, np.uint32)
+        m = [meta[k * nf:(k + 1) * nf] for k in range(6)]
+        contacts = slot.out("contacts", nc, _lib.contact_dtype)[:nc] if want_contacts else None
+        okeys = slot.out("okeys", nc, np.uint64)[:nc] if (want_contacts and p["order_keys"]) else None
+        hbonds = slot.out("hbonds", nh, _lib.hbond_dtype)[:nh] if want_hbonds else None
+        rows = slot.out("rows", nr, _lib.row_dtype)[:nr] if acc else None
+        check(lib.pc_fetch(slot.ctx, slot.stream, ptr(contacts), ptr(hbonds), ptr(rows), ptr(okeys),
+                           ptr(m[0]), ptr(m[1]), ptr(m[2]), ptr(m[3]),
+                           ptr(m[4]) if acc else None, ptr(m[5]) if acc else None))
+        check(lib.pc_stream_sync(slot.stream))
+        slot.pending = None
+        cp = (lambda a: None if a is None else a.copy()) if copy else (lambda a: a)
+        return BatchResult(p["frame0"], nf, cp(contacts), cp(okeys), cp(hbonds), cp(rows),
+                           cp(m[0]), cp(m[1]), cp(m[2]), cp(m[3]), cp(m[4]) if acc else None,
+                           cp(m[5]) if acc else None, ne, int(path.value))
+
+    def accumulate_records(self, contacts, hbonds, ccount, hcount, order_keys=None, frame0=0) -> BatchResult:
+        """Regroup already-fetched records (dense, frame after frame) under the current maps:
+        ``runContactAnalysis`` on stored ``contactResults`` (core/ContactAnalyzer.py:64-70)."""
+        if not self.maps_set:
+            raise ValueError("set_maps() before accumulating")
+        slot = self.slots[0]
+        lib = self.lib
+        nf = int(len(ccount))
+        contacts = np.ascontiguousarray(contacts, _lib.contact_dtype)
+        hbonds = np.ascontiguousarray(hbonds, _lib.hbond_dtype)
+        ccount = np.ascontiguousarray(ccount, np.uint32)
+        hcount = np.ascontiguousarray(hcount, np.uint32)
+        cstart = (np.cumsum(ccount, dtype=np.uint64) - ccount).astype(np.uint32)
+        hstart = (np.cumsum(hcount, dtype=np.uint64) - hcount).astype(np.uint32)
+        ok = None if order_keys is None else np.ascontiguousarray(order_keys, np.uint64)
+        rows_guess = max(self.guess[2] * nf, 1024)
+        for attempt in range(12):
+            slot.reserve(nf, max(contacts.size, 1), max(hbonds.size, 1), rows_guess)
+            check(lib.pc_load_records(slot.ctx, ptr(contacts), ptr(ok), ptr(hbonds), nf, ptr(cstart), ptr(ccount),
+                                      ptr(hstart), ptr(hcount), slot.stream))
+            check(lib.pc_accumulate(slot.ctx, slot.stream))
+            self.launches += 1
+            tot = [ctypes.c_int64() for _ in range(4)]
+            rc = lib.pc_batch_totals(slot.ctx, slot.stream, *[ctypes.byref(t) for t in tot])
+            if rc == _lib.PC_ERR_CAPACITY:
+                st = ctypes.c_uint64()
+                need = ctypes.c_int64()
+                check(lib.pc_last_status(slot.ctx, ctypes.byref(st), None, None, ctypes.byref(need), None))
+                if st.value & _lib.ST_TABLE_OVERFLOW:
+                    self.lim[3] = max(2048, 2 * (self.lim[3] or 1024))
+                    if self.lim[3] > 4096:
+                        raise PcError(_lib.PC_ERR_CAPACITY, "more than 4096 accumulation keys in one frame")
+                    for s in self.slots:
+                        check(lib.pc_set_limits(s.ctx, *self.lim))
+                rows_guess = max(int(need.value * 1.25) + 64, 2 * rows_guess if st.value & _lib.ST_OUT_OVERFLOW else rows_guess)
+                continue
+            check(rc)
+            break
+        else:
+            raise PcError(_lib.PC_ERR_CAPACITY, "accumulation still does not fit after growing the buffers")
+        nr = int(tot[2].value)
+        rows = np.zeros(nr, _lib.row_dtype)
+        rs, rc_ = np.zeros(nf, np.uint32), np.zeros(nf, np.uint32)
+        check(lib.pc_fetch(slot.ctx, slot.stream, None, None, ptr(rows), None, None, None, None, None, ptr(rs), ptr(rc_)))
+        check(lib.pc_stream_sync(slot.stream))
+        return BatchResult(frame0, nf, None, None, None, rows, cstart, ccount, hstart, hcount, rs, rc_, 0, 1)
+
+    def scan_device(self, d_xyz1, d_xyz2, nframes, *, layout=_lib.PC_LAYOUT_XYZ, pitch1=None, pitch2=None,
+                    order_keys=False, accumulate=False, slot_id=0, events=None):
+        """Scan frames that are already in HBM (device pointers); returns
+        (n_contacts, n_hbonds, n_rows, n_pair_evals) after synchronising the slot's stream.
+        ``events`` = (start, end) CUDA events recorded around the scan launch only."""
+        slot = self.slots[slot_id]
+        lib = self.lib
+        nf = int(nframes)
+        pitch1 = self.n1 * layout if pitch1 is None else int(pitch1)
+        pitch2 = self.n2 * layout if pitch2 is None else int(pitch2)
+        tot = [ctypes.c_int64() for _ in range(4)]
+        for attempt in range(12):
+            slot.reserve(nf, nf * self.guess[0], nf * self.guess[1], nf * self.guess[2])
+            if events is not None:
+                check(lib.pc_event_record(events[0], slot.stream))
+            check(lib.pc_scan_device(slot.ctx, d_xyz1, d_xyz2, nf, int(layout), pitch1, pitch2, int(order_keys),
+                                     slot.stream))
+            if events is not None:
+                check(lib.pc_event_record(events[1], slot.stream))
+            if accumulate:
+                check(lib.pc_accumulate(slot.ctx, slot.stream))
+            self.launches += 1
+            rc = lib.pc_batch_totals(slot.ctx, slot.stream, *[ctypes.byref(t) for t in tot])
+            if rc == _lib.PC_ERR_CAPACITY:
+                self._grow(slot, nf)
+                continue
+            check(rc)
+            return tuple(int(t.value) for t in tot)
+        raise PcError(_lib.PC_ERR_CAPACITY, "batch still does not fit after growing the buffers")
+
+    def fetch_rows(self, slot_id=0):
+        """Rows of the slot's last accumulated batch -> (rows, rstart, rcount) host arrays (pinned views)."""
+        slot = self.slots[slot_id]
+        lib = self.lib
+        nr = ctypes.c_int64()
+        st = ctypes.c_uint64()
+        nf = slot.max_frames
+        check(lib.pc_last_status(slot.ctx, ctypes.byref(st), None, None, ctypes.byref(nr), None))
+        n = min(int(nr.value), slot.cap[2])
+        rows = slot.out("rows", n, _lib.row_dtype)[:n]
+        meta = slot.out("meta", 6 * nf, np.uint32)
+        check(lib.pc_fetch(slot.ctx, slot.stream, None, None, ptr(rows), None, None, None, None, None,
+                           ptr(meta[4 * nf:5 * nf]), ptr(meta[5 * nf:6 * nf])))
+        check(lib.pc_stream_sync(slot.stream))
+        return rows, meta[4 * nf:5 * nf], meta[5 * nf:6 * nf]
+
+    # ------------------------------------------------------------------------------------------
+    def scan(self, xyz1, xyz2=None, **kw) -> BatchResult:
+        """One batch, synchronously."""
+        want = {k: kw.pop(k) for k in ("want_contacts", "want_hbonds") if k in kw}
+        self.submit(0, xyz1, xyz2, **kw)
+        return self.collect(0, **want)
+
+    def scan_batches(self, batches: Iterable[Tuple[int, np.ndarray, Optional[np.ndarray]]], **kw) -> Iterator[BatchResult]:
+        """Pipeline ``(frame0, xyz1, xyz2)`` batches over the slots: batch k+1 is staged and
+        uploaded while batch k computes.  Yields results in order."""
+        want = {k: kw.pop(k) for k in ("want_contacts", "want_hbonds", "copy") if k in kw}
+        ns = len(self.slots)
+        inflight = []
+        k = 0
+        for frame0, a, b in batches:
+            sid = k % ns
+            if len(inflight) == ns:
+                yield self.collect(inflight.pop(0), **want)
+            self.submit(sid, a, b, frame0=frame0, **kw)
+            inflight.append(sid)
+            k += 1
+        while inflight:
+            yield self.collect(inflight.pop(0), **want)

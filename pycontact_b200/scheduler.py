@@ -1,0 +1,125 @@
+"""Frame-chunking scheduler.
+
+The reference splits the frame list into ``nproc`` contiguous chunks (``chunks``,
+PyContact/core/multi_trajectory.py:20-30) and hands each to a pool worker
+(:434-443).  Here a chunk goes to a GPU (one ``ContactEngine`` per device) and is
+streamed through it in frame batches sized to keep the copy engines and SMs busy;
+results come back in frame order, like the concatenation at :447-451.
+"""
+from __future__ import annotations
+
+from typing import Callable, List, Optional, Sequence
+
+import numpy as np
+
+from .engine import ContactEngine
+from .results import AccumulationTable, TrajectoryContacts
+
+
+def chunks(seq, num):
+    """Split ``seq`` into ``num`` (almost) equal contiguous slices -- same rule (and the same
+    float stepping) as core/multi_trajectory.py:20-30, so frame -> worker assignment matches."""
+    n = len(seq)
+    step = n / float(num)
+    out, pos = [], 0.0
+    while pos < n:
+        out.append(seq[int(pos):int(pos + step)])
+        pos += step
+    return out
+
+
+def default_batch_frames(n1: int, n2: int, target_bytes: int = 96 << 20) -> int:
+    per_frame = max(1, (n1 + n2) * 12)
+    return int(max(1, min(4096, target_bytes // per_frame)))
+
+
+class ArraySource:
+    """Frames held in host memory: ndarray (F, n, 3) or a list of F arrays (n, 3)."""
+
+    def __init__(self, frames1, frames2=None):
+        self.f1, self.f2 = frames1, frames2
+        self.n_frames = len(frames1)
+
+    @staticmethod
+    def _take(fr, f0, nf):
+        if isinstance(fr, np.ndarray) and fr.ndim == 3:
+            return np.ascontiguousarray(fr[f0:f0 + nf], np.float32)
+        return np.ascontiguousarray(np.stack([np.asarray(fr[f], np.float32).reshape(-1, 3)
+                                              for f in range(f0, f0 + nf)]))
+
+    def read(self, f0, nf):
+        return self._take(self.f1, f0, nf), (None if self.f2 is None else self._take(self.f2, f0, nf))
+
+
+class DCDSource:
+    """Selection coordinates gathered from a DCD file (``sel.positions`` per frame,
+    core/multi_trajectory.py:401-417) batch by batch -- the trajectory is never held whole."""
+
+    def __init__(self, reader, idx1, idx2=None):
+        self.reader, self.idx1, self.idx2 = reader, np.asarray(idx1), None if idx2 is None else np.asarray(idx2)
+        self.n_frames = len(reader)
+
+    def read(self, f0, nf):
+        a = np.empty((nf, self.idx1.size, 3), np.float32)
+        self.reader.read_into(a, f0, nf, self.idx1)
+        b = None
+        if self.idx2 is not None:
+            b = np.empty((nf, self.idx2.size, 3), np.float32)
+            self.reader.read_into(b, f0, nf, self.idx2)
+        return a, b
+
+
+def run_scan(engines: Sequence[ContactEngine], source, *, batch_frames: Optional[int] = None,
+             order_keys: bool = True, accumulate: bool = False, keep_contacts: bool = True,
+             group_maps=None, frame_numbers: Optional[Sequence[int]] = None,
+             progress: Optional[Callable[[float], None]] = None):
+    """Scan every frame of ``source``.  Returns (TrajectoryContacts | None, AccumulationTable | None, stats)."""
+    F = source.n_frames
+    eng0 = engines[0]
+    if batch_frames is None:
+        batch_frames = default_batch_frames(eng0.n1, eng0.n2)
+    labels = list(range(F)) if frame_numbers is None else list(frame_numbers)
+    slices = [s for s in chunks(list(range(F)), len(engines)) if len(s)]
+    traj = TrajectoryContacts(eng0.sel1, eng0.sel2, eng0.hbondcutoff, eng0.hbondcutangle) if keep_contacts else None
+    table = AccumulationTable(F, *group_maps) if accumulate else None
+
+    def batches(sl):
+        for lo in range(sl[0], sl[-1] + 1, batch_frames):
+            nf = min(batch_frames, sl[-1] + 1 - lo)
+            a, b = source.read(lo, nf)
+            yield lo, a, b
+
+    gens = [eng.scan_batches(batches(sl), order_keys=order_keys, accumulate=accumulate,
+                             want_contacts=keep_contacts, want_hbonds=keep_contacts)
+            for eng, sl in zip(engines, slices)]
+    per_engine: List[list] = [[] for _ in gens]
+    stats = dict(frames=F, contacts=0, hbonds=0, pair_evals=0, batches=0, path=0)
+    alive = list(range(len(gens)))
+    done = 0
+    while alive:
+        for e in list(alive):
+            try:
+                r = next(gens[e])
+            except StopIteration:
+                alive.remove(e)
+                continue
+            per_engine[e].append(r)
+            stats["contacts"] += int(r.ccount.sum())
+            stats["hbonds"] += int(r.hcount.sum())
+            stats["pair_evals"] += r.n_pair_evals
+            stats["batches"] += 1
+            stats["path"] = r.path
+            done += r.nframes
+            if progress is not None:
+                progress(done / float(F))
+    for res in per_engine:                    # engine order == frame order (contiguous slices)
+        for r in res:
+            if traj is not None:
+                traj.add_batch(r, labels[r.frame0:r.frame0 + r.nframes])
+            if table is not None:
+                table.add_batch(r, r.frame0)
+    if traj is not None:
+        traj.finalize()
+    if table is not None:
+        table.finalize()
+    return traj, table, stats

@@ -1,0 +1,307 @@
+"""CUDA path vs the oracle / golden vectors -- needs a B200 (``-m gpu``).
+
+Everything goes through the C ABI (ctypes -> libpycontact_b200.so).  The bar
+(BASELINE.json north_star): contact pair sets and H-bond triples bit-exact, including
+the reference's in-frame order; distances, weights, angles and scores within 1e-5
+relative (the device stores float32 records, the reference float64).
+"""
+import numpy as np
+import pytest
+
+from oracle import frame_oracle, native
+from pycontact_b200 import prepare, synth
+from pycontact_b200.core.ContactAnalyzer import Analyzer
+from pycontact_b200.core.multi_trajectory import loop_trajectory_grid, run_load_parallel
+from pycontact_b200.cy_modules.cy_gridsearch import cy_find_contacts, find_contacts_csr
+from pycontact_b200.engine import ContactEngine
+from pycontact_b200.results import TrajectoryContacts
+from pycontact_b200.scheduler import ArraySource, run_scan
+
+pytestmark = pytest.mark.gpu
+RTOL = 1e-5          # north_star: "scores and angles agree within 1e-5 relative tolerance (FP32 vs FP64)"
+
+
+def _selections(topo, idx1, idx2, backbone):
+    hcsr = prepare.hydrogen_csr_from_bond_table(topo.names, topo.types, topo.bonds)
+    bb = np.zeros(topo.n_atoms, bool)
+    bb[backbone] = True
+    seg = prepare.string_codes(topo.segids)
+    s1 = prepare.prepare_selection(idx1, topo.names, topo.resids, seg, bb, hcsr)
+    s2 = None if idx2 is None else prepare.prepare_selection(idx2, topo.names, topo.resids, seg, bb, hcsr)
+    return s1, s2
+
+
+def _compare_traj(traj: TrajectoryContacts, oracle_frames):
+    assert traj.n_frames == len(oracle_frames)
+    for f, fr in enumerate(oracle_frames):
+        lo, hi = traj.frame_ptr[f], traj.frame_ptr[f + 1]
+        assert np.array_equal(traj.idx1[lo:hi], fr["idx1"]), "frame %d: idx1 / order differs" % f
+        assert np.array_equal(traj.idx2[lo:hi], fr["idx2"]), "frame %d: idx2 / order differs" % f
+        np.testing.assert_allclose(traj.distance[lo:hi], fr["distance"], rtol=RTOL)
+        np.testing.assert_allclose(traj.weight[lo:hi], fr["weight"], rtol=RTOL, atol=1e-30)
+        hlo, hhi = traj.hb_ptr[lo], traj.hb_ptr[hi]
+        assert np.array_equal(traj.hb_ptr[lo:hi + 1] - hlo, fr["hb_ptr"]), "frame %d: H-bond flags differ" % f
+        assert np.array_equal(traj.hb_donor[hlo:hhi], fr["hb_donor"])
+        assert np.array_equal(traj.hb_acceptor[hlo:hhi], fr["hb_acceptor"])
+        assert np.array_equal(traj.hb_hydrogen[hlo:hhi], fr["hb_hydrogen"])
+        np.testing.assert_allclose(traj.hb_distance[hlo:hhi], fr["hb_distance"], rtol=RTOL)
+        np.testing.assert_allclose(traj.hb_angle[hlo:hhi], fr["hb_angle"], rtol=RTOL)
+
+
+def _golden_frames(g, prefix=""):
+    fp, hp = g[prefix + "frame_ptr"], g[prefix + "hb_ptr"]
+    out = []
+    for k in range(len(fp) - 1):
+        lo, hi = fp[k], fp[k + 1]
+        hlo, hhi = hp[lo], hp[hi]
+        out.append({"idx1": g[prefix + "idx1"][lo:hi], "idx2": g[prefix + "idx2"][lo:hi],
+                    "distance": g[prefix + "distance"][lo:hi], "weight": g[prefix + "weight"][lo:hi],
+                    "hb_ptr": hp[lo:hi + 1] - hlo, "hb_donor": g[prefix + "hb_donor"][hlo:hhi],
+                    "hb_acceptor": g[prefix + "hb_acceptor"][hlo:hhi], "hb_hydrogen": g[prefix + "hb_hydrogen"][hlo:hhi],
+                    "hb_distance": g[prefix + "hb_distance"][hlo:hhi], "hb_angle": g[prefix + "hb_angle"][hlo:hhi]})
+    return out
+
+
+def _check_accumulated(acc_objs, g, prefix="acc_"):
+    assert len(acc_objs) == len(g[prefix + "key1"])
+    assert [a.key1 for a in acc_objs] == g[prefix + "key1"].tolist()         # first-appearance ORDER
+    assert [a.key2 for a in acc_objs] == g[prefix + "key2"].tolist()
+    assert [a.title for a in acc_objs] == g[prefix + "title"].tolist()
+    score = np.asarray([a.scoreArray for a in acc_objs], float)
+    np.testing.assert_allclose(score, g[prefix + "score"], rtol=RTOL, atol=1e-12)
+    assert np.array_equal(score == 0, g[prefix + "score"] == 0)
+    for k in ("bb1", "sc1", "bb2", "sc2"):
+        np.testing.assert_allclose([getattr(a, k) for a in acc_objs], g[prefix + k], rtol=RTOL, atol=1e-9)
+    assert np.array_equal(np.asarray([a.hbondFramesScan() for a in acc_objs]), g[prefix + "hbonds"])
+    assert np.array_equal(np.asarray([[len(fr) for fr in a.contributingAtoms] for a in acc_objs]), g[prefix + "ncontrib"])
+    np.testing.assert_allclose([a.hbond_percentage() for a in acc_objs], g[prefix + "hbond_percentage"])
+
+
+# ---------------------------------------------------------------------------------------------------
+# B1: cy_find_contacts
+# ---------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("n1,n2,cutoff,seed", [(500, 700, 5.0, 1), (2000, 300, 4.6, 2), (1500, 1500, 7.3, 3),
+                                               (50, 4000, 3.0, 4), (1, 1, 5.0, 5), (300, 300, 12.0, 6),
+                                               (20000, 30000, 5.0, 7)])
+def test_cy_find_contacts_matches_oracle_rows_and_order(n1, n2, cutoff, seed):
+    a, b, _, _ = synth.cloud(n1, n2, seed=seed)
+    rp, cols = find_contacts_csr(a.reshape(1, -1), n1, b.reshape(1, -1), n2, cutoff)
+    orp, ocols = native.oracle_find_contacts(a, b, cutoff)
+    assert np.array_equal(rp, orp)
+    assert np.array_equal(cols, ocols)
+
+
+def test_cy_find_contacts_return_shape_and_fixture(rpn11, golden_ab):
+    s1, s2 = golden_ab["sel1"], golden_ab["sel2"]
+    for f in (0, 31):
+        x1 = np.ascontiguousarray(rpn11.coords[f, s1].reshape(1, -1))
+        x2 = np.ascontiguousarray(rpn11.coords[f, s2].reshape(1, -1))
+        rows = cy_find_contacts(x1, len(s1), x2, len(s2), 5.0)
+        assert len(rows) == len(s1) + len(s2) and all(len(r) == 0 for r in rows[len(s1):])   # Q3
+        orp, ocols = native.oracle_find_contacts(x1, x2, 5.0)
+        assert rows[:len(s1)] == native.as_list_of_lists(orp, ocols, 0)
+        assert sum(len(r) for r in rows) == golden_ab["n_raw"][f]
+    with pytest.raises(ValueError):
+        cy_find_contacts(x1.astype(np.float64), len(s1), x2, len(s2), 5.0)
+
+
+def test_cy_find_contacts_self_keeps_ii_pairs():
+    a, _, _, _ = synth.cloud(400, 1, seed=9)
+    rows = cy_find_contacts(a.reshape(1, -1), 400, a.copy().reshape(1, -1), 400, 5.0)
+    assert all(i in rows[i] for i in range(400))
+
+
+# ---------------------------------------------------------------------------------------------------
+# B2 / B3: frame scan + accumulation on the reference's fixture (golden session)
+# ---------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("path", [1, 2])
+def test_scan_fixture_matches_golden_session(rpn11, golden_ab, path):
+    idx1, idx2 = golden_ab["sel1"].astype(np.int64), golden_ab["sel2"].astype(np.int64)
+    s1, s2 = _selections(rpn11.topology, idx1, idx2, rpn11.backbone)
+    with ContactEngine(s1, s2, 5.0, 2.5, 120) as eng:
+        eng.set_path(path)
+        src = ArraySource(np.ascontiguousarray(rpn11.coords[:, idx1]), np.ascontiguousarray(rpn11.coords[:, idx2]))
+        traj, _, stats = run_scan([eng], src, batch_frames=16, order_keys=True)
+    assert stats["path"] == path
+    assert stats["contacts"] == 23208 and stats["hbonds"] == 457
+    _compare_traj(traj, _golden_frames(golden_ab))
+
+
+def test_analyzer_single_core_like_reference_test(rpn11, golden_ab):
+    """tests/test_basic.py:32-43 of the reference, plus element-wise parity with its golden session."""
+    an = Analyzer("rpn11_ubq.psf", "rpn11_ubq.dcd", 5.0, 2.5, 120, "segid RN11", "segid UBQ",
+                  topology=rpn11.topology, frames=rpn11.coords)
+    an.runFrameScan(1)
+    assert len(an.contactResults) == 50
+    map1 = [0, 0, 1, 1, 0]
+    map2 = [0, 0, 1, 1, 0]
+    an.runContactAnalysis(map1, map2, 1)
+    assert len(an.finalAccumulatedContacts) == 148
+    hbond_sum = 0
+    for c in an.finalAccumulatedContacts:
+        hbond_sum += c.hbond_percentage()
+    assert hbond_sum == 676.0
+    _check_accumulated(an.finalAccumulatedContacts, golden_ab)
+    # object view of a frame
+    fr = an.contactResults[7]
+    lo = golden_ab["frame_ptr"][7]
+    assert [c.idx1 for c in fr] == golden_ab["idx1"][lo:lo + len(fr)].tolist()
+    assert all(c.frame == 7 for c in fr)
+    assert an.backbone == rpn11.backbone.tolist()
+    # a second accumulation with other maps reuses the scan (name-level keys)
+    acc2 = an.runContactAnalysis([0, 1, 1, 1, 1], [0, 1, 1, 1, 1], 1)
+    ora = frame_oracle.accumulate(_as_oracle_frames(golden_ab), [0, 1, 1, 1, 1],
+                                  [0, 1, 1, 1, 1], an.name_array, an.resid_array, an.resname_array, an.segids,
+                                  an.backbone)
+    assert [a.key1 for a in acc2] == ora["key1"] and [a.key2 for a in acc2] == ora["key2"]
+    np.testing.assert_allclose(np.asarray([a.scoreArray for a in acc2], float), ora["score"], rtol=RTOL, atol=1e-12)
+
+
+def _as_oracle_frames(g, prefix=""):
+    out = _golden_frames(g, prefix)
+    for fr in out:
+        fr["idx1"] = fr["idx1"].astype(np.int64)
+        fr["idx2"] = fr["idx2"].astype(np.int64)
+    return out
+
+
+def test_analyzer_self_interaction(rpn11, golden_self):
+    """tests/test_basic.py:45-51 (runs, 50 frames) + the oracle-derived values for this mode."""
+    an = Analyzer("rpn11_ubq.psf", "rpn11_ubq.dcd", 5.0, 2.5, 120, "segid RN11", "self",
+                  topology=rpn11.topology, frames=rpn11.coords)
+    an.runFrameScan(1)
+    assert len(an.contactResults) == 50
+    traj = an.contactResults.traj
+    assert np.diff(traj.frame_ptr).tolist() == golden_self["frame_counts"].tolist()
+    assert np.diff(traj.hb_ptr[traj.frame_ptr]).tolist() == golden_self["frame_hbonds"].tolist()
+    assert (traj.idx1 != traj.idx2).all()
+    wsum = np.add.reduceat(traj.weight, traj.frame_ptr[:-1])
+    np.testing.assert_allclose(wsum, golden_self["frame_weight_sum"], rtol=RTOL)
+    frames = golden_self["full_frames"].tolist()
+    gold = _golden_frames(golden_self, "full_")
+    for k, f in enumerate(frames):
+        lo, hi = traj.frame_ptr[f], traj.frame_ptr[f + 1]
+        assert np.array_equal(traj.idx1[lo:hi], gold[k]["idx1"]) and np.array_equal(traj.idx2[lo:hi], gold[k]["idx2"])
+    acc = an.runContactAnalysis([0, 0, 1, 1, 0], [0, 0, 1, 1, 0], 1)
+    assert len(acc) == 788
+    assert sum(a.hbond_percentage() for a in acc) == 5212.0
+    _check_accumulated(acc, golden_self)
+
+
+def test_zero_atomselection_raises(rpn11):
+    """tests/test_basic.py:53-63."""
+    an = Analyzer("x.psf", "x.dcd", 5.0, 2.5, 120, "segid A", "resid 10000",
+                  topology=rpn11.topology, frames=rpn11.coords)
+    with pytest.raises(Exception):
+        an.runFrameScan(1)
+    with pytest.raises(Exception):
+        an.runFrameScan(4)
+
+
+def test_loop_trajectory_grid_signature_and_q1(rpn11, golden_ab):
+    """B2: the chunk-level entry with the reference's argument shapes."""
+    t = rpn11.topology
+    idx1, idx2 = golden_ab["sel1"].astype(np.int64), golden_ab["sel2"].astype(np.int64)
+    ptr, bid = t.bonds_of_atoms()
+
+    class Bonds:
+        def __init__(self, a):
+            ids = bid[ptr[a]:ptr[a + 1]]
+            self.types = [(t.types[i], t.types[j]) for i, j in t.bonds[ids]]
+            self._idx = [np.asarray(t.bonds[b]) for b in ids]
+
+        def to_indices(self):
+            return self._idx
+    bonds = [Bonds(a) for a in range(t.n_atoms)]
+    frames = list(range(0, 50, 7))
+    res = loop_trajectory_grid([rpn11.coords[f, idx1] for f in frames], [rpn11.coords[f, idx2] for f in frames],
+                               [idx1] * len(frames), [idx2] * len(frames), [5.0, 2.5, 120],
+                               [bonds, t.names], False)
+    assert len(res) == len(frames)
+    gold = _golden_frames(golden_ab)
+    for k, f in enumerate(frames):
+        assert [c.idx1 for c in res[k]] == gold[f]["idx1"].tolist()
+        assert [c.idx2 for c in res[k]] == gold[f]["idx2"].tolist()
+        assert all(c.frame == 0 for c in res[k])                          # Q1
+        assert [len(c.hbondinfo) for c in res[k]] == np.diff(gold[f]["hb_ptr"]).tolist()
+
+
+# ---------------------------------------------------------------------------------------------------
+# synthetic systems vs the oracle on the same seeded inputs, both kernel paths
+# ---------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("name,path,self_mode,nframes", [
+    ("tiny", 1, False, 6), ("tiny", 2, False, 6), ("tiny", 1, True, 6), ("tiny", 2, True, 6),
+    ("small", 1, False, 8), ("small", 2, False, 8), ("small", 2, True, 4),
+    ("c3_small", 0, False, 4), ("c3_small", 2, False, 4), ("c4_small", 0, True, 2), ("c4_small", 2, True, 2)])
+def test_synthetic_matches_oracle(name, path, self_mode, nframes):
+    s = synth.make_system(name)
+    t = s.topology
+    frames = list(range(nframes))
+    coords = synth.frames_host(s, frames)
+    idx1 = s.sel1
+    idx2 = s.sel1 if self_mode else s.sel2
+    ora = frame_oracle.scan_frames([coords[k, idx1] for k in range(nframes)], [coords[k, idx2] for k in range(nframes)],
+                                   idx1, idx2, 5.0, 2.5, 120, t.names, t.types, t.bonds, t.resids, t.segids, self_mode)
+    s1, s2 = _selections(t, idx1, None if self_mode else idx2, s.backbone)
+    with ContactEngine(s1, s2, 5.0, 2.5, 120) as eng:
+        eng.set_path(path)
+        src = ArraySource(np.ascontiguousarray(coords[:, idx1]), None if self_mode else np.ascontiguousarray(coords[:, idx2]))
+        gm1 = prepare.group_map(idx1, s.maps[0], t.names, t.resids, t.resnames, t.segids)
+        gm2 = prepare.group_map(idx2, s.maps[1], t.names, t.resids, t.resnames, t.segids)
+        eng.set_maps(gm1.gid, gm2.gid, gm2.n_groups)
+        traj, table, stats = run_scan([eng], src, batch_frames=3, order_keys=True, accumulate=True,
+                                      group_maps=(gm1, gm2))
+    _compare_traj(traj, ora)
+    acc = frame_oracle.accumulate(ora, s.maps[0], s.maps[1], t.names, t.resids, t.resnames, t.segids, s.backbone)
+    keys = [table.key_arrays(k, t.names, t.resids, t.resnames, t.segids) for k in range(table.n_keys)]
+    assert [k[0] for k in keys] == acc["key1"] and [k[1] for k in keys] == acc["key2"]
+    np.testing.assert_allclose(table.score_matrix(), acc["score"], rtol=RTOL, atol=1e-12)
+    assert np.array_equal(table.hbond_matrix(), acc["hbonds"])
+    np.testing.assert_allclose(table.bb1, acc["bb1"], rtol=RTOL, atol=1e-9)
+    np.testing.assert_allclose(table.sc2, acc["sc2"], rtol=RTOL, atol=1e-9)
+
+
+@pytest.mark.parametrize("cutoff", [3.0, 4.6, 8.0, 12.0])
+def test_cutoff_sweep_small_system(cutoff):
+    """C5-style sweep on a small solvated system: pair sets exact at every cutoff."""
+    s = synth.make_system("small")
+    t = s.topology
+    coords = synth.frames_host(s, [0, 1])
+    ora = frame_oracle.scan_frames([coords[k, s.sel1] for k in range(2)], [coords[k, s.sel2] for k in range(2)],
+                                   s.sel1, s.sel2, cutoff, 2.5, 120, t.names, t.types, t.bonds)
+    s1, s2 = _selections(t, s.sel1, s.sel2, s.backbone)
+    with ContactEngine(s1, s2, cutoff, 2.5, 120) as eng:
+        src = ArraySource(np.ascontiguousarray(coords[:, s.sel1]), np.ascontiguousarray(coords[:, s.sel2]))
+        traj, _, _ = run_scan([eng], src, order_keys=True)
+    _compare_traj(traj, ora)
+
+
+def test_missing_hydrogen_raises_like_reference(rpn11, golden_ab):
+    """A hydrogen bonded to a selected N/O/S atom that is not in the selection: the reference
+    fails at core/multi_trajectory.py:158; the device flags it."""
+    from pycontact_b200._lib import PcError
+    idx1, idx2 = golden_ab["sel1"].astype(np.int64), golden_ab["sel2"].astype(np.int64)
+    names = rpn11.topology.names
+    heavy_only = np.asarray([i for i in idx1 if not names[i].startswith("H")], np.int64)
+    s1, s2 = _selections(rpn11.topology, heavy_only, idx2, rpn11.backbone)
+    with ContactEngine(s1, s2, 5.0, 2.5, 120) as eng:
+        with pytest.raises(PcError):
+            eng.scan(np.ascontiguousarray(rpn11.coords[:4, heavy_only]), np.ascontiguousarray(rpn11.coords[:4, idx2]))
+
+
+def test_device_generator_frames_are_analysed_exactly():
+    """bench.py analyses frames generated ON the device; parity is checked on exactly those bytes."""
+    from pycontact_b200 import device_synth
+    s = synth.make_system("small")
+    t = s.topology
+    gen = device_synth.DeviceTrajectory(s, device=0)
+    host = gen.frames_to_host([0, 5, 63])
+    assert host.shape == (3, t.n_atoms, 3) and np.isfinite(host).all()
+    np.testing.assert_allclose(host, synth.frames_host(s, [0, 5, 63]), atol=2.5)       # same system, other RNG
+    ora = frame_oracle.scan_frames([host[k, s.sel1] for k in range(3)], [host[k, s.sel2] for k in range(3)],
+                                   s.sel1, s.sel2, 5.0, 2.5, 120, t.names, t.types, t.bonds)
+    s1, s2 = _selections(t, s.sel1, s.sel2, s.backbone)
+    with ContactEngine(s1, s2, 5.0, 2.5, 120) as eng:
+        src = ArraySource(np.ascontiguousarray(host[:, s.sel1]), np.ascontiguousarray(host[:, s.sel2]))
+        traj, _, _ = run_scan([eng], src, order_keys=True)
+    _compare_traj(traj, ora)
