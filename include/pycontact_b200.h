@@ -33,6 +33,7 @@ extern "C" {
                                      selection: the reference raises here too
                                      (core/ContactAnalyzer.py:432, core/multi_trajectory.py:158) */
 #define PC_ERR_NOMEM         -5
+#define PC_ST_STAGE_OVERFLOW_BIT 64 /* pc_last_status: small-frame staging too small -> use pc_set_path(ctx, 2) */
 
 /* per-atom flag bits (pc_set_topology) */
 #define PC_ATOM_HYDROGEN   1u   /* name starts with "H"   (core/ContactAnalyzer.py:360)      */
@@ -129,6 +130,11 @@ int pc_load_records(pc_ctx *ctx, const pc_contact *h_contacts, const uint64_t *h
                     const pc_hbond *h_hbonds, int32_t nframes,
                     const uint32_t *h_frame_cstart, const uint32_t *h_frame_ccount,
                     const uint32_t *h_frame_hstart, const uint32_t *h_frame_hcount, void *stream);
+
+/* By default the small-frame scan kernel accumulates on the fly when the maps are set and no order
+ * keys are requested (pc_accumulate is then a no-op for that batch); 0 switches that off so that the
+ * stand-alone accumulation kernel runs (tests compare the two). */
+int pc_set_fused_accumulate(pc_ctx *ctx, int on);
 
 /* Same two steps for frames in HOST memory (pinned or pageable): H2D copy, scan,
  * accumulate if maps are set; all asynchronous on `stream`. */

@@ -12,6 +12,7 @@
 // table).
 #pragma once
 #include "pc_common.cuh"
+#include "pc_scan_small.cuh"   // PC_EMPTY_KEY, pc_hash64
 
 struct PcAccArgs {
     const pc_contact *contacts;
@@ -27,13 +28,6 @@ struct PcAccArgs {
     unsigned long long *counters;
     uint32_t *frame_rstart, *frame_rcount;
 };
-
-#define PC_EMPTY_KEY 0xffffffffffffffffull
-
-__device__ __forceinline__ unsigned pc_hash64(unsigned long long k) {
-    k ^= k >> 33; k *= 0xff51afd7ed558ccdull; k ^= k >> 33; k *= 0xc4ceb9fe1a85ec53ull; k ^= k >> 33;
-    return (unsigned)k;
-}
 
 template <int NT>
 __global__ void __launch_bounds__(NT) pc_accumulate_kernel(const PcAccArgs a) {
@@ -151,5 +145,119 @@ __global__ void __launch_bounds__(256) pc_fold_rows_kernel(const pc_row *rows, c
         if (row.bb1 != 0.0) atomicAdd(t + 1, row.bb1);
         if (row.bb2 != 0.0) atomicAdd(t + 2, row.bb2);
         if (row.nhbonds) atomicAdd(t + 3, 1.0);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Frames with more keys than a shared-memory table holds (1 M-atom systems, residue-pair maps of a
+// capsid): one open-addressing table in global memory for the whole batch, keyed by
+// frame * n_keys + key.  Inserts are 64-bit CAS + float64 atomics in L2; a key's first insertion
+// bumps its frame's row count, so rows can afterwards be emitted grouped by frame.
+// ---------------------------------------------------------------------------------------------------
+struct PcGlobalTable {
+    unsigned long long *keys, *first;        // cap entries each, initialised to PC_EMPTY_KEY
+    double *score, *bb1, *bb2;               // cap entries each, initialised to 0
+    unsigned int *ncont, *nhb;
+    unsigned long long cap;                  // power of two
+    unsigned long long nkeys;                // G1 * G2
+};
+
+__device__ __forceinline__ long long pc_gacc_find(const PcGlobalTable &t, unsigned long long ck, bool insert, bool &fresh) {
+    const unsigned long long mask = t.cap - 1ull;
+    unsigned long long h = ck;
+    h ^= h >> 33; h *= 0xff51afd7ed558ccdull; h ^= h >> 33; h *= 0xc4ceb9fe1a85ec53ull; h ^= h >> 33;
+    unsigned long long s = h & mask;
+    fresh = false;
+    for (unsigned long long probes = 0; probes < t.cap; probes++) {
+        if (insert) {
+            const unsigned long long prev = atomicCAS(&t.keys[s], PC_EMPTY_KEY, ck);
+            if (prev == PC_EMPTY_KEY) { fresh = true; return (long long)s; }
+            if (prev == ck) return (long long)s;
+        } else {
+            const unsigned long long k = t.keys[s];
+            if (k == ck) return (long long)s;
+            if (k == PC_EMPTY_KEY) return -1;
+        }
+        s = (s + 1) & mask;
+    }
+    return -1;
+}
+
+__global__ void __launch_bounds__(256) pc_gacc_insert_kernel(const PcAccArgs a, PcGlobalTable t) {
+    const int f = blockIdx.y;
+    const uint32_t c0 = a.frame_cstart[f], cn = a.frame_ccount[f];
+    unsigned int status = 0;
+    for (uint32_t c = blockIdx.x * blockDim.x + threadIdx.x; c < cn; c += gridDim.x * blockDim.x) {
+        const pc_contact rec = a.contacts[c0 + c];
+        const unsigned long long key =
+            (unsigned long long)__ldg(a.lgid1 + rec.i) * a.ngroups2 + (unsigned long long)__ldg(a.lgid2 + rec.j);
+        bool fresh;
+        const long long s = pc_gacc_find(t, (unsigned long long)f * t.nkeys + key, true, fresh);
+        if (s < 0) { status |= (unsigned)PC_ST_TABLE_OVERFLOW; continue; }
+        if (fresh) atomicAdd(&a.frame_rcount[f], 1u);
+        const double w = (double)rec.weight;
+        atomicAdd(&t.score[s], w);
+        if (__ldg(a.lflag1 + rec.i) & PC_ATOM_BACKBONE) atomicAdd(&t.bb1[s], w);
+        if (__ldg(a.lflag2 + rec.j) & PC_ATOM_BACKBONE) atomicAdd(&t.bb2[s], w);
+        atomicAdd(&t.ncont[s], 1u);
+        const unsigned long long ok = a.order_keys ? a.order_keys[c0 + c]
+                                                   : (((unsigned long long)(unsigned)rec.i << 32) | (unsigned)rec.j);
+        atomicMin(&t.first[s], ok);
+    }
+    status = __reduce_or_sync(PC_FULL_MASK, status);
+    if ((threadIdx.x & 31) == 0 && status) atomicOr(&a.counters[PC_CNT_STATUS], (unsigned long long)status);
+}
+
+__global__ void __launch_bounds__(256) pc_gacc_hbond_kernel(const PcAccArgs a, PcGlobalTable t) {
+    const int f = blockIdx.y;
+    const uint32_t h0 = a.frame_hstart[f], hn = a.frame_hcount[f];
+    for (uint32_t h = blockIdx.x * blockDim.x + threadIdx.x; h < hn; h += gridDim.x * blockDim.x) {
+        const pc_hbond rec = a.hbonds[h0 + h];
+        const unsigned long long key =
+            (unsigned long long)__ldg(a.lgid1 + rec.i) * a.ngroups2 + (unsigned long long)__ldg(a.lgid2 + rec.j);
+        bool fresh;
+        const long long s = pc_gacc_find(t, (unsigned long long)f * t.nkeys + key, false, fresh);
+        if (s >= 0) atomicAdd(&t.nhb[s], 1u);
+    }
+}
+
+// one CTA: frame_rstart = exclusive scan of frame_rcount, total -> counters, cursors zeroed
+__global__ void __launch_bounds__(1024) pc_gacc_offsets_kernel(const PcAccArgs a, uint32_t *cursor) {
+    __shared__ uint32_t wsum[32];
+    __shared__ uint32_t carry;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid == 0) carry = 0;
+    __syncthreads();
+    for (int base = 0; base < a.nframes; base += 1024) {
+        const int f = base + tid;
+        const uint32_t v = f < a.nframes ? a.frame_rcount[f] : 0;
+        const uint32_t incl = warp_incl_scan(v, lane);
+        if (lane == 31) wsum[warp] = incl;
+        __syncthreads();
+        if (warp == 0) { const uint32_t w = wsum[lane]; const uint32_t wi = warp_incl_scan(w, lane); wsum[lane] = wi - w; }
+        __syncthreads();
+        if (f < a.nframes) { a.frame_rstart[f] = carry + wsum[warp] + incl - v; cursor[f] = 0; }
+        __syncthreads();
+        if (tid == 1023) carry += wsum[warp] + incl;
+        __syncthreads();
+    }
+    if (tid == 0) {
+        a.counters[PC_CNT_ROWS] = carry;
+        if ((long long)carry > a.cap_rows) atomicOr(&a.counters[PC_CNT_STATUS], PC_ST_OUT_OVERFLOW);
+    }
+}
+
+__global__ void __launch_bounds__(256) pc_gacc_emit_kernel(const PcAccArgs a, PcGlobalTable t, uint32_t *cursor) {
+    for (unsigned long long s = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x; s < t.cap;
+         s += (unsigned long long)gridDim.x * blockDim.x) {
+        const unsigned long long ck = t.keys[s];
+        if (ck == PC_EMPTY_KEY) continue;
+        const unsigned long long f = ck / t.nkeys;
+        const long long pos = (long long)a.frame_rstart[f] + atomicAdd(&cursor[f], 1u);
+        if (pos >= a.cap_rows) continue;
+        pc_row r;
+        r.key = ck - f * t.nkeys; r.score = t.score[s]; r.bb1 = t.bb1[s]; r.bb2 = t.bb2[s];
+        r.ncontacts = t.ncont[s]; r.nhbonds = t.nhb[s]; r.first = t.first[s];
+        a.rows[pos] = r;
     }
 }

@@ -57,9 +57,10 @@ struct pc_ctx {
     size_t smem_optin = 0;
     bool have_topology = false, have_maps = false;
     int n1 = 0, n2 = 0, n1h = 0, n2h = 0;
-    DevBuf<int> heavy1, heavy2, hres1, hseg1, hres2, hseg2, hhptr1, hidx1, hhptr2, hidx2, lgid1, lgid2;
-    DevBuf<uint8_t> hflag1, hflag2, lflag1, lflag2;
-    unsigned long long ngroups2 = 0;
+    DevBuf<uint32_t> hinfo1, hinfo2, hmask1, hmask2, linfo1, linfo2;
+    DevBuf<int> lres1, lseg1, lres2, lseg2, lhptr1, lhidx1, lhptr2, lhidx2, lgid1, lgid2;
+    DevBuf<uint8_t> lflag1, lflag2;
+    unsigned long long ngroups1 = 0, ngroups2 = 0;
     // limits (0 = automatic)
     int lim_hits = 0, lim_hb = 0, lim_cells = 0, lim_table = 0;
     int force_path = 0;               // 0 = automatic, 1 = small-frame kernel, 2 = large-frame path
@@ -74,10 +75,15 @@ struct pc_ctx {
     DevBuf<uint32_t> frame_meta;      // 6 arrays of max_frames
     DevBuf<float> stage1, stage2;     // H2D staging for pc_scan_host
     PcLargeWork large;                // work buffers of the large-frame path
+    DevBuf<unsigned long long> gacc_u64;   // global accumulation table: keys | first
+    DevBuf<double> gacc_f64;               //   score | bb1 | bb2 | (ncont, nhb as u32 pairs)
+    DevBuf<uint32_t> gacc_cursor;
     int last_nframes = 0;
     bool last_order_keys = false;
     unsigned long long *h_counters = nullptr;   // pinned mirror
     int last_path = 0;                // 1 = small, 2 = large
+    bool want_fused_acc = true;       // accumulate inside the small-frame scan kernel when possible
+    bool last_fused = false;
     std::vector<uint32_t> h_meta;     // host copy of the scan's 4 frame arrays (large path: sliced outputs)
 };
 
@@ -130,25 +136,42 @@ extern "C" int pc_set_limits(pc_ctx *c, int hits_per_frame, int hbonds_per_frame
     return PC_OK;
 }
 
-// Re-index the per-atom topology by "heavy ordinal" (position among the non-hydrogen atoms of the
-// selection) so kernels never touch hydrogens except inside the H-bond test.
-static int build_side(int n, const uint8_t *flags, const int32_t *resid, const int32_t *segid,
-                      const int32_t *hptr, const int32_t *hidx, std::vector<int> &heavy,
-                      std::vector<uint8_t> &hflag, std::vector<int> &hres, std::vector<int> &hseg,
-                      std::vector<int> &hhptr, std::vector<int> &hh) {
-    heavy.clear(); hflag.clear(); hres.clear(); hseg.clear(); hhptr.clear(); hh.clear();
-    hhptr.push_back(0);
+// Device copies of one selection's static data: the packed atom word per heavy atom (heavy atoms in
+// index order -- kernels never touch hydrogens except inside the H-bond test) and per local atom,
+// a heavy-atom bitmask for the streaming kernels, and the per-atom arrays the rare paths read.
+struct SideBufs {
+    DevBuf<uint32_t> *hinfo, *hmask, *linfo;
+    DevBuf<int> *lres, *lseg, *lhptr, *lhidx;
+    DevBuf<uint8_t> *lflag;
+};
+
+static cudaError_t upload_side(int n, const uint8_t *flags, const int32_t *resid, const int32_t *segid,
+                               const int32_t *hptr, const int32_t *hidx, SideBufs b, int &nheavy) {
+    std::vector<uint32_t> hinfo, linfo((size_t)n), hmask(((size_t)n + 31) / 32 + 4, 0u);
+    std::vector<int> res((size_t)n, 0), seg((size_t)n, 0), ptr((size_t)n + 1, 0), idx;
     for (int i = 0; i < n; i++) {
-        if (flags[i] & PC_ATOM_HYDROGEN) continue;
-        heavy.push_back(i);
-        hflag.push_back(flags[i]);
-        hres.push_back(resid ? resid[i] : 0);
-        hseg.push_back(segid ? segid[i] : 0);
-        if (hptr && (flags[i] & PC_ATOM_HBCLASS))
-            for (int p = hptr[i]; p < hptr[i + 1]; p++) hh.push_back(hidx[p]);
-        hhptr.push_back((int)hh.size());
+        uint32_t w = (uint32_t)i;
+        if (flags[i] & PC_ATOM_BACKBONE) w |= PC_W_BACKBONE;
+        if (flags[i] & PC_ATOM_HBCLASS) w |= PC_W_HBCLASS;
+        linfo[i] = w;
+        if (!(flags[i] & PC_ATOM_HYDROGEN)) { hinfo.push_back(w); hmask[i >> 5] |= 1u << (i & 31); }
+        if (resid) res[i] = resid[i];
+        if (segid) seg[i] = segid[i];
+        if (hptr && (flags[i] & PC_ATOM_HBCLASS) && !(flags[i] & PC_ATOM_HYDROGEN))
+            for (int p = hptr[i]; p < hptr[i + 1]; p++) idx.push_back(hidx[p]);
+        ptr[i + 1] = (int)idx.size();
     }
-    return (int)heavy.size();
+    nheavy = (int)hinfo.size();
+    cudaError_t e;
+    if ((e = b.hinfo->upload(hinfo)) != cudaSuccess) return e;
+    if ((e = b.hmask->upload(hmask)) != cudaSuccess) return e;
+    if ((e = b.linfo->upload(linfo)) != cudaSuccess) return e;
+    if ((e = b.lres->upload(res)) != cudaSuccess) return e;
+    if ((e = b.lseg->upload(seg)) != cudaSuccess) return e;
+    if ((e = b.lhptr->upload(ptr)) != cudaSuccess) return e;
+    if ((e = b.lhidx->upload(idx)) != cudaSuccess) return e;
+    if ((e = b.lflag->upload(std::vector<uint8_t>(flags, flags + n))) != cudaSuccess) return e;
+    return cudaDeviceSynchronize();      // the host vectors die with this frame
 }
 
 extern "C" int pc_set_topology(pc_ctx *c, int32_t n1, int32_t n2, const uint8_t *f1, const uint8_t *f2,
@@ -158,24 +181,19 @@ extern "C" int pc_set_topology(pc_ctx *c, int32_t n1, int32_t n2, const uint8_t 
     if (!c) return fail(PC_ERR_INVALID, "pc_set_topology: ctx is NULL");
     if (n1 <= 0 || !f1) return fail(PC_ERR_INVALID, "pc_set_topology: selection 1 is empty");
     if (!c->self_mode && (n2 <= 0 || !f2)) return fail(PC_ERR_INVALID, "pc_set_topology: selection 2 is empty");
+    if (n1 >= (1 << 27) || n2 >= (1 << 27)) return fail(PC_ERR_INVALID, "pc_set_topology: at most 2^27-1 atoms per selection");
     CUDA_TRY(cudaSetDevice(c->device));
-    std::vector<int> heavy, hres, hseg, hhptr, hh;
-    std::vector<uint8_t> hflag;
     c->n1 = n1;
-    c->n1h = build_side(n1, f1, resid1, segid1, hptr1, hidx1, heavy, hflag, hres, hseg, hhptr, hh);
-    CUDA_TRY(c->heavy1.upload(heavy)); CUDA_TRY(c->hflag1.upload(hflag)); CUDA_TRY(c->hres1.upload(hres));
-    CUDA_TRY(c->hseg1.upload(hseg)); CUDA_TRY(c->hhptr1.upload(hhptr)); CUDA_TRY(c->hidx1.upload(hh));
-    CUDA_TRY(c->lflag1.upload(std::vector<uint8_t>(f1, f1 + n1)));
-    CUDA_TRY(cudaDeviceSynchronize());
+    CUDA_TRY(upload_side(n1, f1, resid1, segid1, hptr1, hidx1,
+                         SideBufs{&c->hinfo1, &c->hmask1, &c->linfo1, &c->lres1, &c->lseg1, &c->lhptr1, &c->lhidx1, &c->lflag1},
+                         c->n1h));
     if (c->self_mode) {
         c->n2 = n1; c->n2h = c->n1h;
     } else {
         c->n2 = n2;
-        c->n2h = build_side(n2, f2, resid2, segid2, hptr2, hidx2, heavy, hflag, hres, hseg, hhptr, hh);
-        CUDA_TRY(c->heavy2.upload(heavy)); CUDA_TRY(c->hflag2.upload(hflag)); CUDA_TRY(c->hres2.upload(hres));
-        CUDA_TRY(c->hseg2.upload(hseg)); CUDA_TRY(c->hhptr2.upload(hhptr)); CUDA_TRY(c->hidx2.upload(hh));
-        CUDA_TRY(c->lflag2.upload(std::vector<uint8_t>(f2, f2 + n2)));
-        CUDA_TRY(cudaDeviceSynchronize());
+        CUDA_TRY(upload_side(n2, f2, resid2, segid2, hptr2, hidx2,
+                             SideBufs{&c->hinfo2, &c->hmask2, &c->linfo2, &c->lres2, &c->lseg2, &c->lhptr2, &c->lhidx2, &c->lflag2},
+                             c->n2h));
     }
     c->have_topology = true;
     c->have_maps = false;
@@ -190,6 +208,9 @@ extern "C" int pc_set_maps(pc_ctx *c, const int32_t *gid1, const int32_t *gid2, 
     CUDA_TRY(c->lgid2.upload(std::vector<int>(gid2, gid2 + c->n2)));
     CUDA_TRY(cudaDeviceSynchronize());
     c->ngroups2 = (unsigned long long)ngroups2;
+    int g1max = 0;
+    for (int i = 0; i < c->n1; i++) g1max = std::max(g1max, gid1[i]);
+    c->ngroups1 = (unsigned long long)g1max + 1;
     c->have_maps = true;
     return PC_OK;
 }
@@ -213,52 +234,61 @@ extern "C" int pc_reserve(pc_ctx *c, int32_t max_frames, int64_t cap_contacts, i
 
 static PcTopoDev topo_dev(const pc_ctx *c) {
     PcTopoDev t;
+    const bool self = c->self_mode != 0;
     t.n1 = c->n1; t.n2 = c->n2; t.n1h = c->n1h; t.n2h = c->n2h;
-    t.heavy1 = c->heavy1.p; t.heavy2 = c->self_mode ? c->heavy1.p : c->heavy2.p;
-    t.hflag1 = c->hflag1.p; t.hflag2 = c->self_mode ? c->hflag1.p : c->hflag2.p;
-    t.hres1 = c->hres1.p; t.hseg1 = c->hseg1.p;
-    t.hres2 = c->self_mode ? c->hres1.p : c->hres2.p; t.hseg2 = c->self_mode ? c->hseg1.p : c->hseg2.p;
-    t.hhptr1 = c->hhptr1.p; t.hidx1 = c->hidx1.p;
-    t.hhptr2 = c->self_mode ? c->hhptr1.p : c->hhptr2.p; t.hidx2 = c->self_mode ? c->hidx1.p : c->hidx2.p;
-    t.hgid1 = nullptr; t.hgid2 = nullptr;
+    t.hinfo1 = c->hinfo1.p; t.hinfo2 = self ? c->hinfo1.p : c->hinfo2.p;
+    t.hmask1 = c->hmask1.p; t.hmask2 = self ? c->hmask1.p : c->hmask2.p;
+    t.linfo1 = c->linfo1.p; t.linfo2 = self ? c->linfo1.p : c->linfo2.p;
+    t.lres1 = c->lres1.p; t.lseg1 = c->lseg1.p;
+    t.lres2 = self ? c->lres1.p : c->lres2.p; t.lseg2 = self ? c->lseg1.p : c->lseg2.p;
+    t.lhptr1 = c->lhptr1.p; t.lhidx1 = c->lhidx1.p;
+    t.lhptr2 = self ? c->lhptr1.p : c->lhptr2.p; t.lhidx2 = self ? c->lhidx1.p : c->lhidx2.p;
     t.lgid1 = c->lgid1.p; t.lgid2 = c->lgid2.p;
-    t.lflag1 = c->lflag1.p; t.lflag2 = c->self_mode ? c->lflag1.p : c->lflag2.p;
+    t.lflag1 = c->lflag1.p; t.lflag2 = self ? c->lflag1.p : c->lflag2.p;
     t.ngroups2 = c->ngroups2;
     return t;
 }
 
 static uint32_t *meta(pc_ctx *c, int which) { return c->frame_meta.p + (size_t)which * c->max_frames; }
 
-// Pick shared-memory capacities and CTAs/SM for the small-frame kernel.  Returns false when the
-// frame does not fit one CTA's shared memory (-> large-frame path).
-static bool plan_small(const pc_ctx *c, int order_keys, int &capCells, int &capHits, int &capHb,
-                       PcSmallSmem &L, int &ctas_per_sm) {
-    const int NT = 512;
+// Pick the shared-memory capacities of the small-frame kernel (one 1024-thread CTA per SM).
+// Returns false when the frame does not fit one CTA's shared memory (-> large-frame path).
+#define PC_SMALL_NT 1024
+static bool plan_small(const pc_ctx *c, bool fuse_acc, int &capCells, int &capHits, int &capHb, PcSmallSmem &L) {
     if (c->n1h > 65535 || c->n2h > 65535) return false;
     capHits = c->lim_hits > 0 ? c->lim_hits : 4096;
     capHb = c->lim_hb > 0 ? c->lim_hb : 256;
-    const size_t sm_total = 233472, static_smem = 2048;
+    int capTab = 0;
+    if (fuse_acc) { capTab = 64; const int want = c->lim_table > 0 ? c->lim_table : 1024; while (capTab < want) capTab <<= 1; }
     const size_t optin = c->smem_optin ? c->smem_optin : 232448;
-    const int max_by_threads = 2048 / NT;
+    const size_t budget = optin - 4096;                              // static shared memory of the kernel
     const int cell_arrays = c->self_mode ? 1 : 2;
-    for (int k = max_by_threads; k >= 1; k--) {
-        size_t budget = std::min(optin, sm_total / k - 1024) - static_smem;
-        PcSmallSmem base = pc_small_layout(c->n1h, c->n2h, c->self_mode, 0, capHits, capHb, order_keys);
-        if ((size_t)base.total + cell_arrays * 4 * 513 > budget) continue;
-        int cells = (int)((budget - base.total) / (4 * cell_arrays)) - 8;
-        cells = std::min(cells, 16384);
-        if (c->lim_cells > 0) cells = std::min(cells, c->lim_cells);
-        // prefer more co-resident CTAs unless that would squeeze the grid below 1024 cells
-        if (cells < 1024 && k > 1) {
-            size_t budget_lo = std::min(optin, sm_total / (k - 1) - 1024) - static_smem;
-            if ((size_t)base.total + cell_arrays * 4 * 1025 <= budget_lo) continue;
+    // staging capacity for atoms inside the grid: everything if it fits, else what is left after a
+    // 2048-cell grid (frames that need more take the large-frame path)
+    PcSmallSmem full = pc_small_layout(c->n1h, c->n2h, c->self_mode, 0, capHits, capHb, c->n1h, c->n2h, capTab);
+    int capInA = c->n1h, capInB = c->n2h;
+    const size_t min_cells = (size_t)cell_arrays * 4 * 2049;
+    if ((size_t)full.total + min_cells > budget) {
+        PcSmallSmem none = pc_small_layout(c->n1h, c->n2h, c->self_mode, 0, capHits, capHb, 0, 0, capTab);
+        if ((size_t)none.total + min_cells + 16 * 512 > budget) return false;
+        const size_t left = (budget - none.total - min_cells) / 16;
+        if (c->self_mode) capInA = capInB = (int)std::min<size_t>(left, (size_t)c->n1h);
+        else {
+            // split in proportion to the selection sizes
+            capInA = (int)std::min<size_t>((size_t)c->n1h, left * c->n1h / (size_t)(c->n1h + c->n2h));
+            capInB = (int)std::min<size_t>((size_t)c->n2h, left - capInA);
         }
-        capCells = cells;
-        L = pc_small_layout(c->n1h, c->n2h, c->self_mode, capCells, capHits, capHb, order_keys);
-        ctas_per_sm = k;
-        return true;
+        if (capInA < 64 || capInB < 64) return false;
     }
-    return false;
+    PcSmallSmem base = pc_small_layout(c->n1h, c->n2h, c->self_mode, 0, capHits, capHb, capInA, capInB, capTab);
+    if ((size_t)base.total + min_cells > budget) return false;
+    int cells = (int)((budget - base.total) / (4 * cell_arrays)) - 8;
+    cells = std::min(cells, 16384);
+    if (c->lim_cells > 0) cells = std::min(cells, c->lim_cells);
+    if (cells < 64) return false;
+    capCells = cells;
+    L = pc_small_layout(c->n1h, c->n2h, c->self_mode, capCells, capHits, capHb, capInA, capInB, capTab);
+    return true;
 }
 
 extern "C" int pc_scan_device(pc_ctx *c, const float *d_xyz1, const float *d_xyz2, int32_t nframes,
@@ -291,15 +321,22 @@ extern "C" int pc_scan_device(pc_ctx *c, const float *d_xyz1, const float *d_xyz
     CUDA_TRY(cudaMemsetAsync(c->counters.p, 0, PC_CNT_COUNT * sizeof(unsigned long long), s));
 
     PcSmallSmem L;
-    int ctas = 1;
-    const bool fits_small = c->force_path != 2 && plan_small(c, order_keys, a.capCells, a.capHits, a.capHb, L, ctas);
+    // accumulation inside the scan kernel when the maps are known and the reference's first-appearance
+    // key (an order key) is not asked for; pc_accumulate then has nothing left to do for this batch
+    const bool fuse_acc = c->want_fused_acc && c->have_maps && !order_keys && c->lim_table <= 2048;
+    a.fuse_acc = 0;
+    a.rows = c->rows.p; a.cap_rows = c->cap_rows; a.frame_rstart = meta(c, 4); a.frame_rcount = meta(c, 5);
+    const bool fits_small = c->force_path != 2 && plan_small(c, fuse_acc, a.capCells, a.capHits, a.capHb, L);
+    c->last_fused = false;
     if (c->force_path == 1 && !fits_small)
         return fail(PC_ERR_INVALID, "pc_scan_device: the frame does not fit the small-frame kernel");
     if (fits_small) {
-        auto kern = pc_scan_small_kernel<512>;
+        auto kern = pc_scan_small_kernel<PC_SMALL_NT>;
         CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L.total));
-        const int grid = std::min(nframes, ctas * c->num_sms);
-        kern<<<grid, 512, L.total, s>>>(a, L);
+        a.fuse_acc = fuse_acc ? 1 : 0;
+        const int grid = std::min(nframes, c->num_sms);
+        kern<<<grid, PC_SMALL_NT, L.total, s>>>(a, L);
+        c->last_fused = fuse_acc;
         CUDA_TRY(cudaGetLastError());
         g_launches += 1;
         c->last_path = 1;
@@ -319,9 +356,16 @@ extern "C" int pc_scan_device(pc_ctx *c, const float *d_xyz1, const float *d_xyz
     return PC_OK;
 }
 
+extern "C" int pc_set_fused_accumulate(pc_ctx *c, int on) {
+    if (!c) return fail(PC_ERR_INVALID, "pc_set_fused_accumulate: ctx is NULL");
+    c->want_fused_acc = on != 0;
+    return PC_OK;
+}
+
 extern "C" int pc_accumulate(pc_ctx *c, void *stream) {
     if (!c || !c->have_maps) return fail(PC_ERR_INVALID, "pc_accumulate: set the maps first");
     if (c->last_nframes <= 0) return fail(PC_ERR_INVALID, "pc_accumulate: no scanned batch");
+    if (c->last_fused) return PC_OK;            // the scan kernel already produced this batch's rows
     CUDA_TRY(cudaSetDevice(c->device));
     cudaStream_t s = (cudaStream_t)stream;
     PcAccArgs a;
@@ -338,15 +382,50 @@ extern "C" int pc_accumulate(pc_ctx *c, void *stream) {
     a.rows = c->rows.p; a.cap_rows = c->cap_rows; a.counters = c->counters.p;
     a.frame_rstart = meta(c, 4); a.frame_rcount = meta(c, 5);
     const size_t smem = (size_t)a.cap * 48;
-    if (smem > (c->smem_optin ? c->smem_optin : 232448) - 1024)
-        return fail(PC_ERR_INVALID, "pc_accumulate: table does not fit shared memory");
-    auto kern = pc_accumulate_kernel<256>;
-    CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    int per_sm = (int)std::max<size_t>(1, std::min<size_t>(8, 233472 / (smem + 2048)));
-    const int grid = std::min(a.nframes, per_sm * c->num_sms);
-    kern<<<grid, 256, smem, s>>>(a);
+    const size_t smem_max = (c->smem_optin ? c->smem_optin : 232448) - 1024;
+    // one CTA per frame with the table in shared memory while a frame's keys fit (<= 2048 slots);
+    // otherwise -- and always after the large-frame scan -- one table in global memory for the batch
+    if (c->last_path != 2 && a.cap <= 2048 && smem <= smem_max) {
+        auto kern = pc_accumulate_kernel<256>;
+        CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        int per_sm = (int)std::max<size_t>(1, std::min<size_t>(8, 233472 / (smem + 2048)));
+        const int grid = std::min(a.nframes, per_sm * c->num_sms);
+        kern<<<grid, 256, smem, s>>>(a);
+        CUDA_TRY(cudaGetLastError());
+        g_launches += 1;
+        return PC_OK;
+    }
+    // the table is sized from the number of contacts actually found: read the counters (synchronises)
+    CUDA_TRY(cudaMemcpyAsync(c->h_counters, c->counters.p, PC_CNT_COUNT * sizeof(unsigned long long),
+                             cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(cudaStreamSynchronize(s));
+    if (c->h_counters[PC_CNT_STATUS] & (PC_ST_OUT_OVERFLOW | PC_ST_HITS_OVERFLOW | PC_ST_HB_OVERFLOW | PC_ST_STAGE_OVERFLOW))
+        return PC_OK;                        // the scan overflowed; pc_batch_totals reports it and the caller rescans
+    const unsigned long long ncontacts = std::min<unsigned long long>(c->h_counters[PC_CNT_CONTACTS], c->cap_contacts);
+    PcGlobalTable t;
+    t.cap = 1024;
+    while (t.cap < 2 * ncontacts + 16) t.cap <<= 1;
+    t.nkeys = (unsigned long long)c->ngroups1 * c->ngroups2;
+    if (t.nkeys == 0 || (unsigned long long)a.nframes > 0xffffffffffffffffull / std::max<unsigned long long>(t.nkeys, 1) - 1)
+        return fail(PC_ERR_INVALID, "pc_accumulate: frame * key space exceeds 64 bits");
+    CUDA_TRY(c->gacc_u64.ensure(2 * t.cap));
+    CUDA_TRY(c->gacc_f64.ensure(4 * t.cap));
+    CUDA_TRY(c->gacc_cursor.ensure((size_t)c->max_frames));
+    t.keys = c->gacc_u64.p; t.first = t.keys + t.cap;
+    t.score = c->gacc_f64.p; t.bb1 = t.score + t.cap; t.bb2 = t.bb1 + t.cap;
+    t.ncont = reinterpret_cast<unsigned int *>(t.bb2 + t.cap); t.nhb = t.ncont + t.cap;
+    CUDA_TRY(cudaMemsetAsync(t.keys, 0xff, 2 * t.cap * sizeof(unsigned long long), s));
+    CUDA_TRY(cudaMemsetAsync(t.score, 0, 4 * t.cap * sizeof(double), s));
+    CUDA_TRY(cudaMemsetAsync(a.frame_rcount, 0, (size_t)a.nframes * sizeof(uint32_t), s));
+    const int per_frame_blocks = std::max(1, 4 * c->num_sms / a.nframes);
+    const unsigned long long avg = ncontacts / a.nframes + 1;
+    const int blocks = (int)std::max<unsigned long long>(1, std::min<unsigned long long>((avg * 2 + 255) / 256, per_frame_blocks));
+    pc_gacc_insert_kernel<<<dim3(blocks, a.nframes), 256, 0, s>>>(a, t);
+    pc_gacc_hbond_kernel<<<dim3(std::max(1, blocks / 4), a.nframes), 256, 0, s>>>(a, t);
+    pc_gacc_offsets_kernel<<<1, 1024, 0, s>>>(a, c->gacc_cursor.p);
+    pc_gacc_emit_kernel<<<(int)std::min<unsigned long long>((t.cap + 255) / 256, 8ull * c->num_sms), 256, 0, s>>>(a, t, c->gacc_cursor.p);
     CUDA_TRY(cudaGetLastError());
-    g_launches += 1;
+    g_launches += 4;
     return PC_OK;
 }
 
@@ -391,6 +470,7 @@ extern "C" int pc_load_records(pc_ctx *c, const pc_contact *h_contacts, const ui
     c->last_nframes = nframes;
     c->last_order_keys = h_order_keys != nullptr;
     c->last_path = 1;
+    c->last_fused = false;
     return PC_OK;
 }
 

@@ -14,6 +14,7 @@
 #define PC_ST_MISSING_H       8ull   // bonded hydrogen not in the selection (reference raises)
 #define PC_ST_BAD_COORDS     16ull   // non-finite coordinates
 #define PC_ST_TABLE_OVERFLOW 32ull   // accumulation hash table too small
+#define PC_ST_STAGE_OVERFLOW 64ull   // small-frame path: more atoms inside the grid than the staging arrays hold
 
 enum { PC_CNT_CONTACTS = 0, PC_CNT_HBONDS = 1, PC_CNT_STATUS = 2, PC_CNT_EVALS = 3, PC_CNT_ROWS = 4,
        PC_CNT_WORK = 5, PC_CNT_COUNT = 8 };
@@ -24,15 +25,21 @@ enum { PC_CNT_CONTACTS = 0, PC_CNT_HBONDS = 1, PC_CNT_STATUS = 2, PC_CNT_EVALS =
 // land in the same or adjacent cells (DESIGN.md "grid exactness").
 #define PC_EDGE_SCALE 1.0002f
 
+// Packed atom word carried in the .w of staged float4 coordinates and in PcTopoDev::hinfo:
+//   bits 0..26 local index in the selection, bit 30 backbone, bit 31 name[0] in {O,N,S}
+#define PC_W_INDEX(w)   ((int)((w) & 0x07ffffffu))
+#define PC_W_BACKBONE   0x40000000u
+#define PC_W_HBCLASS    0x80000000u
+
 struct PcTopoDev {
     int n1, n2, n1h, n2h;
-    const int *heavy1, *heavy2;        // heavy ordinal -> local index
-    const uint8_t *hflag1, *hflag2;    // per heavy ordinal: PC_ATOM_* bits
-    const int *hres1, *hseg1, *hres2, *hseg2;   // per heavy ordinal
-    const int *hhptr1, *hidx1, *hhptr2, *hidx2; // bonded-H CSR per heavy ordinal -> local H index
-    const int *hgid1, *hgid2;          // per heavy ordinal group ids (maps)
-    const int *lgid1, *lgid2;          // per LOCAL index group ids (maps)
-    const uint8_t *lflag1, *lflag2;    // per LOCAL index flags
+    const uint32_t *hinfo1, *hinfo2;   // per heavy ordinal: packed atom word (heavy atoms in index order)
+    const uint32_t *hmask1, *hmask2;   // 1 bit per LOCAL atom: not a hydrogen (streaming kernels)
+    const uint32_t *linfo1, *linfo2;   // per LOCAL atom: packed atom word
+    const int *lres1, *lseg1, *lres2, *lseg2;          // per LOCAL atom (self-interaction filter)
+    const int *lhptr1, *lhidx1, *lhptr2, *lhidx2;      // bonded-H CSR per LOCAL atom -> local H index (-1: missing)
+    const int *lgid1, *lgid2;          // per LOCAL atom group ids (maps)
+    const uint8_t *lflag1, *lflag2;    // per LOCAL atom PC_ATOM_* flags
     unsigned long long ngroups2;
 };
 
@@ -45,6 +52,10 @@ struct PcScanArgs {
     float edge, sqdist, cutoff_f;
     double hb_cutoff, hb_angle;
     int capCells, capHits, capHb;      // shared-memory capacities (small-frame path)
+    int fuse_acc;                      // small-frame path: accumulate (frame, key) rows inside the scan kernel
+    pc_row *rows;
+    long long cap_rows;
+    uint32_t *frame_rstart, *frame_rcount;
     pc_contact *contacts;
     pc_hbond *hbonds;
     unsigned long long *order_out;
@@ -82,6 +93,25 @@ __device__ __forceinline__ float dist2_exact(float ax, float ay, float az, float
 // weight_function (core/multi_trajectory.py:15-17), float64 like the reference
 __device__ __forceinline__ double contact_weight(double d) { return 1.0 / (1.0 + exp(5.0 * (d - 4.0))); }
 
+// Same function for the float32 records: the exponent argument is formed in float64 from the
+// float64 distance and only then narrowed, so the relative error of the result stays below
+// |t| * 2^-24 + 3 ulp (< 3e-6 up to a 12 A cutoff) -- inside the 1e-5 bar, at a fraction of the
+// float64 exp's cost.
+__device__ __forceinline__ float contact_weight_f32(double d) {
+    const float t = (float)(5.0 * (d - 4.0));
+    return __fdividef(1.0f, 1.0f + expf(t));
+}
+
+// exp(t) overflows float for t > 88 (d > 21.7 A): the weight is then < 1e-38 and rounds to 0
+// either way.
+
+// The reference's pair test with one fused evaluation in front of it: d2f (2 FFMA) differs from
+// the reference's non-fused value by at most 4 ulp, so pairs with d2f > sqdist*(1+2^-20) are
+// certainly outside; everything else (all hits, plus a sliver of near misses) is decided by
+// dist2_exact.  Same set as the reference, ~30% fewer instructions per candidate.
+__device__ __forceinline__ bool pair_within(float ax, float ay, float az, float bx, float by, float bz,
+                                            float sqdist, float sqdist_hi);
+
 __device__ __forceinline__ void load_xyz(const float *frame, int idx, int stride, float &x, float &y, float &z) {
     if (stride == 4) {
         const float4 v = __ldg(reinterpret_cast<const float4 *>(frame) + idx);
@@ -115,3 +145,11 @@ __constant__ unsigned char PC_STENCIL_RANK[27] = {
     /* dz=-1 */ 23, 19, 24,  18, 16, 21,  25, 22, 26,
     /* dz= 0 */ 17, 15,  7,  14,  0,  1,  20,  2,  4,
     /* dz=+1 */ 13,  9, 12,   8,  3,  5,  11,  6, 10};
+
+__device__ __forceinline__ bool pair_within(float ax, float ay, float az, float bx, float by, float bz,
+                                            float sqdist, float sqdist_hi) {
+    const float dx = ax - bx, dy = ay - by, dz = az - bz;
+    const float d2f = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
+    if (d2f > sqdist_hi) return false;
+    return !(dist2_exact(ax, ay, az, bx, by, bz) > sqdist);
+}

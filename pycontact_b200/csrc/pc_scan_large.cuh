@@ -2,21 +2,24 @@
 // memory (1 M-atom membrane system, 3 M-atom capsid).
 //
 // Same semantics as pc_scan_small.cuh (loop_trajectory_grid, core/multi_trajectory.py:65-219) with
-// the cell list in global memory and many CTAs per frame.  Per sub-batch of FB frames:
-//   L1 bbox     bounding box of A's heavy atoms (and of B's when B is not much larger than A)
-//   L2 grid     grid over (bboxA (+) c) n (bboxB (+) c), cell edge grown until it fits capCells
-//   L3 bin      ONE pass over the raw coordinates: atoms inside the grid are compacted
-//               (x, y, z, heavy ordinal) + cell id, cells counted with global atomics
+// the cell list in global memory and many CTAs per frame.  Per sub-batch of FB frames, every kernel
+// covers all FB frames (grid.y = frame):
+//   L1 bbox     stream A (and B when it is not much larger than A): bounding boxes of the heavy atoms
+//   L2 grid     grid over (bboxA (+) c) n (bboxB (+) c), cell edge grown until it fits capCells; zero cells
+//   L3 bin      stream A and B ONCE: heavy atoms inside the grid are compacted to (x, y, z, atom word)
+//               + cell id, cells counted with global atomics            <- the HBM-bound kernel
 //   L4 scan     exclusive scan of the cell counts (one CTA per frame and side)
-//   L5 scatter  compacted atoms -> cell order (float4, coalesced for the pair kernel)
-//   L6 pairs    persistent warps pull (frame, A-cell) work items; lanes hold B atoms of an x-run,
-//               A atoms are broadcast by shuffle; exact float32 test; hits go through a per-warp
-//               queue and are drained 32 at a time (float64 distance/weight, H-bond test, records)
-//   L7 finish   per-frame counts, totals, overflow status
+//   L5 scatter  compacted atoms -> cell order (float4)
+//   L6 pairs    one thread per (A atom, stencil z-layer): fused pre-test + exact float32 test; hits are
+//               appended to the frame's slice of the contact buffer as (sorted A position, sorted B position)
+//   L7 drain    one thread per hit: float64 distance, weight, contact record (in place), H-bond test
+//   L8 finish   per-frame counts, totals, overflow status
+// L1 and L3 read the packed coordinates through the bulk-copy ring of pc_stream.cuh.
 // Each frame owns a fixed slice of the batch's contact / H-bond buffers (capacity / nframes).
 #pragma once
 #include <string>
 #include "pc_common.cuh"
+#include "pc_stream.cuh"
 
 struct PcLargeFrame {
     unsigned int bbox[12];            // order-preserving encoded floats: minA, maxA, minB, maxB
@@ -25,8 +28,7 @@ struct PcLargeFrame {
     int nx, ny, nz, ncell;
     unsigned int nA_in, nB_in;        // atoms inside the grid
     unsigned int ccursor, hcursor;    // records written into this frame's slices
-    unsigned int item_base;           // first work item (A cell) of this frame in the sub-batch
-    unsigned int pad;
+    unsigned int pad[2];
 };
 
 struct PcLargeWork {
@@ -36,12 +38,11 @@ struct PcLargeWork {
     float4 *candA = nullptr, *candB = nullptr;        // FB x n_h   (compacted, unsorted)
     uint32_t *ccellA = nullptr, *ccellB = nullptr;    // FB x n_h   cell id of each compacted atom
     float4 *sortA = nullptr, *sortB = nullptr;        // FB x n_h   (cell order)
-    unsigned int *work = nullptr;                     // [0] work counter, [1] total items
     void release() {
-        void *ps[] = {frames, cellA, cellB, candA, candB, ccellA, ccellB, sortA, sortB, work};
+        void *ps[] = {frames, cellA, cellB, candA, candB, ccellA, ccellB, sortA, sortB};
         for (void *p : ps) if (p) cudaFree(p);
         frames = nullptr; cellA = cellB = nullptr; candA = candB = sortA = sortB = nullptr;
-        ccellA = ccellB = nullptr; work = nullptr; FB = 0;
+        ccellA = ccellB = nullptr; FB = 0;
     }
     ~PcLargeWork() { release(); }
 };
@@ -55,9 +56,8 @@ __device__ __forceinline__ float pc_dec_float(unsigned int e) {
 }
 
 // ---- L0: reset per-frame state ---------------------------------------------------------------
-__global__ void pc_large_reset_kernel(PcLargeFrame *fr, int nfb, unsigned int *work) {
+__global__ void pc_large_reset_kernel(PcLargeFrame *fr, int nfb) {
     const int f = blockIdx.x * blockDim.x + threadIdx.x;
-    if (f == 0) { work[0] = 0; work[1] = 0; }
     if (f >= nfb) return;
     for (int k = 0; k < 3; k++) {
         fr[f].bbox[k] = 0xffffffffu; fr[f].bbox[3 + k] = 0u;
@@ -66,59 +66,149 @@ __global__ void pc_large_reset_kernel(PcLargeFrame *fr, int nfb, unsigned int *w
     fr[f].nA_in = fr[f].nB_in = 0; fr[f].ccursor = fr[f].hcursor = 0; fr[f].ncell = 0;
 }
 
-// ---- L1: bounding boxes ----------------------------------------------------------------------
-__global__ void __launch_bounds__(256) pc_large_bbox_kernel(const PcScanArgs a, PcLargeFrame *fr, int f0, int side,
-                                                            int slot0) {
-    const int fb = blockIdx.y;
-    const int f = f0 + fb;
-    const float *frame = side == 0 ? a.xyz1 + (long long)f * a.pitch1 : a.xyz2 + (long long)f * a.pitch2;
-    const int *heavy = side == 0 ? a.t.heavy1 : a.t.heavy2;
-    const int nh = side == 0 ? a.t.n1h : a.t.n2h;
-    float mn[3] = {INFINITY, INFINITY, INFINITY}, mx[3] = {-INFINITY, -INFINITY, -INFINITY};
-    for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < nh; k += gridDim.x * blockDim.x) {
-        float x, y, z;
-        load_xyz(frame, __ldg(heavy + k), a.stride, x, y, z);
-        mn[0] = fminf(mn[0], x); mn[1] = fminf(mn[1], y); mn[2] = fminf(mn[2], z);
-        mx[0] = fmaxf(mx[0], x); mx[1] = fmaxf(mx[1], y); mx[2] = fmaxf(mx[2], z);
-    }
-    __shared__ float red[8][6];
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-#pragma unroll
-    for (int k = 0; k < 3; k++) { mn[k] = warp_min(mn[k]); mx[k] = warp_max(mx[k]); }
-    if (lane == 0) for (int k = 0; k < 3; k++) { red[warp][k] = mn[k]; red[warp][3 + k] = mx[k]; }
-    __syncthreads();
-    if (threadIdx.x < 6) {
-        const int k = threadIdx.x;
-        float v = red[0][k];
-        for (int w = 1; w < 8; w++) v = k < 3 ? fminf(v, red[w][k]) : fmaxf(v, red[w][k]);
-        if (k < 3) atomicMin(&fr[fb].bbox[slot0 + k], pc_enc_float(v));
-        else atomicMax(&fr[fb].bbox[slot0 + k], pc_enc_float(v));
-    }
+__device__ __forceinline__ int pc_large_cell_of(const PcLargeFrame &F, float x, float y, float z) {
+    const float ux = (x - F.lo[0]) * F.inv, uy = (y - F.lo[1]) * F.inv, uz = (z - F.lo[2]) * F.inv;
+    if (!(ux >= 0.f && uy >= 0.f && uz >= 0.f)) return -1;
+    const int cx = (int)ux, cy = (int)uy, cz = (int)uz;
+    if (cx >= F.nx || cy >= F.ny || cz >= F.nz) return -1;
+    return (cz * F.ny + cy) * F.nx + cx;
 }
 
-// ---- L2: grid geometry -----------------------------------------------------------------------
-__global__ void pc_large_grid_kernel(const PcScanArgs a, PcLargeFrame *fr, int nfb, int capCells, int use_bboxB,
-                                     unsigned long long *counters, unsigned int *work) {
-    // one thread: the per-frame work-item prefix needs a serial pass anyway (nfb is small)
-    if (blockIdx.x != 0 || threadIdx.x != 0) return;
-    unsigned int items = 0;
-    for (int f = 0; f < nfb; f++) {
-        PcLargeFrame &F = fr[f];
+// ---- L1 / L3: streaming kernels -----------------------------------------------------------------
+#define PC_STREAM_NT 256
+#define PC_STREAM_CHUNK 24576            // 2048 atoms per chunk
+#define PC_STREAM_STAGES 4
+#define PC_STREAM_SMEM (PC_STREAM_STAGES * (PC_STREAM_CHUNK + 16) + PC_STREAM_STAGES * 8 + 16)
+
+enum { PC_MODE_BBOX = 0, PC_MODE_BIN = 1 };
+
+template <int MODE>
+__global__ void __launch_bounds__(PC_STREAM_NT) pc_large_stream_kernel(const PcScanArgs a, PcLargeFrame *fr, int f0, int side,
+                                                                       int slot0, int atoms_per_cta, uint32_t *cells,
+                                                                       int capCells, float4 *cand, uint32_t *ccell,
+                                                                       int nh_alloc) {
+    constexpr int NT = PC_STREAM_NT, CHUNK = PC_STREAM_CHUNK, STAGES = PC_STREAM_STAGES;
+    extern __shared__ __align__(16) unsigned char smem[];
+    PcRing<STAGES, CHUNK> ring;
+    ring.buf = smem;
+    ring.bar = reinterpret_cast<uint64_t *>(smem + STAGES * (CHUNK + 16));
+    __shared__ PcLargeFrame F;
+    __shared__ float red[NT / 32][6];
+    __shared__ unsigned int s_bad;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int fb = blockIdx.y, f = f0 + fb;
+    const int n = side == 0 ? a.t.n1 : a.t.n2;
+    const int r0 = blockIdx.x * atoms_per_cta;
+    if (r0 >= n) return;
+    if (tid == 0) {
+        F = fr[fb];
+        s_bad = 0;
+        for (int s = 0; s < STAGES; s++) pc_mbar_init(ring.bar + s, 1);
+        pc_mbar_fence_init();
+    }
+    __syncthreads();
+    if (MODE == PC_MODE_BIN && F.ncell == 0) return;
+    const float *frame = side == 0 ? a.xyz1 + (long long)f * a.pitch1 : a.xyz2 + (long long)f * a.pitch2;
+    const uint32_t *hmask = side == 0 ? a.t.hmask1 : a.t.hmask2;
+    const uint32_t *linfo = side == 0 ? a.t.linfo1 : a.t.linfo2;
+    PcSegment seg;
+    seg.sb = reinterpret_cast<const unsigned char *>(frame) + 12ll * r0;
+    seg.natoms = min(atoms_per_cta, n - r0);
+    seg.atom0 = r0;
+    const int nch = pc_seg_chunks<CHUNK>(seg);
+
+    uint32_t *mycells = nullptr;
+    float4 *mycand = nullptr;
+    uint32_t *myccell = nullptr;
+    unsigned int *cursor = nullptr;
+    if (MODE == PC_MODE_BIN) {
+        mycells = cells + (size_t)fb * (capCells + 1);
+        mycand = cand + (size_t)fb * nh_alloc;
+        myccell = ccell + (size_t)fb * nh_alloc;
+        cursor = side == 0 ? &fr[fb].nA_in : &fr[fb].nB_in;
+    }
+    float mn[3] = {INFINITY, INFINITY, INFINITY}, mx[3] = {-INFINITY, -INFINITY, -INFINITY};
+
+    if (tid == 0)
+        for (int q = 0; q < min(STAGES - 1, nch); q++) ring.issue((unsigned)q, pc_chunk_of<CHUNK>(seg, q));
+    for (int q = 0; q < nch; q++) {
+        if (tid == 0 && q + STAGES - 1 < nch) ring.issue((unsigned)(q + STAGES - 1), pc_chunk_of<CHUNK>(seg, q + STAGES - 1));
+        if (!ring.wait((unsigned)q)) { s_bad = 1; }
+        const PcChunk c = pc_chunk_of<CHUNK>(seg, q);
+        const unsigned char *slot = ring.slot((unsigned)q) + c.off0;
+        const int cnt = c.k1 - c.k0;
+        for (int kk = tid; kk < ((cnt + 31) & ~31); kk += NT) {
+            const int li = r0 + c.k0 + kk;
+            bool heavy = false;
+            float x = 0.f, y = 0.f, z = 0.f;
+            if (kk < cnt) {
+                heavy = (__ldg(hmask + (li >> 5)) >> (li & 31)) & 1u;
+                if (heavy) {
+                    const float *p = reinterpret_cast<const float *>(slot + 12 * kk);
+                    x = p[0]; y = p[1]; z = p[2];
+                }
+            }
+            if (MODE == PC_MODE_BBOX) {
+                if (heavy) {
+                    mn[0] = fminf(mn[0], x); mn[1] = fminf(mn[1], y); mn[2] = fminf(mn[2], z);
+                    mx[0] = fmaxf(mx[0], x); mx[1] = fmaxf(mx[1], y); mx[2] = fmaxf(mx[2], z);
+                }
+            } else {
+                const int cell = heavy ? pc_large_cell_of(F, x, y, z) : -1;
+                const unsigned m = __ballot_sync(PC_FULL_MASK, cell >= 0);
+                if (m) {
+                    unsigned base = 0;
+                    const int leader = __ffs(m) - 1;
+                    if (lane == leader) base = atomicAdd(cursor, (unsigned)__popc(m));
+                    base = __shfl_sync(PC_FULL_MASK, base, leader);
+                    if (cell >= 0) {
+                        const unsigned p = base + __popc(m & ((1u << lane) - 1u));
+                        mycand[p] = make_float4(x, y, z, __uint_as_float(__ldg(linfo + li)));
+                        myccell[p] = (uint32_t)cell;
+                        atomicAdd(&mycells[cell], 1u);
+                    }
+                }
+            }
+        }
+        __syncthreads();          // the slot may be refilled from here on
+    }
+    if (MODE == PC_MODE_BBOX) {
+#pragma unroll
+        for (int k = 0; k < 3; k++) { mn[k] = warp_min(mn[k]); mx[k] = warp_max(mx[k]); }
+        if (lane == 0) for (int k = 0; k < 3; k++) { red[warp][k] = mn[k]; red[warp][3 + k] = mx[k]; }
+        __syncthreads();
+        if (tid < 6) {
+            float v = red[0][tid];
+            for (int w = 1; w < NT / 32; w++) v = tid < 3 ? fminf(v, red[w][tid]) : fmaxf(v, red[w][tid]);
+            // a selection without heavy atoms leaves +-inf here; the grid kernel treats that as empty
+            if (tid < 3) atomicMin(&fr[fb].bbox[slot0 + tid], pc_enc_float(v));
+            else atomicMax(&fr[fb].bbox[slot0 + tid], pc_enc_float(v));
+        }
+    }
+    if (tid == 0 && s_bad) atomicOr(&a.counters[PC_CNT_STATUS], (unsigned long long)PC_ST_BAD_COORDS);
+}
+
+// ---- L2: grid geometry + zeroed cell counters (one CTA per frame) -----------------------------------
+__global__ void __launch_bounds__(256) pc_large_grid_kernel(const PcScanArgs a, PcLargeFrame *fr, int capCells, int use_bboxB,
+                                                            uint32_t *cellsA, uint32_t *cellsB) {
+    const int fb = blockIdx.x;
+    __shared__ int s_ncell;
+    if (threadIdx.x == 0) {
+        PcLargeFrame &F = fr[fb];
         bool empty = false, bad = false;
         float lo[3], ext[3];
         for (int k = 0; k < 3; k++) {
             const float minA = pc_dec_float(F.bbox[k]), maxA = pc_dec_float(F.bbox[3 + k]);
             float l = minA - a.edge, h = maxA + a.edge;
-            if (a.self_mode) { l = minA; h = maxA; }   // A == B: the joint box is the box itself
-            else if (use_bboxB) {
+            if (!a.self_mode && use_bboxB) {
                 const float minB = pc_dec_float(F.bbox[6 + k]), maxB = pc_dec_float(F.bbox[9 + k]);
                 l = fmaxf(minA, minB) - a.edge; h = fminf(maxA, maxB) + a.edge;
             }
             if (!(l <= h)) empty = true;
-            if (!isfinite(l) || !isfinite(h)) bad = true;
+            else if (!isfinite(l) || !isfinite(h)) bad = true;
             lo[k] = l; ext[k] = h - l;
         }
-        if (bad && !empty) { atomicOr(&counters[PC_CNT_STATUS], PC_ST_BAD_COORDS); empty = true; }
+        if (bad && !empty) { atomicOr(&a.counters[PC_CNT_STATUS], PC_ST_BAD_COORDS); empty = true; }
         int nx = 0, ny = 0, nz = 0;
         float inv = 0.f;
         if (!empty) {
@@ -133,61 +223,13 @@ __global__ void pc_large_grid_kernel(const PcScanArgs a, PcLargeFrame *fr, int n
         }
         F.lo[0] = lo[0]; F.lo[1] = lo[1]; F.lo[2] = lo[2]; F.inv = inv;
         F.nx = nx; F.ny = ny; F.nz = nz; F.ncell = nx * ny * nz;
-        F.item_base = items;
-        items += (unsigned)F.ncell;
+        s_ncell = F.ncell;
     }
-    work[0] = 0; work[1] = items;
-}
-
-__device__ __forceinline__ int pc_large_cell_of(const PcLargeFrame &F, float x, float y, float z) {
-    const float ux = (x - F.lo[0]) * F.inv, uy = (y - F.lo[1]) * F.inv, uz = (z - F.lo[2]) * F.inv;
-    if (!(ux >= 0.f && uy >= 0.f && uz >= 0.f)) return -1;
-    const int cx = (int)ux, cy = (int)uy, cz = (int)uz;
-    if (cx >= F.nx || cy >= F.ny || cz >= F.nz) return -1;
-    return (cz * F.ny + cy) * F.nx + cx;
-}
-
-// ---- L3: bin (single pass over the raw coordinates) ----------------------------------------------
-__global__ void __launch_bounds__(256) pc_large_bin_kernel(const PcScanArgs a, PcLargeFrame *fr, int f0, int side,
-                                                           uint32_t *cells, int capCells, float4 *cand, uint32_t *ccell,
-                                                           int nh_alloc) {
-    const int fb = blockIdx.y;
-    const int f = f0 + fb;
-    __shared__ PcLargeFrame F;
-    if (threadIdx.x == 0) F = fr[fb];
     __syncthreads();
-    if (F.ncell == 0) return;
-    const float *frame = side == 0 ? a.xyz1 + (long long)f * a.pitch1 : a.xyz2 + (long long)f * a.pitch2;
-    const int *heavy = side == 0 ? a.t.heavy1 : a.t.heavy2;
-    const int nh = side == 0 ? a.t.n1h : a.t.n2h;
-    uint32_t *mycells = cells + (size_t)fb * (capCells + 1);
-    float4 *mycand = cand + (size_t)fb * nh_alloc;
-    uint32_t *myccell = ccell + (size_t)fb * nh_alloc;
-    unsigned int *cursor = side == 0 ? &fr[fb].nA_in : &fr[fb].nB_in;
-    const int lane = threadIdx.x & 31;
-    const int stride = gridDim.x * blockDim.x;
-    const int nround = (nh + stride - 1) / stride;
-    for (int r = 0; r < nround; r++) {
-        const int k = r * stride + blockIdx.x * blockDim.x + threadIdx.x;
-        int c = -1;
-        float x = 0, y = 0, z = 0;
-        if (k < nh) {
-            load_xyz(frame, __ldg(heavy + k), a.stride, x, y, z);
-            c = pc_large_cell_of(F, x, y, z);
-        }
-        const unsigned m = __ballot_sync(PC_FULL_MASK, c >= 0);
-        if (m) {
-            unsigned base = 0;
-            if (lane == __ffs(m) - 1) base = atomicAdd(cursor, (unsigned)__popc(m));
-            base = __shfl_sync(PC_FULL_MASK, base, __ffs(m) - 1);
-            if (c >= 0) {
-                const unsigned p = base + __popc(m & ((1u << lane) - 1u));
-                mycand[p] = make_float4(x, y, z, __int_as_float(k));
-                myccell[p] = (uint32_t)c;
-                atomicAdd(&mycells[c], 1u);
-            }
-        }
-    }
+    const int ncell = s_ncell;
+    uint32_t *cA = cellsA + (size_t)fb * (capCells + 1);
+    uint32_t *cB = a.self_mode ? nullptr : cellsB + (size_t)fb * (capCells + 1);
+    for (int c = threadIdx.x; c <= ncell; c += blockDim.x) { cA[c] = 0; if (cB) cB[c] = 0; }
 }
 
 // ---- L4: exclusive scan of cell counts (one CTA per frame and side) ---------------------------
@@ -248,174 +290,132 @@ __global__ void __launch_bounds__(256) pc_large_scatter_kernel(PcLargeFrame *fr,
         mysorted[atomicAdd(&mycells[myccell[p]], 1u)] = mycand[p];
 }
 
-// ---- L6: pair search + drain ---------------------------------------------------------------------
+// ---- L6: pair search ---------------------------------------------------------------------------------
 struct PcLargeOut {
     long long cap_c_frame, cap_h_frame;   // records per frame slice
 };
 
-#define PC_LQ 96    // per-warp hit queue entries (drained when >= 32)
-
-__device__ __forceinline__ void pc_large_drain(const PcScanArgs &a, PcLargeFrame *frp, int f, int fb,
-                                               const float4 *sA, const float4 *sB, const uint2 *q, int n,
-                                               const PcLargeOut &o, unsigned int &status) {
-    const int lane = threadIdx.x & 31;
-    const bool self = a.self_mode != 0;
-    unsigned base = 0;
-    if (lane == 0) base = atomicAdd(&frp->ccursor, (unsigned)n);
-    base = __shfl_sync(PC_FULL_MASK, base, 0);
-    if (lane >= n) return;
-    const uint2 e = q[lane];
-    const float4 pa = sA[e.x], pb = sB[e.y];
-    const int ka = __float_as_int(pa.w), kb = __float_as_int(pb.w);
-    const int li = __ldg(a.t.heavy1 + ka), lj = __ldg((self ? a.t.heavy1 : a.t.heavy2) + kb);
-    const double ax = pa.x, ay = pa.y, az = pa.z, bx = pb.x, by = pb.y, bz = pb.z;
-    const double dx = ax - bx, dy = ay - by, dz = az - bz;
-    const double dist = sqrt(dx * dx + dy * dy + dz * dz);
-    const long long slot = (long long)base + lane;
-    if (slot < o.cap_c_frame) {
-        pc_contact rec;
-        rec.i = li; rec.j = lj; rec.distance = (float)dist; rec.weight = (float)contact_weight(dist);
-        a.contacts[(long long)f * o.cap_c_frame + slot] = rec;
-    } else {
-        status |= (unsigned)PC_ST_OUT_OVERFLOW;
-    }
-    const uint8_t *hflagB = self ? a.t.hflag1 : a.t.hflag2;
-    if ((__ldg(a.t.hflag1 + ka) & PC_ATOM_HBCLASS) && (__ldg(hflagB + kb) & PC_ATOM_HBCLASS)) {
-        const float *fr1 = a.xyz1 + (long long)f * a.pitch1;
-        const float *fr2 = self ? fr1 : a.xyz2 + (long long)f * a.pitch2;
-        const int *hhptrB = self ? a.t.hhptr1 : a.t.hhptr2;
-        const int *hidxB = self ? a.t.hidx1 : a.t.hidx2;
-        for (int side = 0; side < 2; side++) {
-            const int p0 = side == 0 ? __ldg(a.t.hhptr1 + ka) : __ldg(hhptrB + kb);
-            const int p1 = side == 0 ? __ldg(a.t.hhptr1 + ka + 1) : __ldg(hhptrB + kb + 1);
-            for (int p = p0; p < p1; p++) {
-                const int hl = side == 0 ? __ldg(a.t.hidx1 + p) : __ldg(hidxB + p);
-                if (hl < 0) { status |= (unsigned)PC_ST_MISSING_H; continue; }
-                float hxf, hyf, hzf;
-                load_xyz(side == 0 ? fr1 : fr2, hl, a.stride, hxf, hyf, hzf);
-                double d = 0, ang = 0;
-                const bool ok = side == 0
-                    ? hbond_test(hxf, hyf, hzf, ax, ay, az, bx, by, bz, a.hb_cutoff, a.hb_angle, d, ang)
-                    : hbond_test(hxf, hyf, hzf, bx, by, bz, ax, ay, az, a.hb_cutoff, a.hb_angle, d, ang);
-                if (ok) {
-                    const unsigned hq = atomicAdd(&frp->hcursor, 1u);
-                    if ((long long)hq < o.cap_h_frame) {
-                        pc_hbond r;
-                        r.i = li; r.j = lj; r.hyd = (uint32_t)hl | (side ? 0x80000000u : 0u);
-                        r.distance = (float)d; r.angle = (float)ang;
-                        a.hbonds[(long long)f * o.cap_h_frame + hq] = r;
-                    } else {
-                        status |= (unsigned)PC_ST_OUT_OVERFLOW;
-                    }
-                }
-            }
-        }
-    }
-    (void)fb;
-}
-
-template <int NT>
-__global__ void __launch_bounds__(NT) pc_large_pair_kernel(const PcScanArgs a, PcLargeFrame *fr, int f0, int nfb,
-                                                           const uint32_t *cellsA, const uint32_t *cellsB, int capCells,
-                                                           const float4 *sortA, const float4 *sortB, int n1h_alloc,
-                                                           int n2h_alloc, unsigned int *work, PcLargeOut o) {
-    __shared__ uint2 queue[NT / 32][PC_LQ];
-    __shared__ PcLargeFrame sF[64];
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    for (int i = tid; i < nfb; i += NT) sF[i] = fr[i];
+__global__ void __launch_bounds__(256) pc_large_pair_kernel(const PcScanArgs a, PcLargeFrame *fr, int f0,
+                                                            const uint32_t *cellsA, const uint32_t *cellsB, int capCells,
+                                                            const float4 *sortA, const float4 *sortB, int n1h_alloc,
+                                                            int n2h_alloc, PcLargeOut o) {
+    __shared__ PcLargeFrame F;
+    const int fb = blockIdx.y, f = f0 + fb;
+    if (threadIdx.x == 0) F = fr[fb];
     __syncthreads();
     const bool self = a.self_mode != 0;
-    const unsigned total = work[1];
+    const int lane = threadIdx.x & 31;
     unsigned long long evals = 0;
     unsigned int status = 0;
-    uint2 *q = queue[warp];
-    constexpr unsigned CHUNK = 4;      // A cells per work grab
-    for (;;) {
-        unsigned it0 = 0;
-        if (lane == 0) it0 = atomicAdd(&work[0], CHUNK);
-        it0 = __shfl_sync(PC_FULL_MASK, it0, 0);
-        if (it0 >= total) break;
-        for (unsigned it = it0; it < min(it0 + CHUNK, total); it++) {
-            int fb = 0;
-            while (fb + 1 < nfb && sF[fb + 1].item_base <= it) fb++;
-            const PcLargeFrame &F = sF[fb];
-            const int c = (int)(it - F.item_base);
-            const uint32_t *cA = cellsA + (size_t)fb * (capCells + 1);
-            const uint32_t *cB = self ? cA : cellsB + (size_t)fb * (capCells + 1);
-            const int a0 = c ? (int)cA[c - 1] : 0, a1 = (int)cA[c];
-            if (a0 == a1) continue;
-            const float4 *sA = sortA + (size_t)fb * n1h_alloc;
-            const float4 *sB = self ? sA : sortB + (size_t)fb * n2h_alloc;
-            const int nx = F.nx, ny = F.ny, nz = F.nz;
-            const int cx = c % nx, cy = (c / nx) % ny, cz = c / (nx * ny);
-            const int xlo = max(cx - 1, 0), xhi = min(cx + 1, nx - 1);
-            int nq = 0;
-            for (int ab = a0; ab < a1; ab += 32) {
-                const int na = min(32, a1 - ab);
-                float4 pa = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (lane < na) pa = sA[ab + lane];
-                int ares = 0, aseg = 0;
-                if (self && lane < na) {
-                    ares = __ldg(a.t.hres1 + __float_as_int(pa.w)); aseg = __ldg(a.t.hseg1 + __float_as_int(pa.w));
+    const float sqdist = a.sqdist, sqdist_hi = a.sqdist * 1.00000095367431640625f;   // 1 + 2^-20
+    const uint32_t *cB = (self ? cellsA : cellsB) + (size_t)fb * (capCells + 1);
+    const float4 *sA = sortA + (size_t)fb * n1h_alloc;
+    const float4 *sB = self ? sA : sortB + (size_t)fb * n2h_alloc;
+    pc_contact *slice = a.contacts + (long long)f * o.cap_c_frame;
+    const int nx = F.nx, ny = F.ny, nz = F.nz;
+    const long long items = 3ll * F.nA_in;
+    for (long long w = blockIdx.x * (long long)blockDim.x + threadIdx.x; w < items; w += (long long)gridDim.x * blockDim.x) {
+        const int ia = (int)(w / 3);
+        const float4 pa = __ldg(sA + ia);
+        const int cx = (int)((pa.x - F.lo[0]) * F.inv), cy = (int)((pa.y - F.lo[1]) * F.inv),
+                  cz = (int)((pa.z - F.lo[2]) * F.inv);
+        const int z = cz + (int)(w - 3ll * ia) - 1;
+        if (z < 0 || z >= nz) continue;
+        const int xlo = max(cx - 1, 0), xhi = min(cx + 1, nx - 1);
+        int ares = 0, aseg = 0;
+        if (self) {
+            const int li = PC_W_INDEX(__float_as_uint(pa.w));
+            ares = __ldg(a.t.lres1 + li); aseg = __ldg(a.t.lseg1 + li);
+        }
+        for (int y = max(cy - 1, 0); y <= min(cy + 1, ny - 1); y++) {
+            const int row = (z * ny + y) * nx;
+            const int b0 = (row + xlo) ? (int)__ldg(cB + row + xlo - 1) : 0, b1 = (int)__ldg(cB + row + xhi);
+            evals += (unsigned)(b1 - b0);
+            for (int j = b0; j < b1; j++) {
+                const float4 pb = __ldg(sB + j);
+                if (!pair_within(pa.x, pa.y, pa.z, pb.x, pb.y, pb.z, sqdist, sqdist_hi)) continue;
+                if (self) {
+                    // (resid1 - resid2) < 5 and same segment -> dropped (core/multi_trajectory.py:93-95)
+                    const int lj = PC_W_INDEX(__float_as_uint(pb.w));
+                    if ((ares - __ldg(a.t.lres1 + lj)) < 5 && aseg == __ldg(a.t.lseg1 + lj)) continue;
                 }
-                for (int dz = -1; dz <= 1; dz++) {
-                    const int z = cz + dz;
-                    if (z < 0 || z >= nz) continue;
-                    for (int dy = -1; dy <= 1; dy++) {
-                        const int y = cy + dy;
-                        if (y < 0 || y >= ny) continue;
-                        const int row = (z * ny + y) * nx;
-                        const int b0 = (row + xlo) ? (int)cB[row + xlo - 1] : 0, b1 = (int)cB[row + xhi];
-                        for (int base = b0; base < b1; base += 32) {
-                            const int j = base + lane;
-                            const bool valid = j < b1;
-                            float4 pb = make_float4(0.f, 0.f, 0.f, 0.f);
-                            if (valid) pb = sB[j];
-                            int bres = 0, bseg = 0;
-                            if (self && valid) {
-                                bres = __ldg(a.t.hres1 + __float_as_int(pb.w)); bseg = __ldg(a.t.hseg1 + __float_as_int(pb.w));
-                            }
-                            if (lane == 0) evals += (unsigned long long)na * (unsigned)min(32, b1 - base);
-                            for (int ia = 0; ia < na; ia++) {
-                                const float px = __shfl_sync(PC_FULL_MASK, pa.x, ia);
-                                const float py = __shfl_sync(PC_FULL_MASK, pa.y, ia);
-                                const float pz = __shfl_sync(PC_FULL_MASK, pa.z, ia);
-                                bool hit = valid && !(dist2_exact(px, py, pz, pb.x, pb.y, pb.z) > a.sqdist);
-                                if (self) {
-                                    const int r1 = __shfl_sync(PC_FULL_MASK, ares, ia);
-                                    const int s1 = __shfl_sync(PC_FULL_MASK, aseg, ia);
-                                    if (hit && (r1 - bres) < 5 && s1 == bseg) hit = false;
-                                }
-                                const unsigned m = __ballot_sync(PC_FULL_MASK, hit);
-                                if (m) {
-                                    if (hit) q[nq + __popc(m & ((1u << lane) - 1u))] = make_uint2((unsigned)(ab + ia), (unsigned)j);
-                                    nq += __popc(m);
-                                    __syncwarp();
-                                    if (nq >= 64) {      // keep room for one more full ballot (32)
-                                        pc_large_drain(a, &fr[fb], f0 + fb, fb, sA, sB, q, 32, o, status);
-                                        pc_large_drain(a, &fr[fb], f0 + fb, fb, sA, sB, q + 32, 32, o, status);
-                                        __syncwarp();
-                                        if (lane < nq - 64) q[lane] = q[64 + lane];
-                                        nq -= 64;
-                                        __syncwarp();
-                                    }
-                                }
-                            }
-                        }
-                    }
+                const unsigned slot = atomicAdd(&fr[fb].ccursor, 1u);
+                if ((long long)slot < o.cap_c_frame) {
+                    pc_contact rec;
+                    rec.i = ia; rec.j = j; rec.distance = 0.f; rec.weight = 0.f;
+                    slice[slot] = rec;
+                } else {
+                    status |= (unsigned)PC_ST_OUT_OVERFLOW;
                 }
             }
-            for (int d = 0; d < nq; d += 32) pc_large_drain(a, &fr[fb], f0 + fb, fb, sA, sB, q + d, min(32, nq - d), o, status);
-            __syncwarp();
         }
     }
-    evals = __shfl_sync(PC_FULL_MASK, evals, 0);
+#pragma unroll
+    for (int s = 16; s > 0; s >>= 1) evals += __shfl_xor_sync(PC_FULL_MASK, evals, s);
     if (lane == 0 && evals) atomicAdd(&a.counters[PC_CNT_EVALS], evals);
     status = __reduce_or_sync(PC_FULL_MASK, status);
     if (lane == 0 && status) atomicOr(&a.counters[PC_CNT_STATUS], (unsigned long long)status);
 }
 
-// ---- L7: per-frame counts and totals -----------------------------------------------------------------
+// ---- L7: drain: hits -> contact records (in place) + H-bond records ------------------------------------
+__global__ void __launch_bounds__(256) pc_large_drain_kernel(const PcScanArgs a, PcLargeFrame *fr, int f0, const float4 *sortA,
+                                                             const float4 *sortB, int n1h_alloc, int n2h_alloc,
+                                                             PcLargeOut o) {
+    const int fb = blockIdx.y, f = f0 + fb;
+    const bool self = a.self_mode != 0;
+    const long long nhit = min((long long)fr[fb].ccursor, o.cap_c_frame);
+    const float4 *sA = sortA + (size_t)fb * n1h_alloc;
+    const float4 *sB = self ? sA : sortB + (size_t)fb * n2h_alloc;
+    pc_contact *slice = a.contacts + (long long)f * o.cap_c_frame;
+    pc_hbond *hslice = a.hbonds + (long long)f * o.cap_h_frame;
+    const float *fr1 = a.xyz1 + (long long)f * a.pitch1;
+    const float *fr2 = self ? fr1 : a.xyz2 + (long long)f * a.pitch2;
+    unsigned int status = 0;
+    for (long long h = blockIdx.x * (long long)blockDim.x + threadIdx.x; h < nhit; h += (long long)gridDim.x * blockDim.x) {
+        pc_contact rec = slice[h];
+        const float4 pa = __ldg(sA + rec.i), pb = __ldg(sB + rec.j);
+        const unsigned wa = __float_as_uint(pa.w), wb = __float_as_uint(pb.w);
+        const int li = PC_W_INDEX(wa), lj = PC_W_INDEX(wb);
+        const double ax = pa.x, ay = pa.y, az = pa.z, bx = pb.x, by = pb.y, bz = pb.z;
+        const double dx = ax - bx, dy = ay - by, dz = az - bz;
+        const double dist = sqrt(dx * dx + dy * dy + dz * dz);
+        rec.i = li; rec.j = lj; rec.distance = (float)dist; rec.weight = contact_weight_f32(dist);
+        slice[h] = rec;
+        if (wa & wb & PC_W_HBCLASS) {
+            for (int side = 0; side < 2; side++) {
+                const int *hptr = side == 0 ? a.t.lhptr1 : a.t.lhptr2;
+                const int *hidx = side == 0 ? a.t.lhidx1 : a.t.lhidx2;
+                const int heavy = side == 0 ? li : lj;
+                const int p0 = __ldg(hptr + heavy), p1 = __ldg(hptr + heavy + 1);
+                for (int p = p0; p < p1; p++) {
+                    const int hl = __ldg(hidx + p);
+                    if (hl < 0) { status |= (unsigned)PC_ST_MISSING_H; continue; }
+                    float hxf, hyf, hzf;
+                    load_xyz(side == 0 ? fr1 : fr2, hl, a.stride, hxf, hyf, hzf);
+                    double d = 0, ang = 0;
+                    const bool ok = side == 0
+                        ? hbond_test(hxf, hyf, hzf, ax, ay, az, bx, by, bz, a.hb_cutoff, a.hb_angle, d, ang)
+                        : hbond_test(hxf, hyf, hzf, bx, by, bz, ax, ay, az, a.hb_cutoff, a.hb_angle, d, ang);
+                    if (ok) {
+                        const unsigned hq = atomicAdd(&fr[fb].hcursor, 1u);
+                        if ((long long)hq < o.cap_h_frame) {
+                            pc_hbond r;
+                            r.i = li; r.j = lj; r.hyd = (uint32_t)hl | (side ? 0x80000000u : 0u);
+                            r.distance = (float)d; r.angle = (float)ang;
+                            hslice[hq] = r;
+                        } else {
+                            status |= (unsigned)PC_ST_OUT_OVERFLOW;
+                        }
+                    }
+                }
+            }
+        }
+    }
+    status = __reduce_or_sync(PC_FULL_MASK, status);
+    if ((threadIdx.x & 31) == 0 && status) atomicOr(&a.counters[PC_CNT_STATUS], (unsigned long long)status);
+}
+
+// ---- L8: per-frame counts and totals -----------------------------------------------------------------
 __global__ void pc_large_finish_kernel(const PcScanArgs a, PcLargeFrame *fr, int f0, int nfb, PcLargeOut o) {
     const int fb = blockIdx.x * blockDim.x + threadIdx.x;
     if (fb >= nfb) return;
@@ -437,33 +437,50 @@ static inline int pc_large_fail(std::string &err, const char *what, cudaError_t 
 }
 #define PCL_TRY(expr) do { cudaError_t _e = (expr); if (_e != cudaSuccess) return pc_large_fail(err, #expr, _e); } while (0)
 
+// CTAs per frame of a streaming kernel over n atoms: enough to fill the machine about twice over the
+// nfb frames of the launch, but every CTA walks at least two chunks; atom ranges start on multiples
+// of 32 so a warp reads one or two words of the heavy-atom mask.
+static inline void pc_stream_geom(int n, int nfb, int num_sms, int &ctas, int &per) {
+    const int atoms_chunk = PC_STREAM_CHUNK / 12;
+    const int want = std::max(1, (2 * num_sms + nfb - 1) / nfb);
+    const int most = std::max(1, n / (2 * atoms_chunk));
+    ctas = std::min(want, most);
+    per = ((n + ctas - 1) / ctas + 31) & ~31;
+    ctas = (n + per - 1) / per;
+}
+
 static inline int pc_large_scan(PcLargeWork &W, const PcScanArgs &a, int num_sms, cudaStream_t s, std::string &err,
                                 unsigned long long *launches) {
+    const int n1 = a.t.n1, n2 = a.self_mode ? a.t.n1 : a.t.n2;
     const int n1h = a.t.n1h, n2h = a.self_mode ? a.t.n1h : a.t.n2h;
     const bool self = a.self_mode != 0;
+    if (a.stride != 3) { err = "the large-frame path reads packed xyz (PC_LAYOUT_XYZ) only"; return PC_ERR_INVALID; }
+    if ((((uintptr_t)a.xyz1 | (uintptr_t)a.xyz2) & 3) != 0) { err = "coordinates must be 4-byte aligned"; return PC_ERR_INVALID; }
     // cells per frame: a few per atom of the smaller side, bounded like the reference's MAXBOXES
     long long cc = 8ll * std::min(n1h, n2h);
     cc = std::max(4096ll, std::min(cc, 4000000ll));
     const int capCells = (int)cc;
-    // frames in flight: bound the work memory to ~2 GB
-    const size_t per_frame = (size_t)(capCells + 1) * 4 * (self ? 1 : 2) + (size_t)n1h * 36 + (self ? 0 : (size_t)n2h * 36);
-    int FB = (int)std::max<size_t>(1, std::min<size_t>(64, (2ull << 30) / std::max<size_t>(per_frame, 1)));
+    const int a1 = std::max(n1h, 1), a2 = std::max(n2h, 1);
+    // frames in flight: bound the work memory to ~6 GB
+    const size_t per_frame = (size_t)(capCells + 1) * 4 * (self ? 1 : 2) + (size_t)a1 * 36 + (self ? 0 : (size_t)a2 * 36);
+    int FB = (int)std::max<size_t>(1, std::min<size_t>(256, (6ull << 30) / std::max<size_t>(per_frame, 1)));
     FB = std::min(FB, a.nframes);
     if (W.FB < FB || W.capCells != capCells || W.n1h != n1h || W.n2h != n2h || W.self_mode != a.self_mode) {
         W.release();
-        PCL_TRY(cudaMalloc(&W.frames, sizeof(PcLargeFrame) * 64));
+        PCL_TRY(cudaMalloc(&W.frames, sizeof(PcLargeFrame) * FB));
         PCL_TRY(cudaMalloc(&W.cellA, (size_t)FB * (capCells + 1) * 4));
-        PCL_TRY(cudaMalloc(&W.candA, (size_t)FB * n1h * sizeof(float4)));
-        PCL_TRY(cudaMalloc(&W.ccellA, (size_t)FB * n1h * 4));
-        PCL_TRY(cudaMalloc(&W.sortA, (size_t)FB * n1h * sizeof(float4)));
+        PCL_TRY(cudaMalloc(&W.candA, (size_t)FB * a1 * sizeof(float4)));
+        PCL_TRY(cudaMalloc(&W.ccellA, (size_t)FB * a1 * 4));
+        PCL_TRY(cudaMalloc(&W.sortA, (size_t)FB * a1 * sizeof(float4)));
         if (!self) {
             PCL_TRY(cudaMalloc(&W.cellB, (size_t)FB * (capCells + 1) * 4));
-            PCL_TRY(cudaMalloc(&W.candB, (size_t)FB * n2h * sizeof(float4)));
-            PCL_TRY(cudaMalloc(&W.ccellB, (size_t)FB * n2h * 4));
-            PCL_TRY(cudaMalloc(&W.sortB, (size_t)FB * n2h * sizeof(float4)));
+            PCL_TRY(cudaMalloc(&W.candB, (size_t)FB * a2 * sizeof(float4)));
+            PCL_TRY(cudaMalloc(&W.ccellB, (size_t)FB * a2 * 4));
+            PCL_TRY(cudaMalloc(&W.sortB, (size_t)FB * a2 * sizeof(float4)));
         }
-        PCL_TRY(cudaMalloc(&W.work, 16));
         W.FB = FB; W.capCells = capCells; W.n1h = n1h; W.n2h = n2h; W.self_mode = a.self_mode;
+        PCL_TRY(cudaFuncSetAttribute(pc_large_stream_kernel<PC_MODE_BBOX>, cudaFuncAttributeMaxDynamicSharedMemorySize, PC_STREAM_SMEM));
+        PCL_TRY(cudaFuncSetAttribute(pc_large_stream_kernel<PC_MODE_BIN>, cudaFuncAttributeMaxDynamicSharedMemorySize, PC_STREAM_SMEM));
     }
     FB = W.FB;
     PcLargeOut o;
@@ -471,28 +488,38 @@ static inline int pc_large_scan(PcLargeWork &W, const PcScanArgs &a, int num_sms
     o.cap_h_frame = a.cap_hbonds / a.nframes;
     if (o.cap_c_frame < 1 || o.cap_h_frame < 1) { err = "pc_reserve: capacities smaller than the number of frames"; return PC_ERR_INVALID; }
     const int use_bboxB = (!self && (long long)n2h <= 4ll * n1h) ? 1 : 0;
-    const int blocksA = std::max(1, std::min((n1h + 255) / 256, 8 * num_sms));
-    const int blocksB = std::max(1, std::min((n2h + 255) / 256, 8 * num_sms));
     for (int f0 = 0; f0 < a.nframes; f0 += FB) {
         const int nfb = std::min(FB, a.nframes - f0);
-        pc_large_reset_kernel<<<1, 64, 0, s>>>(W.frames, nfb, W.work);
-        PCL_TRY(cudaMemsetAsync(W.cellA, 0, (size_t)nfb * (capCells + 1) * 4, s));
-        if (!self) PCL_TRY(cudaMemsetAsync(W.cellB, 0, (size_t)nfb * (capCells + 1) * 4, s));
-        pc_large_bbox_kernel<<<dim3(blocksA, nfb), 256, 0, s>>>(a, W.frames, f0, 0, 0);
-        if (use_bboxB) pc_large_bbox_kernel<<<dim3(blocksB, nfb), 256, 0, s>>>(a, W.frames, f0, 1, 6);
-        pc_large_grid_kernel<<<1, 32, 0, s>>>(a, W.frames, nfb, capCells, use_bboxB, a.counters, W.work);
-        pc_large_bin_kernel<<<dim3(blocksA, nfb), 256, 0, s>>>(a, W.frames, f0, 0, W.cellA, capCells, W.candA, W.ccellA, n1h);
+        int ctasA, perA, ctasB = 0, perB = 0;
+        pc_stream_geom(n1, nfb, num_sms, ctasA, perA);
+        if (!self) pc_stream_geom(n2, nfb, num_sms, ctasB, perB);
+        pc_large_reset_kernel<<<(nfb + 63) / 64, 64, 0, s>>>(W.frames, nfb);
+        pc_large_stream_kernel<PC_MODE_BBOX><<<dim3(ctasA, nfb), PC_STREAM_NT, PC_STREAM_SMEM, s>>>(
+            a, W.frames, f0, 0, 0, perA, nullptr, 0, nullptr, nullptr, 0);
+        if (use_bboxB)
+            pc_large_stream_kernel<PC_MODE_BBOX><<<dim3(ctasB, nfb), PC_STREAM_NT, PC_STREAM_SMEM, s>>>(
+                a, W.frames, f0, 1, 6, perB, nullptr, 0, nullptr, nullptr, 0);
+        pc_large_grid_kernel<<<nfb, 256, 0, s>>>(a, W.frames, capCells, use_bboxB, W.cellA, W.cellB);
+        pc_large_stream_kernel<PC_MODE_BIN><<<dim3(ctasA, nfb), PC_STREAM_NT, PC_STREAM_SMEM, s>>>(
+            a, W.frames, f0, 0, 0, perA, W.cellA, capCells, W.candA, W.ccellA, a1);
         if (!self)
-            pc_large_bin_kernel<<<dim3(blocksB, nfb), 256, 0, s>>>(a, W.frames, f0, 1, W.cellB, capCells, W.candB, W.ccellB, n2h);
+            pc_large_stream_kernel<PC_MODE_BIN><<<dim3(ctasB, nfb), PC_STREAM_NT, PC_STREAM_SMEM, s>>>(
+                a, W.frames, f0, 1, 0, perB, W.cellB, capCells, W.candB, W.ccellB, a2);
         pc_large_scan_kernel<<<dim3(nfb, self ? 1 : 2), 1024, 0, s>>>(W.frames, W.cellA, W.cellB, capCells);
-        pc_large_scatter_kernel<<<dim3(blocksA, nfb), 256, 0, s>>>(W.frames, 0, W.cellA, capCells, W.candA, W.ccellA, W.sortA, n1h);
+        const int per_frame_blocks = std::max(1, 4 * num_sms / nfb);
+        const int blocksA = std::max(1, std::min((n1h + 255) / 256, per_frame_blocks));
+        const int blocksB = std::max(1, std::min((n2h + 255) / 256, per_frame_blocks));
+        pc_large_scatter_kernel<<<dim3(blocksA, nfb), 256, 0, s>>>(W.frames, 0, W.cellA, capCells, W.candA, W.ccellA, W.sortA, a1);
         if (!self)
-            pc_large_scatter_kernel<<<dim3(blocksB, nfb), 256, 0, s>>>(W.frames, 1, W.cellB, capCells, W.candB, W.ccellB, W.sortB, n2h);
-        pc_large_pair_kernel<256><<<num_sms * 6, 256, 0, s>>>(a, W.frames, f0, nfb, W.cellA, W.cellB, capCells, W.sortA,
-                                                            W.sortB, n1h, n2h, W.work, o);
-        pc_large_finish_kernel<<<1, 64, 0, s>>>(a, W.frames, f0, nfb, o);
+            pc_large_scatter_kernel<<<dim3(blocksB, nfb), 256, 0, s>>>(W.frames, 1, W.cellB, capCells, W.candB, W.ccellB, W.sortB, a2);
+        const int pblocks = (int)std::max<long long>(1, std::min<long long>((3ll * n1h + 255) / 256, 2ll * per_frame_blocks));
+        pc_large_pair_kernel<<<dim3(pblocks, nfb), 256, 0, s>>>(a, W.frames, f0, W.cellA, W.cellB, capCells, W.sortA, W.sortB,
+                                                               a1, a2, o);
+        const int dblocks = (int)std::max<long long>(1, std::min<long long>((o.cap_c_frame + 255) / 256, per_frame_blocks));
+        pc_large_drain_kernel<<<dim3(dblocks, nfb), 256, 0, s>>>(a, W.frames, f0, W.sortA, W.sortB, a1, a2, o);
+        pc_large_finish_kernel<<<(nfb + 63) / 64, 64, 0, s>>>(a, W.frames, f0, nfb, o);
         PCL_TRY(cudaGetLastError());
-        *launches += 7 + (use_bboxB ? 1 : 0) + (self ? 0 : 2);
+        *launches += 8 + (use_bboxB ? 1 : 0) + (self ? 0 : 2);
     }
     return PC_OK;
 }

@@ -3,18 +3,21 @@
 // Replaces, for one frame, the body of loop_trajectory_grid (core/multi_trajectory.py:65-219):
 //   find_contacts / vmd_gridsearch3 (cy_modules/src/gridsearch.C:408-427, 902-1162)
 //   + heavy-atom filter (:89) + self-interaction filter (:93-95) + distance/weight (:98-107)
-//   + H-bond test (:112-209).
+//   + H-bond test (:112-209), and optionally the per-frame accumulation of
+//   analyze_contactResultsWithMaps (core/ContactAnalyzer.py:527-559).
 //
-// Phases (all in one CTA, frames are strided over the grid):
+// Phases (one persistent CTA per SM, frames strided over the grid):
 //   1  heavy atoms of both selections: global -> shared SoA (x[],y[],z[]), bounding boxes
 //   2  grid over (bboxA (+) c) n (bboxB (+) c): only atoms inside it can have a partner
-//   3  count atoms per cell (shared atomics)        4  exclusive scan (in place)
-//   5  scatter heavy ordinals into cell order (perm arrays; the scan array becomes "cell end")
-//   6  pair search: one warp per non-empty A cell; for each of the 9 x-runs of B cells, lanes hold
-//      B atoms, A atoms are broadcast by shuffle; exact float32 test; hits are warp-compacted into a
-//      shared hit queue
-//   7  drain: one thread per hit -> float64 distance + weight, H-bond test on N/O/S pairs, records
-//      written to one contiguous range of the batch output reserved with a single atomicAdd
+//   3  cell id of every heavy atom (0xffff = outside), atoms per cell (shared atomics)
+//   4  exclusive scans
+//   5  scatter the inside atoms into cell order as float4 (x, y, z, packed atom word)
+//   6  pair search: one thread per (A atom, z-layer of its stencil); the three B x-runs of the layer
+//      are contiguous ranges of the sorted B array; fused pre-test + exact float32 test
+//      (pc_common.cuh: pair_within); hits -> shared queue
+//   7  drain: one thread per hit -> float64 distance, weight, H-bond test on N/O/S pairs, contact
+//      record; with fuse_acc the hit is also added to the frame's (key -> score) table in shared memory
+//   8  H-bond records and accumulated rows -> global
 //
 // Hydrogens never enter the search (the reference discards every pair with a hydrogen at :89); they
 // are read from global memory only inside the H-bond test.
@@ -23,24 +26,26 @@
 
 struct PcSmallSmem {
     // offsets (bytes) into dynamic shared memory, computed on the host
-    int off_x, off_y, off_z, off_permA, off_permB, off_cellA, off_cellB, off_hits, off_hb, off_keys, total;
+    int off_x, off_y, off_z, off_cid, off_sortA, off_sortB, off_cellA, off_cellB, off_hits, off_hb, off_tab, total;
+    int capInA, capInB, capTab;
 };
 
-__host__ inline PcSmallSmem pc_small_layout(int n1h, int n2h, int self_mode, int capCells, int capHits,
-                                            int capHb, int order_keys) {
+__host__ inline PcSmallSmem pc_small_layout(int n1h, int n2h, int self_mode, int capCells, int capHits, int capHb,
+                                            int capInA, int capInB, int capTab) {
     PcSmallSmem L;
     const int ntot = self_mode ? n1h : n1h + n2h;
     int o = 0;
     auto take = [&](int bytes) { int r = o; o += (bytes + 15) & ~15; return r; };
     L.off_x = take(4 * ntot); L.off_y = take(4 * ntot); L.off_z = take(4 * ntot);
-    L.off_permA = take(2 * n1h);
-    L.off_permB = self_mode ? L.off_permA : take(2 * n2h);
+    L.off_cid = take(2 * ntot);
+    L.off_sortA = take(16 * capInA);
+    L.off_sortB = self_mode ? L.off_sortA : take(16 * capInB);
     L.off_cellA = take(4 * (capCells + 1));
     L.off_cellB = self_mode ? L.off_cellA : take(4 * (capCells + 1));
     L.off_hits = take(4 * capHits);
     L.off_hb = take((int)sizeof(pc_hbond) * capHb);
-    L.off_keys = 0;
-    (void)order_keys;
+    L.off_tab = take(48 * capTab);
+    L.capInA = capInA; L.capInB = self_mode ? capInA : capInB; L.capTab = capTab;
     L.total = o;
     return L;
 }
@@ -49,11 +54,14 @@ struct PcGridSm {
     float lo[3];
     float inv;
     int nx, ny, nz, ncell;
-    // reference grid (order keys only)
-    float rmin[3];
-    float rinv;
-    int rnb[3];
 };
+
+#define PC_EMPTY_KEY 0xffffffffffffffffull
+
+__device__ __forceinline__ unsigned pc_hash64(unsigned long long k) {
+    k ^= k >> 33; k *= 0xff51afd7ed558ccdull; k ^= k >> 33; k *= 0xc4ceb9fe1a85ec53ull; k ^= k >> 33;
+    return (unsigned)k;
+}
 
 template <int NT>
 __device__ __forceinline__ void block_excl_scan_inplace(uint32_t *arr, int n, uint32_t *wsum) {
@@ -79,34 +87,42 @@ __device__ __forceinline__ void block_excl_scan_inplace(uint32_t *arr, int n, ui
 }
 
 template <int NT>
-__global__ void __launch_bounds__(NT) pc_scan_small_kernel(const PcScanArgs a, const PcSmallSmem L) {
+__global__ void __launch_bounds__(NT, 1) pc_scan_small_kernel(const PcScanArgs a, const PcSmallSmem L) {
     extern __shared__ __align__(16) unsigned char smem[];
     float *sx = reinterpret_cast<float *>(smem + L.off_x);
     float *sy = reinterpret_cast<float *>(smem + L.off_y);
     float *sz = reinterpret_cast<float *>(smem + L.off_z);
-    uint16_t *permA = reinterpret_cast<uint16_t *>(smem + L.off_permA);
-    uint16_t *permB = reinterpret_cast<uint16_t *>(smem + L.off_permB);
+    uint16_t *cid = reinterpret_cast<uint16_t *>(smem + L.off_cid);
+    float4 *sortA = reinterpret_cast<float4 *>(smem + L.off_sortA);
+    float4 *sortB = reinterpret_cast<float4 *>(smem + L.off_sortB);
     uint32_t *cellA = reinterpret_cast<uint32_t *>(smem + L.off_cellA);
     uint32_t *cellB = reinterpret_cast<uint32_t *>(smem + L.off_cellB);
     uint32_t *hits = reinterpret_cast<uint32_t *>(smem + L.off_hits);
     pc_hbond *hbq = reinterpret_cast<pc_hbond *>(smem + L.off_hb);
+    // accumulation table (fuse_acc): structure of arrays over capTab slots
+    const int capTab = L.capTab;
+    unsigned long long *tkey = reinterpret_cast<unsigned long long *>(smem + L.off_tab);
+    double *tscore = reinterpret_cast<double *>(tkey + capTab);
+    double *tbb1 = tscore + capTab;
+    double *tbb2 = tbb1 + capTab;
+    unsigned long long *tfirst = reinterpret_cast<unsigned long long *>(tbb2 + capTab);
+    unsigned int *tncont = reinterpret_cast<unsigned int *>(tfirst + capTab);
+    unsigned int *tnhb = tncont + capTab;
 
     __shared__ float red[NT / 32][12];
     __shared__ uint32_t wsum[32];
     __shared__ PcGridSm g;
-    __shared__ int s_next;
     __shared__ unsigned int s_nhits, s_nhb;
-    __shared__ long long s_cbase, s_hbase;
+    __shared__ long long s_cbase, s_hbase, s_rbase;
     __shared__ unsigned int s_status;
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const bool self = a.self_mode != 0;
+    const bool fuse = a.fuse_acc != 0;
     const int n1h = a.t.n1h, n2h = self ? a.t.n1h : a.t.n2h;
     const int offB = self ? 0 : n1h;                 // B atoms live at sx[offB + k]
-    const int *heavyB = self ? a.t.heavy1 : a.t.heavy2;
-    const uint8_t *hflagB = self ? a.t.hflag1 : a.t.hflag2;
-    const int *hhptrB = self ? a.t.hhptr1 : a.t.hhptr2;
-    const int *hidxB = self ? a.t.hidx1 : a.t.hidx2;
+    const uint32_t *hinfoB = self ? a.t.hinfo1 : a.t.hinfo2;
+    const float sqdist = a.sqdist, sqdist_hi = a.sqdist * 1.00000095367431640625f;   // 1 + 2^-20
     unsigned long long evals = 0;
 
     for (int f = blockIdx.x; f < a.nframes; f += gridDim.x) {
@@ -119,7 +135,7 @@ __global__ void __launch_bounds__(NT) pc_scan_small_kernel(const PcScanArgs a, c
         for (int k = 0; k < 6; k++) { mn[k] = INFINITY; mx[k] = -INFINITY; }
         for (int k = tid; k < n1h; k += NT) {
             float x, y, z;
-            load_xyz(fr1, __ldg(a.t.heavy1 + k), a.stride, x, y, z);
+            load_xyz(fr1, PC_W_INDEX(__ldg(a.t.hinfo1 + k)), a.stride, x, y, z);
             sx[k] = x; sy[k] = y; sz[k] = z;
             mn[0] = fminf(mn[0], x); mn[1] = fminf(mn[1], y); mn[2] = fminf(mn[2], z);
             mx[0] = fmaxf(mx[0], x); mx[1] = fmaxf(mx[1], y); mx[2] = fmaxf(mx[2], z);
@@ -127,7 +143,7 @@ __global__ void __launch_bounds__(NT) pc_scan_small_kernel(const PcScanArgs a, c
         if (!self) {
             for (int k = tid; k < n2h; k += NT) {
                 float x, y, z;
-                load_xyz(fr2, __ldg(a.t.heavy2 + k), a.stride, x, y, z);
+                load_xyz(fr2, PC_W_INDEX(__ldg(a.t.hinfo2 + k)), a.stride, x, y, z);
                 sx[offB + k] = x; sy[offB + k] = y; sz[offB + k] = z;
                 mn[3] = fminf(mn[3], x); mn[4] = fminf(mn[4], y); mn[5] = fminf(mn[5], z);
                 mx[3] = fmaxf(mx[3], x); mx[4] = fmaxf(mx[4], y); mx[5] = fmaxf(mx[5], z);
@@ -139,59 +155,65 @@ __global__ void __launch_bounds__(NT) pc_scan_small_kernel(const PcScanArgs a, c
 #pragma unroll
             for (int k = 0; k < 6; k++) { red[warp][k] = mn[k]; red[warp][6 + k] = mx[k]; }
         }
-        if (tid == 0) { s_nhits = 0; s_nhb = 0; s_next = 0; s_status = 0; }
+        if (tid == 0) { s_nhits = 0; s_nhb = 0; s_status = 0; }
+        if (fuse)
+            for (int s = tid; s < capTab; s += NT) {
+                tkey[s] = PC_EMPTY_KEY; tscore[s] = 0.0; tbb1[s] = 0.0; tbb2[s] = 0.0;
+                tfirst[s] = PC_EMPTY_KEY; tncont[s] = 0; tnhb[s] = 0;
+            }
         __syncthreads();
 
-        // ---- phase 2: grid geometry (thread 0) --------------------------------------------------
-        if (tid == 0) {
-            float lo6[6], hi6[6];
-            for (int k = 0; k < 6; k++) {
-                float l = INFINITY, h = -INFINITY;
-                for (int w = 0; w < NT / 32; w++) { l = fminf(l, red[w][k]); h = fmaxf(h, red[w][6 + k]); }
-                lo6[k] = l; hi6[k] = h;
-            }
-            if (self) for (int k = 0; k < 3; k++) { lo6[3 + k] = lo6[k]; hi6[3 + k] = hi6[k]; }
-            bool empty = (n1h == 0 || n2h == 0), bad = false;
-            float lo[3], ext[3];
-            for (int k = 0; k < 3; k++) {
-                const float l = fmaxf(lo6[k], lo6[3 + k]) - a.edge;
-                const float h = fminf(hi6[k], hi6[3 + k]) + a.edge;
-                if (!(l <= h)) empty = true;
-                if (!isfinite(l) || !isfinite(h)) bad = true;
-                lo[k] = l; ext[k] = h - l;
-            }
-            if (bad && !empty) { atomicOr(&s_status, (unsigned)PC_ST_BAD_COORDS); empty = true; }
-            int nx = 0, ny = 0, nz = 0, ncell = 0;
-            float inv = 0.f;
-            if (!empty) {
-                float e = a.edge;
-                for (;;) {
-                    inv = 1.0f / e;
-                    const long long lx = (long long)(ext[0] * inv) + 1, ly = (long long)(ext[1] * inv) + 1,
-                                    lz = (long long)(ext[2] * inv) + 1;
-                    if (lx * ly * lz <= (long long)a.capCells) { nx = (int)lx; ny = (int)ly; nz = (int)lz; break; }
-                    e *= 1.26f;
+        // ---- phase 2: grid geometry (warp 0 reduces the per-warp boxes) ---------------------------
+        if (warp == 0) {
+            float v = (lane < 12) ? red[0][lane] : 0.f;
+            if (lane < 12)
+                for (int w = 1; w < NT / 32; w++) v = lane < 6 ? fminf(v, red[w][lane]) : fmaxf(v, red[w][lane]);
+            // lanes 0..5: min of A xyz, B xyz; lanes 6..11: max of A xyz, B xyz
+            const float minA = __shfl_sync(PC_FULL_MASK, v, lane % 3), minB = __shfl_sync(PC_FULL_MASK, v, 3 + lane % 3);
+            const float maxA = __shfl_sync(PC_FULL_MASK, v, 6 + lane % 3), maxB = __shfl_sync(PC_FULL_MASK, v, 9 + lane % 3);
+            // lanes 0..2 hold axis k = lane
+            float l, h;
+            if (self) { l = minA - a.edge; h = maxA + a.edge; }
+            else { l = fmaxf(minA, minB) - a.edge; h = fminf(maxA, maxB) + a.edge; }
+            bool empty_k = !(l <= h), bad_k = !isfinite(l) || !isfinite(h);
+            const unsigned em = __ballot_sync(PC_FULL_MASK, lane < 3 && empty_k);
+            const unsigned bm = __ballot_sync(PC_FULL_MASK, lane < 3 && bad_k);
+            const float ext = h - l;
+            const float ex = __shfl_sync(PC_FULL_MASK, ext, 0), ey = __shfl_sync(PC_FULL_MASK, ext, 1),
+                        ez = __shfl_sync(PC_FULL_MASK, ext, 2);
+            const float lx = __shfl_sync(PC_FULL_MASK, l, 0), ly = __shfl_sync(PC_FULL_MASK, l, 1),
+                        lz = __shfl_sync(PC_FULL_MASK, l, 2);
+            if (lane == 0) {
+                bool empty = em != 0 || n1h == 0 || n2h == 0;
+                if (bm && !empty) { atomicOr(&s_status, (unsigned)PC_ST_BAD_COORDS); empty = true; }
+                int nx = 0, ny = 0, nz = 0;
+                float inv = 0.f;
+                if (!empty) {
+                    float e = a.edge;
+                    for (;;) {
+                        inv = 1.0f / e;
+                        const long long cx = (long long)(ex * inv) + 1, cy = (long long)(ey * inv) + 1,
+                                        cz = (long long)(ez * inv) + 1;
+                        if (cx * cy * cz <= (long long)a.capCells) { nx = (int)cx; ny = (int)cy; nz = (int)cz; break; }
+                        e *= 1.26f;
+                    }
                 }
-                ncell = nx * ny * nz;
+                g.lo[0] = lx; g.lo[1] = ly; g.lo[2] = lz;
+                g.inv = inv; g.nx = nx; g.ny = ny; g.nz = nz; g.ncell = nx * ny * nz;
             }
-            g.lo[0] = lo[0]; g.lo[1] = lo[1]; g.lo[2] = lo[2];
-            g.inv = inv; g.nx = nx; g.ny = ny; g.nz = nz; g.ncell = ncell;
         }
         __syncthreads();
         const int ncell = g.ncell;
         if (ncell > 0) {
             const int nx = g.nx, ny = g.ny, nz = g.nz;
             const float lox = g.lo[0], loy = g.lo[1], loz = g.lo[2], inv = g.inv;
-            // upper corner of the grid box: atoms beyond it cannot have a partner
-            const float hix = lox + (float)nx / inv, hiy = loy + (float)ny / inv, hiz = loz + (float)nz / inv;
-            (void)hix; (void)hiy; (void)hiz;
 
-            // ---- phase 3: count ---------------------------------------------------------------------
+            // ---- phase 3: cell ids + counts -------------------------------------------------------
             for (int c = tid; c <= ncell; c += NT) { cellA[c] = 0; if (!self) cellB[c] = 0; }
             __syncthreads();
             auto cell_of = [&](float x, float y, float z) -> int {
-                // inside test in cell units: u in [0, n) -- atoms outside are farther than one cell
-                // edge (> cutoff) from the other selection's bounding box
+                // atoms outside the grid box are farther than one cell edge (> cutoff) from the other
+                // selection's bounding box
                 const float ux = (x - lox) * inv, uy = (y - loy) * inv, uz = (z - loz) * inv;
                 if (!(ux >= 0.f && uy >= 0.f && uz >= 0.f)) return -1;
                 const int cx = (int)ux, cy = (int)uy, cz = (int)uz;
@@ -200,88 +222,66 @@ __global__ void __launch_bounds__(NT) pc_scan_small_kernel(const PcScanArgs a, c
             };
             for (int k = tid; k < n1h; k += NT) {
                 const int c = cell_of(sx[k], sy[k], sz[k]);
+                cid[k] = (uint16_t)c;
                 if (c >= 0) atomicAdd(&cellA[c], 1u);
             }
             if (!self)
                 for (int k = tid; k < n2h; k += NT) {
                     const int c = cell_of(sx[offB + k], sy[offB + k], sz[offB + k]);
+                    cid[offB + k] = (uint16_t)c;
                     if (c >= 0) atomicAdd(&cellB[c], 1u);
                 }
             __syncthreads();
             // ---- phase 4: scans ---------------------------------------------------------------------
             block_excl_scan_inplace<NT>(cellA, ncell, wsum);
             if (!self) block_excl_scan_inplace<NT>(cellB, ncell, wsum);
-            // ---- phase 5: scatter ordinals; afterwards cell[c] == END of cell c -----------------------
-            for (int k = tid; k < n1h; k += NT) {
-                const int c = cell_of(sx[k], sy[k], sz[k]);
-                if (c >= 0) permA[atomicAdd(&cellA[c], 1u)] = (uint16_t)k;
-            }
-            if (!self)
-                for (int k = tid; k < n2h; k += NT) {
-                    const int c = cell_of(sx[offB + k], sy[offB + k], sz[offB + k]);
-                    if (c >= 0) permB[atomicAdd(&cellB[c], 1u)] = (uint16_t)k;
+            const int nInA = (int)cellA[ncell], nInB = (int)cellB[ncell];
+            if (nInA > L.capInA || nInB > L.capInB) {
+                if (tid == 0) atomicOr(&s_status, (unsigned)PC_ST_STAGE_OVERFLOW);
+            } else {
+                // ---- phase 5: scatter into cell order; afterwards cell[c] == END of cell c -----------
+                for (int k = tid; k < n1h; k += NT) {
+                    const unsigned c = cid[k];
+                    if (c != 0xffffu)
+                        sortA[atomicAdd(&cellA[c], 1u)] = make_float4(sx[k], sy[k], sz[k], __uint_as_float(__ldg(a.t.hinfo1 + k)));
                 }
-            __syncthreads();
+                if (!self)
+                    for (int k = tid; k < n2h; k += NT) {
+                        const unsigned c = cid[offB + k];
+                        if (c != 0xffffu)
+                            sortB[atomicAdd(&cellB[c], 1u)] =
+                                make_float4(sx[offB + k], sy[offB + k], sz[offB + k], __uint_as_float(__ldg(a.t.hinfo2 + k)));
+                    }
+                __syncthreads();
 
-            // ---- phase 6: pair search --------------------------------------------------------------
-            for (;;) {
-                int c = 0;
-                if (lane == 0) c = atomicAdd(&s_next, 1);
-                c = __shfl_sync(PC_FULL_MASK, c, 0);
-                if (c >= ncell) break;
-                const int a0 = c ? (int)cellA[c - 1] : 0, a1 = (int)cellA[c];
-                if (a0 == a1) continue;
-                const int cx = c % nx, cy = (c / nx) % ny, cz = c / (nx * ny);
-                const int xlo = max(cx - 1, 0), xhi = min(cx + 1, nx - 1);
-                for (int ab = a0; ab < a1; ab += 32) {
-                    // this warp's chunk of A atoms (<= 32) lives in lane registers
-                    const int na = min(32, a1 - ab);
-                    int ka = 0;
-                    float ax = 0.f, ay = 0.f, az = 0.f;
-                    if (lane < na) { ka = permA[ab + lane]; ax = sx[ka]; ay = sy[ka]; az = sz[ka]; }
+                // ---- phase 6: pair search, one thread per (A atom, stencil layer) --------------------
+                for (int w = tid; w < 3 * nInA; w += NT) {
+                    const int ia = w / 3;
+                    const float4 pa = sortA[ia];
+                    const int cx = (int)((pa.x - lox) * inv), cy = (int)((pa.y - loy) * inv),
+                              cz = (int)((pa.z - loz) * inv);
+                    const int z = cz + (w - 3 * ia) - 1;
+                    if (z < 0 || z >= nz) continue;
+                    const int xlo = max(cx - 1, 0), xhi = min(cx + 1, nx - 1);
                     int ares = 0, aseg = 0;
-                    if (self && lane < na) { ares = __ldg(a.t.hres1 + ka); aseg = __ldg(a.t.hseg1 + ka); }
-                    for (int dz = -1; dz <= 1; dz++) {
-                        const int z = cz + dz;
-                        if (z < 0 || z >= nz) continue;
-                        for (int dy = -1; dy <= 1; dy++) {
-                            const int y = cy + dy;
-                            if (y < 0 || y >= ny) continue;
-                            const int row = (z * ny + y) * nx;
-                            const int b0 = (row + xlo) ? (int)cellB[row + xlo - 1] : 0, b1 = (int)cellB[row + xhi];
-                            for (int base = b0; base < b1; base += 32) {
-                                const int j = base + lane;
-                                const bool valid = j < b1;
-                                int kb = 0;
-                                float bx = 0.f, by = 0.f, bz = 0.f;
-                                if (valid) { kb = permB[j]; bx = sx[offB + kb]; by = sy[offB + kb]; bz = sz[offB + kb]; }
-                                int bres = 0, bseg = 0;
-                                if (self && valid) { bres = __ldg(a.t.hres1 + kb); bseg = __ldg(a.t.hseg1 + kb); }
-                                if (lane == 0) evals += (unsigned long long)na * (unsigned)min(32, b1 - base);
-                                for (int ia = 0; ia < na; ia++) {
-                                    const float px = __shfl_sync(PC_FULL_MASK, ax, ia);
-                                    const float py = __shfl_sync(PC_FULL_MASK, ay, ia);
-                                    const float pz = __shfl_sync(PC_FULL_MASK, az, ia);
-                                    bool hit = valid && !(dist2_exact(px, py, pz, bx, by, bz) > a.sqdist);
-                                    if (self) {
-                                        // (resid1 - resid2) < 5 and same segment -> dropped (core/multi_trajectory.py:93-95)
-                                        const int r1 = __shfl_sync(PC_FULL_MASK, ares, ia);
-                                        const int s1 = __shfl_sync(PC_FULL_MASK, aseg, ia);
-                                        if (hit && (r1 - bres) < 5 && s1 == bseg) hit = false;
-                                    }
-                                    const unsigned m = __ballot_sync(PC_FULL_MASK, hit);
-                                    if (m) {
-                                        unsigned pos = 0;
-                                        if (lane == 0) pos = atomicAdd(&s_nhits, (unsigned)__popc(m));
-                                        pos = __shfl_sync(PC_FULL_MASK, pos, 0);
-                                        const int kA = __shfl_sync(PC_FULL_MASK, ka, ia);
-                                        if (hit) {
-                                            const unsigned p = pos + __popc(m & ((1u << lane) - 1u));
-                                            if (p < (unsigned)a.capHits) hits[p] = ((unsigned)kA << 16) | (unsigned)kb;
-                                        }
-                                    }
-                                }
+                    if (self) {
+                        const int li = PC_W_INDEX(__float_as_uint(pa.w));
+                        ares = __ldg(a.t.lres1 + li); aseg = __ldg(a.t.lseg1 + li);
+                    }
+                    for (int y = max(cy - 1, 0); y <= min(cy + 1, ny - 1); y++) {
+                        const int row = (z * ny + y) * nx;
+                        const int b0 = (row + xlo) ? (int)cellB[row + xlo - 1] : 0, b1 = (int)cellB[row + xhi];
+                        evals += (unsigned)(b1 - b0);
+                        for (int j = b0; j < b1; j++) {
+                            const float4 pb = sortB[j];
+                            if (!pair_within(pa.x, pa.y, pa.z, pb.x, pb.y, pb.z, sqdist, sqdist_hi)) continue;
+                            if (self) {
+                                // (resid1 - resid2) < 5 and same segment -> dropped (core/multi_trajectory.py:93-95)
+                                const int lj = PC_W_INDEX(__float_as_uint(pb.w));
+                                if ((ares - __ldg(a.t.lres1 + lj)) < 5 && aseg == __ldg(a.t.lseg1 + lj)) continue;
                             }
+                            const unsigned p = atomicAdd(&s_nhits, 1u);
+                            if (p < (unsigned)a.capHits) hits[p] = ((unsigned)ia << 16) | (unsigned)j;
                         }
                     }
                 }
@@ -299,26 +299,50 @@ __global__ void __launch_bounds__(NT) pc_scan_small_kernel(const PcScanArgs a, c
         }
         __syncthreads();
         const long long cbase = s_cbase;
+        const unsigned tmask = (unsigned)capTab - 1u;
         for (unsigned h = tid; h < nh; h += NT) {
             const unsigned u = hits[h];
-            const int ka = (int)(u >> 16), kb = (int)(u & 0xffffu);
-            const int li = __ldg(a.t.heavy1 + ka), lj = __ldg(heavyB + kb);
-            const double ax = sx[ka], ay = sy[ka], az = sz[ka];
-            const double bx = sx[offB + kb], by = sy[offB + kb], bz = sz[offB + kb];
+            const float4 pa = sortA[u >> 16], pb = sortB[u & 0xffffu];
+            const unsigned wa = __float_as_uint(pa.w), wb = __float_as_uint(pb.w);
+            const int li = PC_W_INDEX(wa), lj = PC_W_INDEX(wb);
+            const double ax = pa.x, ay = pa.y, az = pa.z, bx = pb.x, by = pb.y, bz = pb.z;
             const double dx = ax - bx, dy = ay - by, dz = az - bz;
             const double dist = sqrt(dx * dx + dy * dy + dz * dz);
+            const float wgt = contact_weight_f32(dist);
             if (cbase >= 0) {
                 pc_contact rec;
-                rec.i = li; rec.j = lj; rec.distance = (float)dist; rec.weight = (float)contact_weight(dist);
+                rec.i = li; rec.j = lj; rec.distance = (float)dist; rec.weight = wgt;
                 a.contacts[cbase + h] = rec;
             }
+            unsigned slot = 0xffffffffu;
+            if (fuse) {
+                const unsigned long long key =
+                    (unsigned long long)__ldg(a.t.lgid1 + li) * a.t.ngroups2 + (unsigned long long)__ldg(a.t.lgid2 + lj);
+                unsigned s = pc_hash64(key) & tmask;
+                for (int probes = 0; probes < capTab; probes++) {
+                    const unsigned long long prev = atomicCAS(&tkey[s], PC_EMPTY_KEY, key);
+                    if (prev == PC_EMPTY_KEY || prev == key) { slot = s; break; }
+                    s = (s + 1) & tmask;
+                }
+                if (slot == 0xffffffffu) atomicOr(&s_status, (unsigned)PC_ST_TABLE_OVERFLOW);
+                else {
+                    const double w = (double)wgt;
+                    atomicAdd(&tscore[slot], w);
+                    if (wa & PC_W_BACKBONE) atomicAdd(&tbb1[slot], w);
+                    if (wb & PC_W_BACKBONE) atomicAdd(&tbb2[slot], w);
+                    atomicAdd(&tncont[slot], 1u);
+                    atomicMin(&tfirst[slot], ((unsigned long long)(unsigned)li << 32) | (unsigned)lj);
+                }
+            }
             // H-bond gate: both names start with O/N/S (core/multi_trajectory.py:112)
-            if ((__ldg(a.t.hflag1 + ka) & PC_ATOM_HBCLASS) && (__ldg(hflagB + kb) & PC_ATOM_HBCLASS)) {
+            if (wa & wb & PC_W_HBCLASS) {
                 for (int side = 0; side < 2; side++) {
-                    const int p0 = side == 0 ? __ldg(a.t.hhptr1 + ka) : __ldg(hhptrB + kb);
-                    const int p1 = side == 0 ? __ldg(a.t.hhptr1 + ka + 1) : __ldg(hhptrB + kb + 1);
+                    const int *hptr = side == 0 ? a.t.lhptr1 : a.t.lhptr2;
+                    const int *hidx = side == 0 ? a.t.lhidx1 : a.t.lhidx2;
+                    const int heavy = side == 0 ? li : lj;
+                    const int p0 = __ldg(hptr + heavy), p1 = __ldg(hptr + heavy + 1);
                     for (int p = p0; p < p1; p++) {
-                        const int hl = side == 0 ? __ldg(a.t.hidx1 + p) : __ldg(hidxB + p);
+                        const int hl = __ldg(hidx + p);
                         if (hl < 0) { atomicOr(&s_status, (unsigned)PC_ST_MISSING_H); continue; }
                         float hxf, hyf, hzf;
                         load_xyz(side == 0 ? fr1 : fr2, hl, a.stride, hxf, hyf, hzf);
@@ -335,30 +359,70 @@ __global__ void __launch_bounds__(NT) pc_scan_small_kernel(const PcScanArgs a, c
                                 r.distance = (float)d; r.angle = (float)ang;
                                 hbq[q] = r;
                             }
+                            if (slot != 0xffffffffu) atomicAdd(&tnhb[slot], 1u);
                         }
                     }
                 }
             }
         }
         __syncthreads();
+
+        // ---- phase 8: H-bond records and accumulated rows -> global -----------------------------
         unsigned nb = s_nhb;
         if (nb > (unsigned)a.capHb) { nb = a.capHb; if (tid == 0) atomicOr(&s_status, (unsigned)PC_ST_HB_OVERFLOW); }
-        if (tid == 0) {
-            long long base = (long long)atomicAdd(&a.counters[PC_CNT_HBONDS], (unsigned long long)nb);
-            if (base + nb > a.cap_hbonds) { atomicOr(&s_status, (unsigned)PC_ST_OUT_OVERFLOW); base = -1; }
-            s_hbase = base;
-            a.frame_cstart[f] = (uint32_t)(cbase < 0 ? 0 : cbase);
-            a.frame_ccount[f] = cbase < 0 ? 0u : nh;
-            a.frame_hstart[f] = (uint32_t)(base < 0 ? 0 : base);
-            a.frame_hcount[f] = base < 0 ? 0u : nb;
+        uint32_t cnt = 0, incl = 0;
+        int tb = 0, te = 0;
+        if (fuse) {
+            const int ch = (capTab + NT - 1) / NT;
+            tb = min(tid * ch, capTab); te = min(tb + ch, capTab);
+            for (int s = tb; s < te; s++) cnt += tkey[s] != PC_EMPTY_KEY;
+            incl = warp_incl_scan(cnt, lane);
+            if (lane == 31) wsum[warp] = incl;
+        }
+        __syncthreads();
+        if (warp == 0) {
+            uint32_t total = 0;
+            if (fuse) {
+                const uint32_t v = lane < NT / 32 ? wsum[lane] : 0;
+                const uint32_t vi = warp_incl_scan(v, lane);
+                wsum[lane] = vi - v;
+                total = __shfl_sync(PC_FULL_MASK, vi, 31);
+            }
+            if (lane == 0) {
+                long long base = (long long)atomicAdd(&a.counters[PC_CNT_HBONDS], (unsigned long long)nb);
+                if (base + nb > a.cap_hbonds) { atomicOr(&s_status, (unsigned)PC_ST_OUT_OVERFLOW); base = -1; }
+                s_hbase = base;
+                a.frame_cstart[f] = (uint32_t)(cbase < 0 ? 0 : cbase);
+                a.frame_ccount[f] = cbase < 0 ? 0u : nh;
+                a.frame_hstart[f] = (uint32_t)(base < 0 ? 0 : base);
+                a.frame_hcount[f] = base < 0 ? 0u : nb;
+                if (fuse) {
+                    long long rb = (long long)atomicAdd(&a.counters[PC_CNT_ROWS], (unsigned long long)total);
+                    if (rb + total > a.cap_rows) { atomicOr(&s_status, (unsigned)PC_ST_OUT_OVERFLOW); rb = -1; }
+                    s_rbase = rb;
+                    a.frame_rstart[f] = (uint32_t)(rb < 0 ? 0 : rb);
+                    a.frame_rcount[f] = rb < 0 ? 0u : total;
+                }
+            }
         }
         __syncthreads();
         if (s_hbase >= 0)
             for (unsigned q = tid; q < nb; q += NT) a.hbonds[s_hbase + q] = hbq[q];
+        if (fuse && s_rbase >= 0) {
+            long long o = s_rbase + wsum[warp] + incl - cnt;
+            for (int s = tb; s < te; s++) {
+                if (tkey[s] == PC_EMPTY_KEY) continue;
+                pc_row r;
+                r.key = tkey[s]; r.score = tscore[s]; r.bb1 = tbb1[s]; r.bb2 = tbb2[s];
+                r.ncontacts = tncont[s]; r.nhbonds = tnhb[s]; r.first = tfirst[s];
+                a.rows[o++] = r;
+            }
+        }
         if (tid == 0 && s_status) atomicOr(&a.counters[PC_CNT_STATUS], (unsigned long long)s_status);
         __syncthreads();
     }
-    // one evaluation counter per warp -> global
-    evals = __shfl_sync(PC_FULL_MASK, evals, 0);
+    // evaluation counter -> global (one atomic per warp)
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) evals += __shfl_xor_sync(PC_FULL_MASK, evals, o);
     if (lane == 0 && evals) atomicAdd(&a.counters[PC_CNT_EVALS], evals);
 }

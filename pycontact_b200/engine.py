@@ -118,6 +118,7 @@ class ContactEngine:
         self.guess = [max(256, 2 * heavy), max(64, heavy // 4), 256]
         self.lim = [0, 0, 0, 0]          # hits/frame, hbonds/frame, cells, table slots (0 = automatic)
         self.launches = 0
+        self.forced_path = 0
 
     # ------------------------------------------------------------------------------------------
     def close(self):
@@ -154,6 +155,7 @@ class ContactEngine:
 
     def set_path(self, path: int):
         """0 = automatic, 1 = small-frame kernel, 2 = large-frame path (tests cover both)."""
+        self.forced_path = int(path)
         for s in self.slots:
             check(self.lib.pc_set_path(s.ctx, int(path)))
 
@@ -171,11 +173,15 @@ class ContactEngine:
         if st & _lib.ST_HB_OVERFLOW:
             self.lim[1] = max(1024, 2 * (self.lim[1] or 256))
         if st & _lib.ST_TABLE_OVERFLOW:
+            # beyond 2048 slots the library switches to its global-memory table
             self.lim[3] = max(2048, 2 * (self.lim[3] or 1024))
-            if self.lim[3] > 4096:
-                raise PcError(_lib.PC_ERR_CAPACITY, "more than 4096 accumulation keys in one frame")
-        if self.lim[0] > 32768 or self.lim[1] > 8192:
-            raise PcError(_lib.PC_ERR_CAPACITY, "frame produces more records than the small-frame path can stage")
+        if (st & _lib.ST_STAGE_OVERFLOW) or self.lim[0] > 16384 or self.lim[1] > 4096:
+            # more atoms / records per frame than one CTA can stage in shared memory: use the
+            # tiled large-frame path from now on
+            if self.forced_path == 1:
+                raise PcError(_lib.PC_ERR_CAPACITY, "frame does not fit the small-frame path")
+            self.lim[0] = self.lim[1] = 0
+            self.set_path(2)
         for s in self.slots:
             check(self.lib.pc_set_limits(s.ctx, *self.lim))
         if st & _lib.ST_OUT_OVERFLOW:
@@ -290,8 +296,6 @@ class ContactEngine:
                 check(lib.pc_last_status(slot.ctx, ctypes.byref(st), None, None, ctypes.byref(need), None))
                 if st.value & _lib.ST_TABLE_OVERFLOW:
                     self.lim[3] = max(2048, 2 * (self.lim[3] or 1024))
-                    if self.lim[3] > 4096:
-                        raise PcError(_lib.PC_ERR_CAPACITY, "more than 4096 accumulation keys in one frame")
                     for s in self.slots:
                         check(lib.pc_set_limits(s.ctx, *self.lim))
                 rows_guess = max(int(need.value * 1.25) + 64, 2 * rows_guess if st.value & _lib.ST_OUT_OVERFLOW else rows_guess)

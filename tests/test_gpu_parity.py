@@ -305,3 +305,34 @@ def test_device_generator_frames_are_analysed_exactly():
         src = ArraySource(np.ascontiguousarray(host[:, s.sel1]), np.ascontiguousarray(host[:, s.sel2]))
         traj, _, _ = run_scan([eng], src, order_keys=True)
     _compare_traj(traj, ora)
+
+
+@pytest.mark.parametrize("name,self_mode", [("small", False), ("small", True), ("tiny", False)])
+def test_fused_accumulation_equals_standalone_kernel(name, self_mode):
+    """The scan kernel's in-kernel accumulation (no order keys) and pc_accumulate give the same rows."""
+    s = synth.make_system(name)
+    t = s.topology
+    coords = synth.frames_host(s, range(5))
+    idx1 = s.sel1
+    idx2 = s.sel1 if self_mode else s.sel2
+    s1, s2 = _selections(t, idx1, None if self_mode else idx2, s.backbone)
+    gm1 = prepare.group_map(idx1, s.maps[0], t.names, t.resids, t.resnames, t.segids)
+    gm2 = prepare.group_map(idx2, s.maps[1], t.names, t.resids, t.resnames, t.segids)
+    tables = []
+    for fused in (1, 0):
+        with ContactEngine(s1, s2, 5.0, 2.5, 120) as eng:
+            eng.set_path(1)
+            for sl in eng.slots:
+                eng.lib.pc_set_fused_accumulate(sl.ctx, fused)
+            eng.set_maps(gm1.gid, gm2.gid, gm2.n_groups)
+            src = ArraySource(np.ascontiguousarray(coords[:, idx1]), None if self_mode else np.ascontiguousarray(coords[:, idx2]))
+            _, table, _ = run_scan([eng], src, batch_frames=2, order_keys=False, accumulate=True, group_maps=(gm1, gm2))
+        tables.append(table)
+    a, b = tables
+    assert a.n_keys == b.n_keys and a.n_keys > 0
+    oa, ob = np.argsort(a.keys), np.argsort(b.keys)
+    assert np.array_equal(a.keys[oa], b.keys[ob])
+    np.testing.assert_allclose(a.score_matrix()[oa], b.score_matrix()[ob], rtol=1e-12, atol=1e-300)
+    assert np.array_equal(a.hbond_matrix()[oa], b.hbond_matrix()[ob])
+    np.testing.assert_allclose(a.bb1[oa], b.bb1[ob], rtol=1e-12, atol=1e-300)
+    np.testing.assert_allclose(a.bb2[oa], b.bb2[ob], rtol=1e-12, atol=1e-300)
