@@ -73,6 +73,8 @@ class ClockSampler(threading.Thread):
         self.lines = []
 
     def run(self):
+        if os.environ.get("PC_NO_CLOCKS"):
+            return
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
                                           "--format=csv,noheader,nounits", "-lms", "200"],
@@ -242,14 +244,15 @@ def run_gpu(args):
     eng = ContactEngine(s1, s2, 5.0, 2.5, 120, device=local, slots=2)
     eng.set_maps(gm1.gid, gm2.gid, gm2.n_groups)
     in_bytes_frame = (n1 + (0 if self_mode else n2)) * 12
-    batch = args.batch or int(max(1, min(F, (256 << 20) // in_bytes_frame)))
+    batch = args.batch or int(max(1, min(F, 2048, (1 << 30) // in_bytes_frame)))
     nb = (F + batch - 1) // batch
     n_keys = gm1.n_groups * gm2.n_groups
-    dense = n_keys <= (1 << 25)
+    dense = n_keys <= (1 << 20)          # aggregated maps as a dense [n_keys][4] table (32 MB at most)
     totals = DeviceBuffer(max(1, n_keys if dense else 1) * 32, local)
     totals_t = None
     if world > 1 and dense:
         totals_t = torch.zeros(n_keys * 4, dtype=torch.float64, device="cuda")
+    totals_host = _lib.PinnedArray((max(1, n_keys if dense else 1) * 4,), np.float64)
     stream = eng.slots[0].stream
     ev = [[ctypes.c_void_p(), ctypes.c_void_p()] for _ in range(nb + 1)]
     for pair in ev:
@@ -268,32 +271,42 @@ def run_gpu(args):
                 totals_t.zero_()
                 torch.cuda.current_stream().synchronize()
             else:
-                check(lib.pc_memcpy(local, totals.ptr, _zeros.ctypes.data, n_keys * 32, 1, stream))
+                check(lib.pc_memset(local, totals.ptr, 0, n_keys * 32, stream))
+        def finish(sid, nf):
+            nonlocal d_rows
+            c = eng.collect_device(sid)
+            tot[:] += c
+            if dense:
+                check(lib.pc_fold_rows(eng.slots[sid].ctx, totals_ptr(), n_keys, eng.slots[sid].stream))
+            rows, _, _ = eng.fetch_rows(sid)               # the per-frame maps of this rank's frames -> host
+            d_rows += rows.nbytes
+
+        # two batches in flight: batch b+1 is scanned while batch b's rows travel to the host
+        pending = None
         for b in range(nb):
             f0 = b * batch
             nf = min(batch, F - f0)
-            p1 = d1.at(f0 * n1 * 12)
-            p2 = None if self_mode else d2.at(f0 * n2 * 12)
-            c = eng.scan_device(p1, p2, nf, accumulate=True, events=ev[b] if timed else None)
-            tot += c
-            if dense:
-                check(lib.pc_fold_rows(eng.slots[0].ctx, totals_ptr(), n_keys, stream))
-            rows, _, _ = eng.fetch_rows()                  # the per-frame maps of this rank's frames
-            d_rows += rows.nbytes
+            sid = b % len(eng.slots)
+            eng.submit_device(sid, d1.at(f0 * n1 * 12), None if self_mode else d2.at(f0 * n2 * 12), nf,
+                              accumulate=True, events=ev[b] if timed else None)
+            if pending is not None:
+                finish(*pending)
+            pending = (sid, nf)
+        finish(*pending)
         if dense:
-            check(lib.pc_stream_sync(stream))
+            for sl in eng.slots:
+                check(lib.pc_stream_sync(sl.stream))
             if totals_t is not None:
                 dist.all_reduce(totals_t)                  # the one collective: aggregated maps over ranks
                 torch.cuda.current_stream().synchronize()
             if rank == 0:
-                host = np.empty(n_keys * 4)
+                host = totals_host.array
                 src = totals_ptr()
                 check(lib.pc_memcpy(local, host.ctypes.data, src, host.nbytes, 2, None))
                 check(lib.pc_device_sync(local))
                 d_rows += host.nbytes
         return tot, d_rows
 
-    _zeros = np.zeros(max(1, n_keys if dense else 1) * 4)
 
     def barrier():
         if dist is not None:

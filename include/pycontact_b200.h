@@ -192,10 +192,12 @@ int pc_stream_sync(void *stream);
 void pc_stream_destroy(void *stream);
 
 /* Device memory helpers for callers without a CUDA binding of their own (bench.py, tests):
- * cudaMalloc / cudaFree / cudaMemcpyAsync (kind 1 = H2D, 2 = D2H, 3 = D2D) / cudaDeviceSynchronize. */
+ * cudaMalloc / cudaFree / cudaMemcpyAsync (kind 1 = H2D, 2 = D2H, 3 = D2D) / cudaMemsetAsync /
+ * cudaDeviceSynchronize. */
 int pc_device_alloc(int device, int64_t bytes, void **out);
 void pc_device_free(int device, void *p);
 int pc_memcpy(int device, void *dst, const void *src, int64_t bytes, int kind, void *stream);
+int pc_memset(int device, void *dst, int value, int64_t bytes, void *stream);
 int pc_device_sync(int device);
 
 /* Measurement helpers (bench.py): kernels launched by this library so far, and CUDA events so that

@@ -55,7 +55,7 @@ EXPORTS = [
     "pc_reserve", "pc_scan_device", "pc_accumulate", "pc_scan_host", "pc_batch_totals", "pc_last_status",
     "pc_device_outputs", "pc_fetch", "pc_find_contacts", "pc_free_host", "pc_synth_frames", "pc_host_alloc",
     "pc_host_free", "pc_load_records", "pc_stream_create", "pc_stream_sync", "pc_stream_destroy",
-    "pc_device_alloc", "pc_device_free", "pc_memcpy", "pc_device_sync",
+    "pc_device_alloc", "pc_device_free", "pc_memcpy", "pc_memset", "pc_device_sync",
     "pc_launch_count", "pc_event_create", "pc_event_record", "pc_event_elapsed_ms", "pc_event_destroy", "pc_fold_rows",
 ]
 
@@ -107,6 +107,7 @@ def load():
     lib.pc_device_free.argtypes = [ctypes.c_int, vp]
     lib.pc_device_free.restype = None
     lib.pc_memcpy.argtypes = [ctypes.c_int, vp, vp, i64, ctypes.c_int, vp]
+    lib.pc_memset.argtypes = [ctypes.c_int, vp, ctypes.c_int, i64, vp]
     lib.pc_device_sync.argtypes = [ctypes.c_int]
     lib.pc_launch_count.restype = ctypes.c_int64
     lib.pc_event_create.argtypes = [ctypes.c_int, P(vp)]

@@ -154,13 +154,32 @@ __global__ void __launch_bounds__(256) pc_fold_rows_kernel(const pc_row *rows, c
 // frame * n_keys + key.  Inserts are 64-bit CAS + float64 atomics in L2; a key's first insertion
 // bumps its frame's row count, so rows can afterwards be emitted grouped by frame.
 // ---------------------------------------------------------------------------------------------------
+struct __align__(64) PcGlobalEntry {         // 64 bytes = two 32-byte sectors per probe + update
+    unsigned long long key, first;
+    double score, bb1, bb2;
+    unsigned int ncont, nhb;
+    unsigned int rowidx;                     // position of this key among its frame's rows (insertion order)
+    unsigned int pad[3];
+};
+
 struct PcGlobalTable {
-    unsigned long long *keys, *first;        // cap entries each, initialised to PC_EMPTY_KEY
-    double *score, *bb1, *bb2;               // cap entries each, initialised to 0
-    unsigned int *ncont, *nhb;
+    PcGlobalEntry *e;                        // cap entries; key / first initialised to PC_EMPTY_KEY, sums to 0
     unsigned long long cap;                  // power of two
     unsigned long long nkeys;                // G1 * G2
+    unsigned int *fresh;                     // slots in order of first insertion (cap_rows entries)
+    unsigned long long *nfresh;              // their number
 };
+
+__global__ void __launch_bounds__(256) pc_gacc_init_kernel(PcGlobalTable t) {
+    for (unsigned long long s = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x; s < t.cap;
+         s += (unsigned long long)gridDim.x * blockDim.x) {
+        PcGlobalEntry v;
+        v.key = PC_EMPTY_KEY; v.first = PC_EMPTY_KEY; v.score = 0.0; v.bb1 = 0.0; v.bb2 = 0.0; v.ncont = 0; v.nhb = 0;
+        v.rowidx = 0; v.pad[0] = v.pad[1] = v.pad[2] = 0;
+        t.e[s] = v;
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) *t.nfresh = 0ull;
+}
 
 __device__ __forceinline__ long long pc_gacc_find(const PcGlobalTable &t, unsigned long long ck, bool insert, bool &fresh) {
     const unsigned long long mask = t.cap - 1ull;
@@ -168,13 +187,15 @@ __device__ __forceinline__ long long pc_gacc_find(const PcGlobalTable &t, unsign
     h ^= h >> 33; h *= 0xff51afd7ed558ccdull; h ^= h >> 33; h *= 0xc4ceb9fe1a85ec53ull; h ^= h >> 33;
     unsigned long long s = h & mask;
     fresh = false;
-    for (unsigned long long probes = 0; probes < t.cap; probes++) {
+    // a table sized from a hint can turn out too small: give up after 512 probes (-> PC_ST_TABLE_OVERFLOW,
+    // the caller retries with the real count) instead of walking a nearly full table
+    for (unsigned long long probes = 0; probes < 512 && probes < t.cap; probes++) {
         if (insert) {
-            const unsigned long long prev = atomicCAS(&t.keys[s], PC_EMPTY_KEY, ck);
+            const unsigned long long prev = atomicCAS(&t.e[s].key, PC_EMPTY_KEY, ck);
             if (prev == PC_EMPTY_KEY) { fresh = true; return (long long)s; }
             if (prev == ck) return (long long)s;
         } else {
-            const unsigned long long k = t.keys[s];
+            const unsigned long long k = t.e[s].key;
             if (k == ck) return (long long)s;
             if (k == PC_EMPTY_KEY) return -1;
         }
@@ -194,15 +215,20 @@ __global__ void __launch_bounds__(256) pc_gacc_insert_kernel(const PcAccArgs a, 
         bool fresh;
         const long long s = pc_gacc_find(t, (unsigned long long)f * t.nkeys + key, true, fresh);
         if (s < 0) { status |= (unsigned)PC_ST_TABLE_OVERFLOW; continue; }
-        if (fresh) atomicAdd(&a.frame_rcount[f], 1u);
+        if (fresh) {
+            t.e[s].rowidx = atomicAdd(&a.frame_rcount[f], 1u);
+            const unsigned long long q = atomicAdd(t.nfresh, 1ull);
+            if ((long long)q < a.cap_rows) t.fresh[q] = (unsigned int)s;
+        }
         const double w = (double)rec.weight;
-        atomicAdd(&t.score[s], w);
-        if (__ldg(a.lflag1 + rec.i) & PC_ATOM_BACKBONE) atomicAdd(&t.bb1[s], w);
-        if (__ldg(a.lflag2 + rec.j) & PC_ATOM_BACKBONE) atomicAdd(&t.bb2[s], w);
-        atomicAdd(&t.ncont[s], 1u);
+        PcGlobalEntry *e = t.e + s;
+        atomicAdd(&e->score, w);
+        if (__ldg(a.lflag1 + rec.i) & PC_ATOM_BACKBONE) atomicAdd(&e->bb1, w);
+        if (__ldg(a.lflag2 + rec.j) & PC_ATOM_BACKBONE) atomicAdd(&e->bb2, w);
+        atomicAdd(&e->ncont, 1u);
         const unsigned long long ok = a.order_keys ? a.order_keys[c0 + c]
                                                    : (((unsigned long long)(unsigned)rec.i << 32) | (unsigned)rec.j);
-        atomicMin(&t.first[s], ok);
+        atomicMin(&e->first, ok);
     }
     status = __reduce_or_sync(PC_FULL_MASK, status);
     if ((threadIdx.x & 31) == 0 && status) atomicOr(&a.counters[PC_CNT_STATUS], (unsigned long long)status);
@@ -217,7 +243,7 @@ __global__ void __launch_bounds__(256) pc_gacc_hbond_kernel(const PcAccArgs a, P
             (unsigned long long)__ldg(a.lgid1 + rec.i) * a.ngroups2 + (unsigned long long)__ldg(a.lgid2 + rec.j);
         bool fresh;
         const long long s = pc_gacc_find(t, (unsigned long long)f * t.nkeys + key, false, fresh);
-        if (s >= 0) atomicAdd(&t.nhb[s], 1u);
+        if (s >= 0) atomicAdd(&t.e[s].nhb, 1u);
     }
 }
 
@@ -248,16 +274,17 @@ __global__ void __launch_bounds__(1024) pc_gacc_offsets_kernel(const PcAccArgs a
 }
 
 __global__ void __launch_bounds__(256) pc_gacc_emit_kernel(const PcAccArgs a, PcGlobalTable t, uint32_t *cursor) {
-    for (unsigned long long s = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x; s < t.cap;
-         s += (unsigned long long)gridDim.x * blockDim.x) {
-        const unsigned long long ck = t.keys[s];
-        if (ck == PC_EMPTY_KEY) continue;
+    const unsigned long long n = min(*t.nfresh, (unsigned long long)a.cap_rows);
+    for (unsigned long long q = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x; q < n;
+         q += (unsigned long long)gridDim.x * blockDim.x) {
+        const PcGlobalEntry e = t.e[t.fresh[q]];
+        const unsigned long long ck = e.key;
         const unsigned long long f = ck / t.nkeys;
-        const long long pos = (long long)a.frame_rstart[f] + atomicAdd(&cursor[f], 1u);
+        const long long pos = (long long)a.frame_rstart[f] + e.rowidx;
         if (pos >= a.cap_rows) continue;
         pc_row r;
-        r.key = ck - f * t.nkeys; r.score = t.score[s]; r.bb1 = t.bb1[s]; r.bb2 = t.bb2[s];
-        r.ncontacts = t.ncont[s]; r.nhbonds = t.nhb[s]; r.first = t.first[s];
+        r.key = ck - f * t.nkeys; r.score = e.score; r.bb1 = e.bb1; r.bb2 = e.bb2;
+        r.ncontacts = e.ncont; r.nhbonds = e.nhb; r.first = e.first;
         a.rows[pos] = r;
     }
 }

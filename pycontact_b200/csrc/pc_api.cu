@@ -57,7 +57,7 @@ struct pc_ctx {
     size_t smem_optin = 0;
     bool have_topology = false, have_maps = false;
     int n1 = 0, n2 = 0, n1h = 0, n2h = 0;
-    DevBuf<uint32_t> hinfo1, hinfo2, hmask1, hmask2, linfo1, linfo2;
+    DevBuf<uint32_t> hinfo1, hinfo2, hmask1, hmask2, hpre1, hpre2, linfo1, linfo2;
     DevBuf<int> lres1, lseg1, lres2, lseg2, lhptr1, lhidx1, lhptr2, lhidx2, lgid1, lgid2;
     DevBuf<uint8_t> lflag1, lflag2;
     unsigned long long ngroups1 = 0, ngroups2 = 0;
@@ -75,13 +75,17 @@ struct pc_ctx {
     DevBuf<uint32_t> frame_meta;      // 6 arrays of max_frames
     DevBuf<float> stage1, stage2;     // H2D staging for pc_scan_host
     PcLargeWork large;                // work buffers of the large-frame path
-    DevBuf<unsigned long long> gacc_u64;   // global accumulation table: keys | first
-    DevBuf<double> gacc_f64;               //   score | bb1 | bb2 | (ncont, nhb as u32 pairs)
-    DevBuf<uint32_t> gacc_cursor;
+    DevBuf<PcGlobalEntry> gacc_tab;        // global accumulation table
+    DevBuf<uint32_t> gacc_cursor, gacc_fresh;
+    DevBuf<unsigned long long> gacc_nfresh;
+    unsigned long long gacc_hint = 0;      // contacts of the previous accumulated batch (table sizing without a sync)
+    unsigned long long gacc_hint_rows = 0; // and its rows
+    int gacc_hint_frames = 0;
     int last_nframes = 0;
     bool last_order_keys = false;
     unsigned long long *h_counters = nullptr;   // pinned mirror
     int last_path = 0;                // 1 = small, 2 = large
+    bool gacc_used = false, gacc_retry = false;
     bool want_fused_acc = true;       // accumulate inside the small-frame scan kernel when possible
     bool last_fused = false;
     std::vector<uint32_t> h_meta;     // host copy of the scan's 4 frame arrays (large path: sliced outputs)
@@ -140,7 +144,7 @@ extern "C" int pc_set_limits(pc_ctx *c, int hits_per_frame, int hbonds_per_frame
 // index order -- kernels never touch hydrogens except inside the H-bond test) and per local atom,
 // a heavy-atom bitmask for the streaming kernels, and the per-atom arrays the rare paths read.
 struct SideBufs {
-    DevBuf<uint32_t> *hinfo, *hmask, *linfo;
+    DevBuf<uint32_t> *hinfo, *hmask, *hpre, *linfo;
     DevBuf<int> *lres, *lseg, *lhptr, *lhidx;
     DevBuf<uint8_t> *lflag;
 };
@@ -162,7 +166,10 @@ static cudaError_t upload_side(int n, const uint8_t *flags, const int32_t *resid
         ptr[i + 1] = (int)idx.size();
     }
     nheavy = (int)hinfo.size();
+    std::vector<uint32_t> hpre(hmask.size() + 1, 0u);
+    for (size_t w = 0; w < hmask.size(); w++) hpre[w + 1] = hpre[w] + (uint32_t)__builtin_popcount(hmask[w]);
     cudaError_t e;
+    if ((e = b.hpre->upload(hpre)) != cudaSuccess) return e;
     if ((e = b.hinfo->upload(hinfo)) != cudaSuccess) return e;
     if ((e = b.hmask->upload(hmask)) != cudaSuccess) return e;
     if ((e = b.linfo->upload(linfo)) != cudaSuccess) return e;
@@ -185,14 +192,14 @@ extern "C" int pc_set_topology(pc_ctx *c, int32_t n1, int32_t n2, const uint8_t 
     CUDA_TRY(cudaSetDevice(c->device));
     c->n1 = n1;
     CUDA_TRY(upload_side(n1, f1, resid1, segid1, hptr1, hidx1,
-                         SideBufs{&c->hinfo1, &c->hmask1, &c->linfo1, &c->lres1, &c->lseg1, &c->lhptr1, &c->lhidx1, &c->lflag1},
+                         SideBufs{&c->hinfo1, &c->hmask1, &c->hpre1, &c->linfo1, &c->lres1, &c->lseg1, &c->lhptr1, &c->lhidx1, &c->lflag1},
                          c->n1h));
     if (c->self_mode) {
         c->n2 = n1; c->n2h = c->n1h;
     } else {
         c->n2 = n2;
         CUDA_TRY(upload_side(n2, f2, resid2, segid2, hptr2, hidx2,
-                             SideBufs{&c->hinfo2, &c->hmask2, &c->linfo2, &c->lres2, &c->lseg2, &c->lhptr2, &c->lhidx2, &c->lflag2},
+                             SideBufs{&c->hinfo2, &c->hmask2, &c->hpre2, &c->linfo2, &c->lres2, &c->lseg2, &c->lhptr2, &c->lhidx2, &c->lflag2},
                              c->n2h));
     }
     c->have_topology = true;
@@ -238,6 +245,7 @@ static PcTopoDev topo_dev(const pc_ctx *c) {
     t.n1 = c->n1; t.n2 = c->n2; t.n1h = c->n1h; t.n2h = c->n2h;
     t.hinfo1 = c->hinfo1.p; t.hinfo2 = self ? c->hinfo1.p : c->hinfo2.p;
     t.hmask1 = c->hmask1.p; t.hmask2 = self ? c->hmask1.p : c->hmask2.p;
+    t.hpre1 = c->hpre1.p; t.hpre2 = self ? c->hpre1.p : c->hpre2.p;
     t.linfo1 = c->linfo1.p; t.linfo2 = self ? c->linfo1.p : c->linfo2.p;
     t.lres1 = c->lres1.p; t.lseg1 = c->lseg1.p;
     t.lres2 = self ? c->lres1.p : c->lres2.p; t.lseg2 = self ? c->lseg1.p : c->lseg2.p;
@@ -395,27 +403,43 @@ extern "C" int pc_accumulate(pc_ctx *c, void *stream) {
         g_launches += 1;
         return PC_OK;
     }
-    // the table is sized from the number of contacts actually found: read the counters (synchronises)
-    CUDA_TRY(cudaMemcpyAsync(c->h_counters, c->counters.p, PC_CNT_COUNT * sizeof(unsigned long long),
-                             cudaMemcpyDeviceToHost, s));
-    CUDA_TRY(cudaStreamSynchronize(s));
-    if (c->h_counters[PC_CNT_STATUS] & (PC_ST_OUT_OVERFLOW | PC_ST_HITS_OVERFLOW | PC_ST_HB_OVERFLOW | PC_ST_STAGE_OVERFLOW))
-        return PC_OK;                        // the scan overflowed; pc_batch_totals reports it and the caller rescans
-    const unsigned long long ncontacts = std::min<unsigned long long>(c->h_counters[PC_CNT_CONTACTS], c->cap_contacts);
+    // The table is sized from the number of contacts: the previous batch's count (scaled by the frame
+    // ratio, +50%) when there is one -- a too small table sets PC_ST_TABLE_OVERFLOW and the caller
+    // retries -- else the counters are read back, which synchronises the stream once.
+    unsigned long long ncontacts;
+    const bool hinted = c->gacc_hint && c->gacc_hint_frames > 0 && !c->gacc_retry;
+    if (hinted) {
+        ncontacts = c->gacc_hint * (unsigned long long)a.nframes / c->gacc_hint_frames;
+        ncontacts += ncontacts / 2 + 1024;
+    } else {
+        CUDA_TRY(cudaMemcpyAsync(c->h_counters, c->counters.p, PC_CNT_COUNT * sizeof(unsigned long long),
+                                 cudaMemcpyDeviceToHost, s));
+        CUDA_TRY(cudaStreamSynchronize(s));
+        if (c->h_counters[PC_CNT_STATUS] & (PC_ST_OUT_OVERFLOW | PC_ST_HITS_OVERFLOW | PC_ST_HB_OVERFLOW | PC_ST_STAGE_OVERFLOW))
+            return PC_OK;                    // the scan overflowed; pc_batch_totals reports it and the caller rescans
+        ncontacts = std::min<unsigned long long>(c->h_counters[PC_CNT_CONTACTS], c->cap_contacts);
+        c->gacc_retry = false;
+    }
+    c->gacc_used = true;
     PcGlobalTable t;
+    // distinct (frame, key) cells are what fills the table: the previous batch's row count when known
+    unsigned long long cells = ncontacts;
+    if (c->gacc_hint_rows && c->gacc_hint_frames > 0 && hinted) {
+        cells = c->gacc_hint_rows * (unsigned long long)a.nframes / c->gacc_hint_frames;
+        cells += cells / 2 + 1024;
+    }
     t.cap = 1024;
-    while (t.cap < 2 * ncontacts + 16) t.cap <<= 1;
+    while (t.cap < 2 * cells + 16) t.cap <<= 1;
     t.nkeys = (unsigned long long)c->ngroups1 * c->ngroups2;
     if (t.nkeys == 0 || (unsigned long long)a.nframes > 0xffffffffffffffffull / std::max<unsigned long long>(t.nkeys, 1) - 1)
         return fail(PC_ERR_INVALID, "pc_accumulate: frame * key space exceeds 64 bits");
-    CUDA_TRY(c->gacc_u64.ensure(2 * t.cap));
-    CUDA_TRY(c->gacc_f64.ensure(4 * t.cap));
+    CUDA_TRY(c->gacc_tab.ensure(t.cap));
     CUDA_TRY(c->gacc_cursor.ensure((size_t)c->max_frames));
-    t.keys = c->gacc_u64.p; t.first = t.keys + t.cap;
-    t.score = c->gacc_f64.p; t.bb1 = t.score + t.cap; t.bb2 = t.bb1 + t.cap;
-    t.ncont = reinterpret_cast<unsigned int *>(t.bb2 + t.cap); t.nhb = t.ncont + t.cap;
-    CUDA_TRY(cudaMemsetAsync(t.keys, 0xff, 2 * t.cap * sizeof(unsigned long long), s));
-    CUDA_TRY(cudaMemsetAsync(t.score, 0, 4 * t.cap * sizeof(double), s));
+    CUDA_TRY(c->gacc_fresh.ensure((size_t)c->cap_rows));
+    CUDA_TRY(c->gacc_nfresh.ensure(1));
+    t.e = c->gacc_tab.p;
+    t.fresh = c->gacc_fresh.p; t.nfresh = c->gacc_nfresh.p;
+    pc_gacc_init_kernel<<<4 * c->num_sms, 256, 0, s>>>(t);
     CUDA_TRY(cudaMemsetAsync(a.frame_rcount, 0, (size_t)a.nframes * sizeof(uint32_t), s));
     const int per_frame_blocks = std::max(1, 4 * c->num_sms / a.nframes);
     const unsigned long long avg = ncontacts / a.nframes + 1;
@@ -423,9 +447,9 @@ extern "C" int pc_accumulate(pc_ctx *c, void *stream) {
     pc_gacc_insert_kernel<<<dim3(blocks, a.nframes), 256, 0, s>>>(a, t);
     pc_gacc_hbond_kernel<<<dim3(std::max(1, blocks / 4), a.nframes), 256, 0, s>>>(a, t);
     pc_gacc_offsets_kernel<<<1, 1024, 0, s>>>(a, c->gacc_cursor.p);
-    pc_gacc_emit_kernel<<<(int)std::min<unsigned long long>((t.cap + 255) / 256, 8ull * c->num_sms), 256, 0, s>>>(a, t, c->gacc_cursor.p);
+    pc_gacc_emit_kernel<<<4 * c->num_sms, 256, 0, s>>>(a, t, c->gacc_cursor.p);
     CUDA_TRY(cudaGetLastError());
-    g_launches += 4;
+    g_launches += 5;
     return PC_OK;
 }
 
@@ -510,6 +534,13 @@ extern "C" int pc_batch_totals(pc_ctx *c, void *stream, int64_t *n_contacts, int
                                 (size_t)c->last_nframes * sizeof(uint32_t), cudaMemcpyDeviceToHost));
     }
     const unsigned long long st = c->h_counters[PC_CNT_STATUS];
+    if (c->gacc_used) {
+        c->gacc_used = false;
+        if (st & PC_ST_TABLE_OVERFLOW) c->gacc_retry = true;           // next pc_accumulate sizes from the real count
+        else { c->gacc_hint_rows = c->h_counters[PC_CNT_ROWS];     // the true count, even beyond cap_rows
+               c->gacc_hint = std::min<unsigned long long>(c->h_counters[PC_CNT_CONTACTS], c->cap_contacts);
+               c->gacc_hint_frames = c->last_nframes; }
+    }
     if (n_contacts) *n_contacts = (int64_t)std::min<unsigned long long>(c->h_counters[PC_CNT_CONTACTS], c->cap_contacts);
     if (n_hbonds) *n_hbonds = (int64_t)std::min<unsigned long long>(c->h_counters[PC_CNT_HBONDS], c->cap_hbonds);
     if (n_rows) *n_rows = (int64_t)std::min<unsigned long long>(c->h_counters[PC_CNT_ROWS], c->cap_rows);
@@ -663,6 +694,12 @@ extern "C" int pc_memcpy(int device, void *dst, const void *src, int64_t bytes, 
     CUDA_TRY(cudaSetDevice(device));
     const cudaMemcpyKind k = kind == 1 ? cudaMemcpyHostToDevice : kind == 2 ? cudaMemcpyDeviceToHost : cudaMemcpyDeviceToDevice;
     CUDA_TRY(cudaMemcpyAsync(dst, src, (size_t)bytes, k, (cudaStream_t)stream));
+    return PC_OK;
+}
+extern "C" int pc_memset(int device, void *dst, int value, int64_t bytes, void *stream) {
+    if (!dst || bytes < 0) return fail(PC_ERR_INVALID, "pc_memset: bad arguments");
+    CUDA_TRY(cudaSetDevice(device));
+    CUDA_TRY(cudaMemsetAsync(dst, value, (size_t)bytes, (cudaStream_t)stream));
     return PC_OK;
 }
 extern "C" int pc_device_sync(int device) {

@@ -35,6 +35,7 @@ struct PcTopoDev {
     int n1, n2, n1h, n2h;
     const uint32_t *hinfo1, *hinfo2;   // per heavy ordinal: packed atom word (heavy atoms in index order)
     const uint32_t *hmask1, *hmask2;   // 1 bit per LOCAL atom: not a hydrogen (streaming kernels)
+    const uint32_t *hpre1, *hpre2;     // per 32 LOCAL atoms: heavy atoms before atom 32*w (heavy ordinal of a range start)
     const uint32_t *linfo1, *linfo2;   // per LOCAL atom: packed atom word
     const int *lres1, *lseg1, *lres2, *lseg2;          // per LOCAL atom (self-interaction filter)
     const int *lhptr1, *lhidx1, *lhptr2, *lhidx2;      // bonded-H CSR per LOCAL atom -> local H index (-1: missing)

@@ -38,11 +38,12 @@ struct PcLargeWork {
     float4 *candA = nullptr, *candB = nullptr;        // FB x n_h   (compacted, unsorted)
     uint32_t *ccellA = nullptr, *ccellB = nullptr;    // FB x n_h   cell id of each compacted atom
     float4 *sortA = nullptr, *sortB = nullptr;        // FB x n_h   (cell order)
+    uint8_t *occ = nullptr;                           // FB x capCells: cell has a B atom in its 27-cell neighbourhood
     void release() {
-        void *ps[] = {frames, cellA, cellB, candA, candB, ccellA, ccellB, sortA, sortB};
+        void *ps[] = {frames, cellA, cellB, candA, candB, ccellA, ccellB, sortA, sortB, occ};
         for (void *p : ps) if (p) cudaFree(p);
         frames = nullptr; cellA = cellB = nullptr; candA = candB = sortA = sortB = nullptr;
-        ccellA = ccellB = nullptr; FB = 0;
+        ccellA = ccellB = nullptr; occ = nullptr; FB = 0;
     }
     ~PcLargeWork() { release(); }
 };
@@ -75,7 +76,7 @@ __device__ __forceinline__ int pc_large_cell_of(const PcLargeFrame &F, float x, 
 }
 
 // ---- L1 / L3: streaming kernels -----------------------------------------------------------------
-#define PC_STREAM_NT 256
+#define PC_STREAM_NT 512
 #define PC_STREAM_CHUNK 24576            // 2048 atoms per chunk
 #define PC_STREAM_STAGES 4
 #define PC_STREAM_SMEM (PC_STREAM_STAGES * (PC_STREAM_CHUNK + 16) + PC_STREAM_STAGES * 8 + 16)
@@ -86,7 +87,7 @@ template <int MODE>
 __global__ void __launch_bounds__(PC_STREAM_NT) pc_large_stream_kernel(const PcScanArgs a, PcLargeFrame *fr, int f0, int side,
                                                                        int slot0, int atoms_per_cta, uint32_t *cells,
                                                                        int capCells, float4 *cand, uint32_t *ccell,
-                                                                       int nh_alloc) {
+                                                                       int nh_alloc, const uint8_t *occ) {
     constexpr int NT = PC_STREAM_NT, CHUNK = PC_STREAM_CHUNK, STAGES = PC_STREAM_STAGES;
     extern __shared__ __align__(16) unsigned char smem[];
     PcRing<STAGES, CHUNK> ring;
@@ -110,7 +111,12 @@ __global__ void __launch_bounds__(PC_STREAM_NT) pc_large_stream_kernel(const PcS
     if (MODE == PC_MODE_BIN && F.ncell == 0) return;
     const float *frame = side == 0 ? a.xyz1 + (long long)f * a.pitch1 : a.xyz2 + (long long)f * a.pitch2;
     const uint32_t *hmask = side == 0 ? a.t.hmask1 : a.t.hmask2;
-    const uint32_t *linfo = side == 0 ? a.t.linfo1 : a.t.linfo2;
+    const uint32_t *hpre = side == 0 ? a.t.hpre1 : a.t.hpre2;
+    const uint32_t *hinfo = side == 0 ? a.t.hinfo1 : a.t.hinfo2;
+    // heavy ordinal of local atom i = number of heavy atoms before it
+    auto heavy_before = [&](int i) -> int {
+        return (int)(__ldg(hpre + (i >> 5)) + __popc(__ldg(hmask + (i >> 5)) & ((1u << (i & 31)) - 1u)));
+    };
     PcSegment seg;
     seg.sb = reinterpret_cast<const unsigned char *>(frame) + 12ll * r0;
     seg.natoms = min(atoms_per_cta, n - r0);
@@ -135,18 +141,19 @@ __global__ void __launch_bounds__(PC_STREAM_NT) pc_large_stream_kernel(const PcS
         if (tid == 0 && q + STAGES - 1 < nch) ring.issue((unsigned)(q + STAGES - 1), pc_chunk_of<CHUNK>(seg, q + STAGES - 1));
         if (!ring.wait((unsigned)q)) { s_bad = 1; }
         const PcChunk c = pc_chunk_of<CHUNK>(seg, q);
+        // only the chunk's heavy atoms are visited: their ordinals are a contiguous range of the
+        // heavy list (hinfo), whose entries give the local index and the packed atom word
+        const int abase = r0 + c.k0;
         const unsigned char *slot = ring.slot((unsigned)q) + c.off0;
-        const int cnt = c.k1 - c.k0;
+        const int h0 = heavy_before(abase), cnt = heavy_before(r0 + c.k1) - h0;
         for (int kk = tid; kk < ((cnt + 31) & ~31); kk += NT) {
-            const int li = r0 + c.k0 + kk;
-            bool heavy = false;
+            const bool heavy = kk < cnt;
+            uint32_t info = 0;
             float x = 0.f, y = 0.f, z = 0.f;
-            if (kk < cnt) {
-                heavy = (__ldg(hmask + (li >> 5)) >> (li & 31)) & 1u;
-                if (heavy) {
-                    const float *p = reinterpret_cast<const float *>(slot + 12 * kk);
-                    x = p[0]; y = p[1]; z = p[2];
-                }
+            if (heavy) {
+                info = __ldg(hinfo + h0 + kk);
+                const float *p = reinterpret_cast<const float *>(slot + 12 * (PC_W_INDEX(info) - abase));
+                x = p[0]; y = p[1]; z = p[2];
             }
             if (MODE == PC_MODE_BBOX) {
                 if (heavy) {
@@ -154,7 +161,9 @@ __global__ void __launch_bounds__(PC_STREAM_NT) pc_large_stream_kernel(const PcS
                     mx[0] = fmaxf(mx[0], x); mx[1] = fmaxf(mx[1], y); mx[2] = fmaxf(mx[2], z);
                 }
             } else {
-                const int cell = heavy ? pc_large_cell_of(F, x, y, z) : -1;
+                int cell = heavy ? pc_large_cell_of(F, x, y, z) : -1;
+                // an A atom whose 27-cell neighbourhood holds no B atom cannot have a partner
+                if (occ != nullptr && cell >= 0 && !occ[(size_t)fb * capCells + cell]) cell = -1;
                 const unsigned m = __ballot_sync(PC_FULL_MASK, cell >= 0);
                 if (m) {
                     unsigned base = 0;
@@ -163,7 +172,7 @@ __global__ void __launch_bounds__(PC_STREAM_NT) pc_large_stream_kernel(const PcS
                     base = __shfl_sync(PC_FULL_MASK, base, leader);
                     if (cell >= 0) {
                         const unsigned p = base + __popc(m & ((1u << lane) - 1u));
-                        mycand[p] = make_float4(x, y, z, __uint_as_float(__ldg(linfo + li)));
+                        mycand[p] = make_float4(x, y, z, __uint_as_float(info));
                         myccell[p] = (uint32_t)cell;
                         atomicAdd(&mycells[cell], 1u);
                     }
@@ -230,6 +239,24 @@ __global__ void __launch_bounds__(256) pc_large_grid_kernel(const PcScanArgs a, 
     uint32_t *cA = cellsA + (size_t)fb * (capCells + 1);
     uint32_t *cB = a.self_mode ? nullptr : cellsB + (size_t)fb * (capCells + 1);
     for (int c = threadIdx.x; c <= ncell; c += blockDim.x) { cA[c] = 0; if (cB) cB[c] = 0; }
+}
+
+// ---- L3b: dilated B occupancy (after B has been binned, before A is) -------------------------------------
+__global__ void __launch_bounds__(256) pc_large_occ_kernel(const PcLargeFrame *fr, const uint32_t *cellsB, int capCells,
+                                                           uint8_t *occ) {
+    const int fb = blockIdx.y;
+    const int nx = fr[fb].nx, ny = fr[fb].ny, nz = fr[fb].nz, ncell = fr[fb].ncell;
+    const uint32_t *cB = cellsB + (size_t)fb * (capCells + 1);
+    uint8_t *o = occ + (size_t)fb * capCells;
+    for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < ncell; c += gridDim.x * blockDim.x) {
+        const int cx = c % nx, cy = (c / nx) % ny, cz = c / (nx * ny);
+        bool any = false;
+        for (int z = max(cz - 1, 0); z <= min(cz + 1, nz - 1) && !any; z++)
+            for (int y = max(cy - 1, 0); y <= min(cy + 1, ny - 1) && !any; y++)
+                for (int x = max(cx - 1, 0); x <= min(cx + 1, nx - 1); x++)
+                    if (cB[(z * ny + y) * nx + x]) { any = true; break; }
+        o[c] = any ? 1 : 0;
+    }
 }
 
 // ---- L4: exclusive scan of cell counts (one CTA per frame and side) ---------------------------
@@ -477,6 +504,7 @@ static inline int pc_large_scan(PcLargeWork &W, const PcScanArgs &a, int num_sms
             PCL_TRY(cudaMalloc(&W.candB, (size_t)FB * a2 * sizeof(float4)));
             PCL_TRY(cudaMalloc(&W.ccellB, (size_t)FB * a2 * 4));
             PCL_TRY(cudaMalloc(&W.sortB, (size_t)FB * a2 * sizeof(float4)));
+            PCL_TRY(cudaMalloc(&W.occ, (size_t)FB * capCells));
         }
         W.FB = FB; W.capCells = capCells; W.n1h = n1h; W.n2h = n2h; W.self_mode = a.self_mode;
         PCL_TRY(cudaFuncSetAttribute(pc_large_stream_kernel<PC_MODE_BBOX>, cudaFuncAttributeMaxDynamicSharedMemorySize, PC_STREAM_SMEM));
@@ -495,16 +523,20 @@ static inline int pc_large_scan(PcLargeWork &W, const PcScanArgs &a, int num_sms
         if (!self) pc_stream_geom(n2, nfb, num_sms, ctasB, perB);
         pc_large_reset_kernel<<<(nfb + 63) / 64, 64, 0, s>>>(W.frames, nfb);
         pc_large_stream_kernel<PC_MODE_BBOX><<<dim3(ctasA, nfb), PC_STREAM_NT, PC_STREAM_SMEM, s>>>(
-            a, W.frames, f0, 0, 0, perA, nullptr, 0, nullptr, nullptr, 0);
+            a, W.frames, f0, 0, 0, perA, nullptr, 0, nullptr, nullptr, 0, nullptr);
         if (use_bboxB)
             pc_large_stream_kernel<PC_MODE_BBOX><<<dim3(ctasB, nfb), PC_STREAM_NT, PC_STREAM_SMEM, s>>>(
-                a, W.frames, f0, 1, 6, perB, nullptr, 0, nullptr, nullptr, 0);
+                a, W.frames, f0, 1, 6, perB, nullptr, 0, nullptr, nullptr, 0, nullptr);
         pc_large_grid_kernel<<<nfb, 256, 0, s>>>(a, W.frames, capCells, use_bboxB, W.cellA, W.cellB);
-        pc_large_stream_kernel<PC_MODE_BIN><<<dim3(ctasA, nfb), PC_STREAM_NT, PC_STREAM_SMEM, s>>>(
-            a, W.frames, f0, 0, 0, perA, W.cellA, capCells, W.candA, W.ccellA, a1);
-        if (!self)
+        if (!self) {
+            // B first: its cell counts tell which A atoms can have a partner at all
             pc_large_stream_kernel<PC_MODE_BIN><<<dim3(ctasB, nfb), PC_STREAM_NT, PC_STREAM_SMEM, s>>>(
-                a, W.frames, f0, 1, 0, perB, W.cellB, capCells, W.candB, W.ccellB, a2);
+                a, W.frames, f0, 1, 0, perB, W.cellB, capCells, W.candB, W.ccellB, a2, nullptr);
+            pc_large_occ_kernel<<<dim3(std::max(1, std::min((capCells + 255) / 256, 4 * num_sms / nfb + 1)), nfb), 256, 0, s>>>(
+                W.frames, W.cellB, capCells, W.occ);
+        }
+        pc_large_stream_kernel<PC_MODE_BIN><<<dim3(ctasA, nfb), PC_STREAM_NT, PC_STREAM_SMEM, s>>>(
+            a, W.frames, f0, 0, 0, perA, W.cellA, capCells, W.candA, W.ccellA, a1, self ? nullptr : W.occ);
         pc_large_scan_kernel<<<dim3(nfb, self ? 1 : 2), 1024, 0, s>>>(W.frames, W.cellA, W.cellB, capCells);
         const int per_frame_blocks = std::max(1, 4 * num_sms / nfb);
         const int blocksA = std::max(1, std::min((n1h + 255) / 256, per_frame_blocks));
@@ -519,7 +551,7 @@ static inline int pc_large_scan(PcLargeWork &W, const PcScanArgs &a, int num_sms
         pc_large_drain_kernel<<<dim3(dblocks, nfb), 256, 0, s>>>(a, W.frames, f0, W.sortA, W.sortB, a1, a2, o);
         pc_large_finish_kernel<<<(nfb + 63) / 64, 64, 0, s>>>(a, W.frames, f0, nfb, o);
         PCL_TRY(cudaGetLastError());
-        *launches += 8 + (use_bboxB ? 1 : 0) + (self ? 0 : 2);
+        *launches += 8 + (use_bboxB ? 1 : 0) + (self ? 0 : 3);
     }
     return PC_OK;
 }

@@ -66,6 +66,7 @@ class _Slot:
         self.pin_in = [None, None]
         self.pin_out = {}
         self.pending = None
+        self.pending_dev = None
 
     def close(self):
         lib = self.eng.lib
@@ -338,6 +339,48 @@ class ContactEngine:
                 self._grow(slot, nf)
                 continue
             check(rc)
+            return tuple(int(t.value) for t in tot)
+        raise PcError(_lib.PC_ERR_CAPACITY, "batch still does not fit after growing the buffers")
+
+    def submit_device(self, slot_id, d_xyz1, d_xyz2, nframes, *, layout=_lib.PC_LAYOUT_XYZ, pitch1=None, pitch2=None,
+                      order_keys=False, accumulate=False, events=None):
+        """Asynchronous form of scan_device: enqueue scan (+ accumulation) on the slot's stream."""
+        slot = self.slots[slot_id]
+        lib = self.lib
+        nf = int(nframes)
+        p = dict(d1=d_xyz1, d2=d_xyz2, nf=nf, layout=int(layout),
+                 pitch1=self.n1 * layout if pitch1 is None else int(pitch1),
+                 pitch2=self.n2 * layout if pitch2 is None else int(pitch2),
+                 order_keys=int(order_keys), accumulate=bool(accumulate), events=events)
+        slot.pending_dev = p
+        slot.reserve(nf, nf * self.guess[0], nf * self.guess[1], nf * self.guess[2])
+        if events is not None:
+            check(lib.pc_event_record(events[0], slot.stream))
+        check(lib.pc_scan_device(slot.ctx, p["d1"], p["d2"], nf, p["layout"], p["pitch1"], p["pitch2"], p["order_keys"],
+                                 slot.stream))
+        if events is not None:
+            check(lib.pc_event_record(events[1], slot.stream))
+        if accumulate:
+            check(lib.pc_accumulate(slot.ctx, slot.stream))
+        self.launches += 1
+
+    def collect_device(self, slot_id):
+        """Wait for submit_device's batch; returns (n_contacts, n_hbonds, n_rows, n_pair_evals).  A batch that
+        overflowed a buffer is re-run (synchronously) after growing it."""
+        slot = self.slots[slot_id]
+        lib = self.lib
+        p = slot.pending_dev
+        tot = [ctypes.c_int64() for _ in range(4)]
+        for attempt in range(12):
+            rc = lib.pc_batch_totals(slot.ctx, slot.stream, *[ctypes.byref(t) for t in tot])
+            if rc == _lib.PC_ERR_CAPACITY:
+                self._grow(slot, p["nf"])
+                self.submit_device(slot_id, p["d1"], p["d2"], p["nf"], layout=p["layout"], pitch1=p["pitch1"],
+                                   pitch2=p["pitch2"], order_keys=p["order_keys"], accumulate=p["accumulate"],
+                                   events=p["events"])
+                continue
+            check(rc)
+            slot.pending_dev = None
             return tuple(int(t.value) for t in tot)
         raise PcError(_lib.PC_ERR_CAPACITY, "batch still does not fit after growing the buffers")
 
