@@ -78,8 +78,12 @@ __device__ __forceinline__ int pc_large_cell_of(const PcLargeFrame &F, float x, 
 // ---- L1 / L3: streaming kernels -----------------------------------------------------------------
 #define PC_STREAM_NT 512
 #define PC_STREAM_CHUNK 24576            // 2048 atoms per chunk
-#define PC_STREAM_STAGES 4
-#define PC_STREAM_SMEM (PC_STREAM_STAGES * (PC_STREAM_CHUNK + 16) + PC_STREAM_STAGES * 8 + 16)
+#define PC_STREAM_STAGES 3
+#define PC_STREAM_HINFO (PC_STREAM_CHUNK / 12 * 4 + 32)      // a chunk's slice of the heavy-atom list
+#define PC_STREAM_SLOT (PC_STREAM_CHUNK + 16 + PC_STREAM_HINFO)
+#define PC_STREAM_SMEM (PC_STREAM_STAGES * PC_STREAM_SLOT + PC_STREAM_STAGES * 8 + 16)
+
+struct PcStreamDesc { int cnt, hoff, off0, abase; };          // per ring slot, written by the issuing thread
 
 enum { PC_MODE_BBOX = 0, PC_MODE_BIN = 1 };
 
@@ -88,12 +92,11 @@ __global__ void __launch_bounds__(PC_STREAM_NT) pc_large_stream_kernel(const PcS
                                                                        int slot0, int atoms_per_cta, uint32_t *cells,
                                                                        int capCells, float4 *cand, uint32_t *ccell,
                                                                        int nh_alloc, const uint8_t *occ) {
-    constexpr int NT = PC_STREAM_NT, CHUNK = PC_STREAM_CHUNK, STAGES = PC_STREAM_STAGES;
+    constexpr int NT = PC_STREAM_NT, CHUNK = PC_STREAM_CHUNK, STAGES = PC_STREAM_STAGES, SLOT = PC_STREAM_SLOT;
     extern __shared__ __align__(16) unsigned char smem[];
-    PcRing<STAGES, CHUNK> ring;
-    ring.buf = smem;
-    ring.bar = reinterpret_cast<uint64_t *>(smem + STAGES * (CHUNK + 16));
+    uint64_t *bars = reinterpret_cast<uint64_t *>(smem + STAGES * SLOT);
     __shared__ PcLargeFrame F;
+    __shared__ PcStreamDesc desc[STAGES];
     __shared__ float red[NT / 32][6];
     __shared__ unsigned int s_bad;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -104,7 +107,7 @@ __global__ void __launch_bounds__(PC_STREAM_NT) pc_large_stream_kernel(const PcS
     if (tid == 0) {
         F = fr[fb];
         s_bad = 0;
-        for (int s = 0; s < STAGES; s++) pc_mbar_init(ring.bar + s, 1);
+        for (int s = 0; s < STAGES; s++) pc_mbar_init(bars + s, 1);
         pc_mbar_fence_init();
     }
     __syncthreads();
@@ -113,15 +116,34 @@ __global__ void __launch_bounds__(PC_STREAM_NT) pc_large_stream_kernel(const PcS
     const uint32_t *hmask = side == 0 ? a.t.hmask1 : a.t.hmask2;
     const uint32_t *hpre = side == 0 ? a.t.hpre1 : a.t.hpre2;
     const uint32_t *hinfo = side == 0 ? a.t.hinfo1 : a.t.hinfo2;
-    // heavy ordinal of local atom i = number of heavy atoms before it
-    auto heavy_before = [&](int i) -> int {
-        return (int)(__ldg(hpre + (i >> 5)) + __popc(__ldg(hmask + (i >> 5)) & ((1u << (i & 31)) - 1u)));
-    };
     PcSegment seg;
     seg.sb = reinterpret_cast<const unsigned char *>(frame) + 12ll * r0;
     seg.natoms = min(atoms_per_cta, n - r0);
     seg.atom0 = r0;
     const int nch = pc_seg_chunks<CHUNK>(seg);
+
+    // Producer side (thread 0): chunk q = CHUNK bytes of coordinates + the slice of the heavy-atom list
+    // (hinfo: local index + packed atom word per heavy atom, in index order) that falls into it, both
+    // by bulk copy onto the slot's mbarrier.  Consumers never touch global memory for their input.
+    auto heavy_before = [&](int i) -> int {       // heavy ordinal of local atom i
+        return (int)(__ldg(hpre + (i >> 5)) + __popc(__ldg(hmask + (i >> 5)) & ((1u << (i & 31)) - 1u)));
+    };
+    auto issue = [&](int q) {
+        const PcChunk c = pc_chunk_of<CHUNK>(seg, q);
+        const int h0 = heavy_before(r0 + c.k0), h1 = heavy_before(r0 + c.k1);
+        const uintptr_t hs = (uintptr_t)(hinfo + h0), hs_al = hs & ~(uintptr_t)15;
+        uintptr_t he = ((uintptr_t)(hinfo + h1) + 15) & ~(uintptr_t)15;
+        if (he <= hs_al) he = hs_al + 16;
+        const uint32_t hbytes = (uint32_t)(he - hs_al);
+        const int st = q % STAGES;
+        PcStreamDesc d;
+        d.cnt = h1 - h0; d.hoff = (int)(hs - hs_al); d.off0 = c.off0; d.abase = r0 + c.k0;
+        desc[st] = d;
+        unsigned char *slot = smem + (size_t)st * SLOT;
+        pc_mbar_expect_tx(bars + st, c.bytes + hbytes);          // release: desc is visible to whoever sees the phase flip
+        pc_bulk_g2s(slot, c.g0, c.bytes, bars + st);
+        pc_bulk_g2s(slot + CHUNK + 16, reinterpret_cast<const void *>(hs_al), hbytes, bars + st);
+    };
 
     uint32_t *mycells = nullptr;
     float4 *mycand = nullptr;
@@ -136,23 +158,23 @@ __global__ void __launch_bounds__(PC_STREAM_NT) pc_large_stream_kernel(const PcS
     float mn[3] = {INFINITY, INFINITY, INFINITY}, mx[3] = {-INFINITY, -INFINITY, -INFINITY};
 
     if (tid == 0)
-        for (int q = 0; q < min(STAGES - 1, nch); q++) ring.issue((unsigned)q, pc_chunk_of<CHUNK>(seg, q));
+        for (int q = 0; q < min(STAGES - 1, nch); q++) issue(q);
     for (int q = 0; q < nch; q++) {
-        if (tid == 0 && q + STAGES - 1 < nch) ring.issue((unsigned)(q + STAGES - 1), pc_chunk_of<CHUNK>(seg, q + STAGES - 1));
-        if (!ring.wait((unsigned)q)) { s_bad = 1; }
-        const PcChunk c = pc_chunk_of<CHUNK>(seg, q);
-        // only the chunk's heavy atoms are visited: their ordinals are a contiguous range of the
-        // heavy list (hinfo), whose entries give the local index and the packed atom word
-        const int abase = r0 + c.k0;
-        const unsigned char *slot = ring.slot((unsigned)q) + c.off0;
-        const int h0 = heavy_before(abase), cnt = heavy_before(r0 + c.k1) - h0;
+        if (tid == 0 && q + STAGES - 1 < nch) issue(q + STAGES - 1);
+        const int st = q % STAGES;
+        if (!pc_mbar_wait(bars + st, (unsigned)(q / STAGES) & 1u)) { s_bad = 1; }
+        const PcStreamDesc d = desc[st];
+        const unsigned char *slot = smem + (size_t)st * SLOT;
+        const unsigned char *xyz = slot + d.off0;
+        const uint32_t *hin = reinterpret_cast<const uint32_t *>(slot + CHUNK + 16 + d.hoff);
+        const int cnt = d.cnt, abase = d.abase;
         for (int kk = tid; kk < ((cnt + 31) & ~31); kk += NT) {
             const bool heavy = kk < cnt;
             uint32_t info = 0;
             float x = 0.f, y = 0.f, z = 0.f;
             if (heavy) {
-                info = __ldg(hinfo + h0 + kk);
-                const float *p = reinterpret_cast<const float *>(slot + 12 * (PC_W_INDEX(info) - abase));
+                info = hin[kk];
+                const float *p = reinterpret_cast<const float *>(xyz + 12 * (PC_W_INDEX(info) - abase));
                 x = p[0]; y = p[1]; z = p[2];
             }
             if (MODE == PC_MODE_BBOX) {
@@ -179,7 +201,7 @@ __global__ void __launch_bounds__(PC_STREAM_NT) pc_large_stream_kernel(const PcS
                 }
             }
         }
-        __syncthreads();          // the slot may be refilled from here on
+        __syncthreads();          // the slot (and its descriptor) may be refilled from here on
     }
     if (MODE == PC_MODE_BBOX) {
 #pragma unroll
