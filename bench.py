@@ -272,14 +272,19 @@ def run_gpu(args):
                 torch.cuda.current_stream().synchronize()
             else:
                 check(lib.pc_memset(local, totals.ptr, 0, n_keys * 32, stream))
+        trace = bool(os.environ.get("PC_TRACE"))
+
         def finish(sid, nf):
             nonlocal d_rows
+            _t0 = time.perf_counter()
             c = eng.collect_device(sid)
+            _t1 = time.perf_counter()
             tot[:] += c
-            if dense:
-                check(lib.pc_fold_rows(eng.slots[sid].ctx, totals_ptr(), n_keys, eng.slots[sid].stream))
-            rows, _, _ = eng.fetch_rows(sid)               # the per-frame maps of this rank's frames -> host
+            rows, _, _ = eng.fetch_rows(sid, packed=True)  # the per-frame maps of this rank's frames -> host
             d_rows += rows.nbytes
+            if trace:
+                print("slot %d nf %d: wait %.3f ms, fold+fetch %.3f ms (%d rows)" % (
+                    sid, nf, (_t1 - _t0) * 1e3, (time.perf_counter() - _t1) * 1e3, rows.size), file=sys.stderr)
 
         # two batches in flight: batch b+1 is scanned while batch b's rows travel to the host
         pending = None
@@ -287,8 +292,12 @@ def run_gpu(args):
             f0 = b * batch
             nf = min(batch, F - f0)
             sid = b % len(eng.slots)
+            _ts = time.perf_counter()
             eng.submit_device(sid, d1.at(f0 * n1 * 12), None if self_mode else d2.at(f0 * n2 * 12), nf,
-                              accumulate=True, events=ev[b] if timed else None)
+                              accumulate=True, events=ev[b] if timed else None, pack_rows=True,
+                              fold=(totals_ptr(), n_keys) if dense else None)
+            if trace:
+                print("submit slot %d: %.3f ms" % (sid, (time.perf_counter() - _ts) * 1e3), file=sys.stderr)
             if pending is not None:
                 finish(*pending)
             pending = (sid, nf)

@@ -64,6 +64,16 @@ typedef struct {
     uint64_t first;        /* smallest order key of a contributing contact (first appearance) */
 } pc_row;
 
+/* The same cell in 24 bytes for bulk transfer to the host: float32 sums (the 1e-5 bar leaves room),
+ * counts saturating at 65535, no first-appearance key (callers that need the reference's key ORDER
+ * fetch pc_row).  Everything AccumulatedContact keeps per frame -- scoreArray, hbondFrames -- and the
+ * per-frame parts of its bb/sc totals are in here. */
+typedef struct {
+    uint64_t key;
+    float    score, bb1, bb2;
+    uint16_t ncontacts, nhbonds;
+} pc_row_packed;
+
 typedef struct pc_ctx pc_ctx;
 
 const char *pc_last_error(void);
@@ -167,6 +177,13 @@ int pc_fetch(pc_ctx *ctx, void *stream,
              uint32_t *h_frame_cstart, uint32_t *h_frame_ccount,
              uint32_t *h_frame_hstart, uint32_t *h_frame_hcount,
              uint32_t *h_frame_rstart, uint32_t *h_frame_rcount);
+
+/* Rows of the last accumulated batch as pc_row_packed (packed on the device, then copied): the
+ * transfer format of throughput runs, half the bytes of pc_row.  h_rows needs room for the n_rows that
+ * pc_batch_totals reported.  Asynchronous on `stream`. */
+int pc_pack_rows(pc_ctx *ctx, void *stream);     /* the packing kernel alone (enqueue it right behind pc_accumulate) */
+int pc_fetch_packed_rows(pc_ctx *ctx, void *stream, pc_row_packed *h_rows,
+                         uint32_t *h_frame_rstart, uint32_t *h_frame_rcount);
 
 /* cy_find_contacts(xyz1, natoms1, xyz2, natoms2, r)  (cy_modules/cy_gridsearch.pyx:31-35 ->
  * find_contacts, cy_modules/src/gridsearch.C:408-427): ALL atoms, no filters.  Returns a CSR:

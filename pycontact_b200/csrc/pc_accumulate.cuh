@@ -136,6 +136,9 @@ __global__ void __launch_bounds__(NT) pc_accumulate_kernel(const PcAccArgs a) {
 __global__ void __launch_bounds__(256) pc_fold_rows_kernel(const pc_row *rows, const unsigned long long *counters,
                                                            long long cap_rows, double *totals,
                                                            unsigned long long n_keys) {
+    // a batch that overflowed a buffer is re-run by the caller: do not fold its partial rows
+    if (counters[PC_CNT_STATUS] & (PC_ST_HITS_OVERFLOW | PC_ST_HB_OVERFLOW | PC_ST_OUT_OVERFLOW | PC_ST_TABLE_OVERFLOW |
+                                   PC_ST_STAGE_OVERFLOW)) return;
     const long long n = min((long long)counters[PC_CNT_ROWS], cap_rows);
     for (long long r = blockIdx.x * (long long)blockDim.x + threadIdx.x; r < n; r += (long long)gridDim.x * blockDim.x) {
         const pc_row row = rows[r];
@@ -286,5 +289,18 @@ __global__ void __launch_bounds__(256) pc_gacc_emit_kernel(const PcAccArgs a, Pc
         r.key = ck - f * t.nkeys; r.score = e.score; r.bb1 = e.bb1; r.bb2 = e.bb2;
         r.ncontacts = e.ncont; r.nhbonds = e.nhb; r.first = e.first;
         a.rows[pos] = r;
+    }
+}
+
+// pc_row -> pc_row_packed for the D2H transfer of throughput runs
+__global__ void __launch_bounds__(256) pc_pack_rows_kernel(const pc_row *rows, const unsigned long long *counters,
+                                                           long long cap_rows, pc_row_packed *out) {
+    const long long n = min((long long)counters[PC_CNT_ROWS], cap_rows);
+    for (long long r = blockIdx.x * (long long)blockDim.x + threadIdx.x; r < n; r += (long long)gridDim.x * blockDim.x) {
+        const pc_row v = rows[r];
+        pc_row_packed p;
+        p.key = v.key; p.score = (float)v.score; p.bb1 = (float)v.bb1; p.bb2 = (float)v.bb2;
+        p.ncontacts = (uint16_t)min(v.ncontacts, 65535u); p.nhbonds = (uint16_t)min(v.nhbonds, 65535u);
+        out[r] = p;
     }
 }

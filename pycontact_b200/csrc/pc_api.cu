@@ -70,6 +70,7 @@ struct pc_ctx {
     DevBuf<pc_contact> contacts;
     DevBuf<pc_hbond> hbonds;
     DevBuf<pc_row> rows;
+    DevBuf<pc_row_packed> rows_packed;
     DevBuf<unsigned long long> order_keys;
     DevBuf<unsigned long long> counters;
     DevBuf<uint32_t> frame_meta;      // 6 arrays of max_frames
@@ -86,6 +87,7 @@ struct pc_ctx {
     unsigned long long *h_counters = nullptr;   // pinned mirror
     int last_path = 0;                // 1 = small, 2 = large
     bool gacc_used = false, gacc_retry = false;
+    bool packed_valid = false;        // rows_packed holds the last accumulated batch
     bool want_fused_acc = true;       // accumulate inside the small-frame scan kernel when possible
     bool last_fused = false;
     std::vector<uint32_t> h_meta;     // host copy of the scan's 4 frame arrays (large path: sliced outputs)
@@ -336,6 +338,7 @@ extern "C" int pc_scan_device(pc_ctx *c, const float *d_xyz1, const float *d_xyz
     a.rows = c->rows.p; a.cap_rows = c->cap_rows; a.frame_rstart = meta(c, 4); a.frame_rcount = meta(c, 5);
     const bool fits_small = c->force_path != 2 && plan_small(c, fuse_acc, a.capCells, a.capHits, a.capHb, L);
     c->last_fused = false;
+    c->packed_valid = false;
     if (c->force_path == 1 && !fits_small)
         return fail(PC_ERR_INVALID, "pc_scan_device: the frame does not fit the small-frame kernel");
     if (fits_small) {
@@ -374,6 +377,7 @@ extern "C" int pc_accumulate(pc_ctx *c, void *stream) {
     if (!c || !c->have_maps) return fail(PC_ERR_INVALID, "pc_accumulate: set the maps first");
     if (c->last_nframes <= 0) return fail(PC_ERR_INVALID, "pc_accumulate: no scanned batch");
     if (c->last_fused) return PC_OK;            // the scan kernel already produced this batch's rows
+    c->packed_valid = false;
     CUDA_TRY(cudaSetDevice(c->device));
     cudaStream_t s = (cudaStream_t)stream;
     PcAccArgs a;
@@ -632,6 +636,29 @@ extern "C" int pc_fetch(pc_ctx *c, void *stream, pc_contact *h_contacts, pc_hbon
         if (outs[k])
             CUDA_TRY(cudaMemcpyAsync(outs[k], meta(c, k), (size_t)c->last_nframes * sizeof(uint32_t),
                                      cudaMemcpyDeviceToHost, s));
+    return PC_OK;
+}
+
+extern "C" int pc_pack_rows(pc_ctx *c, void *stream) {
+    if (!c) return fail(PC_ERR_INVALID, "pc_pack_rows: ctx is NULL");
+    CUDA_TRY(cudaSetDevice(c->device));
+    CUDA_TRY(c->rows_packed.ensure((size_t)c->cap_rows));
+    pc_pack_rows_kernel<<<2 * c->num_sms, 256, 0, (cudaStream_t)stream>>>(c->rows.p, c->counters.p, c->cap_rows, c->rows_packed.p);
+    CUDA_TRY(cudaGetLastError());
+    g_launches += 1;
+    c->packed_valid = true;
+    return PC_OK;
+}
+
+extern "C" int pc_fetch_packed_rows(pc_ctx *c, void *stream, pc_row_packed *h_rows, uint32_t *rs, uint32_t *rc) {
+    if (!c || !h_rows) return fail(PC_ERR_INVALID, "pc_fetch_packed_rows: bad arguments");
+    CUDA_TRY(cudaSetDevice(c->device));
+    cudaStream_t s = (cudaStream_t)stream;
+    const size_t nr = std::min<unsigned long long>(c->h_counters[PC_CNT_ROWS], c->cap_rows);
+    if (!c->packed_valid) { int r = pc_pack_rows(c, stream); if (r != PC_OK) return r; }
+    if (nr) CUDA_TRY(cudaMemcpyAsync(h_rows, c->rows_packed.p, nr * sizeof(pc_row_packed), cudaMemcpyDeviceToHost, s));
+    if (rs) CUDA_TRY(cudaMemcpyAsync(rs, meta(c, 4), (size_t)c->last_nframes * sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
+    if (rc) CUDA_TRY(cudaMemcpyAsync(rc, meta(c, 5), (size_t)c->last_nframes * sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
     return PC_OK;
 }
 

@@ -486,13 +486,13 @@ static inline int pc_large_fail(std::string &err, const char *what, cudaError_t 
 }
 #define PCL_TRY(expr) do { cudaError_t _e = (expr); if (_e != cudaSuccess) return pc_large_fail(err, #expr, _e); } while (0)
 
-// CTAs per frame of a streaming kernel over n atoms: enough to fill the machine about twice over the
-// nfb frames of the launch, but every CTA walks at least two chunks; atom ranges start on multiples
-// of 32 so a warp reads one or two words of the heavy-atom mask.
+// CTAs per frame of a streaming kernel over n atoms: about eight waves of resident CTAs (2 per SM)
+// over the nfb frames of the launch, so the last, partly filled wave costs little, but every CTA
+// walks at least four chunks; atom ranges start on multiples of 32.
 static inline void pc_stream_geom(int n, int nfb, int num_sms, int &ctas, int &per) {
     const int atoms_chunk = PC_STREAM_CHUNK / 12;
-    const int want = std::max(1, (2 * num_sms + nfb - 1) / nfb);
-    const int most = std::max(1, n / (2 * atoms_chunk));
+    const int want = std::max(1, (16 * num_sms + nfb - 1) / nfb);
+    const int most = std::max(1, n / (4 * atoms_chunk));
     ctas = std::min(want, most);
     per = ((n + ctas - 1) / ctas + 31) & ~31;
     ctas = (n + per - 1) / per;
@@ -566,7 +566,8 @@ static inline int pc_large_scan(PcLargeWork &W, const PcScanArgs &a, int num_sms
         pc_large_scatter_kernel<<<dim3(blocksA, nfb), 256, 0, s>>>(W.frames, 0, W.cellA, capCells, W.candA, W.ccellA, W.sortA, a1);
         if (!self)
             pc_large_scatter_kernel<<<dim3(blocksB, nfb), 256, 0, s>>>(W.frames, 1, W.cellB, capCells, W.candB, W.ccellB, W.sortB, a2);
-        const int pblocks = (int)std::max<long long>(1, std::min<long long>((3ll * n1h + 255) / 256, 2ll * per_frame_blocks));
+        // the number of in-grid A atoms is only known on the device: launch for the worst case, surplus CTAs exit
+        const int pblocks = (int)std::max<long long>(1, std::min<long long>((3ll * n1h + 255) / 256, std::max(64, 2 * per_frame_blocks)));
         pc_large_pair_kernel<<<dim3(pblocks, nfb), 256, 0, s>>>(a, W.frames, f0, W.cellA, W.cellB, capCells, W.sortA, W.sortB,
                                                                a1, a2, o);
         const int dblocks = (int)std::max<long long>(1, std::min<long long>((o.cap_c_frame + 255) / 256, per_frame_blocks));

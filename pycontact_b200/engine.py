@@ -343,15 +343,19 @@ class ContactEngine:
         raise PcError(_lib.PC_ERR_CAPACITY, "batch still does not fit after growing the buffers")
 
     def submit_device(self, slot_id, d_xyz1, d_xyz2, nframes, *, layout=_lib.PC_LAYOUT_XYZ, pitch1=None, pitch2=None,
-                      order_keys=False, accumulate=False, events=None):
-        """Asynchronous form of scan_device: enqueue scan (+ accumulation) on the slot's stream."""
+                      order_keys=False, accumulate=False, events=None, pack_rows=False, fold=None):
+        """Asynchronous form of scan_device: enqueue scan (+ accumulation) on the slot's stream.
+        pack_rows: also pack the rows for transfer; fold=(d_totals, n_keys): also fold them into the
+        dense aggregated table -- both right behind the accumulation, so that nothing has to be
+        launched (and wait for free SMs) once the host has seen the batch complete."""
         slot = self.slots[slot_id]
         lib = self.lib
         nf = int(nframes)
         p = dict(d1=d_xyz1, d2=d_xyz2, nf=nf, layout=int(layout),
                  pitch1=self.n1 * layout if pitch1 is None else int(pitch1),
                  pitch2=self.n2 * layout if pitch2 is None else int(pitch2),
-                 order_keys=int(order_keys), accumulate=bool(accumulate), events=events)
+                 order_keys=int(order_keys), accumulate=bool(accumulate), events=events, pack_rows=bool(pack_rows),
+                 fold=fold)
         slot.pending_dev = p
         slot.reserve(nf, nf * self.guess[0], nf * self.guess[1], nf * self.guess[2])
         if events is not None:
@@ -362,6 +366,10 @@ class ContactEngine:
             check(lib.pc_event_record(events[1], slot.stream))
         if accumulate:
             check(lib.pc_accumulate(slot.ctx, slot.stream))
+            if fold is not None:
+                check(lib.pc_fold_rows(slot.ctx, fold[0], int(fold[1]), slot.stream))
+            if pack_rows:
+                check(lib.pc_pack_rows(slot.ctx, slot.stream))
         self.launches += 1
 
     def collect_device(self, slot_id):
@@ -377,15 +385,16 @@ class ContactEngine:
                 self._grow(slot, p["nf"])
                 self.submit_device(slot_id, p["d1"], p["d2"], p["nf"], layout=p["layout"], pitch1=p["pitch1"],
                                    pitch2=p["pitch2"], order_keys=p["order_keys"], accumulate=p["accumulate"],
-                                   events=p["events"])
+                                   events=p["events"], pack_rows=p["pack_rows"], fold=p["fold"])
                 continue
             check(rc)
             slot.pending_dev = None
             return tuple(int(t.value) for t in tot)
         raise PcError(_lib.PC_ERR_CAPACITY, "batch still does not fit after growing the buffers")
 
-    def fetch_rows(self, slot_id=0):
-        """Rows of the slot's last accumulated batch -> (rows, rstart, rcount) host arrays (pinned views)."""
+    def fetch_rows(self, slot_id=0, packed=False):
+        """Rows of the slot's last accumulated batch -> (rows, rstart, rcount) host arrays (pinned views).
+        packed=True transfers pc_row_packed (24 B, float32 sums, no first-appearance key)."""
         slot = self.slots[slot_id]
         lib = self.lib
         nr = ctypes.c_int64()
@@ -393,10 +402,15 @@ class ContactEngine:
         nf = slot.max_frames
         check(lib.pc_last_status(slot.ctx, ctypes.byref(st), None, None, ctypes.byref(nr), None))
         n = min(int(nr.value), slot.cap[2])
-        rows = slot.out("rows", n, _lib.row_dtype)[:n]
         meta = slot.out("meta", 6 * nf, np.uint32)
-        check(lib.pc_fetch(slot.ctx, slot.stream, None, None, ptr(rows), None, None, None, None, None,
-                           ptr(meta[4 * nf:5 * nf]), ptr(meta[5 * nf:6 * nf])))
+        if packed:
+            rows = slot.out("rows_packed", n, _lib.packed_row_dtype)[:n]
+            check(lib.pc_fetch_packed_rows(slot.ctx, slot.stream, ptr(rows), ptr(meta[4 * nf:5 * nf]),
+                                           ptr(meta[5 * nf:6 * nf])))
+        else:
+            rows = slot.out("rows", n, _lib.row_dtype)[:n]
+            check(lib.pc_fetch(slot.ctx, slot.stream, None, None, ptr(rows), None, None, None, None, None,
+                               ptr(meta[4 * nf:5 * nf]), ptr(meta[5 * nf:6 * nf])))
         check(lib.pc_stream_sync(slot.stream))
         return rows, meta[4 * nf:5 * nf], meta[5 * nf:6 * nf]
 

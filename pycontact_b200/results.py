@@ -191,6 +191,20 @@ class AccumulationTable:
         self._rows.append(b.rows[src])
         self._frames.append(np.repeat(np.arange(b.nframes, dtype=np.int64) + frame_pos0, cnt))
 
+    def add_packed(self, rows: np.ndarray, rstart, rcount, frame_pos0: int):
+        """A batch's rows in the transfer format (_lib.packed_row_dtype).  Without first-appearance
+        keys the output order of keys falls back to (first frame, key id)."""
+        from ._lib import row_dtype
+        cnt = np.asarray(rcount, np.int64)
+        src = np.repeat(np.asarray(rstart, np.int64), cnt) + (np.arange(cnt.sum()) - np.repeat(np.cumsum(cnt) - cnt, cnt))
+        p = rows[src]
+        full = np.zeros(p.size, row_dtype)
+        for k in ("key", "score", "bb1", "bb2", "ncontacts", "nhbonds"):
+            full[k] = p[k]
+        full["first"] = p["key"]
+        self._rows.append(full)
+        self._frames.append(np.repeat(np.arange(cnt.size, dtype=np.int64) + frame_pos0, cnt))
+
     def add_rows(self, rows: np.ndarray, frames: np.ndarray):
         self._rows.append(rows)
         self._frames.append(np.asarray(frames, np.int64))

@@ -336,3 +336,36 @@ def test_fused_accumulation_equals_standalone_kernel(name, self_mode):
     assert np.array_equal(a.hbond_matrix()[oa], b.hbond_matrix()[ob])
     np.testing.assert_allclose(a.bb1[oa], b.bb1[ob], rtol=1e-12, atol=1e-300)
     np.testing.assert_allclose(a.bb2[oa], b.bb2[ob], rtol=1e-12, atol=1e-300)
+
+
+def test_packed_rows_equal_full_rows():
+    """pc_fetch_packed_rows (the 24-byte transfer format) carries the same cells as pc_fetch."""
+    s = synth.make_system("small")
+    t = s.topology
+    coords = synth.frames_host(s, range(6))
+    s1, s2 = _selections(t, s.sel1, s.sel2, s.backbone)
+    gm1 = prepare.group_map(s.sel1, s.maps[0], t.names, t.resids, t.resnames, t.segids)
+    gm2 = prepare.group_map(s.sel2, s.maps[1], t.names, t.resids, t.resnames, t.segids)
+    from pycontact_b200._lib import DeviceBuffer
+    from pycontact_b200.results import AccumulationTable
+    with ContactEngine(s1, s2, 5.0, 2.5, 120) as eng:
+        eng.set_maps(gm1.gid, gm2.gid, gm2.n_groups)
+        d1 = DeviceBuffer.from_array(np.ascontiguousarray(coords[:, s.sel1]))
+        d2 = DeviceBuffer.from_array(np.ascontiguousarray(coords[:, s.sel2]))
+        eng.scan_device(d1.ptr, d2.ptr, 6, accumulate=True)
+        full, rs, rc = (a.copy() for a in eng.fetch_rows(0))
+        packed, ps, pc = (a.copy() for a in eng.fetch_rows(0, packed=True))
+    assert full.size == packed.size > 0 and np.array_equal(rs[:6], ps[:6]) and np.array_equal(rc[:6], pc[:6])
+    assert np.array_equal(full["key"], packed["key"])
+    np.testing.assert_allclose(packed["score"], full["score"], rtol=2e-7)
+    np.testing.assert_allclose(packed["bb1"], full["bb1"], rtol=2e-7)
+    assert np.array_equal(packed["nhbonds"], full["nhbonds"]) and np.array_equal(packed["ncontacts"], full["ncontacts"])
+    ta, tb = AccumulationTable(6, gm1, gm2), AccumulationTable(6, gm1, gm2)
+    ta.add_packed(packed, ps[:6], pc[:6], 0)
+    frame_of = np.zeros(full.size, np.int64)
+    for f in range(6):
+        frame_of[rs[f]:rs[f] + rc[f]] = f
+    tb.add_rows(full, frame_of)
+    ta.finalize(); tb.finalize()
+    oa, ob = np.argsort(ta.keys), np.argsort(tb.keys)
+    np.testing.assert_allclose(ta.score_matrix()[oa], tb.score_matrix()[ob], rtol=2e-7)
