@@ -111,6 +111,11 @@ int pc_set_limits(pc_ctx *ctx, int32_t hits_per_frame, int32_t hbonds_per_frame,
  * 2 = tiled large-frame path.  Both give the same records; tests use this to cover both. */
 int pc_set_path(pc_ctx *ctx, int path);
 
+/* Small-frame kernel: CTAs per SM.  0 = automatic (two 512-thread CTAs when a frame's working set fits
+ * half an SM's shared memory, else one 1024-thread CTA), 1 or 2 force it.  After PC_ST_STAGE_OVERFLOW
+ * with two CTAs the caller retries with 1 before switching to the large-frame path. */
+int pc_set_small_ctas(pc_ctx *ctx, int ctas);
+
 /* Output capacities for one batch (totals over the batch, not per frame). */
 int pc_reserve(pc_ctx *ctx, int32_t max_frames, int64_t cap_contacts, int64_t cap_hbonds, int64_t cap_rows);
 

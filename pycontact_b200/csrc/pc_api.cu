@@ -88,6 +88,8 @@ struct pc_ctx {
     int last_path = 0;                // 1 = small, 2 = large
     bool gacc_used = false, gacc_retry = false;
     bool packed_valid = false;        // rows_packed holds the last accumulated batch
+    int small_ctas = 0;               // small-frame kernel CTAs per SM: 0 = automatic, 1, 2
+    int last_small_ctas = 0;
     bool want_fused_acc = true;       // accumulate inside the small-frame scan kernel when possible
     bool last_fused = false;
     std::vector<uint32_t> h_meta;     // host copy of the scan's 4 frame arrays (large path: sliced outputs)
@@ -133,6 +135,12 @@ extern "C" void pc_destroy(pc_ctx *c) {
 extern "C" int pc_set_path(pc_ctx *c, int path) {
     if (!c || path < 0 || path > 2) return fail(PC_ERR_INVALID, "pc_set_path: path must be 0, 1 or 2");
     c->force_path = path;
+    return PC_OK;
+}
+
+extern "C" int pc_set_small_ctas(pc_ctx *c, int ctas) {
+    if (!c || ctas < 0 || ctas > 2) return fail(PC_ERR_INVALID, "pc_set_small_ctas: 0 (automatic), 1 or 2");
+    c->small_ctas = ctas;
     return PC_OK;
 }
 
@@ -261,44 +269,56 @@ static PcTopoDev topo_dev(const pc_ctx *c) {
 
 static uint32_t *meta(pc_ctx *c, int which) { return c->frame_meta.p + (size_t)which * c->max_frames; }
 
-// Pick the shared-memory capacities of the small-frame kernel (one 1024-thread CTA per SM).
-// Returns false when the frame does not fit one CTA's shared memory (-> large-frame path).
-#define PC_SMALL_NT 1024
-static bool plan_small(const pc_ctx *c, bool fuse_acc, int &capCells, int &capHits, int &capHb, PcSmallSmem &L) {
-    if (c->n1h > 65535 || c->n2h > 65535) return false;
+// Pick the shared-memory plan of the small-frame kernel: two 512-thread CTAs per SM when a frame's
+// working set fits half an SM's shared memory (latency of one frame's barriers hides behind the
+// other frame's work), else one 1024-thread CTA per SM.  Returns false when the frame does not fit
+// one CTA's shared memory at all (-> large-frame path).
+static bool plan_small_cfg(const pc_ctx *c, bool fuse_acc, int ctas, int &capCells, int &capHits, int &capHb, PcSmallSmem &L) {
     capHits = c->lim_hits > 0 ? c->lim_hits : 4096;
     capHb = c->lim_hb > 0 ? c->lim_hb : 256;
     int capTab = 0;
     if (fuse_acc) { capTab = 64; const int want = c->lim_table > 0 ? c->lim_table : 1024; while (capTab < want) capTab <<= 1; }
     const size_t optin = c->smem_optin ? c->smem_optin : 232448;
-    const size_t budget = optin - 4096;                              // static shared memory of the kernel
+    const size_t per_sm = 233472;
+    const size_t budget = (ctas == 1 ? optin : std::min(optin, per_sm / ctas - 1024)) - 3072;   // static shared memory
     const int cell_arrays = c->self_mode ? 1 : 2;
-    // staging capacity for atoms inside the grid: everything if it fits, else what is left after a
-    // 2048-cell grid (frames that need more take the large-frame path)
-    PcSmallSmem full = pc_small_layout(c->n1h, c->n2h, c->self_mode, 0, capHits, capHb, c->n1h, c->n2h, capTab);
+    const int use_cid = ctas == 1 ? 1 : 0;
+    const size_t min_cells = (size_t)cell_arrays * 4 * (ctas == 1 ? 2049 : 1025);
+    // staging capacity for atoms inside the grid: everything if it fits, else what is left after the
+    // minimum grid (frames with more in-grid atoms set PC_ST_STAGE_OVERFLOW; the host then asks for one
+    // CTA per SM and, failing that, for the large-frame path)
+    PcSmallSmem full = pc_small_layout(c->n1h, c->n2h, c->self_mode, 0, capHits, capHb, c->n1h, c->n2h, capTab, use_cid);
     int capInA = c->n1h, capInB = c->n2h;
-    const size_t min_cells = (size_t)cell_arrays * 4 * 2049;
     if ((size_t)full.total + min_cells > budget) {
-        PcSmallSmem none = pc_small_layout(c->n1h, c->n2h, c->self_mode, 0, capHits, capHb, 0, 0, capTab);
+        PcSmallSmem none = pc_small_layout(c->n1h, c->n2h, c->self_mode, 0, capHits, capHb, 0, 0, capTab, use_cid);
         if ((size_t)none.total + min_cells + 16 * 512 > budget) return false;
         const size_t left = (budget - none.total - min_cells) / 16;
         if (c->self_mode) capInA = capInB = (int)std::min<size_t>(left, (size_t)c->n1h);
         else {
-            // split in proportion to the selection sizes
             capInA = (int)std::min<size_t>((size_t)c->n1h, left * c->n1h / (size_t)(c->n1h + c->n2h));
             capInB = (int)std::min<size_t>((size_t)c->n2h, left - capInA);
         }
         if (capInA < 64 || capInB < 64) return false;
+        // two CTAs per SM only pay when at least a fifth of the atoms can be staged
+        if (ctas > 1 && (long long)(capInA + (c->self_mode ? 0 : capInB)) * 5 < (long long)(c->n1h + (c->self_mode ? 0 : c->n2h))) return false;
     }
-    PcSmallSmem base = pc_small_layout(c->n1h, c->n2h, c->self_mode, 0, capHits, capHb, capInA, capInB, capTab);
+    PcSmallSmem base = pc_small_layout(c->n1h, c->n2h, c->self_mode, 0, capHits, capHb, capInA, capInB, capTab, use_cid);
     if ((size_t)base.total + min_cells > budget) return false;
     int cells = (int)((budget - base.total) / (4 * cell_arrays)) - 8;
     cells = std::min(cells, 16384);
     if (c->lim_cells > 0) cells = std::min(cells, c->lim_cells);
     if (cells < 64) return false;
     capCells = cells;
-    L = pc_small_layout(c->n1h, c->n2h, c->self_mode, capCells, capHits, capHb, capInA, capInB, capTab);
+    L = pc_small_layout(c->n1h, c->n2h, c->self_mode, capCells, capHits, capHb, capInA, capInB, capTab, use_cid);
     return true;
+}
+
+static bool plan_small(const pc_ctx *c, bool fuse_acc, int &ctas, int &capCells, int &capHits, int &capHb, PcSmallSmem &L) {
+    if (c->n1h > 65535 || c->n2h > 65535) return false;
+    if (c->small_ctas != 1 && plan_small_cfg(c, fuse_acc, 2, capCells, capHits, capHb, L)) { ctas = 2; return true; }
+    if (c->small_ctas == 2) return false;
+    ctas = 1;
+    return plan_small_cfg(c, fuse_acc, 1, capCells, capHits, capHb, L);
 }
 
 extern "C" int pc_scan_device(pc_ctx *c, const float *d_xyz1, const float *d_xyz2, int32_t nframes,
@@ -336,17 +356,24 @@ extern "C" int pc_scan_device(pc_ctx *c, const float *d_xyz1, const float *d_xyz
     const bool fuse_acc = c->want_fused_acc && c->have_maps && !order_keys && c->lim_table <= 2048;
     a.fuse_acc = 0;
     a.rows = c->rows.p; a.cap_rows = c->cap_rows; a.frame_rstart = meta(c, 4); a.frame_rcount = meta(c, 5);
-    const bool fits_small = c->force_path != 2 && plan_small(c, fuse_acc, a.capCells, a.capHits, a.capHb, L);
+    int small_ctas = 1;
+    const bool fits_small = c->force_path != 2 && plan_small(c, fuse_acc, small_ctas, a.capCells, a.capHits, a.capHb, L);
     c->last_fused = false;
     c->packed_valid = false;
     if (c->force_path == 1 && !fits_small)
         return fail(PC_ERR_INVALID, "pc_scan_device: the frame does not fit the small-frame kernel");
     if (fits_small) {
-        auto kern = pc_scan_small_kernel<PC_SMALL_NT>;
-        CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L.total));
         a.fuse_acc = fuse_acc ? 1 : 0;
-        const int grid = std::min(nframes, c->num_sms);
-        kern<<<grid, PC_SMALL_NT, L.total, s>>>(a, L);
+        if (small_ctas == 2) {
+            auto kern = pc_scan_small_kernel<512>;
+            CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L.total));
+            kern<<<std::min(nframes, 2 * c->num_sms), 512, L.total, s>>>(a, L);
+        } else {
+            auto kern = pc_scan_small_kernel<1024>;
+            CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L.total));
+            kern<<<std::min(nframes, c->num_sms), 1024, L.total, s>>>(a, L);
+        }
+        c->last_small_ctas = small_ctas;
         c->last_fused = fuse_acc;
         CUDA_TRY(cudaGetLastError());
         g_launches += 1;
@@ -571,7 +598,7 @@ extern "C" int pc_last_status(pc_ctx *c, uint64_t *status, int64_t *need_contact
     if (need_contacts) *need_contacts = (int64_t)c->h_counters[PC_CNT_CONTACTS];
     if (need_hbonds) *need_hbonds = (int64_t)c->h_counters[PC_CNT_HBONDS];
     if (need_rows) *need_rows = (int64_t)c->h_counters[PC_CNT_ROWS];
-    if (path) *path = c->last_path;
+    if (path) *path = c->last_path == 1 ? (c->last_small_ctas == 2 ? 1 : 1) : c->last_path;
     return PC_OK;
 }
 

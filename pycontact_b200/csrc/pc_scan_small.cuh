@@ -30,21 +30,28 @@ struct PcSmallSmem {
     int capInA, capInB, capTab;
 };
 
+// Shared-memory plan.  Two regions are time-shared inside a frame: the SoA copy of all heavy atoms
+// (+ their cell ids) lives from phase 1 to phase 5; hit queue, H-bond staging and the accumulation
+// table live from phase 6 to phase 8 and are laid over it.  use_cid = 0 drops the cell-id array (cells
+// are recomputed in phase 5) when that makes a second CTA per SM fit.
 __host__ inline PcSmallSmem pc_small_layout(int n1h, int n2h, int self_mode, int capCells, int capHits, int capHb,
-                                            int capInA, int capInB, int capTab) {
+                                            int capInA, int capInB, int capTab, int use_cid = 1) {
     PcSmallSmem L;
     const int ntot = self_mode ? n1h : n1h + n2h;
     int o = 0;
     auto take = [&](int bytes) { int r = o; o += (bytes + 15) & ~15; return r; };
     L.off_x = take(4 * ntot); L.off_y = take(4 * ntot); L.off_z = take(4 * ntot);
-    L.off_cid = take(2 * ntot);
+    L.off_cid = use_cid ? take(2 * ntot) : -1;
+    const int end_early = o;
+    o = 0;
+    L.off_hits = take(4 * capHits);
+    L.off_hb = take((int)sizeof(pc_hbond) * capHb);
+    L.off_tab = take(48 * capTab);
+    o = o > end_early ? o : end_early;
     L.off_sortA = take(16 * capInA);
     L.off_sortB = self_mode ? L.off_sortA : take(16 * capInB);
     L.off_cellA = take(4 * (capCells + 1));
     L.off_cellB = self_mode ? L.off_cellA : take(4 * (capCells + 1));
-    L.off_hits = take(4 * capHits);
-    L.off_hb = take((int)sizeof(pc_hbond) * capHb);
-    L.off_tab = take(48 * capTab);
     L.capInA = capInA; L.capInB = self_mode ? capInA : capInB; L.capTab = capTab;
     L.total = o;
     return L;
@@ -87,12 +94,12 @@ __device__ __forceinline__ void block_excl_scan_inplace(uint32_t *arr, int n, ui
 }
 
 template <int NT>
-__global__ void __launch_bounds__(NT, 1) pc_scan_small_kernel(const PcScanArgs a, const PcSmallSmem L) {
+__global__ void __launch_bounds__(NT, NT >= 1024 ? 1 : 2) pc_scan_small_kernel(const PcScanArgs a, const PcSmallSmem L) {
     extern __shared__ __align__(16) unsigned char smem[];
     float *sx = reinterpret_cast<float *>(smem + L.off_x);
     float *sy = reinterpret_cast<float *>(smem + L.off_y);
     float *sz = reinterpret_cast<float *>(smem + L.off_z);
-    uint16_t *cid = reinterpret_cast<uint16_t *>(smem + L.off_cid);
+    uint16_t *cid = L.off_cid >= 0 ? reinterpret_cast<uint16_t *>(smem + L.off_cid) : nullptr;
     float4 *sortA = reinterpret_cast<float4 *>(smem + L.off_sortA);
     float4 *sortB = reinterpret_cast<float4 *>(smem + L.off_sortB);
     uint32_t *cellA = reinterpret_cast<uint32_t *>(smem + L.off_cellA);
@@ -156,11 +163,6 @@ __global__ void __launch_bounds__(NT, 1) pc_scan_small_kernel(const PcScanArgs a
             for (int k = 0; k < 6; k++) { red[warp][k] = mn[k]; red[warp][6 + k] = mx[k]; }
         }
         if (tid == 0) { s_nhits = 0; s_nhb = 0; s_status = 0; }
-        if (fuse)
-            for (int s = tid; s < capTab; s += NT) {
-                tkey[s] = PC_EMPTY_KEY; tscore[s] = 0.0; tbb1[s] = 0.0; tbb2[s] = 0.0;
-                tfirst[s] = PC_EMPTY_KEY; tncont[s] = 0; tnhb[s] = 0;
-            }
         __syncthreads();
 
         // ---- phase 2: grid geometry (warp 0 reduces the per-warp boxes) ---------------------------
@@ -222,13 +224,13 @@ __global__ void __launch_bounds__(NT, 1) pc_scan_small_kernel(const PcScanArgs a
             };
             for (int k = tid; k < n1h; k += NT) {
                 const int c = cell_of(sx[k], sy[k], sz[k]);
-                cid[k] = (uint16_t)c;
+                if (cid) cid[k] = (uint16_t)c;
                 if (c >= 0) atomicAdd(&cellA[c], 1u);
             }
             if (!self)
                 for (int k = tid; k < n2h; k += NT) {
                     const int c = cell_of(sx[offB + k], sy[offB + k], sz[offB + k]);
-                    cid[offB + k] = (uint16_t)c;
+                    if (cid) cid[offB + k] = (uint16_t)c;
                     if (c >= 0) atomicAdd(&cellB[c], 1u);
                 }
             __syncthreads();
@@ -241,13 +243,14 @@ __global__ void __launch_bounds__(NT, 1) pc_scan_small_kernel(const PcScanArgs a
             } else {
                 // ---- phase 5: scatter into cell order; afterwards cell[c] == END of cell c -----------
                 for (int k = tid; k < n1h; k += NT) {
-                    const unsigned c = cid[k];
+                    const unsigned c = cid ? (unsigned)cid[k] : ((unsigned)cell_of(sx[k], sy[k], sz[k]) & 0xffffu);
                     if (c != 0xffffu)
                         sortA[atomicAdd(&cellA[c], 1u)] = make_float4(sx[k], sy[k], sz[k], __uint_as_float(__ldg(a.t.hinfo1 + k)));
                 }
                 if (!self)
                     for (int k = tid; k < n2h; k += NT) {
-                        const unsigned c = cid[offB + k];
+                        const unsigned c = cid ? (unsigned)cid[offB + k]
+                                               : ((unsigned)cell_of(sx[offB + k], sy[offB + k], sz[offB + k]) & 0xffffu);
                         if (c != 0xffffu)
                             sortB[atomicAdd(&cellB[c], 1u)] =
                                 make_float4(sx[offB + k], sy[offB + k], sz[offB + k], __uint_as_float(__ldg(a.t.hinfo2 + k)));
@@ -287,6 +290,13 @@ __global__ void __launch_bounds__(NT, 1) pc_scan_small_kernel(const PcScanArgs a
                 }
             }
         }
+        // The accumulation table is laid over the SoA copy of the heavy atoms, which nobody reads any
+        // more: every warp that gets here is past the barrier that ended phase 5 (or skipped the grid).
+        if (fuse)
+            for (int s = tid; s < capTab; s += NT) {
+                tkey[s] = PC_EMPTY_KEY; tscore[s] = 0.0; tbb1[s] = 0.0; tbb2[s] = 0.0;
+                tfirst[s] = PC_EMPTY_KEY; tncont[s] = 0; tnhb[s] = 0;
+            }
         __syncthreads();
 
         // ---- phase 7: drain -----------------------------------------------------------------------

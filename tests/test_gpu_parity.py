@@ -114,12 +114,14 @@ def test_cy_find_contacts_self_keeps_ii_pairs():
 # ---------------------------------------------------------------------------------------------------
 # B2 / B3: frame scan + accumulation on the reference's fixture (golden session)
 # ---------------------------------------------------------------------------------------------------
-@pytest.mark.parametrize("path", [1, 2])
-def test_scan_fixture_matches_golden_session(rpn11, golden_ab, path):
+@pytest.mark.parametrize("path,ctas", [(1, 1), (1, 2), (2, 0)])
+def test_scan_fixture_matches_golden_session(rpn11, golden_ab, path, ctas):
     idx1, idx2 = golden_ab["sel1"].astype(np.int64), golden_ab["sel2"].astype(np.int64)
     s1, s2 = _selections(rpn11.topology, idx1, idx2, rpn11.backbone)
     with ContactEngine(s1, s2, 5.0, 2.5, 120) as eng:
         eng.set_path(path)
+        for sl in eng.slots:
+            eng.lib.pc_set_small_ctas(sl.ctx, ctas)
         src = ArraySource(np.ascontiguousarray(rpn11.coords[:, idx1]), np.ascontiguousarray(rpn11.coords[:, idx2]))
         traj, _, stats = run_scan([eng], src, batch_frames=16, order_keys=True)
     assert stats["path"] == path
@@ -319,16 +321,19 @@ def test_fused_accumulation_equals_standalone_kernel(name, self_mode):
     gm1 = prepare.group_map(idx1, s.maps[0], t.names, t.resids, t.resnames, t.segids)
     gm2 = prepare.group_map(idx2, s.maps[1], t.names, t.resids, t.resnames, t.segids)
     tables = []
-    for fused in (1, 0):
+    for fused, ctas in ((1, 2), (0, 2), (1, 1)):
         with ContactEngine(s1, s2, 5.0, 2.5, 120) as eng:
             eng.set_path(1)
             for sl in eng.slots:
                 eng.lib.pc_set_fused_accumulate(sl.ctx, fused)
+                eng.lib.pc_set_small_ctas(sl.ctx, ctas)
             eng.set_maps(gm1.gid, gm2.gid, gm2.n_groups)
             src = ArraySource(np.ascontiguousarray(coords[:, idx1]), None if self_mode else np.ascontiguousarray(coords[:, idx2]))
             _, table, _ = run_scan([eng], src, batch_frames=2, order_keys=False, accumulate=True, group_maps=(gm1, gm2))
         tables.append(table)
-    a, b = tables
+    a, b, c1 = tables
+    assert np.array_equal(np.sort(a.keys), np.sort(c1.keys))
+    np.testing.assert_allclose(a.score_matrix()[np.argsort(a.keys)], c1.score_matrix()[np.argsort(c1.keys)], rtol=1e-12)
     assert a.n_keys == b.n_keys and a.n_keys > 0
     oa, ob = np.argsort(a.keys), np.argsort(b.keys)
     assert np.array_equal(a.keys[oa], b.keys[ob])
