@@ -88,7 +88,8 @@ struct pc_ctx {
     int last_path = 0;                // 1 = small, 2 = large
     bool gacc_used = false, gacc_retry = false;
     bool packed_valid = false;        // rows_packed holds the last accumulated batch
-    int small_ctas = 0;               // small-frame kernel CTAs per SM: 0 = automatic, 1, 2
+    DevBuf<int> retry;                // [0] count, [4..] frames the fast small-frame plan handed to the full plan
+    int small_ctas = 0;               // small-frame kernel plans: 0 = fast + full (automatic), 1 = full only, 2 = fast only
     int last_small_ctas = 0;
     bool want_fused_acc = true;       // accumulate inside the small-frame scan kernel when possible
     bool last_fused = false;
@@ -269,56 +270,46 @@ static PcTopoDev topo_dev(const pc_ctx *c) {
 
 static uint32_t *meta(pc_ctx *c, int which) { return c->frame_meta.p + (size_t)which * c->max_frames; }
 
-// Pick the shared-memory plan of the small-frame kernel: two 512-thread CTAs per SM when a frame's
-// working set fits half an SM's shared memory (latency of one frame's barriers hides behind the
-// other frame's work), else one 1024-thread CTA per SM.  Returns false when the frame does not fit
-// one CTA's shared memory at all (-> large-frame path).
+// Shared-memory plans of the small-frame kernel.  "Fast": two 512-thread CTAs per SM, staging for a
+// few thousand in-grid atoms (one frame's barrier and load latency hides behind the other CTA's
+// work).  "Full": one 1024-thread CTA per SM with the largest staging that fits.  A batch runs the
+// fast plan over all frames and the full plan over the frames the fast plan could not stage; when
+// not even the full plan can hold every heavy atom of a frame, overflowing frames report
+// PC_ST_STAGE_OVERFLOW and the caller switches to the large-frame path.
 static bool plan_small_cfg(const pc_ctx *c, bool fuse_acc, int ctas, int &capCells, int &capHits, int &capHb, PcSmallSmem &L) {
+    const int ntot = c->self_mode ? c->n1h : c->n1h + c->n2h;
     capHits = c->lim_hits > 0 ? c->lim_hits : 4096;
     capHb = c->lim_hb > 0 ? c->lim_hb : 256;
     int capTab = 0;
-    if (fuse_acc) { capTab = 64; const int want = c->lim_table > 0 ? c->lim_table : 1024; while (capTab < want) capTab <<= 1; }
+    if (fuse_acc) {
+        capTab = 64;
+        const int want = c->lim_table > 0 ? c->lim_table : (ctas == 2 ? 512 : 1024);
+        while (capTab < want) capTab <<= 1;
+    }
     const size_t optin = c->smem_optin ? c->smem_optin : 232448;
     const size_t per_sm = 233472;
-    const size_t budget = (ctas == 1 ? optin : std::min(optin, per_sm / ctas - 1024)) - 3072;   // static shared memory
+    const size_t budget = (ctas == 1 ? optin : std::min(optin, per_sm / ctas - 1024)) - 3072;   // minus static shared memory
     const int cell_arrays = c->self_mode ? 1 : 2;
-    const int use_cid = ctas == 1 ? 1 : 0;
     const size_t min_cells = (size_t)cell_arrays * 4 * (ctas == 1 ? 2049 : 1025);
-    // staging capacity for atoms inside the grid: everything if it fits, else what is left after the
-    // minimum grid (frames with more in-grid atoms set PC_ST_STAGE_OVERFLOW; the host then asks for one
-    // CTA per SM and, failing that, for the large-frame path)
-    PcSmallSmem full = pc_small_layout(c->n1h, c->n2h, c->self_mode, 0, capHits, capHb, c->n1h, c->n2h, capTab, use_cid);
-    int capInA = c->n1h, capInB = c->n2h;
-    if ((size_t)full.total + min_cells > budget) {
-        PcSmallSmem none = pc_small_layout(c->n1h, c->n2h, c->self_mode, 0, capHits, capHb, 0, 0, capTab, use_cid);
-        if ((size_t)none.total + min_cells + 16 * 512 > budget) return false;
-        const size_t left = (budget - none.total - min_cells) / 16;
-        if (c->self_mode) capInA = capInB = (int)std::min<size_t>(left, (size_t)c->n1h);
-        else {
-            capInA = (int)std::min<size_t>((size_t)c->n1h, left * c->n1h / (size_t)(c->n1h + c->n2h));
-            capInB = (int)std::min<size_t>((size_t)c->n2h, left - capInA);
-        }
-        if (capInA < 64 || capInB < 64) return false;
-        // two CTAs per SM only pay when at least a fifth of the atoms can be staged
-        if (ctas > 1 && (long long)(capInA + (c->self_mode ? 0 : capInB)) * 5 < (long long)(c->n1h + (c->self_mode ? 0 : c->n2h))) return false;
+    // the largest candidate pool that leaves room for the minimum grid
+    int lo = 0, hi = std::min(ntot, 65535);
+    while (lo < hi) {
+        const int mid = (lo + hi + 1) / 2;
+        PcSmallSmem t = pc_small_layout(c->self_mode, 0, capHits, capHb, mid, capTab);
+        if ((size_t)t.total + min_cells <= budget) lo = mid; else hi = mid - 1;
     }
-    PcSmallSmem base = pc_small_layout(c->n1h, c->n2h, c->self_mode, 0, capHits, capHb, capInA, capInB, capTab, use_cid);
-    if ((size_t)base.total + min_cells > budget) return false;
+    const int capCand = lo;
+    if (capCand < 128) return false;
+    // the fast plan only pays when a fair share of the atoms can be staged
+    if (ctas > 1 && capCand < ntot && (long long)capCand * 6 < (long long)ntot) return false;
+    PcSmallSmem base = pc_small_layout(c->self_mode, 0, capHits, capHb, capCand, capTab);
     int cells = (int)((budget - base.total) / (4 * cell_arrays)) - 8;
     cells = std::min(cells, 16384);
     if (c->lim_cells > 0) cells = std::min(cells, c->lim_cells);
     if (cells < 64) return false;
     capCells = cells;
-    L = pc_small_layout(c->n1h, c->n2h, c->self_mode, capCells, capHits, capHb, capInA, capInB, capTab, use_cid);
+    L = pc_small_layout(c->self_mode, capCells, capHits, capHb, capCand, capTab);
     return true;
-}
-
-static bool plan_small(const pc_ctx *c, bool fuse_acc, int &ctas, int &capCells, int &capHits, int &capHb, PcSmallSmem &L) {
-    if (c->n1h > 65535 || c->n2h > 65535) return false;
-    if (c->small_ctas != 1 && plan_small_cfg(c, fuse_acc, 2, capCells, capHits, capHb, L)) { ctas = 2; return true; }
-    if (c->small_ctas == 2) return false;
-    ctas = 1;
-    return plan_small_cfg(c, fuse_acc, 1, capCells, capHits, capHb, L);
 }
 
 extern "C" int pc_scan_device(pc_ctx *c, const float *d_xyz1, const float *d_xyz2, int32_t nframes,
@@ -356,27 +347,46 @@ extern "C" int pc_scan_device(pc_ctx *c, const float *d_xyz1, const float *d_xyz
     const bool fuse_acc = c->want_fused_acc && c->have_maps && !order_keys && c->lim_table <= 2048;
     a.fuse_acc = 0;
     a.rows = c->rows.p; a.cap_rows = c->cap_rows; a.frame_rstart = meta(c, 4); a.frame_rcount = meta(c, 5);
-    int small_ctas = 1;
-    const bool fits_small = c->force_path != 2 && plan_small(c, fuse_acc, small_ctas, a.capCells, a.capHits, a.capHb, L);
+    PcSmallSmem L2;
+    int cells1 = 0, hits1 = 0, hb1 = 0, cells2 = 0, hits2 = 0, hb2 = 0;
+    const bool small_ok = c->force_path != 2 && c->n1h <= 65535 && c->n2h <= 65535;
+    const bool have_full = small_ok && c->small_ctas != 2 && plan_small_cfg(c, fuse_acc, 1, cells1, hits1, hb1, L);
+    const bool have_fast = small_ok && c->small_ctas != 1 && plan_small_cfg(c, fuse_acc, 2, cells2, hits2, hb2, L2);
+    const bool fits_small = have_full || have_fast;
     c->last_fused = false;
     c->packed_valid = false;
     if (c->force_path == 1 && !fits_small)
         return fail(PC_ERR_INVALID, "pc_scan_device: the frame does not fit the small-frame kernel");
     if (fits_small) {
         a.fuse_acc = fuse_acc ? 1 : 0;
-        if (small_ctas == 2) {
+        CUDA_TRY(c->retry.ensure((size_t)c->max_frames + 4));
+        unsigned int *retry_count = reinterpret_cast<unsigned int *>(c->retry.p);
+        int *retry_list = c->retry.p + 4;
+        CUDA_TRY(cudaMemsetAsync(retry_count, 0, sizeof(unsigned int), s));
+        PcSmallFrames fl;
+        if (have_fast) {
             auto kern = pc_scan_small_kernel<512>;
-            CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L.total));
-            kern<<<std::min(nframes, 2 * c->num_sms), 512, L.total, s>>>(a, L);
-        } else {
+            CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L2.total));
+            PcScanArgs a2 = a;
+            a2.capCells = cells2; a2.capHits = hits2; a2.capHb = hb2;
+            fl.frame_list = nullptr; fl.frame_count = nullptr;
+            fl.retry_list = have_full ? retry_list : nullptr; fl.retry_count = have_full ? retry_count : nullptr;
+            kern<<<std::min(nframes, 2 * c->num_sms), 512, L2.total, s>>>(a2, L2, fl);
+            CUDA_TRY(cudaGetLastError());
+            g_launches += 1;
+        }
+        if (have_full) {
             auto kern = pc_scan_small_kernel<1024>;
             CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L.total));
-            kern<<<std::min(nframes, c->num_sms), 1024, L.total, s>>>(a, L);
+            a.capCells = cells1; a.capHits = hits1; a.capHb = hb1;
+            fl.frame_list = have_fast ? retry_list : nullptr; fl.frame_count = have_fast ? retry_count : nullptr;
+            fl.retry_list = nullptr; fl.retry_count = nullptr;
+            kern<<<std::min(nframes, c->num_sms), 1024, L.total, s>>>(a, L, fl);
+            CUDA_TRY(cudaGetLastError());
+            g_launches += 1;
         }
-        c->last_small_ctas = small_ctas;
+        c->last_small_ctas = have_fast ? 2 : 1;
         c->last_fused = fuse_acc;
-        CUDA_TRY(cudaGetLastError());
-        g_launches += 1;
         c->last_path = 1;
     } else {
         int rc = pc_large_scan(c->large, a, c->num_sms, s, g_err, &g_launches);
@@ -579,10 +589,11 @@ extern "C" int pc_batch_totals(pc_ctx *c, void *stream, int64_t *n_contacts, int
     if (st & PC_ST_BAD_COORDS) return fail(PC_ERR_INVALID, "non-finite coordinates in a frame");
     if (st & PC_ST_MISSING_H)
         return fail(PC_ERR_MISSING_H, "a hydrogen bonded to a selected N/O/S atom is not part of that selection");
-    if (st & (PC_ST_HITS_OVERFLOW | PC_ST_HB_OVERFLOW | PC_ST_OUT_OVERFLOW | PC_ST_TABLE_OVERFLOW)) {
+    if (st & (PC_ST_HITS_OVERFLOW | PC_ST_HB_OVERFLOW | PC_ST_OUT_OVERFLOW | PC_ST_TABLE_OVERFLOW | PC_ST_STAGE_OVERFLOW)) {
         char buf[256];
         snprintf(buf, sizeof buf,
-                 "capacity exceeded (status 0x%llx: 1=hits/frame 2=hbonds/frame 4=batch buffers 32=accumulation table); "
+                 "capacity exceeded (status 0x%llx: 1=hits/frame 2=hbonds/frame 4=batch buffers 32=accumulation table "
+                 "64=small-frame staging); "
                  "needed contacts=%llu hbonds=%llu rows=%llu",
                  st, c->h_counters[PC_CNT_CONTACTS], c->h_counters[PC_CNT_HBONDS], c->h_counters[PC_CNT_ROWS]);
         g_err = buf;

@@ -26,33 +26,30 @@
 
 struct PcSmallSmem {
     // offsets (bytes) into dynamic shared memory, computed on the host
-    int off_x, off_y, off_z, off_cid, off_sortA, off_sortB, off_cellA, off_cellB, off_hits, off_hb, off_tab, total;
-    int capInA, capInB, capTab;
+    int off_cand, off_ccell, off_hits, off_hb, off_tab, off_sort, off_cellA, off_cellB, total;
+    int capCand, capTab;
 };
 
-// Shared-memory plan.  Two regions are time-shared inside a frame: the SoA copy of all heavy atoms
-// (+ their cell ids) lives from phase 1 to phase 5; hit queue, H-bond staging and the accumulation
-// table live from phase 6 to phase 8 and are laid over it.  use_cid = 0 drops the cell-id array (cells
-// are recomputed in phase 5) when that makes a second CTA per SM fit.
-__host__ inline PcSmallSmem pc_small_layout(int n1h, int n2h, int self_mode, int capCells, int capHits, int capHb,
-                                            int capInA, int capInB, int capTab, int use_cid = 1) {
+// Shared-memory plan.  One region is time-shared inside a frame: the candidate pool (atoms inside the
+// grid, unsorted, + their cell ids) lives in phases 3-5; hit queue, H-bond staging and the
+// accumulation table live in phases 6-8 and are laid over it.  Both pools hold selection A from the
+// bottom up and selection B from the top down, so only the SUM of in-grid atoms is bounded.
+__host__ inline PcSmallSmem pc_small_layout(int self_mode, int capCells, int capHits, int capHb, int capCand, int capTab) {
     PcSmallSmem L;
-    const int ntot = self_mode ? n1h : n1h + n2h;
     int o = 0;
     auto take = [&](int bytes) { int r = o; o += (bytes + 15) & ~15; return r; };
-    L.off_x = take(4 * ntot); L.off_y = take(4 * ntot); L.off_z = take(4 * ntot);
-    L.off_cid = use_cid ? take(2 * ntot) : -1;
+    L.off_cand = take(16 * capCand);
+    L.off_ccell = take(2 * capCand);
     const int end_early = o;
     o = 0;
     L.off_hits = take(4 * capHits);
     L.off_hb = take((int)sizeof(pc_hbond) * capHb);
     L.off_tab = take(48 * capTab);
     o = o > end_early ? o : end_early;
-    L.off_sortA = take(16 * capInA);
-    L.off_sortB = self_mode ? L.off_sortA : take(16 * capInB);
+    L.off_sort = take(16 * capCand);
     L.off_cellA = take(4 * (capCells + 1));
     L.off_cellB = self_mode ? L.off_cellA : take(4 * (capCells + 1));
-    L.capInA = capInA; L.capInB = self_mode ? capInA : capInB; L.capTab = capTab;
+    L.capCand = capCand; L.capTab = capTab;
     L.total = o;
     return L;
 }
@@ -93,21 +90,29 @@ __device__ __forceinline__ void block_excl_scan_inplace(uint32_t *arr, int n, ui
     __syncthreads();
 }
 
+// One launch covers either all frames of the batch (frame_list == nullptr) or the frames another
+// launch could not stage (frame_list / frame_count on the device).  With retry_list set, a frame whose
+// in-grid atoms or hits overflow this launch's staging is appended there instead of being reported.
+struct PcSmallFrames {
+    const int *frame_list;
+    const unsigned int *frame_count;
+    int *retry_list;
+    unsigned int *retry_count;
+};
+
 template <int NT>
-__global__ void __launch_bounds__(NT, NT >= 1024 ? 1 : 2) pc_scan_small_kernel(const PcScanArgs a, const PcSmallSmem L) {
+__global__ void __launch_bounds__(NT, NT >= 1024 ? 1 : 2) pc_scan_small_kernel(const PcScanArgs a, const PcSmallSmem L,
+                                                                               const PcSmallFrames fl) {
     extern __shared__ __align__(16) unsigned char smem[];
-    float *sx = reinterpret_cast<float *>(smem + L.off_x);
-    float *sy = reinterpret_cast<float *>(smem + L.off_y);
-    float *sz = reinterpret_cast<float *>(smem + L.off_z);
-    uint16_t *cid = L.off_cid >= 0 ? reinterpret_cast<uint16_t *>(smem + L.off_cid) : nullptr;
-    float4 *sortA = reinterpret_cast<float4 *>(smem + L.off_sortA);
-    float4 *sortB = reinterpret_cast<float4 *>(smem + L.off_sortB);
+    float4 *cand = reinterpret_cast<float4 *>(smem + L.off_cand);
+    uint16_t *ccell = reinterpret_cast<uint16_t *>(smem + L.off_ccell);
+    float4 *sortp = reinterpret_cast<float4 *>(smem + L.off_sort);
     uint32_t *cellA = reinterpret_cast<uint32_t *>(smem + L.off_cellA);
     uint32_t *cellB = reinterpret_cast<uint32_t *>(smem + L.off_cellB);
     uint32_t *hits = reinterpret_cast<uint32_t *>(smem + L.off_hits);
     pc_hbond *hbq = reinterpret_cast<pc_hbond *>(smem + L.off_hb);
     // accumulation table (fuse_acc): structure of arrays over capTab slots
-    const int capTab = L.capTab;
+    const int capTab = L.capTab, capCand = L.capCand;
     unsigned long long *tkey = reinterpret_cast<unsigned long long *>(smem + L.off_tab);
     double *tscore = reinterpret_cast<double *>(tkey + capTab);
     double *tbb1 = tscore + capTab;
@@ -119,7 +124,7 @@ __global__ void __launch_bounds__(NT, NT >= 1024 ? 1 : 2) pc_scan_small_kernel(c
     __shared__ float red[NT / 32][12];
     __shared__ uint32_t wsum[32];
     __shared__ PcGridSm g;
-    __shared__ unsigned int s_nhits, s_nhb;
+    __shared__ unsigned int s_nhits, s_nhb, s_nA, s_nB;
     __shared__ long long s_cbase, s_hbase, s_rbase;
     __shared__ unsigned int s_status;
 
@@ -127,23 +132,22 @@ __global__ void __launch_bounds__(NT, NT >= 1024 ? 1 : 2) pc_scan_small_kernel(c
     const bool self = a.self_mode != 0;
     const bool fuse = a.fuse_acc != 0;
     const int n1h = a.t.n1h, n2h = self ? a.t.n1h : a.t.n2h;
-    const int offB = self ? 0 : n1h;                 // B atoms live at sx[offB + k]
-    const uint32_t *hinfoB = self ? a.t.hinfo1 : a.t.hinfo2;
     const float sqdist = a.sqdist, sqdist_hi = a.sqdist * 1.00000095367431640625f;   // 1 + 2^-20
     unsigned long long evals = 0;
 
-    for (int f = blockIdx.x; f < a.nframes; f += gridDim.x) {
+    const int nfr = fl.frame_list ? (int)*fl.frame_count : a.nframes;
+    for (int fi = blockIdx.x; fi < nfr; fi += gridDim.x) {
+        const int f = fl.frame_list ? fl.frame_list[fi] : fi;
         const float *fr1 = a.xyz1 + (long long)f * a.pitch1;
         const float *fr2 = self ? fr1 : a.xyz2 + (long long)f * a.pitch2;
 
-        // ---- phase 1: heavy atoms -> shared, bounding boxes ---------------------------------
+        // ---- phase 1: bounding boxes of the heavy atoms (first pass over the frame) -----------------
         float mn[6], mx[6];
 #pragma unroll
         for (int k = 0; k < 6; k++) { mn[k] = INFINITY; mx[k] = -INFINITY; }
         for (int k = tid; k < n1h; k += NT) {
             float x, y, z;
             load_xyz(fr1, PC_W_INDEX(__ldg(a.t.hinfo1 + k)), a.stride, x, y, z);
-            sx[k] = x; sy[k] = y; sz[k] = z;
             mn[0] = fminf(mn[0], x); mn[1] = fminf(mn[1], y); mn[2] = fminf(mn[2], z);
             mx[0] = fmaxf(mx[0], x); mx[1] = fmaxf(mx[1], y); mx[2] = fmaxf(mx[2], z);
         }
@@ -151,7 +155,6 @@ __global__ void __launch_bounds__(NT, NT >= 1024 ? 1 : 2) pc_scan_small_kernel(c
             for (int k = tid; k < n2h; k += NT) {
                 float x, y, z;
                 load_xyz(fr2, PC_W_INDEX(__ldg(a.t.hinfo2 + k)), a.stride, x, y, z);
-                sx[offB + k] = x; sy[offB + k] = y; sz[offB + k] = z;
                 mn[3] = fminf(mn[3], x); mn[4] = fminf(mn[4], y); mn[5] = fminf(mn[5], z);
                 mx[3] = fmaxf(mx[3], x); mx[4] = fmaxf(mx[4], y); mx[5] = fmaxf(mx[5], z);
             }
@@ -162,7 +165,7 @@ __global__ void __launch_bounds__(NT, NT >= 1024 ? 1 : 2) pc_scan_small_kernel(c
 #pragma unroll
             for (int k = 0; k < 6; k++) { red[warp][k] = mn[k]; red[warp][6 + k] = mx[k]; }
         }
-        if (tid == 0) { s_nhits = 0; s_nhb = 0; s_status = 0; }
+        if (tid == 0) { s_nhits = 0; s_nhb = 0; s_status = 0; s_nA = 0; s_nB = 0; }
         __syncthreads();
 
         // ---- phase 2: grid geometry (warp 0 reduces the per-warp boxes) ---------------------------
@@ -206,11 +209,15 @@ __global__ void __launch_bounds__(NT, NT >= 1024 ? 1 : 2) pc_scan_small_kernel(c
         }
         __syncthreads();
         const int ncell = g.ncell;
+        int nInA = 0, nInB = 0;
+        bool staged = true;               // false: the frame does not fit this launch's staging
+        float4 *sortA = sortp, *sortB = sortp;
         if (ncell > 0) {
             const int nx = g.nx, ny = g.ny, nz = g.nz;
             const float lox = g.lo[0], loy = g.lo[1], loz = g.lo[2], inv = g.inv;
 
-            // ---- phase 3: cell ids + counts -------------------------------------------------------
+            // ---- phase 3: second pass over the frame (it is in L2 now): atoms inside the grid go to
+            //      the candidate pool with their cell id; atoms per cell (shared atomics) -----------------
             for (int c = tid; c <= ncell; c += NT) { cellA[c] = 0; if (!self) cellB[c] = 0; }
             __syncthreads();
             auto cell_of = [&](float x, float y, float z) -> int {
@@ -223,38 +230,45 @@ __global__ void __launch_bounds__(NT, NT >= 1024 ? 1 : 2) pc_scan_small_kernel(c
                 return (cz * ny + cy) * nx + cx;
             };
             for (int k = tid; k < n1h; k += NT) {
-                const int c = cell_of(sx[k], sy[k], sz[k]);
-                if (cid) cid[k] = (uint16_t)c;
-                if (c >= 0) atomicAdd(&cellA[c], 1u);
+                const uint32_t info = __ldg(a.t.hinfo1 + k);
+                float x, y, z;
+                load_xyz(fr1, PC_W_INDEX(info), a.stride, x, y, z);
+                const int c = cell_of(x, y, z);
+                if (c >= 0) {
+                    const unsigned p = atomicAdd(&s_nA, 1u);
+                    if (p < (unsigned)capCand) { cand[p] = make_float4(x, y, z, __uint_as_float(info)); ccell[p] = (uint16_t)c; }
+                    atomicAdd(&cellA[c], 1u);
+                }
             }
             if (!self)
                 for (int k = tid; k < n2h; k += NT) {
-                    const int c = cell_of(sx[offB + k], sy[offB + k], sz[offB + k]);
-                    if (cid) cid[offB + k] = (uint16_t)c;
-                    if (c >= 0) atomicAdd(&cellB[c], 1u);
+                    const uint32_t info = __ldg(a.t.hinfo2 + k);
+                    float x, y, z;
+                    load_xyz(fr2, PC_W_INDEX(info), a.stride, x, y, z);
+                    const int c = cell_of(x, y, z);
+                    if (c >= 0) {
+                        const unsigned p = atomicAdd(&s_nB, 1u);
+                        if (p < (unsigned)capCand) {
+                            cand[capCand - 1 - p] = make_float4(x, y, z, __uint_as_float(info));
+                            ccell[capCand - 1 - p] = (uint16_t)c;
+                        }
+                        atomicAdd(&cellB[c], 1u);
+                    }
                 }
             __syncthreads();
-            // ---- phase 4: scans ---------------------------------------------------------------------
-            block_excl_scan_inplace<NT>(cellA, ncell, wsum);
-            if (!self) block_excl_scan_inplace<NT>(cellB, ncell, wsum);
-            const int nInA = (int)cellA[ncell], nInB = (int)cellB[ncell];
-            if (nInA > L.capInA || nInB > L.capInB) {
-                if (tid == 0) atomicOr(&s_status, (unsigned)PC_ST_STAGE_OVERFLOW);
+            nInA = (int)s_nA; nInB = self ? nInA : (int)s_nB;
+            if (nInA + (self ? 0 : nInB) > capCand) {
+                staged = false;
             } else {
+                // ---- phase 4: scans ---------------------------------------------------------------------
+                block_excl_scan_inplace<NT>(cellA, ncell, wsum);
+                if (!self) block_excl_scan_inplace<NT>(cellB, ncell, wsum);
                 // ---- phase 5: scatter into cell order; afterwards cell[c] == END of cell c -----------
-                for (int k = tid; k < n1h; k += NT) {
-                    const unsigned c = cid ? (unsigned)cid[k] : ((unsigned)cell_of(sx[k], sy[k], sz[k]) & 0xffffu);
-                    if (c != 0xffffu)
-                        sortA[atomicAdd(&cellA[c], 1u)] = make_float4(sx[k], sy[k], sz[k], __uint_as_float(__ldg(a.t.hinfo1 + k)));
-                }
+                sortA = sortp;
+                sortB = self ? sortp : sortp + (capCand - nInB);
+                for (int p = tid; p < nInA; p += NT) sortA[atomicAdd(&cellA[ccell[p]], 1u)] = cand[p];
                 if (!self)
-                    for (int k = tid; k < n2h; k += NT) {
-                        const unsigned c = cid ? (unsigned)cid[offB + k]
-                                               : ((unsigned)cell_of(sx[offB + k], sy[offB + k], sz[offB + k]) & 0xffffu);
-                        if (c != 0xffffu)
-                            sortB[atomicAdd(&cellB[c], 1u)] =
-                                make_float4(sx[offB + k], sy[offB + k], sz[offB + k], __uint_as_float(__ldg(a.t.hinfo2 + k)));
-                    }
+                    for (int p = tid; p < nInB; p += NT) sortB[atomicAdd(&cellB[ccell[capCand - 1 - p]], 1u)] = cand[capCand - 1 - p];
                 __syncthreads();
 
                 // ---- phase 6: pair search, one thread per (A atom, stencil layer) --------------------
@@ -290,8 +304,8 @@ __global__ void __launch_bounds__(NT, NT >= 1024 ? 1 : 2) pc_scan_small_kernel(c
                 }
             }
         }
-        // The accumulation table is laid over the SoA copy of the heavy atoms, which nobody reads any
-        // more: every warp that gets here is past the barrier that ended phase 5 (or skipped the grid).
+        // The accumulation table is laid over the candidate pool, which nobody reads any more: every
+        // warp that gets here is past the barrier that ended phase 5 (or skipped the grid).
         if (fuse)
             for (int s = tid; s < capTab; s += NT) {
                 tkey[s] = PC_EMPTY_KEY; tscore[s] = 0.0; tbb1[s] = 0.0; tbb2[s] = 0.0;
@@ -299,9 +313,20 @@ __global__ void __launch_bounds__(NT, NT >= 1024 ? 1 : 2) pc_scan_small_kernel(c
             }
         __syncthreads();
 
-        // ---- phase 7: drain -----------------------------------------------------------------------
+        // A frame that does not fit this launch's staging (in-grid atoms, hits) is handed to the launch
+        // with the larger plan when there is one; nothing of it has been written to global memory yet.
         unsigned nh = s_nhits;
-        if (nh > (unsigned)a.capHits) { nh = a.capHits; if (tid == 0) atomicOr(&s_status, (unsigned)PC_ST_HITS_OVERFLOW); }
+        if (!staged || nh > (unsigned)a.capHits) {
+            if (fl.retry_list != nullptr) {
+                if (tid == 0) fl.retry_list[atomicAdd(fl.retry_count, 1u)] = f;
+                __syncthreads();
+                continue;
+            }
+            if (tid == 0) atomicOr(&s_status, (unsigned)(staged ? PC_ST_HITS_OVERFLOW : PC_ST_STAGE_OVERFLOW));
+            nh = staged ? (unsigned)a.capHits : 0u;
+        }
+
+        // ---- phase 7: drain -----------------------------------------------------------------------
         if (tid == 0) {
             long long base = (long long)atomicAdd(&a.counters[PC_CNT_CONTACTS], (unsigned long long)nh);
             if (base + nh > a.cap_contacts) { atomicOr(&s_status, (unsigned)PC_ST_OUT_OVERFLOW); base = -1; }

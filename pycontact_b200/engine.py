@@ -177,12 +177,7 @@ class ContactEngine:
         if st & _lib.ST_TABLE_OVERFLOW:
             # beyond 2048 slots the library switches to its global-memory table
             self.lim[3] = max(2048, 2 * (self.lim[3] or 1024))
-        if (st & _lib.ST_STAGE_OVERFLOW) and self.small_ctas != 1:
-            # two CTAs per SM leave too little staging room for this frame: one CTA per SM
-            self.small_ctas = 1
-            for s in self.slots:
-                check(self.lib.pc_set_small_ctas(s.ctx, 1))
-        elif (st & _lib.ST_STAGE_OVERFLOW) or self.lim[0] > 16384 or self.lim[1] > 4096:
+        if (st & _lib.ST_STAGE_OVERFLOW) or self.lim[0] > 16384 or self.lim[1] > 4096:
             # more atoms / records per frame than one CTA can stage in shared memory: use the
             # tiled large-frame path from now on
             if self.forced_path == 1:
