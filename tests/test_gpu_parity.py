@@ -374,3 +374,56 @@ def test_packed_rows_equal_full_rows():
     ta.finalize(); tb.finalize()
     oa, ob = np.argsort(ta.keys), np.argsort(tb.keys)
     np.testing.assert_allclose(ta.score_matrix()[oa], tb.score_matrix()[ob], rtol=2e-7)
+
+
+def test_run_load_parallel_returns_reference_shape(rpn11, golden_ab):
+    """run_load_parallel (core/multi_trajectory.py:354-455): [allContacts, resname, resid, name, segids, backbone],
+    contacts labelled frame 0 like the reference's pool path (Q1)."""
+    res = run_load_parallel(1, "rpn11_ubq.psf", "rpn11_ubq.dcd", 5.0, 2.5, 120, "segid RN11", "segid UBQ",
+                            topology=rpn11.topology, frames=rpn11.coords[:6])
+    contacts, resname, resid, name, segids, backbone = res
+    assert len(contacts) == 6 and len(resname) == len(resid) == len(name) == len(segids) == 4327
+    assert backbone == rpn11.backbone.tolist()
+    fp = golden_ab["frame_ptr"]
+    assert [len(fr) for fr in contacts] == np.diff(fp[:7]).tolist()
+    assert all(c.frame == 0 for c in contacts[3])
+    assert [c.idx2 for c in contacts[5]] == golden_ab["idx2"][fp[5]:fp[6]].tolist()
+
+
+def test_analyzer_two_gpus_equals_one(rpn11, golden_ab):
+    """The analogue of test_multiCore_analysis (tests/test_basic.py:73-84): frames sharded over 2 GPUs."""
+    from pycontact_b200 import _lib
+    if _lib.load().pc_device_count() < 2:
+        pytest.skip("needs two GPUs")
+    an = Analyzer("rpn11_ubq.psf", "rpn11_ubq.dcd", 5.0, 2.5, 120, "segid RN11", "segid UBQ",
+                  topology=rpn11.topology, frames=rpn11.coords)
+    an.runFrameScan(2)
+    assert len(an.contactResults) == 50
+    an.runContactAnalysis([0, 0, 1, 1, 0], [0, 0, 1, 1, 0], 2)
+    assert len(an.finalAccumulatedContacts) == 148
+    assert sum(c.hbond_percentage() for c in an.finalAccumulatedContacts) == 676.0
+    _check_accumulated(an.finalAccumulatedContacts, golden_ab)
+
+
+def test_analyzer_from_psf_dcd_files(tmp_path):
+    """The file-based constructor path (PSF + DCD readers, selection strings) end to end."""
+    from tests.test_io_cpu import _write_dcd, _write_psf
+    s = synth.make_system("tiny")
+    t = s.topology
+    coords = synth.frames_host(s, range(6))
+    psf, dcd = str(tmp_path / "tiny.psf"), str(tmp_path / "tiny.dcd")
+    _write_psf(psf, t)
+    _write_dcd(dcd, coords)
+    an = Analyzer(psf, dcd, 5.0, 2.5, 120, s.sel1text, s.sel2text, batch_frames=4)
+    seen = []
+    an.frameUpdate.connect(seen.append)
+    an.runFrameScan(1)
+    acc = an.runContactAnalysis(s.maps[0], s.maps[1], 1)
+    ora = frame_oracle.scan_frames([coords[f, s.sel1] for f in range(6)], [coords[f, s.sel2] for f in range(6)],
+                                   s.sel1, s.sel2, 5.0, 2.5, 120, t.names, t.types, t.bonds)
+    _compare_traj(an.contactResults.traj, ora)
+    oacc = frame_oracle.accumulate(ora, s.maps[0], s.maps[1], t.names, t.resids, t.resnames, t.segids, s.backbone)
+    assert [a.key1 for a in acc] == oacc["key1"] and [a.key2 for a in acc] == oacc["key2"]
+    np.testing.assert_allclose(np.asarray([a.scoreArray for a in acc], float), oacc["score"], rtol=RTOL, atol=1e-12)
+    assert seen and seen[-1] == 1.0
+    assert an.getFilePaths() == (psf, dcd) and an.lastMap1 == s.maps[0]
