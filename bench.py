@@ -35,7 +35,7 @@ WORKLOADS = {
     # name: (synthetic system, default frames per GPU per step, description)
     "c2": ("c2", 10000, "synthetic 100k-atom solvated protein (2 chains x 6000 atoms selected), "
                         "protein-protein interface contacts + H-bonds, cutoff 5.0 / 2.5 A / 120 deg"),
-    "c3": ("c3", 256, "synthetic 1M-atom membrane-protein complex, protein (50k atoms) vs lipid+water (950k atoms)"),
+    "c3": ("c3", 712, "synthetic 1M-atom membrane-protein complex, protein (50k atoms) vs lipid+water (950k atoms)"),
     "c4s": ("c4_small", 256, "synthetic capsid-like shell, 64k atoms, all-vs-all self contacts"),
     "c4": ("c4", 16, "synthetic 3M-atom virus-capsid-like shell, all-vs-all residue contact map (self)"),
     "small": ("small", 2048, "small solvated two-chain system (debug)"),
@@ -245,7 +245,7 @@ def run_gpu(args):
     eng = ContactEngine(s1, s2, 5.0, 2.5, 120, device=local, slots=2)
     eng.set_maps(gm1.gid, gm2.gid, gm2.n_groups)
     in_bytes_frame = (n1 + (0 if self_mode else n2)) * 12
-    batch = args.batch or int(max(1, min(F, 2048, (1 << 30) // in_bytes_frame)))
+    batch = args.batch or int(max(1, min(F, 2048, (2 << 30) // in_bytes_frame)))
     nb = (F + batch - 1) // batch
     n_keys = gm1.n_groups * gm2.n_groups
     dense = n_keys <= (1 << 20)          # aggregated maps as a dense [n_keys][4] table (32 MB at most)

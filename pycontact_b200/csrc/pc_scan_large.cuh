@@ -371,16 +371,26 @@ __global__ void __launch_bounds__(256) pc_large_pair_kernel(const PcScanArgs a, 
         const int z = cz + (int)(w - 3ll * ia) - 1;
         if (z < 0 || z >= nz) continue;
         const int xlo = max(cx - 1, 0), xhi = min(cx + 1, nx - 1);
+        // the bounds of the layer's three B runs first (six independent loads in flight)
+        int b0[3], b1[3];
+#pragma unroll
+        for (int dy = 0; dy < 3; dy++) {
+            const int y = cy + dy - 1;
+            if (y < 0 || y >= ny) { b0[dy] = 0; b1[dy] = 0; continue; }
+            const int row = (z * ny + y) * nx;
+            b0[dy] = (row + xlo) ? (int)__ldg(cB + row + xlo - 1) : 0;
+            b1[dy] = (int)__ldg(cB + row + xhi);
+        }
+        if (b0[0] == b1[0] && b0[1] == b1[1] && b0[2] == b1[2]) continue;
         int ares = 0, aseg = 0;
         if (self) {
             const int li = PC_W_INDEX(__float_as_uint(pa.w));
             ares = __ldg(a.t.lres1 + li); aseg = __ldg(a.t.lseg1 + li);
         }
-        for (int y = max(cy - 1, 0); y <= min(cy + 1, ny - 1); y++) {
-            const int row = (z * ny + y) * nx;
-            const int b0 = (row + xlo) ? (int)__ldg(cB + row + xlo - 1) : 0, b1 = (int)__ldg(cB + row + xhi);
-            evals += (unsigned)(b1 - b0);
-            for (int j = b0; j < b1; j++) {
+#pragma unroll
+        for (int dy = 0; dy < 3; dy++) {
+            evals += (unsigned)(b1[dy] - b0[dy]);
+            for (int j = b0[dy]; j < b1[dy]; j++) {
                 const float4 pb = __ldg(sB + j);
                 if (!pair_within(pa.x, pa.y, pa.z, pb.x, pb.y, pb.z, sqdist, sqdist_hi)) continue;
                 if (self) {
