@@ -230,6 +230,11 @@ int pc_event_record(void *event, void *stream);
 int pc_event_elapsed_ms(void *start_event, void *end_event, float *ms);   /* synchronises on end_event */
 void pc_event_destroy(void *event);
 
+/* Measurement: the large-frame path records these two events (pc_event_create) around its dominant
+ * kernel -- the streaming bin of selection 2, or of selection 1 in self mode -- for the first
+ * sub-batch of every pc_scan_device call.  NULL, NULL switches it off. */
+int pc_set_probe(pc_ctx *ctx, void *start_event, void *end_event);
+
 /* Pinned host memory helpers for the Python layer (cudaHostAlloc / cudaFreeHost). */
 int pc_host_alloc(void **out, int64_t bytes);
 void pc_host_free(void *p);

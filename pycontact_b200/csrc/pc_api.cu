@@ -88,6 +88,7 @@ struct pc_ctx {
     int last_path = 0;                // 1 = small, 2 = large
     bool gacc_used = false, gacc_retry = false;
     bool packed_valid = false;        // rows_packed holds the last accumulated batch
+    void *probe[2] = {nullptr, nullptr};   // optional events around the large path's dominant kernel (pc_set_probe)
     DevBuf<int> retry;                // [0] count, [4..] frames the fast small-frame plan handed to the full plan
     int small_ctas = 0;               // small-frame kernel plans: 0 = fast + full (automatic), 1 = full only, 2 = fast only
     int last_small_ctas = 0;
@@ -136,6 +137,12 @@ extern "C" void pc_destroy(pc_ctx *c) {
 extern "C" int pc_set_path(pc_ctx *c, int path) {
     if (!c || path < 0 || path > 2) return fail(PC_ERR_INVALID, "pc_set_path: path must be 0, 1 or 2");
     c->force_path = path;
+    return PC_OK;
+}
+
+extern "C" int pc_set_probe(pc_ctx *c, void *start_event, void *end_event) {
+    if (!c) return fail(PC_ERR_INVALID, "pc_set_probe: ctx is NULL");
+    c->probe[0] = start_event; c->probe[1] = end_event;
     return PC_OK;
 }
 
@@ -389,7 +396,7 @@ extern "C" int pc_scan_device(pc_ctx *c, const float *d_xyz1, const float *d_xyz
         c->last_fused = fuse_acc;
         c->last_path = 1;
     } else {
-        int rc = pc_large_scan(c->large, a, c->num_sms, s, g_err, &g_launches);
+        int rc = pc_large_scan(c->large, a, c->num_sms, s, g_err, &g_launches, (cudaEvent_t)c->probe[0], (cudaEvent_t)c->probe[1]);
         if (rc != PC_OK) return rc;
         c->last_path = 2;
     }

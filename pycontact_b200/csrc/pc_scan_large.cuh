@@ -509,7 +509,7 @@ static inline void pc_stream_geom(int n, int nfb, int num_sms, int &ctas, int &p
 }
 
 static inline int pc_large_scan(PcLargeWork &W, const PcScanArgs &a, int num_sms, cudaStream_t s, std::string &err,
-                                unsigned long long *launches) {
+                                unsigned long long *launches, cudaEvent_t probe0 = nullptr, cudaEvent_t probe1 = nullptr) {
     const int n1 = a.t.n1, n2 = a.self_mode ? a.t.n1 : a.t.n2;
     const int n1h = a.t.n1h, n2h = a.self_mode ? a.t.n1h : a.t.n2h;
     const bool self = a.self_mode != 0;
@@ -562,13 +562,17 @@ static inline int pc_large_scan(PcLargeWork &W, const PcScanArgs &a, int num_sms
         pc_large_grid_kernel<<<nfb, 256, 0, s>>>(a, W.frames, capCells, use_bboxB, W.cellA, W.cellB);
         if (!self) {
             // B first: its cell counts tell which A atoms can have a partner at all
+            if (probe0 && f0 == 0) cudaEventRecord(probe0, s);
             pc_large_stream_kernel<PC_MODE_BIN><<<dim3(ctasB, nfb), PC_STREAM_NT, PC_STREAM_SMEM, s>>>(
                 a, W.frames, f0, 1, 0, perB, W.cellB, capCells, W.candB, W.ccellB, a2, nullptr);
+            if (probe1 && f0 == 0) cudaEventRecord(probe1, s);
             pc_large_occ_kernel<<<dim3(std::max(1, std::min((capCells + 255) / 256, 4 * num_sms / nfb + 1)), nfb), 256, 0, s>>>(
                 W.frames, W.cellB, capCells, W.occ);
         }
+        if (self && probe0 && f0 == 0) cudaEventRecord(probe0, s);
         pc_large_stream_kernel<PC_MODE_BIN><<<dim3(ctasA, nfb), PC_STREAM_NT, PC_STREAM_SMEM, s>>>(
             a, W.frames, f0, 0, 0, perA, W.cellA, capCells, W.candA, W.ccellA, a1, self ? nullptr : W.occ);
+        if (self && probe1 && f0 == 0) cudaEventRecord(probe1, s);
         pc_large_scan_kernel<<<dim3(nfb, self ? 1 : 2), 1024, 0, s>>>(W.frames, W.cellA, W.cellB, capCells);
         const int per_frame_blocks = std::max(1, 4 * num_sms / nfb);
         const int blocksA = std::max(1, std::min((n1h + 255) / 256, per_frame_blocks));
