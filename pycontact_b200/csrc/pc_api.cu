@@ -616,7 +616,7 @@ extern "C" int pc_last_status(pc_ctx *c, uint64_t *status, int64_t *need_contact
     if (need_contacts) *need_contacts = (int64_t)c->h_counters[PC_CNT_CONTACTS];
     if (need_hbonds) *need_hbonds = (int64_t)c->h_counters[PC_CNT_HBONDS];
     if (need_rows) *need_rows = (int64_t)c->h_counters[PC_CNT_ROWS];
-    if (path) *path = c->last_path == 1 ? (c->last_small_ctas == 2 ? 1 : 1) : c->last_path;
+    if (path) *path = c->last_path;
     return PC_OK;
 }
 

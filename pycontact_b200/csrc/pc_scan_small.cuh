@@ -6,18 +6,23 @@
 //   + H-bond test (:112-209), and optionally the per-frame accumulation of
 //   analyze_contactResultsWithMaps (core/ContactAnalyzer.py:527-559).
 //
-// Phases (one persistent CTA per SM, frames strided over the grid):
-//   1  heavy atoms of both selections: global -> shared SoA (x[],y[],z[]), bounding boxes
+// Phases (persistent CTAs, frames strided over the grid; CTA barriers between phases):
+//   1  first pass over the frame: bounding boxes of the heavy atoms of both selections
 //   2  grid over (bboxA (+) c) n (bboxB (+) c): only atoms inside it can have a partner
-//   3  cell id of every heavy atom (0xffff = outside), atoms per cell (shared atomics)
+//   3  second pass over the frame (an L2 hit): atoms inside the grid -> candidate pool in shared memory
+//      (x, y, z, packed atom word) + cell id, atoms per cell (shared atomics)
 //   4  exclusive scans
-//   5  scatter the inside atoms into cell order as float4 (x, y, z, packed atom word)
+//   5  scatter the candidates into cell order
 //   6  pair search: one thread per (A atom, z-layer of its stencil); the three B x-runs of the layer
 //      are contiguous ranges of the sorted B array; fused pre-test + exact float32 test
 //      (pc_common.cuh: pair_within); hits -> shared queue
 //   7  drain: one thread per hit -> float64 distance, weight, H-bond test on N/O/S pairs, contact
 //      record; with fuse_acc the hit is also added to the frame's (key -> score) table in shared memory
 //   8  H-bond records and accumulated rows -> global
+// Only in-grid atoms are ever staged, so a frame needs little shared memory: the "fast" plan runs two
+// 512-thread CTAs per SM (one frame's barriers and loads hide behind the other's work); frames whose
+// in-grid atoms or hits do not fit it are queued on the device and redone by the "full" plan (one
+// 1024-thread CTA per SM with the largest staging) in a second launch.
 //
 // Hydrogens never enter the search (the reference discards every pair with a hydrogen at :89); they
 // are read from global memory only inside the H-bond test.

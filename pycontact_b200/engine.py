@@ -120,7 +120,6 @@ class ContactEngine:
         self.lim = [0, 0, 0, 0]          # hits/frame, hbonds/frame, cells, table slots (0 = automatic)
         self.launches = 0
         self.forced_path = 0
-        self.small_ctas = 0
 
     # ------------------------------------------------------------------------------------------
     def close(self):
