@@ -299,14 +299,14 @@ static bool plan_small_cfg(const pc_ctx *c, bool fuse_acc, int ctas, int &capCel
     const int cell_arrays = c->self_mode ? 1 : 2;
     const size_t min_cells = (size_t)cell_arrays * 4 * (ctas == 1 ? 2049 : 1025);
     // the largest candidate pool that leaves room for the minimum grid
-    int lo = 0, hi = std::min(ntot, 65535);
+    int lo = 0, hi = std::max(1, std::min(ntot, 65535));
     while (lo < hi) {
         const int mid = (lo + hi + 1) / 2;
         PcSmallSmem t = pc_small_layout(c->self_mode, 0, capHits, capHb, mid, capTab);
         if ((size_t)t.total + min_cells <= budget) lo = mid; else hi = mid - 1;
     }
     const int capCand = lo;
-    if (capCand < 128) return false;
+    if (capCand < std::min(128, std::max(ntot, 1))) return false;
     // the fast plan only pays when a fair share of the atoms can be staged
     if (ctas > 1 && capCand < ntot && (long long)capCand * 6 < (long long)ntot) return false;
     PcSmallSmem base = pc_small_layout(c->self_mode, 0, capHits, capHb, capCand, capTab);

@@ -277,12 +277,14 @@ __global__ void __launch_bounds__(NT, NT >= 1024 ? 1 : 2) pc_scan_small_kernel(c
                 __syncthreads();
 
                 // ---- phase 6: pair search, one thread per (A atom, stencil layer) --------------------
+                // items are layer-major: the lanes of a warp hold neighbouring atoms (same or adjacent
+                // cells, A is cell-sorted) on the same layer, so their run lengths are alike
                 for (int w = tid; w < 3 * nInA; w += NT) {
-                    const int ia = w / 3;
+                    const int layer = w / nInA, ia = w - layer * nInA;
                     const float4 pa = sortA[ia];
                     const int cx = (int)((pa.x - lox) * inv), cy = (int)((pa.y - loy) * inv),
                               cz = (int)((pa.z - loz) * inv);
-                    const int z = cz + (w - 3 * ia) - 1;
+                    const int z = cz + layer - 1;
                     if (z < 0 || z >= nz) continue;
                     const int xlo = max(cx - 1, 0), xhi = min(cx + 1, nx - 1);
                     int ares = 0, aseg = 0;

@@ -427,3 +427,39 @@ def test_analyzer_from_psf_dcd_files(tmp_path):
     np.testing.assert_allclose(np.asarray([a.scoreArray for a in acc], float), oacc["score"], rtol=RTOL, atol=1e-12)
     assert seen and seen[-1] == 1.0
     assert an.getFilePaths() == (psf, dcd) and an.lastMap1 == s.maps[0]
+
+
+@pytest.mark.parametrize("path", [1, 2])
+def test_edge_cases_empty_results_and_zero_distance(path):
+    """Selections of hydrogens only, far-apart selections (empty grid), single atoms, coincident atoms."""
+    from pycontact_b200.io.psf import Topology
+    names = ["N", "HN", "O", "H1", "CA", "OH2"]
+    n = len(names)
+    topo = Topology(["A"] * 3 + ["B"] * 3, np.arange(1, n + 1), ["ALA"] * n, names, ["NH1", "H", "O", "HT", "CT1", "OT"],
+                    np.zeros(n), np.ones(n), np.asarray([[0, 1], [5, 3]], np.int64))
+    xyz = np.asarray([[0, 0, 0], [1, 0, 0], [3, 0, 0], [50, 0, 0], [0, 0, 0], [2.9, 0, 0]], np.float32)
+    frames = np.stack([xyz, xyz + np.float32(0.25)])
+
+    def scan(i1, i2):
+        s1, s2 = _selections(topo, np.asarray(i1, np.int64), np.asarray(i2, np.int64), [])
+        with ContactEngine(s1, s2, 5.0, 2.5, 120) as eng:
+            eng.set_path(path)
+            src = ArraySource(np.ascontiguousarray(frames[:, i1]), np.ascontiguousarray(frames[:, i2]))
+            traj, _, st = run_scan([eng], src, order_keys=True)
+        ora = frame_oracle.scan_frames([frames[f, i1] for f in range(2)], [frames[f, i2] for f in range(2)],
+                                       np.asarray(i1), np.asarray(i2), 5.0, 2.5, 120, topo.names, topo.types, topo.bonds)
+        _compare_traj(traj, ora)
+        return traj
+    assert scan([1], [3]).idx1.size == 0                       # hydrogens only: every pair is dropped
+    assert scan([0, 1], [3]).idx1.size == 0                    # heavy atom vs a far hydrogen
+    t = scan([0, 1, 2], [4, 5, 3])                             # coincident atoms N / CA: distance 0 is a contact
+    assert (t.distance == 0).sum() == 2 and t.idx1.size == 8
+    assert t.hb_donor.size > 0                                 # OH2-H1 ... wait: N-HN...OH2 geometry gives H-bonds
+    far = frames.copy()
+    far[:, 3:] += np.float32(500.0)
+    src_far = (np.ascontiguousarray(far[:, [0, 1, 2]]), np.ascontiguousarray(far[:, [4, 5, 3]]))
+    s1, s2 = _selections(topo, np.asarray([0, 1, 2]), np.asarray([4, 5, 3]), [])
+    with ContactEngine(s1, s2, 5.0, 2.5, 120) as eng:
+        eng.set_path(path)
+        traj, _, st = run_scan([eng], ArraySource(*src_far), order_keys=True)
+    assert traj.idx1.size == 0 and st["contacts"] == 0        # bounding boxes do not touch: empty grid
