@@ -242,7 +242,7 @@ def run_gpu(args):
         gen2.generate(d2.ptr, frame0, F)
     check(lib.pc_device_sync(local))
 
-    eng = ContactEngine(s1, s2, 5.0, 2.5, 120, device=local, slots=2)
+    eng = ContactEngine(s1, s2, 5.0, 2.5, 120, device=local, slots=args.slots)
     eng.set_maps(gm1.gid, gm2.gid, gm2.n_groups)
     in_bytes_frame = (n1 + (0 if self_mode else n2)) * 12
     batch = args.batch or int(max(1, min(F, 2048, (2 << 30) // in_bytes_frame)))
@@ -287,22 +287,24 @@ def run_gpu(args):
                 print("slot %d nf %d: wait %.3f ms, fold+fetch %.3f ms (%d rows)" % (
                     sid, nf, (_t1 - _t0) * 1e3, (time.perf_counter() - _t1) * 1e3, rows.size), file=sys.stderr)
 
-        # two batches in flight: batch b+1 is scanned while batch b's rows travel to the host
-        pending = None
+        # several batches in flight (one per slot): later batches are scanned while an earlier batch's
+        # rows travel to the host
+        pending = []
         for b in range(nb):
             f0 = b * batch
             nf = min(batch, F - f0)
             sid = b % len(eng.slots)
+            if len(pending) == len(eng.slots):
+                finish(*pending.pop(0))
             _ts = time.perf_counter()
             eng.submit_device(sid, d1.at(f0 * n1 * 12), None if self_mode else d2.at(f0 * n2 * 12), nf,
                               accumulate=True, events=ev[b] if timed else None, pack_rows=True,
                               fold=(totals_ptr(), n_keys) if dense else None)
             if trace:
                 print("submit slot %d: %.3f ms" % (sid, (time.perf_counter() - _ts) * 1e3), file=sys.stderr)
-            if pending is not None:
-                finish(*pending)
-            pending = (sid, nf)
-        finish(*pending)
+            pending.append((sid, nf))
+        while pending:
+            finish(*pending.pop(0))
         if dense:
             for sl in eng.slots:
                 check(lib.pc_stream_sync(sl.stream))
@@ -512,6 +514,7 @@ def main():
     ap.add_argument("--frames", type=int, default=0, help="frames per GPU per step (default: per workload)")
     ap.add_argument("--batch", type=int, default=0, help="frames per launch")
     ap.add_argument("--e2e-frames", type=int, default=0)
+    ap.add_argument("--slots", type=int, default=3, help="frame batches in flight per GPU")
     ap.add_argument("--no-cpu", action="store_true", help="skip the CPU baseline leg")
     ap.add_argument("--quick", action="store_true", help="profiling runs: 1 warm-up step")
     args = ap.parse_args()

@@ -152,6 +152,102 @@ __global__ void __launch_bounds__(256) pc_fold_rows_kernel(const pc_row *rows, c
 }
 
 // ---------------------------------------------------------------------------------------------------
+// Mid-size frames (thousands of keys per frame, e.g. protein vs. solvent at 1 M atoms): still one CTA
+// per frame and a shared-memory table, but with 24-byte slots -- key, three float32 sums, packed
+// counts -- so that 8192 slots fit one SM.  float32 sums of a handful of float32 weights stay within
+// ~1e-7 relative of the float64 sum (the parity bar is 1e-5).  No first-appearance key: only used when
+// no order keys were requested.
+// ---------------------------------------------------------------------------------------------------
+template <int NT>
+__global__ void __launch_bounds__(NT) pc_accumulate_compact_kernel(const PcAccArgs a) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    const int cap = a.cap;
+    unsigned long long *keys = reinterpret_cast<unsigned long long *>(smem);
+    float *score = reinterpret_cast<float *>(keys + cap);
+    float *bb1 = score + cap;
+    float *bb2 = bb1 + cap;
+    unsigned int *cnt = reinterpret_cast<unsigned int *>(bb2 + cap);       // contacts | hbonds << 16 (saturating on emit)
+    __shared__ uint32_t wsum[32];
+    __shared__ long long s_base;
+    __shared__ unsigned int s_status;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const unsigned mask = (unsigned)cap - 1u;
+
+    for (int f = blockIdx.x; f < a.nframes; f += gridDim.x) {
+        for (int s = tid; s < cap; s += NT) { keys[s] = PC_EMPTY_KEY; score[s] = 0.f; bb1[s] = 0.f; bb2[s] = 0.f; cnt[s] = 0u; }
+        if (tid == 0) s_status = 0;
+        __syncthreads();
+        const uint32_t c0 = a.frame_cstart[f], cn = a.frame_ccount[f];
+        for (uint32_t c = tid; c < cn; c += NT) {
+            const pc_contact rec = a.contacts[c0 + c];
+            const unsigned long long key =
+                (unsigned long long)__ldg(a.lgid1 + rec.i) * a.ngroups2 + (unsigned long long)__ldg(a.lgid2 + rec.j);
+            unsigned s = pc_hash64(key) & mask;
+            int probes = 0;
+            for (;;) {
+                const unsigned long long prev = atomicCAS(&keys[s], PC_EMPTY_KEY, key);
+                if (prev == PC_EMPTY_KEY || prev == key) break;
+                s = (s + 1) & mask;
+                if (++probes >= 256) { s = 0xffffffffu; break; }
+            }
+            if (s == 0xffffffffu) { atomicOr(&s_status, (unsigned)PC_ST_TABLE_OVERFLOW); continue; }
+            atomicAdd(&score[s], rec.weight);
+            if (__ldg(a.lflag1 + rec.i) & PC_ATOM_BACKBONE) atomicAdd(&bb1[s], rec.weight);
+            if (__ldg(a.lflag2 + rec.j) & PC_ATOM_BACKBONE) atomicAdd(&bb2[s], rec.weight);
+            atomicAdd(&cnt[s], 1u);
+        }
+        __syncthreads();
+        const uint32_t h0 = a.frame_hstart[f], hn = a.frame_hcount[f];
+        for (uint32_t h = tid; h < hn; h += NT) {
+            const pc_hbond rec = a.hbonds[h0 + h];
+            const unsigned long long key =
+                (unsigned long long)__ldg(a.lgid1 + rec.i) * a.ngroups2 + (unsigned long long)__ldg(a.lgid2 + rec.j);
+            unsigned s = pc_hash64(key) & mask;
+            for (int probes = 0; probes < 256; probes++) {
+                const unsigned long long k = keys[s];
+                if (k == key) { atomicAdd(&cnt[s], 65536u); break; }
+                if (k == PC_EMPTY_KEY) break;
+                s = (s + 1) & mask;
+            }
+        }
+        __syncthreads();
+        const int ch = (cap + NT - 1) / NT;
+        const int b = min(tid * ch, cap), e = min(b + ch, cap);
+        uint32_t n = 0;
+        for (int s = b; s < e; s++) n += keys[s] != PC_EMPTY_KEY;
+        const uint32_t incl = warp_incl_scan(n, lane);
+        if (lane == 31) wsum[warp] = incl;
+        __syncthreads();
+        if (warp == 0) {
+            const uint32_t v = lane < NT / 32 ? wsum[lane] : 0;
+            const uint32_t vi = warp_incl_scan(v, lane);
+            wsum[lane] = vi - v;
+            const uint32_t total = __shfl_sync(PC_FULL_MASK, vi, 31);
+            if (lane == 0) {
+                long long base = (long long)atomicAdd(&a.counters[PC_CNT_ROWS], (unsigned long long)total);
+                if (base + total > a.cap_rows) { atomicOr(&s_status, (unsigned)PC_ST_OUT_OVERFLOW); base = -1; }
+                s_base = base;
+                a.frame_rstart[f] = (uint32_t)(base < 0 ? 0 : base);
+                a.frame_rcount[f] = base < 0 ? 0u : total;
+            }
+        }
+        __syncthreads();
+        if (s_base >= 0) {
+            long long o = s_base + wsum[warp] + incl - n;
+            for (int s = b; s < e; s++) {
+                if (keys[s] == PC_EMPTY_KEY) continue;
+                pc_row r;
+                r.key = keys[s]; r.score = (double)score[s]; r.bb1 = (double)bb1[s]; r.bb2 = (double)bb2[s];
+                r.ncontacts = cnt[s] & 0xffffu; r.nhbonds = cnt[s] >> 16; r.first = keys[s];
+                a.rows[o++] = r;
+            }
+        }
+        if (tid == 0 && s_status) atomicOr(&a.counters[PC_CNT_STATUS], (unsigned long long)s_status);
+        __syncthreads();
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------
 // Frames with more keys than a shared-memory table holds (1 M-atom systems, residue-pair maps of a
 // capsid): one open-addressing table in global memory for the whole batch, keyed by
 // frame * n_keys + key.  Inserts are 64-bit CAS + float64 atomics in L2; a key's first insertion

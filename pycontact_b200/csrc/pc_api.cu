@@ -451,6 +451,17 @@ extern "C" int pc_accumulate(pc_ctx *c, void *stream) {
         g_launches += 1;
         return PC_OK;
     }
+    // Thousands of keys per frame, no order keys: compact 24-byte slots, 8192 of them in one SM's shared memory
+    if (!c->last_order_keys && c->lim_table <= 8192) {
+        a.cap = 8192;
+        const size_t sm2 = (size_t)a.cap * 24;
+        auto kern = pc_accumulate_compact_kernel<1024>;
+        CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm2));
+        kern<<<std::min(a.nframes, c->num_sms), 1024, sm2, s>>>(a);
+        CUDA_TRY(cudaGetLastError());
+        g_launches += 1;
+        return PC_OK;
+    }
     // The table is sized from the number of contacts: the previous batch's count (scaled by the frame
     // ratio, +50%) when there is one -- a too small table sets PC_ST_TABLE_OVERFLOW and the caller
     // retries -- else the counters are read back, which synchronises the stream once.

@@ -174,8 +174,9 @@ class ContactEngine:
         if st & _lib.ST_HB_OVERFLOW:
             self.lim[1] = max(1024, 2 * (self.lim[1] or 256))
         if st & _lib.ST_TABLE_OVERFLOW:
-            # beyond 2048 slots the library switches to its global-memory table
-            self.lim[3] = max(2048, 2 * (self.lim[3] or 1024))
+            # beyond 2048 slots the library switches to compact shared-memory slots (<= 8192), then to its
+            # global-memory table
+            self.lim[3] = 16384 if (path.value == 2 or (self.lim[3] or 0) >= 8192) else max(2048, 2 * (self.lim[3] or 1024))
         if (st & _lib.ST_STAGE_OVERFLOW) or self.lim[0] > 16384 or self.lim[1] > 4096:
             # more atoms / records per frame than one CTA can stage in shared memory: use the
             # tiled large-frame path from now on
