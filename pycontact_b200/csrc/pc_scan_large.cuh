@@ -344,11 +344,17 @@ struct PcLargeOut {
     long long cap_c_frame, cap_h_frame;   // records per frame slice
 };
 
+// Hits are staged in a per-CTA queue in shared memory and appended to the frame's slice with ONE global
+// atomic per tile of 256 work items: in dense systems (a hit every ~6 candidates) a global atomic per
+// hit would make every hit an L2 round trip inside the candidate loop.
+#define PC_PAIR_Q 4096
 __global__ void __launch_bounds__(256) pc_large_pair_kernel(const PcScanArgs a, PcLargeFrame *fr, int f0,
                                                             const uint32_t *cellsA, const uint32_t *cellsB, int capCells,
                                                             const float4 *sortA, const float4 *sortB, int n1h_alloc,
                                                             int n2h_alloc, PcLargeOut o) {
     __shared__ PcLargeFrame F;
+    __shared__ uint2 q[PC_PAIR_Q];
+    __shared__ unsigned int qn, qbase;
     const int fb = blockIdx.y, f = f0 + fb;
     if (threadIdx.x == 0) F = fr[fb];
     __syncthreads();
@@ -363,51 +369,77 @@ __global__ void __launch_bounds__(256) pc_large_pair_kernel(const PcScanArgs a, 
     pc_contact *slice = a.contacts + (long long)f * o.cap_c_frame;
     const int nx = F.nx, ny = F.ny, nz = F.nz;
     const long long items = 3ll * F.nA_in;
-    for (long long w = blockIdx.x * (long long)blockDim.x + threadIdx.x; w < items; w += (long long)gridDim.x * blockDim.x) {
-        const int ia = (int)(w / 3);
-        const float4 pa = __ldg(sA + ia);
-        const int cx = (int)((pa.x - F.lo[0]) * F.inv), cy = (int)((pa.y - F.lo[1]) * F.inv),
-                  cz = (int)((pa.z - F.lo[2]) * F.inv);
-        const int z = cz + (int)(w - 3ll * ia) - 1;
-        if (z < 0 || z >= nz) continue;
-        const int xlo = max(cx - 1, 0), xhi = min(cx + 1, nx - 1);
-        // the bounds of the layer's three B runs first (six independent loads in flight)
-        int b0[3], b1[3];
+    for (long long tile = blockIdx.x * (long long)blockDim.x; tile < items; tile += (long long)gridDim.x * blockDim.x) {
+        if (threadIdx.x == 0) qn = 0;
+        __syncthreads();
+        const long long w = tile + threadIdx.x;
+        if (w < items) {
+            const int ia = (int)(w / 3);
+            const float4 pa = __ldg(sA + ia);
+            const int cx = (int)((pa.x - F.lo[0]) * F.inv), cy = (int)((pa.y - F.lo[1]) * F.inv),
+                      cz = (int)((pa.z - F.lo[2]) * F.inv);
+            const int z = cz + (int)(w - 3ll * ia) - 1;
+            if (z >= 0 && z < nz) {
+                const int xlo = max(cx - 1, 0), xhi = min(cx + 1, nx - 1);
+                // the bounds of the layer's three B runs first (six independent loads in flight)
+                int b0[3], b1[3];
 #pragma unroll
-        for (int dy = 0; dy < 3; dy++) {
-            const int y = cy + dy - 1;
-            if (y < 0 || y >= ny) { b0[dy] = 0; b1[dy] = 0; continue; }
-            const int row = (z * ny + y) * nx;
-            b0[dy] = (row + xlo) ? (int)__ldg(cB + row + xlo - 1) : 0;
-            b1[dy] = (int)__ldg(cB + row + xhi);
-        }
-        if (b0[0] == b1[0] && b0[1] == b1[1] && b0[2] == b1[2]) continue;
-        int ares = 0, aseg = 0;
-        if (self) {
-            const int li = PC_W_INDEX(__float_as_uint(pa.w));
-            ares = __ldg(a.t.lres1 + li); aseg = __ldg(a.t.lseg1 + li);
-        }
-#pragma unroll
-        for (int dy = 0; dy < 3; dy++) {
-            evals += (unsigned)(b1[dy] - b0[dy]);
-            for (int j = b0[dy]; j < b1[dy]; j++) {
-                const float4 pb = __ldg(sB + j);
-                if (!pair_within(pa.x, pa.y, pa.z, pb.x, pb.y, pb.z, sqdist, sqdist_hi)) continue;
-                if (self) {
-                    // (resid1 - resid2) < 5 and same segment -> dropped (core/multi_trajectory.py:93-95)
-                    const int lj = PC_W_INDEX(__float_as_uint(pb.w));
-                    if ((ares - __ldg(a.t.lres1 + lj)) < 5 && aseg == __ldg(a.t.lseg1 + lj)) continue;
+                for (int dy = 0; dy < 3; dy++) {
+                    const int y = cy + dy - 1;
+                    if (y < 0 || y >= ny) { b0[dy] = 0; b1[dy] = 0; continue; }
+                    const int row = (z * ny + y) * nx;
+                    b0[dy] = (row + xlo) ? (int)__ldg(cB + row + xlo - 1) : 0;
+                    b1[dy] = (int)__ldg(cB + row + xhi);
                 }
-                const unsigned slot = atomicAdd(&fr[fb].ccursor, 1u);
-                if ((long long)slot < o.cap_c_frame) {
-                    pc_contact rec;
-                    rec.i = ia; rec.j = j; rec.distance = 0.f; rec.weight = 0.f;
-                    slice[slot] = rec;
-                } else {
-                    status |= (unsigned)PC_ST_OUT_OVERFLOW;
+                int ares = 0, aseg = 0;
+                if (self) {
+                    const int li = PC_W_INDEX(__float_as_uint(pa.w));
+                    ares = __ldg(a.t.lres1 + li); aseg = __ldg(a.t.lseg1 + li);
+                }
+#pragma unroll
+                for (int dy = 0; dy < 3; dy++) {
+                    evals += (unsigned)(b1[dy] - b0[dy]);
+                    for (int j = b0[dy]; j < b1[dy]; j++) {
+                        const float4 pb = __ldg(sB + j);
+                        if (!pair_within(pa.x, pa.y, pa.z, pb.x, pb.y, pb.z, sqdist, sqdist_hi)) continue;
+                        if (self) {
+                            // (resid1 - resid2) < 5 and same segment -> dropped (core/multi_trajectory.py:93-95)
+                            const int lj = PC_W_INDEX(__float_as_uint(pb.w));
+                            if ((ares - __ldg(a.t.lres1 + lj)) < 5 && aseg == __ldg(a.t.lseg1 + lj)) continue;
+                        }
+                        const unsigned p = atomicAdd(&qn, 1u);
+                        if (p < PC_PAIR_Q) {
+                            q[p] = make_uint2((unsigned)ia, (unsigned)j);
+                        } else {
+                            // queue full (very long cutoffs): this hit goes straight to the slice
+                            const unsigned slot = atomicAdd(&fr[fb].ccursor, 1u);
+                            if ((long long)slot < o.cap_c_frame) {
+                                pc_contact rec;
+                                rec.i = ia; rec.j = j; rec.distance = 0.f; rec.weight = 0.f;
+                                slice[slot] = rec;
+                            } else {
+                                status |= (unsigned)PC_ST_OUT_OVERFLOW;
+                            }
+                        }
+                    }
                 }
             }
         }
+        __syncthreads();
+        const unsigned n = min(qn, (unsigned)PC_PAIR_Q);
+        if (threadIdx.x == 0 && n) qbase = atomicAdd(&fr[fb].ccursor, n);
+        __syncthreads();
+        for (unsigned k = threadIdx.x; k < n; k += blockDim.x) {
+            const long long slot = (long long)qbase + k;
+            if (slot < o.cap_c_frame) {
+                pc_contact rec;
+                rec.i = (int)q[k].x; rec.j = (int)q[k].y; rec.distance = 0.f; rec.weight = 0.f;
+                slice[slot] = rec;
+            } else {
+                status |= (unsigned)PC_ST_OUT_OVERFLOW;
+            }
+        }
+        __syncthreads();
     }
 #pragma unroll
     for (int s = 16; s > 0; s >>= 1) evals += __shfl_xor_sync(PC_FULL_MASK, evals, s);
