@@ -399,27 +399,45 @@ __global__ void __launch_bounds__(256) pc_large_pair_kernel(const PcScanArgs a, 
 #pragma unroll
                 for (int dy = 0; dy < 3; dy++) {
                     evals += (unsigned)(b1[dy] - b0[dy]);
-                    for (int j = b0[dy]; j < b1[dy]; j++) {
-                        const float4 pb = __ldg(sB + j);
-                        if (!pair_within(pa.x, pa.y, pa.z, pb.x, pb.y, pb.z, sqdist, sqdist_hi)) continue;
-                        if (self) {
-                            // (resid1 - resid2) < 5 and same segment -> dropped (core/multi_trajectory.py:93-95)
-                            const int lj = PC_W_INDEX(__float_as_uint(pb.w));
-                            if ((ares - __ldg(a.t.lres1 + lj)) < 5 && aseg == __ldg(a.t.lseg1 + lj)) continue;
+                    // 32 candidates at a time into a hit mask: the candidate loop has no side effects (the
+                    // compiler can batch its loads), and the queue is touched once per chunk, not per hit
+                    for (int jb = b0[dy]; jb < b1[dy]; jb += 32) {
+                        const int cnt = min(32, b1[dy] - jb);
+                        unsigned m = 0;
+#pragma unroll 4
+                        for (int k = 0; k < cnt; k++) {
+                            const float4 pb = __ldg(sB + jb + k);
+                            m |= (unsigned)pair_within(pa.x, pa.y, pa.z, pb.x, pb.y, pb.z, sqdist, sqdist_hi) << k;
                         }
-                        const unsigned p = atomicAdd(&qn, 1u);
-                        if (p < PC_PAIR_Q) {
-                            q[p] = make_uint2((unsigned)ia, (unsigned)j);
-                        } else {
-                            // queue full (very long cutoffs): this hit goes straight to the slice
-                            const unsigned slot = atomicAdd(&fr[fb].ccursor, 1u);
-                            if ((long long)slot < o.cap_c_frame) {
-                                pc_contact rec;
-                                rec.i = ia; rec.j = j; rec.distance = 0.f; rec.weight = 0.f;
-                                slice[slot] = rec;
-                            } else {
-                                status |= (unsigned)PC_ST_OUT_OVERFLOW;
+                        if (self && m) {
+                            // (resid1 - resid2) < 5 and same segment -> dropped (core/multi_trajectory.py:93-95)
+                            unsigned t = m;
+                            while (t) {
+                                const int k = __ffs(t) - 1;
+                                t &= t - 1;
+                                const int lj = PC_W_INDEX(__float_as_uint(__ldg(sB + jb + k).w));
+                                if ((ares - __ldg(a.t.lres1 + lj)) < 5 && aseg == __ldg(a.t.lseg1 + lj)) m &= ~(1u << k);
                             }
+                        }
+                        if (!m) continue;
+                        unsigned p = atomicAdd(&qn, (unsigned)__popc(m));
+                        while (m) {
+                            const int j = jb + __ffs(m) - 1;
+                            m &= m - 1;
+                            if (p < PC_PAIR_Q) {
+                                q[p] = make_uint2((unsigned)ia, (unsigned)j);
+                            } else {
+                                // queue full (very long cutoffs): this hit goes straight to the slice
+                                const unsigned slot = atomicAdd(&fr[fb].ccursor, 1u);
+                                if ((long long)slot < o.cap_c_frame) {
+                                    pc_contact rec;
+                                    rec.i = ia; rec.j = j; rec.distance = 0.f; rec.weight = 0.f;
+                                    slice[slot] = rec;
+                                } else {
+                                    status |= (unsigned)PC_ST_OUT_OVERFLOW;
+                                }
+                            }
+                            p++;
                         }
                     }
                 }
