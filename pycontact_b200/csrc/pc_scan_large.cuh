@@ -374,11 +374,13 @@ __global__ void __launch_bounds__(256) pc_large_pair_kernel(const PcScanArgs a, 
         __syncthreads();
         const long long w = tile + threadIdx.x;
         if (w < items) {
-            const int ia = (int)(w / 3);
+            // layer-major items: a warp holds 32 neighbouring atoms (A is cell-sorted) on the same layer,
+            // so its lanes walk the same or adjacent B runs (few distinct cache lines per load)
+            const int layer = (int)(w / F.nA_in), ia = (int)(w - (long long)layer * F.nA_in);
             const float4 pa = __ldg(sA + ia);
             const int cx = (int)((pa.x - F.lo[0]) * F.inv), cy = (int)((pa.y - F.lo[1]) * F.inv),
                       cz = (int)((pa.z - F.lo[2]) * F.inv);
-            const int z = cz + (int)(w - 3ll * ia) - 1;
+            const int z = cz + layer - 1;
             if (z >= 0 && z < nz) {
                 const int xlo = max(cx - 1, 0), xhi = min(cx + 1, nx - 1);
                 // the bounds of the layer's three B runs first (six independent loads in flight)
