@@ -296,16 +296,33 @@ __global__ void __launch_bounds__(NT, NT >= 1024 ? 1 : 2) pc_scan_small_kernel(c
                         const int row = (z * ny + y) * nx;
                         const int b0 = (row + xlo) ? (int)cellB[row + xlo - 1] : 0, b1 = (int)cellB[row + xhi];
                         evals += (unsigned)(b1 - b0);
-                        for (int j = b0; j < b1; j++) {
-                            const float4 pb = sortB[j];
-                            if (!pair_within(pa.x, pa.y, pa.z, pb.x, pb.y, pb.z, sqdist, sqdist_hi)) continue;
-                            if (self) {
-                                // (resid1 - resid2) < 5 and same segment -> dropped (core/multi_trajectory.py:93-95)
-                                const int lj = PC_W_INDEX(__float_as_uint(pb.w));
-                                if ((ares - __ldg(a.t.lres1 + lj)) < 5 && aseg == __ldg(a.t.lseg1 + lj)) continue;
+                        // 32 candidates at a time into a hit mask; the queue is touched once per chunk
+                        for (int jb = b0; jb < b1; jb += 32) {
+                            const int cnt = min(32, b1 - jb);
+                            unsigned m = 0;
+#pragma unroll 4
+                            for (int k = 0; k < cnt; k++) {
+                                const float4 pb = sortB[jb + k];
+                                m |= (unsigned)pair_within(pa.x, pa.y, pa.z, pb.x, pb.y, pb.z, sqdist, sqdist_hi) << k;
                             }
-                            const unsigned p = atomicAdd(&s_nhits, 1u);
-                            if (p < (unsigned)a.capHits) hits[p] = ((unsigned)ia << 16) | (unsigned)j;
+                            if (self && m) {
+                                // (resid1 - resid2) < 5 and same segment -> dropped (core/multi_trajectory.py:93-95)
+                                unsigned t = m;
+                                while (t) {
+                                    const int k = __ffs(t) - 1;
+                                    t &= t - 1;
+                                    const int lj = PC_W_INDEX(__float_as_uint(sortB[jb + k].w));
+                                    if ((ares - __ldg(a.t.lres1 + lj)) < 5 && aseg == __ldg(a.t.lseg1 + lj)) m &= ~(1u << k);
+                                }
+                            }
+                            if (!m) continue;
+                            unsigned p = atomicAdd(&s_nhits, (unsigned)__popc(m));
+                            while (m) {
+                                const int j = jb + __ffs(m) - 1;
+                                m &= m - 1;
+                                if (p < (unsigned)a.capHits) hits[p] = ((unsigned)ia << 16) | (unsigned)j;
+                                p++;
+                            }
                         }
                     }
                 }
