@@ -244,6 +244,8 @@ def run_gpu(args):
 
     eng = ContactEngine(s1, s2, 5.0, 2.5, 120, device=local, slots=args.slots)
     eng.set_maps(gm1.gid, gm2.gid, gm2.n_groups)
+    if gm1.n_groups * gm2.n_groups <= (1 << 20):
+        eng.set_pack_format(12)         # bb sums travel in the dense aggregated table instead of per (frame, key) cell
     in_bytes_frame = (n1 + (0 if self_mode else n2)) * 12
     batch = args.batch or int(max(1, min(F, 2048, (2 << 30) // in_bytes_frame)))
     nb = (F + batch - 1) // batch

@@ -74,6 +74,14 @@ typedef struct {
     uint16_t ncontacts, nhbonds;
 } pc_row_packed;
 
+/* 12-byte variant for key spaces below 2^32 (residue-pair maps of all but the largest systems) when the
+ * caller keeps the per-key bb sums elsewhere (pc_fold_rows' aggregated table): key, score, counts. */
+typedef struct {
+    uint32_t key;
+    float    score;
+    uint16_t ncontacts, nhbonds;
+} pc_row_slim;
+
 typedef struct pc_ctx pc_ctx;
 
 const char *pc_last_error(void);
@@ -187,6 +195,7 @@ int pc_fetch(pc_ctx *ctx, void *stream,
  * transfer format of throughput runs, half the bytes of pc_row.  h_rows needs room for the n_rows that
  * pc_batch_totals reported.  Asynchronous on `stream`. */
 int pc_pack_rows(pc_ctx *ctx, void *stream);     /* the packing kernel alone (enqueue it right behind pc_accumulate) */
+int pc_set_pack_format(pc_ctx *ctx, int bytes_per_row);   /* 24 = pc_row_packed (default), 12 = pc_row_slim */
 int pc_fetch_packed_rows(pc_ctx *ctx, void *stream, pc_row_packed *h_rows,
                          uint32_t *h_frame_rstart, uint32_t *h_frame_rcount);
 

@@ -400,3 +400,15 @@ __global__ void __launch_bounds__(256) pc_pack_rows_kernel(const pc_row *rows, c
         out[r] = p;
     }
 }
+
+__global__ void __launch_bounds__(256) pc_pack_rows_slim_kernel(const pc_row *rows, const unsigned long long *counters,
+                                                                long long cap_rows, pc_row_slim *out) {
+    const long long n = min((long long)counters[PC_CNT_ROWS], cap_rows);
+    for (long long r = blockIdx.x * (long long)blockDim.x + threadIdx.x; r < n; r += (long long)gridDim.x * blockDim.x) {
+        const pc_row v = rows[r];
+        pc_row_slim p;
+        p.key = (uint32_t)v.key; p.score = (float)v.score;
+        p.ncontacts = (uint16_t)min(v.ncontacts, 65535u); p.nhbonds = (uint16_t)min(v.nhbonds, 65535u);
+        out[r] = p;
+    }
+}

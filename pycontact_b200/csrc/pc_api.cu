@@ -88,6 +88,7 @@ struct pc_ctx {
     int last_path = 0;                // 1 = small, 2 = large
     bool gacc_used = false, gacc_retry = false;
     bool packed_valid = false;        // rows_packed holds the last accumulated batch
+    int pack_bytes = 24;              // transfer format of pc_pack_rows: 24 (pc_row_packed) or 12 (pc_row_slim)
     void *probe[2] = {nullptr, nullptr};   // optional events around the large path's dominant kernel (pc_set_probe)
     DevBuf<int> retry;                // [0] count, [4..] frames the fast small-frame plan handed to the full plan
     int small_ctas = 0;               // small-frame kernel plans: 0 = fast + full (automatic), 1 = full only, 2 = fast only
@@ -699,10 +700,23 @@ extern "C" int pc_pack_rows(pc_ctx *c, void *stream) {
     if (!c) return fail(PC_ERR_INVALID, "pc_pack_rows: ctx is NULL");
     CUDA_TRY(cudaSetDevice(c->device));
     CUDA_TRY(c->rows_packed.ensure((size_t)c->cap_rows));
-    pc_pack_rows_kernel<<<2 * c->num_sms, 256, 0, (cudaStream_t)stream>>>(c->rows.p, c->counters.p, c->cap_rows, c->rows_packed.p);
+    if (c->pack_bytes == 12) {
+        if (c->ngroups1 * c->ngroups2 > 0xffffffffull) return fail(PC_ERR_INVALID, "pc_pack_rows: key space exceeds 32 bits");
+        pc_pack_rows_slim_kernel<<<2 * c->num_sms, 256, 0, (cudaStream_t)stream>>>(
+            c->rows.p, c->counters.p, c->cap_rows, reinterpret_cast<pc_row_slim *>(c->rows_packed.p));
+    } else {
+        pc_pack_rows_kernel<<<2 * c->num_sms, 256, 0, (cudaStream_t)stream>>>(c->rows.p, c->counters.p, c->cap_rows, c->rows_packed.p);
+    }
     CUDA_TRY(cudaGetLastError());
     g_launches += 1;
     c->packed_valid = true;
+    return PC_OK;
+}
+
+extern "C" int pc_set_pack_format(pc_ctx *c, int bytes_per_row) {
+    if (!c || (bytes_per_row != 24 && bytes_per_row != 12)) return fail(PC_ERR_INVALID, "pc_set_pack_format: 24 or 12");
+    c->pack_bytes = bytes_per_row;
+    c->packed_valid = false;
     return PC_OK;
 }
 
@@ -712,7 +726,7 @@ extern "C" int pc_fetch_packed_rows(pc_ctx *c, void *stream, pc_row_packed *h_ro
     cudaStream_t s = (cudaStream_t)stream;
     const size_t nr = std::min<unsigned long long>(c->h_counters[PC_CNT_ROWS], c->cap_rows);
     if (!c->packed_valid) { int r = pc_pack_rows(c, stream); if (r != PC_OK) return r; }
-    if (nr) CUDA_TRY(cudaMemcpyAsync(h_rows, c->rows_packed.p, nr * sizeof(pc_row_packed), cudaMemcpyDeviceToHost, s));
+    if (nr) CUDA_TRY(cudaMemcpyAsync(h_rows, c->rows_packed.p, nr * (size_t)c->pack_bytes, cudaMemcpyDeviceToHost, s));
     if (rs) CUDA_TRY(cudaMemcpyAsync(rs, meta(c, 4), (size_t)c->last_nframes * sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
     if (rc) CUDA_TRY(cudaMemcpyAsync(rc, meta(c, 5), (size_t)c->last_nframes * sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
     return PC_OK;

@@ -120,6 +120,7 @@ class ContactEngine:
         self.lim = [0, 0, 0, 0]          # hits/frame, hbonds/frame, cells, table slots (0 = automatic)
         self.launches = 0
         self.forced_path = 0
+        self.pack_bytes = 24
 
     # ------------------------------------------------------------------------------------------
     def close(self):
@@ -153,6 +154,13 @@ class ContactEngine:
         self.lim = [int(hits), int(hbonds), int(cells), int(table)]
         for s in self.slots:
             check(self.lib.pc_set_limits(s.ctx, *self.lim))
+
+    def set_pack_format(self, bytes_per_row: int):
+        """Transfer format of packed rows: 24 (pc_row_packed) or 12 (pc_row_slim: 32-bit key, score, counts;
+        the per-key bb sums then come from the aggregated table of pc_fold_rows)."""
+        for s in self.slots:
+            check(self.lib.pc_set_pack_format(s.ctx, int(bytes_per_row)))
+        self.pack_bytes = int(bytes_per_row)
 
     def set_path(self, path: int):
         """0 = automatic, 1 = small-frame kernel, 2 = large-frame path (tests cover both)."""
@@ -405,7 +413,10 @@ class ContactEngine:
         n = min(int(nr.value), slot.cap[2])
         meta = slot.out("meta", 6 * nf, np.uint32)
         if packed:
-            rows = slot.out("rows_packed", n, _lib.packed_row_dtype)[:n]
+            if self.pack_bytes == 12:
+                rows = slot.out("rows_slim", n, _lib.slim_row_dtype)[:n]
+            else:
+                rows = slot.out("rows_packed", n, _lib.packed_row_dtype)[:n]
             check(lib.pc_fetch_packed_rows(slot.ctx, slot.stream, ptr(rows), ptr(meta[4 * nf:5 * nf]),
                                            ptr(meta[5 * nf:6 * nf])))
         else:

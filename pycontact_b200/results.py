@@ -200,7 +200,8 @@ class AccumulationTable:
         p = rows[src]
         full = np.zeros(p.size, row_dtype)
         for k in ("key", "score", "bb1", "bb2", "ncontacts", "nhbonds"):
-            full[k] = p[k]
+            if k in p.dtype.names:          # the 12-byte slim rows carry no per-cell bb sums
+                full[k] = p[k]
         full["first"] = p["key"]
         self._rows.append(full)
         self._frames.append(np.repeat(np.arange(cnt.size, dtype=np.int64) + frame_pos0, cnt))

@@ -360,6 +360,10 @@ def test_packed_rows_equal_full_rows():
         eng.scan_device(d1.ptr, d2.ptr, 6, accumulate=True)
         full, rs, rc = (a.copy() for a in eng.fetch_rows(0))
         packed, ps, pc = (a.copy() for a in eng.fetch_rows(0, packed=True))
+        eng.set_pack_format(12)
+        slim, ss, sc = (a.copy() for a in eng.fetch_rows(0, packed=True))
+    assert slim.dtype.itemsize == 12 and np.array_equal(slim["key"], full["key"].astype(np.uint32))
+    assert np.array_equal(slim["score"], packed["score"]) and np.array_equal(slim["nhbonds"], packed["nhbonds"])
     assert full.size == packed.size > 0 and np.array_equal(rs[:6], ps[:6]) and np.array_equal(rc[:6], pc[:6])
     assert np.array_equal(full["key"], packed["key"])
     np.testing.assert_allclose(packed["score"], full["score"], rtol=2e-7)
