@@ -244,13 +244,17 @@ def run_gpu(args):
 
     eng = ContactEngine(s1, s2, 5.0, 2.5, 120, device=local, slots=args.slots)
     eng.set_maps(gm1.gid, gm2.gid, gm2.n_groups)
-    if gm1.n_groups * gm2.n_groups <= (1 << 20):
-        eng.set_pack_format(12)         # bb sums travel in the dense aggregated table instead of per (frame, key) cell
+    n_keys_all = gm1.n_groups * gm2.n_groups
+    if n_keys_all <= (1 << 20) or (args.sparse_fold and n_keys_all < (1 << 32)):
+        # bb sums travel in the time-aggregated table (dense or sparse) instead of per (frame, key) cell
+        eng.set_pack_format(12)
     in_bytes_frame = (n1 + (0 if self_mode else n2)) * 12
     batch = args.batch or int(max(1, min(F, 2048, (2 << 30) // in_bytes_frame)))
     nb = (F + batch - 1) // batch
     n_keys = gm1.n_groups * gm2.n_groups
     dense = n_keys <= (1 << 20)          # aggregated maps as a dense [n_keys][4] table (32 MB at most)
+    sparse = args.sparse_fold and (not dense) and n_keys < (1 << 32)   # opt-in: a hash table per slot, merged per step
+    sparse_entries = 1 << 22
     totals = DeviceBuffer(max(1, n_keys if dense else 1) * 32, local)
     totals_t = None
     if world > 1 and dense:
@@ -275,6 +279,8 @@ def run_gpu(args):
                 torch.cuda.current_stream().synchronize()
             else:
                 check(lib.pc_memset(local, totals.ptr, 0, n_keys * 32, stream))
+        if sparse:
+            eng.fold_sparse_init(sparse_entries)
         trace = bool(os.environ.get("PC_TRACE"))
 
         def finish(sid, nf):
@@ -301,7 +307,7 @@ def run_gpu(args):
             _ts = time.perf_counter()
             eng.submit_device(sid, d1.at(f0 * n1 * 12), None if self_mode else d2.at(f0 * n2 * 12), nf,
                               accumulate=True, events=ev[b] if timed else None, pack_rows=True,
-                              fold=(totals_ptr(), n_keys) if dense else None)
+                              fold=(totals_ptr(), n_keys) if dense else ("sparse" if sparse else None))
             if trace:
                 print("submit slot %d: %.3f ms" % (sid, (time.perf_counter() - _ts) * 1e3), file=sys.stderr)
             pending.append((sid, nf))
@@ -319,6 +325,27 @@ def run_gpu(args):
                 check(lib.pc_memcpy(local, host.ctypes.data, src, host.nbytes, 2, None))
                 check(lib.pc_device_sync(local))
                 d_rows += host.nbytes
+        if sparse:
+            ent = eng.fold_sparse_fetch()                  # per-key sums of this rank's frames
+            d_rows += ent.nbytes
+            if dist is not None:                           # ranks hold disjoint frames: sum per key on rank 0
+                cnt = torch.tensor([ent.size], device="cuda")
+                dist.all_reduce(cnt, op=dist.ReduceOp.MAX)
+                pad = np.zeros(int(cnt.item()), ent.dtype)
+                pad["key"] = np.uint64(0xffffffffffffffff)
+                pad[:ent.size] = ent
+                mine = torch.from_numpy(pad.view(np.uint8).copy()).cuda()
+                allv = [torch.empty_like(mine) for _ in range(world)] if rank == 0 else None
+                dist.gather(mine, allv, dst=0)
+                if rank == 0:
+                    merged = np.concatenate([t.cpu().numpy().view(ent.dtype) for t in allv])
+                    merged = merged[merged["key"] != np.uint64(0xffffffffffffffff)]
+                    keys, inv = np.unique(merged["key"], return_inverse=True)
+                    ent = np.zeros(keys.size, ent.dtype)
+                    ent["key"] = keys
+                    for fld in ("score", "bb1", "bb2", "hbframes"):
+                        ent[fld] = np.bincount(inv, weights=merged[fld], minlength=keys.size)
+            device_step.last_entries = int(ent.size)
         return tot, d_rows
 
 
@@ -517,6 +544,8 @@ def main():
     ap.add_argument("--batch", type=int, default=0, help="frames per launch")
     ap.add_argument("--e2e-frames", type=int, default=0)
     ap.add_argument("--slots", type=int, default=3, help="frame batches in flight per GPU")
+    ap.add_argument("--sparse-fold", action="store_true",
+                    help="large key spaces: 12-byte rows + on-device sparse aggregation (less D2H, more device work)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the CPU baseline leg")
     ap.add_argument("--quick", action="store_true", help="profiling runs: 1 warm-up step")
     args = ap.parse_args()

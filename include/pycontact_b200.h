@@ -146,6 +146,17 @@ int pc_accumulate(pc_ctx *ctx, void *stream);
  * hbond_percentage, core/Biochemistry.py:150-186, core/ContactAnalyzer.py:588-591). */
 int pc_fold_rows(pc_ctx *ctx, double *d_totals, int64_t n_keys, void *stream);
 
+/* The same aggregation for key spaces too large for a dense table: a per-context open-addressing table
+ * (key -> sum score, sum bb1, sum bb2, frames with an H-bond) that lives across batches.
+ * pc_fold_sparse_init sizes it (entries, rounded up to a power of two) and clears it;
+ * pc_fold_rows_sparse adds the last accumulated batch; pc_fold_sparse_fetch compacts the occupied entries
+ * on the device, copies them to h_entries (room for max_entries) and reports their number -- it
+ * synchronises the stream and fails with PC_ERR_CAPACITY when the table overflowed. */
+typedef struct { uint64_t key; double score, bb1, bb2, hbframes; } pc_fold_entry;
+int pc_fold_sparse_init(pc_ctx *ctx, int64_t entries, void *stream);
+int pc_fold_rows_sparse(pc_ctx *ctx, void *stream);
+int pc_fold_sparse_fetch(pc_ctx *ctx, void *stream, pc_fold_entry *h_entries, int64_t max_entries, int64_t *n_entries);
+
 /* Analyzer.runContactAnalysis(map1, map2) may be called again with other maps on the SAME
  * contactResults (core/ContactAnalyzer.py:64-70): loads previously fetched records of `nframes`
  * frames back into the context so that pc_accumulate can regroup them.  Synchronous. */

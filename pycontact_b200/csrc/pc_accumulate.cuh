@@ -412,3 +412,53 @@ __global__ void __launch_bounds__(256) pc_pack_rows_slim_kernel(const pc_row *ro
         out[r] = p;
     }
 }
+
+// ---- sparse time-aggregated maps (key spaces too large for pc_fold_rows' dense table) ----------------------
+__global__ void __launch_bounds__(256) pc_fold_sparse_clear_kernel(pc_fold_entry *tab, unsigned long long cap, unsigned long long *meta) {
+    for (unsigned long long s = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x; s < cap;
+         s += (unsigned long long)gridDim.x * blockDim.x) {
+        pc_fold_entry e;
+        e.key = PC_EMPTY_KEY; e.score = 0.0; e.bb1 = 0.0; e.bb2 = 0.0; e.hbframes = 0.0;
+        tab[s] = e;
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) { meta[0] = 0; meta[1] = 0; }      // [0] overflow flag, [1] compaction cursor
+}
+
+__global__ void __launch_bounds__(256) pc_fold_sparse_kernel(const pc_row *rows, const unsigned long long *counters,
+                                                             long long cap_rows, pc_fold_entry *tab, unsigned long long cap,
+                                                             unsigned long long *meta) {
+    if (counters[PC_CNT_STATUS] & (PC_ST_HITS_OVERFLOW | PC_ST_HB_OVERFLOW | PC_ST_OUT_OVERFLOW | PC_ST_TABLE_OVERFLOW |
+                                   PC_ST_STAGE_OVERFLOW)) return;
+    const long long n = min((long long)counters[PC_CNT_ROWS], cap_rows);
+    const unsigned long long mask = cap - 1ull;
+    for (long long r = blockIdx.x * (long long)blockDim.x + threadIdx.x; r < n; r += (long long)gridDim.x * blockDim.x) {
+        const pc_row row = rows[r];
+        unsigned long long h = row.key;
+        h ^= h >> 33; h *= 0xff51afd7ed558ccdull; h ^= h >> 33; h *= 0xc4ceb9fe1a85ec53ull; h ^= h >> 33;
+        unsigned long long s = h & mask;
+        bool found = false;
+        for (int probes = 0; probes < 512; probes++) {
+            const unsigned long long prev = atomicCAS(reinterpret_cast<unsigned long long *>(&tab[s].key), PC_EMPTY_KEY,
+                                                       (unsigned long long)row.key);
+            if (prev == PC_EMPTY_KEY || prev == row.key) { found = true; break; }
+            s = (s + 1) & mask;
+        }
+        if (!found) { meta[0] = 1ull; continue; }
+        atomicAdd(&tab[s].score, row.score);
+        if (row.bb1 != 0.0) atomicAdd(&tab[s].bb1, row.bb1);
+        if (row.bb2 != 0.0) atomicAdd(&tab[s].bb2, row.bb2);
+        if (row.nhbonds) atomicAdd(&tab[s].hbframes, 1.0);
+    }
+}
+
+__global__ void __launch_bounds__(256) pc_fold_sparse_compact_kernel(const pc_fold_entry *tab, unsigned long long cap,
+                                                                     pc_fold_entry *out, unsigned long long max_out,
+                                                                     unsigned long long *meta) {
+    for (unsigned long long s = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x; s < cap;
+         s += (unsigned long long)gridDim.x * blockDim.x) {
+        const pc_fold_entry e = tab[s];
+        if (e.key == PC_EMPTY_KEY) continue;
+        const unsigned long long p = atomicAdd(&meta[1], 1ull);
+        if (p < max_out) out[p] = e;
+    }
+}

@@ -77,6 +77,10 @@ struct pc_ctx {
     DevBuf<float> stage1, stage2;     // H2D staging for pc_scan_host
     PcLargeWork large;                // work buffers of the large-frame path
     DevBuf<PcGlobalEntry> gacc_tab;        // global accumulation table
+    DevBuf<pc_fold_entry> fold_tab, fold_out;      // sparse time-aggregated maps (pc_fold_rows_sparse)
+    DevBuf<unsigned long long> fold_meta;
+    unsigned long long fold_cap = 0;
+    unsigned long long *h_fold_meta = nullptr;
     DevBuf<uint32_t> gacc_cursor, gacc_fresh;
     DevBuf<unsigned long long> gacc_nfresh;
     unsigned long long gacc_hint = 0;      // contacts of the previous accumulated batch (table sizing without a sync)
@@ -132,6 +136,7 @@ extern "C" void pc_destroy(pc_ctx *c) {
     if (!c) return;
     cudaSetDevice(c->device);
     if (c->h_counters) cudaFreeHost(c->h_counters);
+    if (c->h_fold_meta) cudaFreeHost(c->h_fold_meta);
     delete c;
 }
 
@@ -520,6 +525,55 @@ extern "C" int pc_fold_rows(pc_ctx *c, double *d_totals, int64_t n_keys, void *s
                                                                          (unsigned long long)n_keys);
     CUDA_TRY(cudaGetLastError());
     g_launches += 1;
+    return PC_OK;
+}
+
+extern "C" int pc_fold_sparse_init(pc_ctx *c, int64_t entries, void *stream) {
+    if (!c || entries <= 0) return fail(PC_ERR_INVALID, "pc_fold_sparse_init: bad arguments");
+    CUDA_TRY(cudaSetDevice(c->device));
+    unsigned long long cap = 1024;
+    while (cap < (unsigned long long)entries) cap <<= 1;
+    CUDA_TRY(c->fold_tab.ensure(cap));
+    CUDA_TRY(c->fold_meta.ensure(2));
+    if (!c->h_fold_meta) CUDA_TRY(cudaHostAlloc(&c->h_fold_meta, 2 * sizeof(unsigned long long), cudaHostAllocDefault));
+    c->fold_cap = cap;
+    pc_fold_sparse_clear_kernel<<<4 * c->num_sms, 256, 0, (cudaStream_t)stream>>>(c->fold_tab.p, cap, c->fold_meta.p);
+    CUDA_TRY(cudaGetLastError());
+    g_launches += 1;
+    return PC_OK;
+}
+
+extern "C" int pc_fold_rows_sparse(pc_ctx *c, void *stream) {
+    if (!c || !c->have_maps || !c->fold_cap) return fail(PC_ERR_INVALID, "pc_fold_rows_sparse: call pc_fold_sparse_init first");
+    CUDA_TRY(cudaSetDevice(c->device));
+    pc_fold_sparse_kernel<<<2 * c->num_sms, 256, 0, (cudaStream_t)stream>>>(c->rows.p, c->counters.p, c->cap_rows, c->fold_tab.p,
+                                                                           c->fold_cap, c->fold_meta.p);
+    CUDA_TRY(cudaGetLastError());
+    g_launches += 1;
+    return PC_OK;
+}
+
+extern "C" int pc_fold_sparse_fetch(pc_ctx *c, void *stream, pc_fold_entry *h_entries, int64_t max_entries, int64_t *n_entries) {
+    if (!c || !c->fold_cap || !h_entries || max_entries <= 0 || !n_entries)
+        return fail(PC_ERR_INVALID, "pc_fold_sparse_fetch: bad arguments");
+    CUDA_TRY(cudaSetDevice(c->device));
+    cudaStream_t s = (cudaStream_t)stream;
+    CUDA_TRY(c->fold_out.ensure((size_t)max_entries));
+    CUDA_TRY(cudaMemsetAsync(c->fold_meta.p + 1, 0, sizeof(unsigned long long), s));
+    pc_fold_sparse_compact_kernel<<<4 * c->num_sms, 256, 0, s>>>(c->fold_tab.p, c->fold_cap, c->fold_out.p,
+                                                                 (unsigned long long)max_entries, c->fold_meta.p);
+    CUDA_TRY(cudaGetLastError());
+    g_launches += 1;
+    CUDA_TRY(cudaMemcpyAsync(c->h_fold_meta, c->fold_meta.p, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(cudaStreamSynchronize(s));
+    if (c->h_fold_meta[0]) return fail(PC_ERR_CAPACITY, "pc_fold_sparse_fetch: the aggregation table overflowed; re-init it larger");
+    if (c->h_fold_meta[1] > (unsigned long long)max_entries)
+        return fail(PC_ERR_CAPACITY, "pc_fold_sparse_fetch: more entries than max_entries");
+    *n_entries = (int64_t)c->h_fold_meta[1];
+    if (*n_entries) {
+        CUDA_TRY(cudaMemcpyAsync(h_entries, c->fold_out.p, (size_t)*n_entries * sizeof(pc_fold_entry), cudaMemcpyDeviceToHost, s));
+        CUDA_TRY(cudaStreamSynchronize(s));
+    }
     return PC_OK;
 }
 

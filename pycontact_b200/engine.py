@@ -155,6 +155,30 @@ class ContactEngine:
         for s in self.slots:
             check(self.lib.pc_set_limits(s.ctx, *self.lim))
 
+    def fold_sparse_init(self, entries: int):
+        """Clear (and size) every slot's sparse aggregated table (key -> sums over frames)."""
+        for s in self.slots:
+            check(self.lib.pc_fold_sparse_init(s.ctx, int(entries), s.stream))
+        self.fold_entries = int(entries)
+
+    def fold_sparse_fetch(self) -> np.ndarray:
+        """Occupied entries of all slots' tables merged per key (_lib.fold_entry_dtype)."""
+        parts = []
+        for s in self.slots:
+            buf = s.out("fold", self.fold_entries, _lib.fold_entry_dtype)
+            n = ctypes.c_int64()
+            check(self.lib.pc_fold_sparse_fetch(s.ctx, s.stream, ptr(buf), self.fold_entries, ctypes.byref(n)))
+            parts.append(buf[:n.value].copy())
+        ent = np.concatenate(parts) if parts else np.zeros(0, _lib.fold_entry_dtype)
+        if ent.size == 0:
+            return ent
+        keys, inv = np.unique(ent["key"], return_inverse=True)
+        out = np.zeros(keys.size, _lib.fold_entry_dtype)
+        out["key"] = keys
+        for k in ("score", "bb1", "bb2", "hbframes"):
+            out[k] = np.bincount(inv, weights=ent[k], minlength=keys.size)
+        return out
+
     def set_pack_format(self, bytes_per_row: int):
         """Transfer format of packed rows: 24 (pc_row_packed) or 12 (pc_row_slim: 32-bit key, score, counts;
         the per-key bb sums then come from the aggregated table of pc_fold_rows)."""
@@ -375,7 +399,9 @@ class ContactEngine:
             check(lib.pc_event_record(events[1], slot.stream))
         if accumulate:
             check(lib.pc_accumulate(slot.ctx, slot.stream))
-            if fold is not None:
+            if fold == "sparse":
+                check(lib.pc_fold_rows_sparse(slot.ctx, slot.stream))
+            elif fold is not None:
                 check(lib.pc_fold_rows(slot.ctx, fold[0], int(fold[1]), slot.stream))
             if pack_rows:
                 check(lib.pc_pack_rows(slot.ctx, slot.stream))

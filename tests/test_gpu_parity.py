@@ -467,3 +467,39 @@ def test_edge_cases_empty_results_and_zero_distance(path):
         eng.set_path(path)
         traj, _, st = run_scan([eng], ArraySource(*src_far), order_keys=True)
     assert traj.idx1.size == 0 and st["contacts"] == 0        # bounding boxes do not touch: empty grid
+
+
+def test_sparse_fold_equals_dense_fold_and_host_sums():
+    """pc_fold_rows_sparse (hash table across batches) == pc_fold_rows (dense table) == sums over the rows."""
+    import ctypes
+    from pycontact_b200 import _lib
+    from pycontact_b200._lib import DeviceBuffer, check
+    s = synth.make_system("small")
+    t = s.topology
+    coords = synth.frames_host(s, range(8))
+    s1, s2 = _selections(t, s.sel1, s.sel2, s.backbone)
+    gm1 = prepare.group_map(s.sel1, s.maps[0], t.names, t.resids, t.resnames, t.segids)
+    gm2 = prepare.group_map(s.sel2, s.maps[1], t.names, t.resids, t.resnames, t.segids)
+    n_keys = gm1.n_groups * gm2.n_groups
+    lib = _lib.load()
+    with ContactEngine(s1, s2, 5.0, 2.5, 120, slots=2) as eng:
+        eng.set_maps(gm1.gid, gm2.gid, gm2.n_groups)
+        eng.fold_sparse_init(1 << 14)
+        dense = DeviceBuffer.from_array(np.zeros(n_keys * 4))
+        host = np.zeros((n_keys, 4))
+        for b, sid in ((0, 0), (1, 1)):
+            d1 = DeviceBuffer.from_array(np.ascontiguousarray(coords[4 * b:4 * b + 4][:, s.sel1]))
+            d2 = DeviceBuffer.from_array(np.ascontiguousarray(coords[4 * b:4 * b + 4][:, s.sel2]))
+            eng.submit_device(sid, d1.ptr, d2.ptr, 4, accumulate=True, fold="sparse")
+            eng.collect_device(sid)
+            check(lib.pc_fold_rows(eng.slots[sid].ctx, dense.ptr, n_keys, eng.slots[sid].stream))
+            rows, _, _ = eng.fetch_rows(sid)
+            k = rows["key"].astype(np.int64)
+            np.add.at(host[:, 0], k, rows["score"]); np.add.at(host[:, 1], k, rows["bb1"])
+            np.add.at(host[:, 2], k, rows["bb2"]); np.add.at(host[:, 3], k, (rows["nhbonds"] > 0) * 1.0)
+        ent = eng.fold_sparse_fetch()
+        dn = dense.download(np.float64, n_keys * 4).reshape(n_keys, 4)
+    np.testing.assert_allclose(dn, host, rtol=1e-12, atol=1e-300)
+    assert ent.size == np.count_nonzero(host[:, 0]) and np.all(np.diff(ent["key"].astype(np.int64)) > 0)
+    k = ent["key"].astype(np.int64)
+    np.testing.assert_allclose(np.stack([ent["score"], ent["bb1"], ent["bb2"], ent["hbframes"]], 1), host[k], rtol=1e-12)
