@@ -344,6 +344,14 @@ struct PcLargeOut {
     long long cap_c_frame, cap_h_frame;   // records per frame slice
 };
 
+// Which pair kernel searches a frame: with a few B atoms per cell on average every B atom is a candidate
+// of several A atoms, and loading it once per A CELL (warp per cell, lanes over B) beats loading it once
+// per A ATOM (thread per atom).
+__device__ __forceinline__ bool pc_large_is_dense(const PcLargeFrame &F, bool self) {
+    const unsigned nB = self ? F.nA_in : F.nB_in;
+    return F.ncell > 0 && (unsigned long long)nB * 2ull >= 5ull * (unsigned long long)F.ncell;      // >= 2.5 per cell
+}
+
 // Hits are staged in a per-CTA queue in shared memory and appended to the frame's slice with ONE global
 // atomic per tile of 256 work items: in dense systems (a hit every ~6 candidates) a global atomic per
 // hit would make every hit an L2 round trip inside the candidate loop.
@@ -369,6 +377,7 @@ __global__ void __launch_bounds__(256) pc_large_pair_kernel(const PcScanArgs a, 
     pc_contact *slice = a.contacts + (long long)f * o.cap_c_frame;
     const int nx = F.nx, ny = F.ny, nz = F.nz;
     const long long items = 3ll * F.nA_in;
+    if (pc_large_is_dense(F, self)) return;          // dense frames are searched by pc_large_pair_dense_kernel
     for (long long tile = blockIdx.x * (long long)blockDim.x; tile < items; tile += (long long)gridDim.x * blockDim.x) {
         if (threadIdx.x == 0) qn = 0;
         __syncthreads();
@@ -463,6 +472,162 @@ __global__ void __launch_bounds__(256) pc_large_pair_kernel(const PcScanArgs a, 
     }
 #pragma unroll
     for (int s = 16; s > 0; s >>= 1) evals += __shfl_xor_sync(PC_FULL_MASK, evals, s);
+    if (lane == 0 && evals) atomicAdd(&a.counters[PC_CNT_EVALS], evals);
+    status = __reduce_or_sync(PC_FULL_MASK, status);
+    if (lane == 0 && status) atomicOr(&a.counters[PC_CNT_STATUS], (unsigned long long)status);
+}
+
+// Dense variant: one warp per (A cell, stencil z-layer).  The cell's A atoms sit in lane registers; the
+// layer's three B runs are walked as ONE list, 32 atoms at a time (each B atom is loaded once per cell),
+// and every lane tests its B atom against all A atoms of the cell (broadcast by shuffle) into a hit
+// mask.  Hits go through a per-WARP queue in shared memory that the warp itself appends to the frame's
+// slice (one global atomic per flush), so there is no CTA barrier and no per-hit global atomic however
+// dense the system is.
+#define PC_DENSE_WQ 512
+__device__ __forceinline__ void pc_dense_flush(PcLargeFrame *frp, pc_contact *slice, const PcLargeOut &o, const uint2 *wq,
+                                               unsigned n, int lane, unsigned int &status) {
+    if (n == 0) return;
+    unsigned base = 0;
+    if (lane == 0) base = atomicAdd(&frp->ccursor, n);
+    base = __shfl_sync(PC_FULL_MASK, base, 0);
+    for (unsigned k = lane; k < n; k += 32) {
+        const long long slot = (long long)base + k;
+        if (slot < o.cap_c_frame) {
+            pc_contact rec;
+            rec.i = (int)wq[k].x; rec.j = (int)wq[k].y; rec.distance = 0.f; rec.weight = 0.f;
+            slice[slot] = rec;
+        } else {
+            status |= (unsigned)PC_ST_OUT_OVERFLOW;
+        }
+    }
+    __syncwarp();
+}
+
+__global__ void __launch_bounds__(256) pc_large_pair_dense_kernel(const PcScanArgs a, PcLargeFrame *fr, int f0,
+                                                                  const uint32_t *cellsA, const uint32_t *cellsB, int capCells,
+                                                                  const float4 *sortA, const float4 *sortB, int n1h_alloc,
+                                                                  int n2h_alloc, PcLargeOut o) {
+    __shared__ PcLargeFrame F;
+    __shared__ uint2 q[8][PC_DENSE_WQ];
+    const int fb = blockIdx.y, f = f0 + fb;
+    if (threadIdx.x == 0) F = fr[fb];
+    __syncthreads();
+    const bool self = a.self_mode != 0;
+    if (!pc_large_is_dense(F, self)) return;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
+    uint2 *wq = q[warp];
+    unsigned wn = 0;                      // entries in this warp's queue (same value in every lane)
+    unsigned long long evals = 0;
+    unsigned int status = 0;
+    const float sqdist = a.sqdist, sqdist_hi = a.sqdist * 1.00000095367431640625f;   // 1 + 2^-20
+    const uint32_t *cA = cellsA + (size_t)fb * (capCells + 1);
+    const uint32_t *cB = (self ? cellsA : cellsB) + (size_t)fb * (capCells + 1);
+    const float4 *sA = sortA + (size_t)fb * n1h_alloc;
+    const float4 *sB = self ? sA : sortB + (size_t)fb * n2h_alloc;
+    pc_contact *slice = a.contacts + (long long)f * o.cap_c_frame;
+    const int nx = F.nx, ny = F.ny, nz = F.nz;
+    const long long items = 3ll * F.ncell;
+    for (long long w = (long long)blockIdx.x * nwarp + warp; w < items; w += (long long)gridDim.x * nwarp) {
+        const int layer = (int)(w / F.ncell), c = (int)(w - (long long)layer * F.ncell);
+        const int a0 = c ? (int)__ldg(cA + c - 1) : 0, a1 = (int)__ldg(cA + c);
+        if (a0 == a1) continue;
+        const int cx = c % nx, cy = (c / nx) % ny, cz = c / (nx * ny);
+        const int z = cz + layer - 1;
+        if (z < 0 || z >= nz) continue;
+        const int xlo = max(cx - 1, 0), xhi = min(cx + 1, nx - 1);
+        // the layer's three runs as one list: run r covers list positions [st[r], st[r+1])
+        int rb[3], st[4];
+        st[0] = 0;
+#pragma unroll
+        for (int dy = 0; dy < 3; dy++) {
+            const int y = cy + dy - 1;
+            int b0 = 0, b1 = 0;
+            if (y >= 0 && y < ny) {
+                const int row = (z * ny + y) * nx;
+                b0 = (row + xlo) ? (int)__ldg(cB + row + xlo - 1) : 0;
+                b1 = (int)__ldg(cB + row + xhi);
+            }
+            rb[dy] = b0; st[dy + 1] = st[dy] + (b1 - b0);
+        }
+        const int nb = st[3];
+        if (nb == 0) continue;
+        for (int ab = a0; ab < a1; ab += 32) {
+            const int na = min(32, a1 - ab);
+            float4 pa = make_float4(0.f, 0.f, 0.f, 0.f);
+            int ares = 0, aseg = 0;
+            if (lane < na) {
+                pa = __ldg(sA + ab + lane);
+                if (self) {
+                    const int li = PC_W_INDEX(__float_as_uint(pa.w));
+                    ares = __ldg(a.t.lres1 + li); aseg = __ldg(a.t.lseg1 + li);
+                }
+            }
+            if (lane == 0) evals += (unsigned long long)na * (unsigned)nb;
+            for (int t0 = 0; t0 < nb; t0 += 32) {
+                const int t = t0 + lane;
+                const bool valid = t < nb;
+                const int r = (t >= st[1]) + (t >= st[2]);
+                const int j = rb[r] + (t - st[r]);
+                float4 pb = make_float4(0.f, 0.f, 0.f, 0.f);
+                int bres = 0, bseg = 0;
+                if (valid) {
+                    pb = __ldg(sB + j);
+                    if (self) {
+                        const int lj = PC_W_INDEX(__float_as_uint(pb.w));
+                        bres = __ldg(a.t.lres1 + lj); bseg = __ldg(a.t.lseg1 + lj);
+                    }
+                }
+                unsigned hm = 0;          // bit ia: A atom ab + ia is within the cutoff of this lane's B atom
+                for (int ia = 0; ia < na; ia++) {
+                    const float px = __shfl_sync(PC_FULL_MASK, pa.x, ia);
+                    const float py = __shfl_sync(PC_FULL_MASK, pa.y, ia);
+                    const float pz = __shfl_sync(PC_FULL_MASK, pa.z, ia);
+                    bool hit = valid && pair_within(px, py, pz, pb.x, pb.y, pb.z, sqdist, sqdist_hi);
+                    if (self) {
+                        // (resid1 - resid2) < 5 and same segment -> dropped (core/multi_trajectory.py:93-95)
+                        const int r1 = __shfl_sync(PC_FULL_MASK, ares, ia), s1 = __shfl_sync(PC_FULL_MASK, aseg, ia);
+                        if (hit && (r1 - bres) < 5 && s1 == bseg) hit = false;
+                    }
+                    hm |= (unsigned)hit << ia;
+                }
+                const unsigned cnt = (unsigned)__popc(hm);
+                const unsigned incl = warp_incl_scan(cnt, lane);
+                const unsigned total = __shfl_sync(PC_FULL_MASK, incl, 31);
+                if (total == 0) continue;
+                if (wn + total > PC_DENSE_WQ) { pc_dense_flush(&fr[fb], slice, o, wq, wn, lane, status); wn = 0; }
+                if (total > PC_DENSE_WQ) {
+                    // more hits in one chunk than the queue holds: straight to the slice
+                    unsigned base = 0;
+                    if (lane == 31) base = atomicAdd(&fr[fb].ccursor, total);
+                    base = __shfl_sync(PC_FULL_MASK, base, 31);
+                    long long p = (long long)base + incl - cnt;
+                    while (hm) {
+                        const int ia = __ffs(hm) - 1;
+                        hm &= hm - 1;
+                        if (p < o.cap_c_frame) {
+                            pc_contact rec;
+                            rec.i = ab + ia; rec.j = j; rec.distance = 0.f; rec.weight = 0.f;
+                            slice[p] = rec;
+                        } else {
+                            status |= (unsigned)PC_ST_OUT_OVERFLOW;
+                        }
+                        p++;
+                    }
+                } else {
+                    unsigned p = wn + incl - cnt;
+                    while (hm) {
+                        const int ia = __ffs(hm) - 1;
+                        hm &= hm - 1;
+                        wq[p++] = make_uint2((unsigned)(ab + ia), (unsigned)j);
+                    }
+                    wn += total;
+                    __syncwarp();
+                }
+            }
+        }
+    }
+    pc_dense_flush(&fr[fb], slice, o, wq, wn, lane, status);
+    evals = __shfl_sync(PC_FULL_MASK, evals, 0);
     if (lane == 0 && evals) atomicAdd(&a.counters[PC_CNT_EVALS], evals);
     status = __reduce_or_sync(PC_FULL_MASK, status);
     if (lane == 0 && status) atomicOr(&a.counters[PC_CNT_STATUS], (unsigned long long)status);
@@ -636,11 +801,16 @@ static inline int pc_large_scan(PcLargeWork &W, const PcScanArgs &a, int num_sms
         const int pblocks = (int)std::max<long long>(1, std::min<long long>((3ll * n1h + 255) / 256, std::max(64, 2 * per_frame_blocks)));
         pc_large_pair_kernel<<<dim3(pblocks, nfb), 256, 0, s>>>(a, W.frames, f0, W.cellA, W.cellB, capCells, W.sortA, W.sortB,
                                                                a1, a2, o);
+        // every frame is searched by exactly one of the two kernels (pc_large_is_dense, decided on the device)
+        const int dper = 8 * 4;
+        const int dblocks_pair = (int)std::max<long long>(1, std::min<long long>((3ll * capCells + dper - 1) / dper, std::max(64, 2 * per_frame_blocks)));
+        pc_large_pair_dense_kernel<<<dim3(dblocks_pair, nfb), 256, 0, s>>>(a, W.frames, f0, W.cellA, W.cellB, capCells, W.sortA,
+                                                                          W.sortB, a1, a2, o);
         const int dblocks = (int)std::max<long long>(1, std::min<long long>((o.cap_c_frame + 255) / 256, per_frame_blocks));
         pc_large_drain_kernel<<<dim3(dblocks, nfb), 256, 0, s>>>(a, W.frames, f0, W.sortA, W.sortB, a1, a2, o);
         pc_large_finish_kernel<<<(nfb + 63) / 64, 64, 0, s>>>(a, W.frames, f0, nfb, o);
         PCL_TRY(cudaGetLastError());
-        *launches += 8 + (use_bboxB ? 1 : 0) + (self ? 0 : 3);
+        *launches += 9 + (use_bboxB ? 1 : 0) + (self ? 0 : 3);
     }
     return PC_OK;
 }
