@@ -255,6 +255,11 @@ def run_gpu(args):
     dense = n_keys <= (1 << 20)          # aggregated maps as a dense [n_keys][4] table (32 MB at most)
     sparse = args.sparse_fold and (not dense) and n_keys < (1 << 32)   # opt-in: a hash table per slot, merged per step
     sparse_entries = 1 << 22
+    # `value` keeps all per-frame records (contacts, H-bonds, rows) in HBM, like its inputs; what goes to the
+    # host is the time-aggregated map (after the all-reduce over ranks).  Without such a map (key spaces too
+    # large for the dense table and no --sparse-fold) the packed per-frame rows are copied to the host instead.
+    # `e2e` always returns every record to the host.
+    rows_to_host = args.rows_to_host or not (dense or sparse)
     totals = DeviceBuffer(max(1, n_keys if dense else 1) * 32, local)
     totals_t = None
     if world > 1 and dense:
@@ -289,11 +294,14 @@ def run_gpu(args):
             c = eng.collect_device(sid)
             _t1 = time.perf_counter()
             tot[:] += c
-            rows, _, _ = eng.fetch_rows(sid, packed=True)  # the per-frame maps of this rank's frames -> host
-            d_rows += rows.nbytes
+            nrows = 0
+            if rows_to_host:
+                rows, _, _ = eng.fetch_rows(sid, packed=True)  # the per-frame maps of this rank's frames -> host
+                d_rows += rows.nbytes
+                nrows = rows.size
             if trace:
                 print("slot %d nf %d: wait %.3f ms, fold+fetch %.3f ms (%d rows)" % (
-                    sid, nf, (_t1 - _t0) * 1e3, (time.perf_counter() - _t1) * 1e3, rows.size), file=sys.stderr)
+                    sid, nf, (_t1 - _t0) * 1e3, (time.perf_counter() - _t1) * 1e3, nrows), file=sys.stderr)
 
         # several batches in flight (one per slot): later batches are scanned while an earlier batch's
         # rows travel to the host
@@ -512,6 +520,9 @@ def run_gpu(args):
             "config": {"workload": "%s: %s" % (args.workload, w["desc"]), "frames_per_gpu_per_step": F,
                        "atoms_sel1": n1, "atoms_sel2": n2, "batch_frames": batch, "batches_per_step": nb,
                        "l2": "inputs (%.0f MB per step) exceed the 126 MB L2" % (F * in_bytes_frame / 1e6),
+                       "results": ("per-frame records stay in HBM; " if not rows_to_host else "packed per-frame rows -> host; ")
+                                  + ("aggregated maps (dense table) all-reduced and copied to the host" if dense else
+                                     "aggregated maps (sparse table) merged on the host" if sparse else "no aggregated table"),
                        "parallelism": "frames sharded over %d GPU(s), one all-reduce of the aggregated maps" % world},
             "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu,
             "per_step": {"contacts": contacts_step, "hbonds": hbonds_step, "rows": rows_step,
@@ -544,6 +555,8 @@ def main():
     ap.add_argument("--batch", type=int, default=0, help="frames per launch")
     ap.add_argument("--e2e-frames", type=int, default=0)
     ap.add_argument("--slots", type=int, default=3, help="frame batches in flight per GPU")
+    ap.add_argument("--rows-to-host", action="store_true",
+                    help="value: also copy the packed per-frame rows to the host inside the timed step")
     ap.add_argument("--sparse-fold", action="store_true",
                     help="large key spaces: 12-byte rows + on-device sparse aggregation (less D2H, more device work)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the CPU baseline leg")
