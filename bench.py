@@ -254,7 +254,7 @@ def run_gpu(args):
     n_keys = gm1.n_groups * gm2.n_groups
     dense = n_keys <= (1 << 20)          # aggregated maps as a dense [n_keys][4] table (32 MB at most)
     sparse = args.sparse_fold and (not dense) and n_keys < (1 << 32)   # opt-in: a hash table per slot, merged per step
-    sparse_entries = 1 << 22
+    sparse_entries = args.sparse_entries
     # `value` keeps all per-frame records (contacts, H-bonds, rows) in HBM, like its inputs; what goes to the
     # host is the time-aggregated map (after the all-reduce over ranks).  Without such a map (key spaces too
     # large for the dense table and no --sparse-fold) the packed per-frame rows are copied to the host instead.
@@ -334,8 +334,11 @@ def run_gpu(args):
                 check(lib.pc_device_sync(local))
                 d_rows += host.nbytes
         if sparse:
+            _tf = time.perf_counter()
             ent = eng.fold_sparse_fetch()                  # per-key sums of this rank's frames
             d_rows += ent.nbytes
+            if trace:
+                print("sparse fetch+merge %.3f ms, %d keys" % ((time.perf_counter() - _tf) * 1e3, ent.size), file=sys.stderr)
             if dist is not None:                           # ranks hold disjoint frames: sum per key on rank 0
                 cnt = torch.tensor([ent.size], device="cuda")
                 dist.all_reduce(cnt, op=dist.ReduceOp.MAX)
@@ -555,6 +558,7 @@ def main():
     ap.add_argument("--batch", type=int, default=0, help="frames per launch")
     ap.add_argument("--e2e-frames", type=int, default=0)
     ap.add_argument("--slots", type=int, default=3, help="frame batches in flight per GPU")
+    ap.add_argument("--sparse-entries", type=int, default=1 << 21)
     ap.add_argument("--rows-to-host", action="store_true",
                     help="value: also copy the packed per-frame rows to the host inside the timed step")
     ap.add_argument("--sparse-fold", action="store_true",

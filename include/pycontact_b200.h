@@ -155,6 +155,9 @@ int pc_fold_rows(pc_ctx *ctx, double *d_totals, int64_t n_keys, void *stream);
 typedef struct { uint64_t key; double score, bb1, bb2, hbframes; } pc_fold_entry;
 int pc_fold_sparse_init(pc_ctx *ctx, int64_t entries, void *stream);
 int pc_fold_rows_sparse(pc_ctx *ctx, void *stream);
+/* Several contexts of one GPU (batches in flight on different streams) can fold into ONE table: ctx then
+ * adds its rows to owner's table (owner = NULL undoes it).  Synchronise ctx's stream before fetching. */
+int pc_fold_sparse_share(pc_ctx *ctx, pc_ctx *owner);
 int pc_fold_sparse_fetch(pc_ctx *ctx, void *stream, pc_fold_entry *h_entries, int64_t max_entries, int64_t *n_entries);
 
 /* Analyzer.runContactAnalysis(map1, map2) may be called again with other maps on the SAME

@@ -61,7 +61,7 @@ EXPORTS = [
     "pc_device_outputs", "pc_fetch", "pc_find_contacts", "pc_free_host", "pc_synth_frames", "pc_host_alloc",
     "pc_host_free", "pc_load_records", "pc_stream_create", "pc_stream_sync", "pc_stream_destroy",
     "pc_device_alloc", "pc_device_free", "pc_memcpy", "pc_memset", "pc_device_sync",
-    "pc_launch_count", "pc_event_create", "pc_event_record", "pc_event_elapsed_ms", "pc_event_destroy", "pc_fold_rows", "pc_fetch_packed_rows", "pc_pack_rows", "pc_set_pack_format", "pc_fold_sparse_init", "pc_fold_rows_sparse", "pc_fold_sparse_fetch", "pc_set_probe",
+    "pc_launch_count", "pc_event_create", "pc_event_record", "pc_event_elapsed_ms", "pc_event_destroy", "pc_fold_rows", "pc_fetch_packed_rows", "pc_pack_rows", "pc_set_pack_format", "pc_fold_sparse_init", "pc_fold_rows_sparse", "pc_fold_sparse_fetch", "pc_fold_sparse_share", "pc_set_probe",
 ]
 
 _lib = None
@@ -124,6 +124,7 @@ def load():
     lib.pc_fetch_packed_rows.argtypes = [vp, vp, vp, vp, vp]
     lib.pc_fold_sparse_init.argtypes = [vp, i64, vp]
     lib.pc_fold_rows_sparse.argtypes = [vp, vp]
+    lib.pc_fold_sparse_share.argtypes = [vp, vp]
     lib.pc_fold_sparse_fetch.argtypes = [vp, vp, vp, i64, P(i64)]
     lib.pc_pack_rows.argtypes = [vp, vp]
     lib.pc_set_pack_format.argtypes = [vp, ctypes.c_int]

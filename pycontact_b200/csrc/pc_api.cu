@@ -80,6 +80,7 @@ struct pc_ctx {
     DevBuf<pc_fold_entry> fold_tab, fold_out;      // sparse time-aggregated maps (pc_fold_rows_sparse)
     DevBuf<unsigned long long> fold_meta;
     unsigned long long fold_cap = 0;
+    pc_ctx *fold_owner = nullptr;          // fold into another context's table (contexts of one GPU share one)
     unsigned long long *h_fold_meta = nullptr;
     DevBuf<uint32_t> gacc_cursor, gacc_fresh;
     DevBuf<unsigned long long> gacc_nfresh;
@@ -543,11 +544,19 @@ extern "C" int pc_fold_sparse_init(pc_ctx *c, int64_t entries, void *stream) {
     return PC_OK;
 }
 
+extern "C" int pc_fold_sparse_share(pc_ctx *c, pc_ctx *owner) {
+    if (!c || (owner && (owner->device != c->device || owner == c)))
+        return fail(PC_ERR_INVALID, "pc_fold_sparse_share: owner must be another context of the same GPU");
+    c->fold_owner = owner;
+    return PC_OK;
+}
+
 extern "C" int pc_fold_rows_sparse(pc_ctx *c, void *stream) {
-    if (!c || !c->have_maps || !c->fold_cap) return fail(PC_ERR_INVALID, "pc_fold_rows_sparse: call pc_fold_sparse_init first");
+    pc_ctx *t = c && c->fold_owner ? c->fold_owner : c;
+    if (!c || !c->have_maps || !t->fold_cap) return fail(PC_ERR_INVALID, "pc_fold_rows_sparse: call pc_fold_sparse_init first");
     CUDA_TRY(cudaSetDevice(c->device));
-    pc_fold_sparse_kernel<<<2 * c->num_sms, 256, 0, (cudaStream_t)stream>>>(c->rows.p, c->counters.p, c->cap_rows, c->fold_tab.p,
-                                                                           c->fold_cap, c->fold_meta.p);
+    pc_fold_sparse_kernel<<<2 * c->num_sms, 256, 0, (cudaStream_t)stream>>>(c->rows.p, c->counters.p, c->cap_rows, t->fold_tab.p,
+                                                                           t->fold_cap, t->fold_meta.p);
     CUDA_TRY(cudaGetLastError());
     g_launches += 1;
     return PC_OK;

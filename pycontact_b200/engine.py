@@ -156,28 +156,26 @@ class ContactEngine:
             check(self.lib.pc_set_limits(s.ctx, *self.lim))
 
     def fold_sparse_init(self, entries: int):
-        """Clear (and size) every slot's sparse aggregated table (key -> sums over frames)."""
-        for s in self.slots:
-            check(self.lib.pc_fold_sparse_init(s.ctx, int(entries), s.stream))
+        """Clear (and size) the engine's sparse aggregated table (key -> sums over frames); all slots fold
+        into the table of slot 0."""
+        s0 = self.slots[0]
+        for s in self.slots[1:]:
+            check(self.lib.pc_stream_sync(s.stream))
+            check(self.lib.pc_fold_sparse_share(s.ctx, s0.ctx))
+        check(self.lib.pc_fold_sparse_init(s0.ctx, int(entries), s0.stream))
+        check(self.lib.pc_stream_sync(s0.stream))
         self.fold_entries = int(entries)
 
     def fold_sparse_fetch(self) -> np.ndarray:
-        """Occupied entries of all slots' tables merged per key (_lib.fold_entry_dtype)."""
-        parts = []
-        for s in self.slots:
-            buf = s.out("fold", self.fold_entries, _lib.fold_entry_dtype)
-            n = ctypes.c_int64()
-            check(self.lib.pc_fold_sparse_fetch(s.ctx, s.stream, ptr(buf), self.fold_entries, ctypes.byref(n)))
-            parts.append(buf[:n.value].copy())
-        ent = np.concatenate(parts) if parts else np.zeros(0, _lib.fold_entry_dtype)
-        if ent.size == 0:
-            return ent
-        keys, inv = np.unique(ent["key"], return_inverse=True)
-        out = np.zeros(keys.size, _lib.fold_entry_dtype)
-        out["key"] = keys
-        for k in ("score", "bb1", "bb2", "hbframes"):
-            out[k] = np.bincount(inv, weights=ent[k], minlength=keys.size)
-        return out
+        """Occupied entries of the table, sorted by key (_lib.fold_entry_dtype)."""
+        for s in self.slots[1:]:
+            check(self.lib.pc_stream_sync(s.stream))
+        s0 = self.slots[0]
+        buf = s0.out("fold", self.fold_entries, _lib.fold_entry_dtype)
+        n = ctypes.c_int64()
+        check(self.lib.pc_fold_sparse_fetch(s0.ctx, s0.stream, ptr(buf), self.fold_entries, ctypes.byref(n)))
+        ent = buf[:n.value]
+        return ent[np.argsort(ent["key"], kind="stable")]
 
     def set_pack_format(self, bytes_per_row: int):
         """Transfer format of packed rows: 24 (pc_row_packed) or 12 (pc_row_slim: 32-bit key, score, counts;
