@@ -49,7 +49,7 @@ __host__ inline PcSmallSmem pc_small_layout(int self_mode, int capCells, int cap
     o = 0;
     L.off_hits = take(4 * capHits);
     L.off_hb = take((int)sizeof(pc_hbond) * capHb);
-    L.off_tab = take(48 * capTab);
+    L.off_tab = take(36 * capTab);
     o = o > end_early ? o : end_early;
     L.off_sort = take(16 * capCand);
     L.off_cellA = take(4 * (capCells + 1));
@@ -118,12 +118,14 @@ __global__ void __launch_bounds__(NT, NT >= 1024 ? 1 : 2) pc_scan_small_kernel(c
     pc_hbond *hbq = reinterpret_cast<pc_hbond *>(smem + L.off_hb);
     // accumulation table (fuse_acc): structure of arrays over capTab slots
     const int capTab = L.capTab, capCand = L.capCand;
+    // sums are float32: shared-memory float atomics are native (float64 ones are CAS loops), and a sum of a
+    // few dozen float32 weights stays within ~1e-7 relative of the float64 sum (the parity bar is 1e-5)
     unsigned long long *tkey = reinterpret_cast<unsigned long long *>(smem + L.off_tab);
-    double *tscore = reinterpret_cast<double *>(tkey + capTab);
-    double *tbb1 = tscore + capTab;
-    double *tbb2 = tbb1 + capTab;
-    unsigned long long *tfirst = reinterpret_cast<unsigned long long *>(tbb2 + capTab);
-    unsigned int *tncont = reinterpret_cast<unsigned int *>(tfirst + capTab);
+    unsigned long long *tfirst = tkey + capTab;
+    float *tscore = reinterpret_cast<float *>(tfirst + capTab);
+    float *tbb1 = tscore + capTab;
+    float *tbb2 = tbb1 + capTab;
+    unsigned int *tncont = reinterpret_cast<unsigned int *>(tbb2 + capTab);
     unsigned int *tnhb = tncont + capTab;
 
     __shared__ float red[NT / 32][12];
@@ -332,7 +334,7 @@ __global__ void __launch_bounds__(NT, NT >= 1024 ? 1 : 2) pc_scan_small_kernel(c
         // warp that gets here is past the barrier that ended phase 5 (or skipped the grid).
         if (fuse)
             for (int s = tid; s < capTab; s += NT) {
-                tkey[s] = PC_EMPTY_KEY; tscore[s] = 0.0; tbb1[s] = 0.0; tbb2[s] = 0.0;
+                tkey[s] = PC_EMPTY_KEY; tscore[s] = 0.f; tbb1[s] = 0.f; tbb2[s] = 0.f;
                 tfirst[s] = PC_EMPTY_KEY; tncont[s] = 0; tnhb[s] = 0;
             }
         __syncthreads();
@@ -385,10 +387,9 @@ __global__ void __launch_bounds__(NT, NT >= 1024 ? 1 : 2) pc_scan_small_kernel(c
                 }
                 if (slot == 0xffffffffu) atomicOr(&s_status, (unsigned)PC_ST_TABLE_OVERFLOW);
                 else {
-                    const double w = (double)wgt;
-                    atomicAdd(&tscore[slot], w);
-                    if (wa & PC_W_BACKBONE) atomicAdd(&tbb1[slot], w);
-                    if (wb & PC_W_BACKBONE) atomicAdd(&tbb2[slot], w);
+                    atomicAdd(&tscore[slot], wgt);
+                    if (wa & PC_W_BACKBONE) atomicAdd(&tbb1[slot], wgt);
+                    if (wb & PC_W_BACKBONE) atomicAdd(&tbb2[slot], wgt);
                     atomicAdd(&tncont[slot], 1u);
                     atomicMin(&tfirst[slot], ((unsigned long long)(unsigned)li << 32) | (unsigned)lj);
                 }
@@ -472,7 +473,7 @@ __global__ void __launch_bounds__(NT, NT >= 1024 ? 1 : 2) pc_scan_small_kernel(c
             for (int s = tb; s < te; s++) {
                 if (tkey[s] == PC_EMPTY_KEY) continue;
                 pc_row r;
-                r.key = tkey[s]; r.score = tscore[s]; r.bb1 = tbb1[s]; r.bb2 = tbb2[s];
+                r.key = tkey[s]; r.score = (double)tscore[s]; r.bb1 = (double)tbb1[s]; r.bb2 = (double)tbb2[s];
                 r.ncontacts = tncont[s]; r.nhbonds = tnhb[s]; r.first = tfirst[s];
                 a.rows[o++] = r;
             }

@@ -333,14 +333,15 @@ def test_fused_accumulation_equals_standalone_kernel(name, self_mode):
         tables.append(table)
     a, b, c1 = tables
     assert np.array_equal(np.sort(a.keys), np.sort(c1.keys))
-    np.testing.assert_allclose(a.score_matrix()[np.argsort(a.keys)], c1.score_matrix()[np.argsort(c1.keys)], rtol=1e-12)
+    # the fused table sums in float32 (order-dependent in the last bits), the stand-alone kernel in float64
+    np.testing.assert_allclose(a.score_matrix()[np.argsort(a.keys)], c1.score_matrix()[np.argsort(c1.keys)], rtol=2e-6)
     assert a.n_keys == b.n_keys and a.n_keys > 0
     oa, ob = np.argsort(a.keys), np.argsort(b.keys)
     assert np.array_equal(a.keys[oa], b.keys[ob])
-    np.testing.assert_allclose(a.score_matrix()[oa], b.score_matrix()[ob], rtol=1e-12, atol=1e-300)
+    np.testing.assert_allclose(a.score_matrix()[oa], b.score_matrix()[ob], rtol=2e-6, atol=1e-300)
     assert np.array_equal(a.hbond_matrix()[oa], b.hbond_matrix()[ob])
-    np.testing.assert_allclose(a.bb1[oa], b.bb1[ob], rtol=1e-12, atol=1e-300)
-    np.testing.assert_allclose(a.bb2[oa], b.bb2[ob], rtol=1e-12, atol=1e-300)
+    np.testing.assert_allclose(a.bb1[oa], b.bb1[ob], rtol=2e-6, atol=1e-300)
+    np.testing.assert_allclose(a.bb2[oa], b.bb2[ob], rtol=2e-6, atol=1e-300)
 
 
 def test_packed_rows_equal_full_rows():
@@ -499,7 +500,7 @@ def test_sparse_fold_equals_dense_fold_and_host_sums():
             np.add.at(host[:, 2], k, rows["bb2"]); np.add.at(host[:, 3], k, (rows["nhbonds"] > 0) * 1.0)
         ent = eng.fold_sparse_fetch()
         dn = dense.download(np.float64, n_keys * 4).reshape(n_keys, 4)
-    np.testing.assert_allclose(dn, host, rtol=1e-12, atol=1e-300)
+    np.testing.assert_allclose(dn, host, rtol=1e-12, atol=1e-300)      # same rows folded two ways
     assert ent.size == np.count_nonzero(host[:, 0]) and np.all(np.diff(ent["key"].astype(np.int64)) > 0)
     k = ent["key"].astype(np.int64)
     np.testing.assert_allclose(np.stack([ent["score"], ent["bb1"], ent["bb2"], ent["hbframes"]], 1), host[k], rtol=1e-12)

@@ -17,7 +17,7 @@ import subprocess
 import tempfile
 
 
-def sass_lines(so, kernel):
+def sass_lines(so, kernel, sym=None):
     tmp = tempfile.mkdtemp()
     subprocess.run(["cuobjdump", "-xelf", "all", os.path.abspath(so)], cwd=tmp, check=True, capture_output=True)
     out = []
@@ -34,7 +34,7 @@ def sass_lines(so, kernel):
                 cur_file, cur_line = os.path.basename(m.group(1)), int(m.group(2))
                 continue
             m = re.match(r"\s+/\*([0-9a-f]{4,})\*/\s+(.*?);", ln)
-            if m and cur_fn and kernel in cur_fn:
+            if m and cur_fn and kernel in cur_fn and (sym is None or sym in cur_fn):
                 out.append((int(m.group(1), 16), cur_file, cur_line, m.group(2).strip()))
     return out
 
@@ -47,6 +47,7 @@ def main():
                                                  "pycontact_b200", "libpycontact_b200.so"))
     ap.add_argument("--top", type=int, default=40)
     ap.add_argument("--launch", type=int, default=0)
+    ap.add_argument("--sym", default=None, help="substring of the mangled name (e.g. ILi512E) to pick one instantiation")
     args = ap.parse_args()
     raw = subprocess.run(["ncu", "-i", args.report, "--page", "source", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(raw.split("\n")))
@@ -67,7 +68,7 @@ def main():
     hdr = L["hdr"]
     ci = {n: hdr.index(n) for n in ("Source", "# Samples", "Instructions Executed", "Thread Instructions Executed")}
     stall_cols = [i for i, n in enumerate(hdr) if n.startswith("stall_") and "Not Issued" not in n]
-    sl = sass_lines(args.so, args.kernel.split("<")[0])
+    sl = sass_lines(args.so, args.kernel.split("<")[0], args.sym)
     n = min(len(sl), len(L["rows"]))
     if len(sl) != len(L["rows"]):
         print("warning: %d SASS rows in report vs %d in library (joined by position)" % (len(L["rows"]), len(sl)))
