@@ -119,9 +119,10 @@ int pc_set_limits(pc_ctx *ctx, int32_t hits_per_frame, int32_t hbonds_per_frame,
  * 2 = tiled large-frame path.  Both give the same records; tests use this to cover both. */
 int pc_set_path(pc_ctx *ctx, int path);
 
-/* Small-frame kernel: CTAs per SM.  0 = automatic (two 512-thread CTAs when a frame's working set fits
- * half an SM's shared memory, else one 1024-thread CTA), 1 or 2 force it.  After PC_ST_STAGE_OVERFLOW
- * with two CTAs the caller retries with 1 before switching to the large-frame path. */
+/* Small-frame kernel: CTAs per SM.  0 = automatic (a "fast" plan of two 512-thread CTAs per SM; frames whose
+ * in-grid atoms or hits do not fit it are redone by the "full" plan, one 1024-thread CTA), 1 = full plan
+ * only, 2 = fast plan only (PC_ST_STAGE_OVERFLOW when a frame does not fit), 3 / 4 = fast plan with
+ * 3 x 384 / 4 x 256 threads per SM, then the full plan. */
 int pc_set_small_ctas(pc_ctx *ctx, int ctas);
 
 /* Output capacities for one batch (totals over the batch, not per frame). */

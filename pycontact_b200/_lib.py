@@ -11,7 +11,8 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libpycontact_b200.so")
+# PYCONTACT_B200_LIB: load another build of the same library (tools/phase_clocks.py uses a profiling build)
+LIB_PATH = os.environ.get("PYCONTACT_B200_LIB") or os.path.join(_HERE, "libpycontact_b200.so")
 
 PC_OK = 0
 PC_ERR_INVALID = -1

@@ -44,6 +44,15 @@ def _stale():
     return any(os.path.getmtime(d) > t for d in deps)
 
 
+def build_variant(out: str, defines) -> str:
+    """A second build of the library with extra -D flags (profiling variants used by tools/)."""
+    cmd = [_nvcc()] + NVCC_FLAGS + ["-D" + d for d in defines] + ["-I", INCLUDE, "-o", out] + sources()
+    res = subprocess.run(cmd, capture_output=True, text=True)
+    if res.returncode != 0:
+        raise RuntimeError("nvcc failed (%d): %s\n%s" % (res.returncode, " ".join(cmd), res.stderr))
+    return out
+
+
 def build(force: bool = False, verbose: bool = False) -> str:
     if not force and not _stale():
         return OUT

@@ -96,7 +96,8 @@ struct pc_ctx {
     int pack_bytes = 24;              // transfer format of pc_pack_rows: 24 (pc_row_packed) or 12 (pc_row_slim)
     void *probe[2] = {nullptr, nullptr};   // optional events around the large path's dominant kernel (pc_set_probe)
     DevBuf<int> retry;                // [0] count, [4..] frames the fast small-frame plan handed to the full plan
-    int small_ctas = 0;               // small-frame kernel plans: 0 = fast + full (automatic), 1 = full only, 2 = fast only
+    int small_ctas = 0;               // small-frame kernel plans: 0 = fast (2 CTAs/SM) + full (automatic), 1 = full only, 2 = fast only,
+                                      // 3 / 4 = fast plan with 3 x 384 / 4 x 256 threads per SM + full
     int last_small_ctas = 0;
     bool want_fused_acc = true;       // accumulate inside the small-frame scan kernel when possible
     bool last_fused = false;
@@ -154,7 +155,7 @@ extern "C" int pc_set_probe(pc_ctx *c, void *start_event, void *end_event) {
 }
 
 extern "C" int pc_set_small_ctas(pc_ctx *c, int ctas) {
-    if (!c || ctas < 0 || ctas > 2) return fail(PC_ERR_INVALID, "pc_set_small_ctas: 0 (automatic), 1 or 2");
+    if (!c || ctas < 0 || ctas > 4) return fail(PC_ERR_INVALID, "pc_set_small_ctas: 0 (automatic) .. 4");
     c->small_ctas = ctas;
     return PC_OK;
 }
@@ -292,12 +293,12 @@ static uint32_t *meta(pc_ctx *c, int which) { return c->frame_meta.p + (size_t)w
 // PC_ST_STAGE_OVERFLOW and the caller switches to the large-frame path.
 static bool plan_small_cfg(const pc_ctx *c, bool fuse_acc, int ctas, int &capCells, int &capHits, int &capHb, PcSmallSmem &L) {
     const int ntot = c->self_mode ? c->n1h : c->n1h + c->n2h;
-    capHits = c->lim_hits > 0 ? c->lim_hits : 4096;
+    capHits = c->lim_hits > 0 ? c->lim_hits : (ctas >= 3 ? 3072 : 4096);
     capHb = c->lim_hb > 0 ? c->lim_hb : 256;
     int capTab = 0;
     if (fuse_acc) {
         capTab = 64;
-        const int want = c->lim_table > 0 ? c->lim_table : (ctas == 2 ? 512 : 1024);
+        const int want = c->lim_table > 0 ? c->lim_table : (ctas >= 2 ? 512 : 1024);
         while (capTab < want) capTab <<= 1;
     }
     const size_t optin = c->smem_optin ? c->smem_optin : 232448;
@@ -365,7 +366,8 @@ extern "C" int pc_scan_device(pc_ctx *c, const float *d_xyz1, const float *d_xyz
     int cells1 = 0, hits1 = 0, hb1 = 0, cells2 = 0, hits2 = 0, hb2 = 0;
     const bool small_ok = c->force_path != 2 && c->n1h <= 65535 && c->n2h <= 65535;
     const bool have_full = small_ok && c->small_ctas != 2 && plan_small_cfg(c, fuse_acc, 1, cells1, hits1, hb1, L);
-    const bool have_fast = small_ok && c->small_ctas != 1 && plan_small_cfg(c, fuse_acc, 2, cells2, hits2, hb2, L2);
+    const int fast_ctas = c->small_ctas >= 3 ? c->small_ctas : 2;     // CTAs per SM of the fast plan
+    const bool have_fast = small_ok && c->small_ctas != 1 && plan_small_cfg(c, fuse_acc, fast_ctas, cells2, hits2, hb2, L2);
     const bool fits_small = have_full || have_fast;
     c->last_fused = false;
     c->packed_valid = false;
@@ -379,13 +381,14 @@ extern "C" int pc_scan_device(pc_ctx *c, const float *d_xyz1, const float *d_xyz
         CUDA_TRY(cudaMemsetAsync(retry_count, 0, sizeof(unsigned int), s));
         PcSmallFrames fl;
         if (have_fast) {
-            auto kern = pc_scan_small_kernel<512>;
+            auto kern = fast_ctas == 4 ? pc_scan_small_kernel<256> : fast_ctas == 3 ? pc_scan_small_kernel<384> : pc_scan_small_kernel<512>;
+            const int nt = fast_ctas == 4 ? 256 : fast_ctas == 3 ? 384 : 512;
             CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L2.total));
             PcScanArgs a2 = a;
             a2.capCells = cells2; a2.capHits = hits2; a2.capHb = hb2;
             fl.frame_list = nullptr; fl.frame_count = nullptr;
             fl.retry_list = have_full ? retry_list : nullptr; fl.retry_count = have_full ? retry_count : nullptr;
-            kern<<<std::min(nframes, 2 * c->num_sms), 512, L2.total, s>>>(a2, L2, fl);
+            kern<<<std::min(nframes, fast_ctas * c->num_sms), nt, L2.total, s>>>(a2, L2, fl);
             CUDA_TRY(cudaGetLastError());
             g_launches += 1;
         }
@@ -399,7 +402,7 @@ extern "C" int pc_scan_device(pc_ctx *c, const float *d_xyz1, const float *d_xyz
             CUDA_TRY(cudaGetLastError());
             g_launches += 1;
         }
-        c->last_small_ctas = have_fast ? 2 : 1;
+        c->last_small_ctas = have_fast ? fast_ctas : 1;
         c->last_fused = fuse_acc;
         c->last_path = 1;
     } else {
@@ -694,6 +697,17 @@ extern "C" int pc_last_status(pc_ctx *c, uint64_t *status, int64_t *need_contact
     if (path) *path = c->last_path;
     return PC_OK;
 }
+
+#ifdef PC_PHASE_CLOCKS
+// profiling build only: cycles per phase of the last scan (valid after pc_batch_totals)
+extern "C" int pc_phase_clocks(pc_ctx *c, unsigned long long *out16) {
+    for (int i = 0; i < 14; i++) out16[i] = c->h_counters[PC_CNT_PHASE + i];
+    unsigned int retried = 0;                    // frames the fast plan handed to the full plan
+    if (c->retry.p) CUDA_TRY(cudaMemcpy(&retried, c->retry.p, sizeof(retried), cudaMemcpyDeviceToHost));
+    out16[14] = retried; out16[15] = (unsigned long long)c->last_small_ctas;
+    return PC_OK;
+}
+#endif
 
 extern "C" int pc_device_outputs(pc_ctx *c, pc_contact **d_contacts, pc_hbond **d_hbonds, pc_row **d_rows,
                                  uint64_t **d_order_keys, uint32_t **cs, uint32_t **cc, uint32_t **hs,

@@ -106,7 +106,7 @@ struct PcSmallFrames {
 };
 
 template <int NT>
-__global__ void __launch_bounds__(NT, NT >= 1024 ? 1 : 2) pc_scan_small_kernel(const PcScanArgs a, const PcSmallSmem L,
+__global__ void __launch_bounds__(NT, NT >= 1024 ? 1 : NT >= 512 ? 2 : NT >= 384 ? 3 : 4) pc_scan_small_kernel(const PcScanArgs a, const PcSmallSmem L,
                                                                                const PcSmallFrames fl) {
     extern __shared__ __align__(16) unsigned char smem[];
     float4 *cand = reinterpret_cast<float4 *>(smem + L.off_cand);
@@ -131,7 +131,7 @@ __global__ void __launch_bounds__(NT, NT >= 1024 ? 1 : 2) pc_scan_small_kernel(c
     __shared__ float red[NT / 32][12];
     __shared__ uint32_t wsum[32];
     __shared__ PcGridSm g;
-    __shared__ unsigned int s_nhits, s_nhb, s_nA, s_nB;
+    __shared__ unsigned int s_nhits, s_nhb, s_nA, s_nB, s_ngate;
     __shared__ long long s_cbase, s_hbase, s_rbase;
     __shared__ unsigned int s_status;
 
@@ -147,33 +147,39 @@ __global__ void __launch_bounds__(NT, NT >= 1024 ? 1 : 2) pc_scan_small_kernel(c
         const int f = fl.frame_list ? fl.frame_list[fi] : fi;
         const float *fr1 = a.xyz1 + (long long)f * a.pitch1;
         const float *fr2 = self ? fr1 : a.xyz2 + (long long)f * a.pitch2;
+        PC_PHASE_BEGIN();
 
         // ---- phase 1: bounding boxes of the heavy atoms (first pass over the frame) -----------------
         float mn[6], mx[6];
 #pragma unroll
         for (int k = 0; k < 6; k++) { mn[k] = INFINITY; mx[k] = -INFINITY; }
-        for (int k = tid; k < n1h; k += NT) {
-            float x, y, z;
-            load_xyz(fr1, PC_W_INDEX(__ldg(a.t.hinfo1 + k)), a.stride, x, y, z);
-            mn[0] = fminf(mn[0], x); mn[1] = fminf(mn[1], y); mn[2] = fminf(mn[2], z);
-            mx[0] = fmaxf(mx[0], x); mx[1] = fmaxf(mx[1], y); mx[2] = fmaxf(mx[2], z);
-        }
-        if (!self) {
-            for (int k = tid; k < n2h; k += NT) {
-                float x, y, z;
-                load_xyz(fr2, PC_W_INDEX(__ldg(a.t.hinfo2 + k)), a.stride, x, y, z);
-                mn[3] = fminf(mn[3], x); mn[4] = fminf(mn[4], y); mn[5] = fminf(mn[5], z);
-                mx[3] = fmaxf(mx[3], x); mx[4] = fmaxf(mx[4], y); mx[5] = fmaxf(mx[5], z);
+        // four atoms per iteration: the index loads, then the coordinate loads, are issued back to back
+        auto bbox_pass = [&](const float *fr, const uint32_t *hinfo, int nh, float *lo3, float *hi3) {
+            for (int k0 = tid; k0 < nh; k0 += 4 * NT) {
+                uint32_t info[4];
+                float x[4], y[4], z[4];
+#pragma unroll
+                for (int u = 0; u < 4; u++) info[u] = __ldg(hinfo + min(k0 + u * NT, nh - 1));
+#pragma unroll
+                for (int u = 0; u < 4; u++) load_xyz(fr, PC_W_INDEX(info[u]), a.stride, x[u], y[u], z[u]);
+#pragma unroll
+                for (int u = 0; u < 4; u++) {       // a clamped duplicate of the last atom leaves min/max unchanged
+                    lo3[0] = fminf(lo3[0], x[u]); lo3[1] = fminf(lo3[1], y[u]); lo3[2] = fminf(lo3[2], z[u]);
+                    hi3[0] = fmaxf(hi3[0], x[u]); hi3[1] = fmaxf(hi3[1], y[u]); hi3[2] = fmaxf(hi3[2], z[u]);
+                }
             }
-        }
+        };
+        bbox_pass(fr1, a.t.hinfo1, n1h, mn, mx);
+        if (!self) bbox_pass(fr2, a.t.hinfo2, n2h, mn + 3, mx + 3);
 #pragma unroll
         for (int k = 0; k < 6; k++) { mn[k] = warp_min(mn[k]); mx[k] = warp_max(mx[k]); }
         if (lane == 0) {
 #pragma unroll
             for (int k = 0; k < 6; k++) { red[warp][k] = mn[k]; red[warp][6 + k] = mx[k]; }
         }
-        if (tid == 0) { s_nhits = 0; s_nhb = 0; s_status = 0; s_nA = 0; s_nB = 0; }
+        if (tid == 0) { s_nhits = 0; s_nhb = 0; s_status = 0; s_nA = 0; s_nB = 0; s_ngate = 0; }
         __syncthreads();
+        PC_PHASE_MARK(0);
 
         // ---- phase 2: grid geometry (warp 0 reduces the per-warp boxes) ---------------------------
         if (warp == 0) {
@@ -215,6 +221,7 @@ __global__ void __launch_bounds__(NT, NT >= 1024 ? 1 : 2) pc_scan_small_kernel(c
             }
         }
         __syncthreads();
+        PC_PHASE_MARK(1);
         const int ncell = g.ncell;
         int nInA = 0, nInB = 0;
         bool staged = true;               // false: the frame does not fit this launch's staging
@@ -236,33 +243,36 @@ __global__ void __launch_bounds__(NT, NT >= 1024 ? 1 : 2) pc_scan_small_kernel(c
                 if (cx >= nx || cy >= ny || cz >= nz) return -1;
                 return (cz * ny + cy) * nx + cx;
             };
-            for (int k = tid; k < n1h; k += NT) {
-                const uint32_t info = __ldg(a.t.hinfo1 + k);
-                float x, y, z;
-                load_xyz(fr1, PC_W_INDEX(info), a.stride, x, y, z);
-                const int c = cell_of(x, y, z);
-                if (c >= 0) {
-                    const unsigned p = atomicAdd(&s_nA, 1u);
-                    if (p < (unsigned)capCand) { cand[p] = make_float4(x, y, z, __uint_as_float(info)); ccell[p] = (uint16_t)c; }
-                    atomicAdd(&cellA[c], 1u);
-                }
-            }
-            if (!self)
-                for (int k = tid; k < n2h; k += NT) {
-                    const uint32_t info = __ldg(a.t.hinfo2 + k);
-                    float x, y, z;
-                    load_xyz(fr2, PC_W_INDEX(info), a.stride, x, y, z);
-                    const int c = cell_of(x, y, z);
-                    if (c >= 0) {
-                        const unsigned p = atomicAdd(&s_nB, 1u);
-                        if (p < (unsigned)capCand) {
-                            cand[capCand - 1 - p] = make_float4(x, y, z, __uint_as_float(info));
-                            ccell[capCand - 1 - p] = (uint16_t)c;
+            // selection A fills the pool from the bottom, B from the top; four atoms per iteration so that
+            // the loads of an iteration are in flight together
+            auto stage_pass = [&](const float *fr, const uint32_t *hinfo, int nh, unsigned int *counter, uint32_t *cells,
+                                  const bool top) {
+                for (int k0 = tid; k0 < nh; k0 += 4 * NT) {
+                    uint32_t info[4];
+                    float x[4], y[4], z[4];
+#pragma unroll
+                    for (int u = 0; u < 4; u++) info[u] = __ldg(hinfo + min(k0 + u * NT, nh - 1));
+#pragma unroll
+                    for (int u = 0; u < 4; u++) load_xyz(fr, PC_W_INDEX(info[u]), a.stride, x[u], y[u], z[u]);
+#pragma unroll
+                    for (int u = 0; u < 4; u++) {
+                        const int c = k0 + u * NT < nh ? cell_of(x[u], y[u], z[u]) : -1;
+                        if (c >= 0) {
+                            const unsigned p = atomicAdd(counter, 1u);
+                            if (p < (unsigned)capCand) {
+                                const unsigned q = top ? (unsigned)capCand - 1u - p : p;
+                                cand[q] = make_float4(x[u], y[u], z[u], __uint_as_float(info[u]));
+                                ccell[q] = (uint16_t)c;
+                            }
+                            atomicAdd(&cells[c], 1u);
                         }
-                        atomicAdd(&cellB[c], 1u);
                     }
                 }
+            };
+            stage_pass(fr1, a.t.hinfo1, n1h, &s_nA, cellA, false);
+            if (!self) stage_pass(fr2, a.t.hinfo2, n2h, &s_nB, cellB, true);
             __syncthreads();
+            PC_PHASE_MARK(2);
             nInA = (int)s_nA; nInB = self ? nInA : (int)s_nB;
             if (nInA + (self ? 0 : nInB) > capCand) {
                 staged = false;
@@ -270,6 +280,7 @@ __global__ void __launch_bounds__(NT, NT >= 1024 ? 1 : 2) pc_scan_small_kernel(c
                 // ---- phase 4: scans ---------------------------------------------------------------------
                 block_excl_scan_inplace<NT>(cellA, ncell, wsum);
                 if (!self) block_excl_scan_inplace<NT>(cellB, ncell, wsum);
+                PC_PHASE_MARK(3);
                 // ---- phase 5: scatter into cell order; afterwards cell[c] == END of cell c -----------
                 sortA = sortp;
                 sortB = self ? sortp : sortp + (capCand - nInB);
@@ -277,6 +288,7 @@ __global__ void __launch_bounds__(NT, NT >= 1024 ? 1 : 2) pc_scan_small_kernel(c
                 if (!self)
                     for (int p = tid; p < nInB; p += NT) sortB[atomicAdd(&cellB[ccell[capCand - 1 - p]], 1u)] = cand[capCand - 1 - p];
                 __syncthreads();
+                PC_PHASE_MARK(4);
 
                 // ---- phase 6: pair search, one thread per (A atom, stencil layer) --------------------
                 // items are layer-major: the lanes of a warp hold neighbouring atoms (same or adjacent
@@ -328,6 +340,7 @@ __global__ void __launch_bounds__(NT, NT >= 1024 ? 1 : 2) pc_scan_small_kernel(c
                         }
                     }
                 }
+                PC_PHASE_MARK(5);       // thread 0's own share of the search
             }
         }
         // The accumulation table is laid over the candidate pool, which nobody reads any more: every
@@ -338,6 +351,7 @@ __global__ void __launch_bounds__(NT, NT >= 1024 ? 1 : 2) pc_scan_small_kernel(c
                 tfirst[s] = PC_EMPTY_KEY; tncont[s] = 0; tnhb[s] = 0;
             }
         __syncthreads();
+        PC_PHASE_MARK(6);
 
         // A frame that does not fit this launch's staging (in-grid atoms, hits) is handed to the launch
         // with the larger plan when there is one; nothing of it has been written to global memory yet.
@@ -359,15 +373,69 @@ __global__ void __launch_bounds__(NT, NT >= 1024 ? 1 : 2) pc_scan_small_kernel(c
             s_cbase = base;
         }
         __syncthreads();
+        PC_PHASE_MARK(7);
         const long long cbase = s_cbase;
         const unsigned tmask = (unsigned)capTab - 1u;
-        for (unsigned h = tid; h < nh; h += NT) {
+        // One donor-H...acceptor side of a gated pair (core/multi_trajectory.py:112-209).
+        // side 0: donor = atom1, acceptor = atom2; side 1: donor = atom2, acceptor = atom1
+        auto hbond_side = [&](const unsigned u, const int side) {
+            const float4 pa = sortA[u >> 16], pb = sortB[u & 0xffffu];
+            const int li = PC_W_INDEX(__float_as_uint(pa.w)), lj = PC_W_INDEX(__float_as_uint(pb.w));
+            const int *hptr = side == 0 ? a.t.lhptr1 : a.t.lhptr2;
+            const int *hidx = side == 0 ? a.t.lhidx1 : a.t.lhidx2;
+            const int heavy = side == 0 ? li : lj;
+            const int p0 = __ldg(hptr + heavy), p1 = __ldg(hptr + heavy + 1);
+            if (p0 == p1) return;
+            const double ax = pa.x, ay = pa.y, az = pa.z, bx = pb.x, by = pb.y, bz = pb.z;
+            for (int p = p0; p < p1; p++) {
+                const int hl = __ldg(hidx + p);
+                if (hl < 0) { atomicOr(&s_status, (unsigned)PC_ST_MISSING_H); continue; }
+                float hxf, hyf, hzf;
+                load_xyz(side == 0 ? fr1 : fr2, hl, a.stride, hxf, hyf, hzf);
+                double d = 0, ang = 0;
+                const bool ok = side == 0
+                    ? hbond_test(hxf, hyf, hzf, ax, ay, az, bx, by, bz, a.hb_cutoff, a.hb_angle, d, ang)
+                    : hbond_test(hxf, hyf, hzf, bx, by, bz, ax, ay, az, a.hb_cutoff, a.hb_angle, d, ang);
+                if (!ok) continue;
+                const unsigned q = atomicAdd(&s_nhb, 1u);
+                if (q < (unsigned)a.capHb) {
+                    pc_hbond r;
+                    r.i = li; r.j = lj; r.hyd = (uint32_t)hl | (side ? 0x80000000u : 0u);
+                    r.distance = (float)d; r.angle = (float)ang;
+                    hbq[q] = r;
+                }
+                if (fuse) {
+                    // the pair's key was inserted by 7a (unless the table overflowed, which 7a reports)
+                    const unsigned long long key =
+                        (unsigned long long)__ldg(a.t.lgid1 + li) * a.t.ngroups2 + (unsigned long long)__ldg(a.t.lgid2 + lj);
+                    unsigned s = pc_hash64(key) & tmask;
+                    for (int probes = 0; probes < capTab; probes++) {
+                        const unsigned long long k = *(volatile unsigned long long *)&tkey[s];
+                        if (k == key) { atomicAdd(&tnhb[s], 1u); break; }
+                        if (k == PC_EMPTY_KEY) break;
+                        s = (s + 1) & tmask;
+                    }
+                }
+            }
+        };
+
+        // 7a: one thread per hit -> contact record and accumulation.  Neighbouring hits come from the same
+        // A atom and B run, i.e. mostly from the same (group, group) key: the lanes of a warp take hits
+        // NT/32 apart so that their shared-memory atomics land on different table slots.  Pairs that pass
+        // the H-bond gate (both names start with O/N/S, core/multi_trajectory.py:112) are queued for 7b in
+        // the memory of the cell arrays, which the search no longer needs.
+        uint32_t *gateq = cellA;
+        const unsigned capGate = (unsigned)((self ? 1 : 2) * (a.capCells + 1));
+        constexpr int NW = NT / 32;
+        for (unsigned base = 0; base < nh; base += NT) {
+            const unsigned h = base + (unsigned)(lane * NW + ((warp + lane) % NW));
+            if (h >= nh) continue;
             const unsigned u = hits[h];
             const float4 pa = sortA[u >> 16], pb = sortB[u & 0xffffu];
             const unsigned wa = __float_as_uint(pa.w), wb = __float_as_uint(pb.w);
             const int li = PC_W_INDEX(wa), lj = PC_W_INDEX(wb);
-            const double ax = pa.x, ay = pa.y, az = pa.z, bx = pb.x, by = pb.y, bz = pb.z;
-            const double dx = ax - bx, dy = ay - by, dz = az - bz;
+            const double dx = (double)pa.x - (double)pb.x, dy = (double)pa.y - (double)pb.y,
+                         dz = (double)pa.z - (double)pb.z;
             const double dist = sqrt(dx * dx + dy * dy + dz * dz);
             const float wgt = contact_weight_f32(dist);
             if (cbase >= 0) {
@@ -375,11 +443,10 @@ __global__ void __launch_bounds__(NT, NT >= 1024 ? 1 : 2) pc_scan_small_kernel(c
                 rec.i = li; rec.j = lj; rec.distance = (float)dist; rec.weight = wgt;
                 a.contacts[cbase + h] = rec;
             }
-            unsigned slot = 0xffffffffu;
             if (fuse) {
                 const unsigned long long key =
                     (unsigned long long)__ldg(a.t.lgid1 + li) * a.t.ngroups2 + (unsigned long long)__ldg(a.t.lgid2 + lj);
-                unsigned s = pc_hash64(key) & tmask;
+                unsigned slot = 0xffffffffu, s = pc_hash64(key) & tmask;
                 for (int probes = 0; probes < capTab; probes++) {
                     const unsigned long long prev = atomicCAS(&tkey[s], PC_EMPTY_KEY, key);
                     if (prev == PC_EMPTY_KEY || prev == key) { slot = s; break; }
@@ -391,41 +458,26 @@ __global__ void __launch_bounds__(NT, NT >= 1024 ? 1 : 2) pc_scan_small_kernel(c
                     if (wa & PC_W_BACKBONE) atomicAdd(&tbb1[slot], wgt);
                     if (wb & PC_W_BACKBONE) atomicAdd(&tbb2[slot], wgt);
                     atomicAdd(&tncont[slot], 1u);
-                    atomicMin(&tfirst[slot], ((unsigned long long)(unsigned)li << 32) | (unsigned)lj);
+                    // the minimum only ever decreases: a (possibly stale) read that is already smaller settles it
+                    const unsigned long long mine = ((unsigned long long)(unsigned)li << 32) | (unsigned)lj;
+                    if (*(volatile unsigned long long *)&tfirst[slot] > mine) atomicMin(&tfirst[slot], mine);
                 }
             }
-            // H-bond gate: both names start with O/N/S (core/multi_trajectory.py:112)
             if (wa & wb & PC_W_HBCLASS) {
-                for (int side = 0; side < 2; side++) {
-                    const int *hptr = side == 0 ? a.t.lhptr1 : a.t.lhptr2;
-                    const int *hidx = side == 0 ? a.t.lhidx1 : a.t.lhidx2;
-                    const int heavy = side == 0 ? li : lj;
-                    const int p0 = __ldg(hptr + heavy), p1 = __ldg(hptr + heavy + 1);
-                    for (int p = p0; p < p1; p++) {
-                        const int hl = __ldg(hidx + p);
-                        if (hl < 0) { atomicOr(&s_status, (unsigned)PC_ST_MISSING_H); continue; }
-                        float hxf, hyf, hzf;
-                        load_xyz(side == 0 ? fr1 : fr2, hl, a.stride, hxf, hyf, hzf);
-                        double d = 0, ang = 0;
-                        // side 0: donor = atom1, acceptor = atom2; side 1: donor = atom2, acceptor = atom1
-                        const bool ok = side == 0
-                            ? hbond_test(hxf, hyf, hzf, ax, ay, az, bx, by, bz, a.hb_cutoff, a.hb_angle, d, ang)
-                            : hbond_test(hxf, hyf, hzf, bx, by, bz, ax, ay, az, a.hb_cutoff, a.hb_angle, d, ang);
-                        if (ok) {
-                            const unsigned q = atomicAdd(&s_nhb, 1u);
-                            if (q < (unsigned)a.capHb) {
-                                pc_hbond r;
-                                r.i = li; r.j = lj; r.hyd = (uint32_t)hl | (side ? 0x80000000u : 0u);
-                                r.distance = (float)d; r.angle = (float)ang;
-                                hbq[q] = r;
-                            }
-                            if (slot != 0xffffffffu) atomicAdd(&tnhb[slot], 1u);
-                        }
-                    }
-                }
+                const unsigned q = atomicAdd(&s_ngate, 1u);
+                if (q < capGate) gateq[q] = u;
+                else { hbond_side(u, 0); hbond_side(u, 1); }      // queue full: tested in place
             }
         }
+        PC_PHASE_MARK(8);           // thread 0's own share of the drain
         __syncthreads();
+        PC_PHASE_MARK(9);
+
+        // 7b: one thread per (gated pair, side)
+        const unsigned ngate = min(s_ngate, capGate);
+        for (unsigned it = tid; it < 2u * ngate; it += NT) hbond_side(gateq[it >> 1], (int)(it & 1u));
+        __syncthreads();
+        PC_PHASE_MARK(11);
 
         // ---- phase 8: H-bond records and accumulated rows -> global -----------------------------
         unsigned nb = s_nhb;
@@ -480,6 +532,7 @@ __global__ void __launch_bounds__(NT, NT >= 1024 ? 1 : 2) pc_scan_small_kernel(c
         }
         if (tid == 0 && s_status) atomicOr(&a.counters[PC_CNT_STATUS], (unsigned long long)s_status);
         __syncthreads();
+        PC_PHASE_MARK(10);
     }
     // evaluation counter -> global (one atomic per warp)
 #pragma unroll
