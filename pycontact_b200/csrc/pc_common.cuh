@@ -151,6 +151,18 @@ __device__ __forceinline__ bool hbond_test(double hx, double hy, double hz, doub
     return true;
 }
 
+// The reference's pair test on Blackwell's packed float32 pipe: (bx-ax, by-ay) in one FADD2, both squares in
+// one FMUL2.  Every operation is a separately rounded IEEE float32 one like dist2_exact's; b - a is the
+// exact negative of a - b (round-to-nearest is symmetric), so the squares, the sums and the decision are
+// bit-identical to gridsearch.C:48-55.  nxy = (-ax, -ay), naz = -az.
+__device__ __forceinline__ bool pair_within_packed(const float2 nxy, const float naz, const float4 pb, const float sqdist) {
+    const float2 dxy = __fadd2_rn(make_float2(pb.x, pb.y), nxy);
+    const float dz = __fadd_rn(pb.z, naz);
+    const float2 sxy = __fmul2_rn(dxy, dxy);
+    const float sz = __fmul_rn(dz, dz);
+    return !(__fadd_rn(__fadd_rn(sxy.x, sxy.y), sz) > sqdist);
+}
+
 // stencil rank of a box offset in make_neighborlist_sym order (gridsearch.C:858-885, App. A.3);
 // index = (dx+1) + 3*(dy+1) + 9*(dz+1)
 __constant__ unsigned char PC_STENCIL_RANK[27] = {

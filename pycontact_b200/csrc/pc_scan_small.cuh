@@ -139,7 +139,7 @@ __global__ void __launch_bounds__(NT, NT >= 1024 ? 1 : NT >= 512 ? 2 : NT >= 384
     const bool self = a.self_mode != 0;
     const bool fuse = a.fuse_acc != 0;
     const int n1h = a.t.n1h, n2h = self ? a.t.n1h : a.t.n2h;
-    const float sqdist = a.sqdist, sqdist_hi = a.sqdist * 1.00000095367431640625f;   // 1 + 2^-20
+    const float sqdist = a.sqdist;
     unsigned long long evals = 0;
 
     const int nfr = fl.frame_list ? (int)*fl.frame_count : a.nframes;
@@ -301,6 +301,8 @@ __global__ void __launch_bounds__(NT, NT >= 1024 ? 1 : NT >= 512 ? 2 : NT >= 384
                     const int z = cz + layer - 1;
                     if (z < 0 || z >= nz) continue;
                     const int xlo = max(cx - 1, 0), xhi = min(cx + 1, nx - 1);
+                    const float2 nxy = make_float2(-pa.x, -pa.y);
+                    const float naz = -pa.z;
                     int ares = 0, aseg = 0;
                     if (self) {
                         const int li = PC_W_INDEX(__float_as_uint(pa.w));
@@ -314,11 +316,16 @@ __global__ void __launch_bounds__(NT, NT >= 1024 ? 1 : NT >= 512 ? 2 : NT >= 384
                         for (int jb = b0; jb < b1; jb += 32) {
                             const int cnt = min(32, b1 - jb);
                             unsigned m = 0;
-#pragma unroll 4
-                            for (int k = 0; k < cnt; k++) {
-                                const float4 pb = sortB[jb + k];
-                                m |= (unsigned)pair_within(pa.x, pa.y, pa.z, pb.x, pb.y, pb.z, sqdist, sqdist_hi) << k;
+                            int k0 = 0;
+                            for (; k0 + 4 <= cnt; k0 += 4) {
+                                unsigned m4 = 0;
+#pragma unroll
+                                for (int u = 0; u < 4; u++)
+                                    if (pair_within_packed(nxy, naz, sortB[jb + k0 + u], sqdist)) m4 |= 1u << u;
+                                m |= m4 << k0;
                             }
+                            for (; k0 < cnt; k0++)
+                                if (pair_within_packed(nxy, naz, sortB[jb + k0], sqdist)) m |= 1u << k0;
                             if (self && m) {
                                 // (resid1 - resid2) < 5 and same segment -> dropped (core/multi_trajectory.py:93-95)
                                 unsigned t = m;
