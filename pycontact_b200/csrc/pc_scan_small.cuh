@@ -59,10 +59,16 @@ __host__ inline PcSmallSmem pc_small_layout(int self_mode, int capCells, int cap
     return L;
 }
 
+// Cells are numbered with the axis that has the fewest cells running fastest ("f"), the one with the most
+// slowest ("s"): contact interfaces are slabs, and when the thin axis has <= 3 cells an atom's three-cell
+// run is the whole row, so the three rows of a stencil layer are one contiguous range of the sorted array.
 struct PcGridSm {
     float lo[3];
     float inv;
     int nx, ny, nz, ncell;
+    int sx, sy, sz;       // cell id = cx * sx + cy * sy + cz * sz
+    int pf, pm, ps;       // axis (0 = x, 1 = y, 2 = z) that runs fastest / middle / slowest
+    int nf, nm, ns;       // cells along those axes
 };
 
 #define PC_EMPTY_KEY 0xffffffffffffffffull
@@ -131,7 +137,7 @@ __global__ void __launch_bounds__(NT, NT >= 1024 ? 1 : NT >= 512 ? 2 : NT >= 384
     __shared__ float red[NT / 32][12];
     __shared__ uint32_t wsum[32];
     __shared__ PcGridSm g;
-    __shared__ unsigned int s_nhits, s_nhb, s_nA, s_nB, s_ngate;
+    __shared__ unsigned int s_nhits, s_nhb, s_nA, s_nB, s_ngate, s_next;
     __shared__ long long s_cbase, s_hbase, s_rbase;
     __shared__ unsigned int s_status;
 
@@ -177,7 +183,7 @@ __global__ void __launch_bounds__(NT, NT >= 1024 ? 1 : NT >= 512 ? 2 : NT >= 384
 #pragma unroll
             for (int k = 0; k < 6; k++) { red[warp][k] = mn[k]; red[warp][6 + k] = mx[k]; }
         }
-        if (tid == 0) { s_nhits = 0; s_nhb = 0; s_status = 0; s_nA = 0; s_nB = 0; s_ngate = 0; }
+        if (tid == 0) { s_nhits = 0; s_nhb = 0; s_status = 0; s_nA = 0; s_nB = 0; s_ngate = 0; s_next = 0; }
         __syncthreads();
         PC_PHASE_MARK(0);
 
@@ -218,6 +224,17 @@ __global__ void __launch_bounds__(NT, NT >= 1024 ? 1 : NT >= 512 ? 2 : NT >= 384
                 }
                 g.lo[0] = lx; g.lo[1] = ly; g.lo[2] = lz;
                 g.inv = inv; g.nx = nx; g.ny = ny; g.nz = nz; g.ncell = nx * ny * nz;
+                // axes by cell count, ascending (ties keep x < y < z)
+                int pf = 0, pm = 1, ps = 2;
+                int nn[3] = {nx, ny, nz};
+                if (nn[pm] < nn[pf]) { const int t = pf; pf = pm; pm = t; }
+                if (nn[ps] < nn[pm]) { const int t = pm; pm = ps; ps = t; }
+                if (nn[pm] < nn[pf]) { const int t = pf; pf = pm; pm = t; }
+                g.pf = pf; g.pm = pm; g.ps = ps;
+                g.nf = nn[pf]; g.nm = nn[pm]; g.ns = nn[ps];
+                int st[3];
+                st[pf] = 1; st[pm] = nn[pf]; st[ps] = nn[pf] * nn[pm];
+                g.sx = st[0]; g.sy = st[1]; g.sz = st[2];
             }
         }
         __syncthreads();
@@ -229,6 +246,7 @@ __global__ void __launch_bounds__(NT, NT >= 1024 ? 1 : NT >= 512 ? 2 : NT >= 384
         if (ncell > 0) {
             const int nx = g.nx, ny = g.ny, nz = g.nz;
             const float lox = g.lo[0], loy = g.lo[1], loz = g.lo[2], inv = g.inv;
+            const int sx = g.sx, sy = g.sy, sz = g.sz;
 
             // ---- phase 3: second pass over the frame (it is in L2 now): atoms inside the grid go to
             //      the candidate pool with their cell id; atoms per cell (shared atomics) -----------------
@@ -241,7 +259,7 @@ __global__ void __launch_bounds__(NT, NT >= 1024 ? 1 : NT >= 512 ? 2 : NT >= 384
                 if (!(ux >= 0.f && uy >= 0.f && uz >= 0.f)) return -1;
                 const int cx = (int)ux, cy = (int)uy, cz = (int)uz;
                 if (cx >= nx || cy >= ny || cz >= nz) return -1;
-                return (cz * ny + cy) * nx + cx;
+                return cx * sx + cy * sy + cz * sz;
             };
             // selection A fills the pool from the bottom, B from the top; four atoms per iteration so that
             // the loads of an iteration are in flight together
@@ -258,6 +276,7 @@ __global__ void __launch_bounds__(NT, NT >= 1024 ? 1 : NT >= 512 ? 2 : NT >= 384
                     for (int u = 0; u < 4; u++) {
                         const int c = k0 + u * NT < nh ? cell_of(x[u], y[u], z[u]) : -1;
                         if (c >= 0) {
+                            // (the compiler already merges the same-address atomics of a warp into one)
                             const unsigned p = atomicAdd(counter, 1u);
                             if (p < (unsigned)capCand) {
                                 const unsigned q = top ? (unsigned)capCand - 1u - p : p;
@@ -293,14 +312,25 @@ __global__ void __launch_bounds__(NT, NT >= 1024 ? 1 : NT >= 512 ? 2 : NT >= 384
                 // ---- phase 6: pair search, one thread per (A atom, stencil layer) --------------------
                 // items are layer-major: the lanes of a warp hold neighbouring atoms (same or adjacent
                 // cells, A is cell-sorted) on the same layer, so their run lengths are alike
-                for (int w = tid; w < 3 * nInA; w += NT) {
+                const int pf = g.pf, pm = g.pm, ps = g.ps, nf = g.nf, nm = g.nm, ns = g.ns;
+                // batches of 32 items are handed out dynamically: the warps finish the phase together
+                const int nitems = 3 * nInA;
+                for (;;) {
+                    int w = 0;
+                    if (lane == 0) w = (int)atomicAdd(&s_next, 32u);
+                    w = __shfl_sync(PC_FULL_MASK, w, 0);
+                    if (w >= nitems) break;
+                    w += lane;
+                    if (w >= nitems) continue;
                     const int layer = w / nInA, ia = w - layer * nInA;
                     const float4 pa = sortA[ia];
                     const int cx = (int)((pa.x - lox) * inv), cy = (int)((pa.y - loy) * inv),
                               cz = (int)((pa.z - loz) * inv);
-                    const int z = cz + layer - 1;
-                    if (z < 0 || z >= nz) continue;
-                    const int xlo = max(cx - 1, 0), xhi = min(cx + 1, nx - 1);
+                    const int cf = pf == 0 ? cx : pf == 1 ? cy : cz, cm = pm == 0 ? cx : pm == 1 ? cy : cz,
+                              cs = ps == 0 ? cx : ps == 1 ? cy : cz;
+                    const int sl = cs + layer - 1;
+                    if (sl < 0 || sl >= ns) continue;
+                    const int flo = max(cf - 1, 0), fhi = min(cf + 1, nf - 1);
                     const float2 nxy = make_float2(-pa.x, -pa.y);
                     const float naz = -pa.z;
                     int ares = 0, aseg = 0;
@@ -308,15 +338,43 @@ __global__ void __launch_bounds__(NT, NT >= 1024 ? 1 : NT >= 512 ? 2 : NT >= 384
                         const int li = PC_W_INDEX(__float_as_uint(pa.w));
                         ares = __ldg(a.t.lres1 + li); aseg = __ldg(a.t.lseg1 + li);
                     }
-                    for (int y = max(cy - 1, 0); y <= min(cy + 1, ny - 1); y++) {
-                        const int row = (z * ny + y) * nx;
-                        const int b0 = (row + xlo) ? (int)cellB[row + xlo - 1] : 0, b1 = (int)cellB[row + xhi];
-                        evals += (unsigned)(b1 - b0);
+                    // The (up to) three rows of the layer -> up to three runs of the sorted B array; rows that
+                    // follow each other in the array are merged (always, when the fast axis has <= 3 cells).
+                    // Built before the candidate loop so that lanes with one merged run stay converged.
+                    int ab = 0, ae = 0, bb = 0, be = 0, cb = 0, ce = 0;
+                    {
+                        const int row1 = (sl * nm + cm) * nf;
+                        if (cm > 0) {
+                            const int row0 = row1 - nf;
+                            ab = (row0 + flo) ? (int)cellB[row0 + flo - 1] : 0; ae = (int)cellB[row0 + fhi];
+                        }
+                        const int b0 = (row1 + flo) ? (int)cellB[row1 + flo - 1] : 0, b1 = (int)cellB[row1 + fhi];
+                        if (ab == ae) { ab = b0; ae = b1; }
+                        else if (b0 == ae) ae = b1;
+                        else if (b0 != b1) { bb = b0; be = b1; }
+                        if (cm + 1 < nm) {
+                            const int row2 = row1 + nf;
+                            const int c0 = (int)cellB[row2 + flo - 1], c1 = (int)cellB[row2 + fhi];
+                            if (c0 != c1) {
+                                if (bb != be) { if (c0 == be) be = c1; else { cb = c0; ce = c1; } }
+                                else if (ab == ae) { ab = c0; ae = c1; }
+                                else if (c0 == ae) ae = c1;
+                                else { bb = c0; be = c1; }
+                            }
+                        }
+                    }
+                    evals += (unsigned)((ae - ab) + (be - bb) + (ce - cb));
+                    for (int ri = 0; ri < 3; ri++) {
+                        const int rb0 = ri == 0 ? ab : ri == 1 ? bb : cb, rb1 = ri == 0 ? ae : ri == 1 ? be : ce;
+                        if (rb0 == rb1) break;
                         // 32 candidates at a time into a hit mask; the queue is touched once per chunk
-                        for (int jb = b0; jb < b1; jb += 32) {
-                            const int cnt = min(32, b1 - jb);
+                        for (int jb = rb0; jb < rb1; jb += 32) {
+                            const int cnt = min(32, rb1 - jb);
                             unsigned m = 0;
                             int k0 = 0;
+                            // no further unrolling: a 16-wide and a 4-wide body would be two paths that the
+                            // lanes of a warp (different run lengths) execute one after the other
+#pragma unroll 1
                             for (; k0 + 4 <= cnt; k0 += 4) {
                                 unsigned m4 = 0;
 #pragma unroll
@@ -324,6 +382,7 @@ __global__ void __launch_bounds__(NT, NT >= 1024 ? 1 : NT >= 512 ? 2 : NT >= 384
                                     if (pair_within_packed(nxy, naz, sortB[jb + k0 + u], sqdist)) m4 |= 1u << u;
                                 m |= m4 << k0;
                             }
+#pragma unroll 1
                             for (; k0 < cnt; k0++)
                                 if (pair_within_packed(nxy, naz, sortB[jb + k0], sqdist)) m |= 1u << k0;
                             if (self && m) {

@@ -17,18 +17,20 @@ import subprocess
 import tempfile
 
 
-def sass_lines(so, kernel, sym=None):
+def sass_lines(so, kernel, sym=None, outer=False):
     tmp = tempfile.mkdtemp()
     subprocess.run(["cuobjdump", "-xelf", "all", os.path.abspath(so)], cwd=tmp, check=True, capture_output=True)
     out = []
     for cubin in glob.glob(os.path.join(tmp, "*.cubin")):
-        txt = subprocess.run(["nvdisasm", "-g", "-c", cubin], capture_output=True, text=True).stdout
+        txt = subprocess.run(["nvdisasm", "-gi" if outer else "-g", "-c", cubin], capture_output=True, text=True).stdout
         cur_fn, cur_line, cur_file = None, 0, ""
         for ln in txt.split("\n"):
             m = re.match(r"\s*\.text\.(\S+):", ln)
             if m:
                 cur_fn = m.group(1)
                 continue
+            # with -gi an inlined instruction carries one marker per frame, innermost first; each marker
+            # overwrites the previous one, so the outermost frame (the kernel's own line) wins
             m = re.search(r'//## File "([^"]+)", line (\d+)', ln)
             if m:
                 cur_file, cur_line = os.path.basename(m.group(1)), int(m.group(2))
@@ -47,6 +49,8 @@ def main():
                                                  "pycontact_b200", "libpycontact_b200.so"))
     ap.add_argument("--top", type=int, default=40)
     ap.add_argument("--launch", type=int, default=0)
+    ap.add_argument("--outer", action="store_true", help="attribute inlined code to the line of the kernel that called it")
+    ap.add_argument("--ranges", default=None, help="sum over line ranges of the kernel's file: 152-182:bbox,233-275:stage,...")
     ap.add_argument("--sym", default=None, help="substring of the mangled name (e.g. ILi512E) to pick one instantiation")
     args = ap.parse_args()
     raw = subprocess.run(["ncu", "-i", args.report, "--page", "source", "--csv"], capture_output=True, text=True).stdout
@@ -68,7 +72,7 @@ def main():
     hdr = L["hdr"]
     ci = {n: hdr.index(n) for n in ("Source", "# Samples", "Instructions Executed", "Thread Instructions Executed")}
     stall_cols = [i for i, n in enumerate(hdr) if n.startswith("stall_") and "Not Issued" not in n]
-    sl = sass_lines(args.so, args.kernel.split("<")[0], args.sym)
+    sl = sass_lines(args.so, args.kernel.split("<")[0], args.sym, args.outer or bool(args.ranges))
     n = min(len(sl), len(L["rows"]))
     if len(sl) != len(L["rows"]):
         print("warning: %d SASS rows in report vs %d in library (joined by position)" % (len(L["rows"]), len(sl)))
@@ -88,6 +92,26 @@ def main():
                 a[3][hdr[i]] += v
         tot_inst += inst; tot_samp += samp
     print("kernel %s: %d warp-instructions, %d samples" % (L["name"][:70], tot_inst, tot_samp))
+    if args.ranges:
+        print("%-28s %12s %6s %8s %6s  %s" % ("range", "warp-inst", "%", "samples", "%", "top stalls"))
+        rest = [0, 0, collections.Counter()]
+        used = set()
+        for spec in args.ranges.split(","):
+            rng, name = spec.split(":")
+            lo, hi = [int(x) for x in rng.split("-")]
+            acc = [0, 0, collections.Counter()]
+            for (f, line), a in agg.items():
+                if lo <= line <= hi and f.startswith("pc_scan_small"):
+                    acc[0] += a[0]; acc[1] += a[1]; acc[2].update(a[3]); used.add((f, line))
+            st = ", ".join("%s %d" % (k.replace("stall_", ""), v) for k, v in acc[2].most_common(4))
+            print("%-28s %12d %5.1f%% %8d %5.1f%%  %s" % (name, acc[0], 100.0 * acc[0] / max(tot_inst, 1), acc[1],
+                                                          100.0 * acc[1] / max(tot_samp, 1), st))
+        for k, a in agg.items():
+            if k not in used:
+                rest[0] += a[0]; rest[1] += a[1]; rest[2].update(a[3])
+        print("%-28s %12d %5.1f%% %8d %5.1f%%" % ("(other)", rest[0], 100.0 * rest[0] / max(tot_inst, 1), rest[1],
+                                                  100.0 * rest[1] / max(tot_samp, 1)))
+        return
     print("%-24s %6s %12s %6s %8s %6s  %s" % ("file", "line", "warp-inst", "%", "samples", "%", "top stalls"))
     for (f, line), a in sorted(agg.items(), key=lambda kv: -kv[1][1])[: args.top]:
         st = ", ".join("%s %d" % (k.replace("stall_", ""), v) for k, v in a[3].most_common(3))
