@@ -78,6 +78,13 @@ __device__ __forceinline__ unsigned pc_hash64(unsigned long long k) {
     return (unsigned)k;
 }
 
+// Slot of a key in the per-frame shared-memory table: multiplicative hash, top bits (the table is private to
+// one frame of one CTA, so this hash need not match any other table's).
+__device__ __forceinline__ unsigned pc_hash_tab(unsigned long long k, int shift) {
+    const unsigned h = (unsigned)k * 0x9E3779B1u + (unsigned)(k >> 32) * 0x85EBCA6Bu;
+    return (h * 0x2545F491u) >> shift;
+}
+
 template <int NT>
 __device__ __forceinline__ void block_excl_scan_inplace(uint32_t *arr, int n, uint32_t *wsum) {
     // arr[0..n) -> exclusive prefix sums, arr[n] = total.  Each thread owns a contiguous chunk.
@@ -442,6 +449,7 @@ __global__ void __launch_bounds__(NT, NT >= 1024 ? 1 : NT >= 512 ? 2 : NT >= 384
         PC_PHASE_MARK(7);
         const long long cbase = s_cbase;
         const unsigned tmask = (unsigned)capTab - 1u;
+        const int tshift = 33 - __ffs(capTab);        // 32 - log2(capTab); capTab is a power of two
         // One donor-H...acceptor side of a gated pair (core/multi_trajectory.py:112-209).
         // side 0: donor = atom1, acceptor = atom2; side 1: donor = atom2, acceptor = atom1
         auto hbond_side = [&](const unsigned u, const int side) {
@@ -474,7 +482,7 @@ __global__ void __launch_bounds__(NT, NT >= 1024 ? 1 : NT >= 512 ? 2 : NT >= 384
                     // the pair's key was inserted by 7a (unless the table overflowed, which 7a reports)
                     const unsigned long long key =
                         (unsigned long long)__ldg(a.t.lgid1 + li) * a.t.ngroups2 + (unsigned long long)__ldg(a.t.lgid2 + lj);
-                    unsigned s = pc_hash64(key) & tmask;
+                    unsigned s = pc_hash_tab(key, tshift);
                     for (int probes = 0; probes < capTab; probes++) {
                         const unsigned long long k = *(volatile unsigned long long *)&tkey[s];
                         if (k == key) { atomicAdd(&tnhb[s], 1u); break; }
@@ -512,7 +520,7 @@ __global__ void __launch_bounds__(NT, NT >= 1024 ? 1 : NT >= 512 ? 2 : NT >= 384
             if (fuse) {
                 const unsigned long long key =
                     (unsigned long long)__ldg(a.t.lgid1 + li) * a.t.ngroups2 + (unsigned long long)__ldg(a.t.lgid2 + lj);
-                unsigned slot = 0xffffffffu, s = pc_hash64(key) & tmask;
+                unsigned slot = 0xffffffffu, s = pc_hash_tab(key, tshift);
                 for (int probes = 0; probes < capTab; probes++) {
                     const unsigned long long prev = atomicCAS(&tkey[s], PC_EMPTY_KEY, key);
                     if (prev == PC_EMPTY_KEY || prev == key) { slot = s; break; }
