@@ -515,7 +515,9 @@ __global__ void __launch_bounds__(NT, NT >= 1024 ? 1 : NT >= 512 ? 2 : NT >= 384
             if (cbase >= 0) {
                 pc_contact rec;
                 rec.i = li; rec.j = lj; rec.distance = (float)dist; rec.weight = wgt;
-                a.contacts[cbase + h] = rec;
+                // the queue has no order of its own: in a full round the records are written in thread order
+                // (one 512-byte run per warp) instead of the scattered order in which the hits are taken
+                a.contacts[cbase + (base + NT <= nh ? base + (unsigned)tid : h)] = rec;
             }
             if (fuse) {
                 const unsigned long long key =
@@ -575,7 +577,9 @@ __global__ void __launch_bounds__(NT, NT >= 1024 ? 1 : NT >= 512 ? 2 : NT >= 384
                 total = __shfl_sync(PC_FULL_MASK, vi, 31);
             }
             if (lane == 0) {
+                // both claims are issued before either result is looked at (one round trip to L2, not two)
                 long long base = (long long)atomicAdd(&a.counters[PC_CNT_HBONDS], (unsigned long long)nb);
+                long long rb = fuse ? (long long)atomicAdd(&a.counters[PC_CNT_ROWS], (unsigned long long)total) : 0;
                 if (base + nb > a.cap_hbonds) { atomicOr(&s_status, (unsigned)PC_ST_OUT_OVERFLOW); base = -1; }
                 s_hbase = base;
                 a.frame_cstart[f] = (uint32_t)(cbase < 0 ? 0 : cbase);
@@ -583,7 +587,6 @@ __global__ void __launch_bounds__(NT, NT >= 1024 ? 1 : NT >= 512 ? 2 : NT >= 384
                 a.frame_hstart[f] = (uint32_t)(base < 0 ? 0 : base);
                 a.frame_hcount[f] = base < 0 ? 0u : nb;
                 if (fuse) {
-                    long long rb = (long long)atomicAdd(&a.counters[PC_CNT_ROWS], (unsigned long long)total);
                     if (rb + total > a.cap_rows) { atomicOr(&s_status, (unsigned)PC_ST_OUT_OVERFLOW); rb = -1; }
                     s_rbase = rb;
                     a.frame_rstart[f] = (uint32_t)(rb < 0 ? 0 : rb);
