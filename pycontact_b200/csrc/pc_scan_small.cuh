@@ -329,7 +329,7 @@ __global__ void __launch_bounds__(NT, NT >= 1024 ? 1 : NT >= 512 ? 2 : NT >= 384
                     if (w >= nitems) break;
                     w += lane;
                     if (w >= nitems) continue;
-                    const int layer = w / nInA, ia = w - layer * nInA;
+                    const int layer = (w >= nInA) + (w >= 2 * nInA), ia = w - layer * nInA;
                     const float4 pa = sortA[ia];
                     const int cx = (int)((pa.x - lox) * inv), cy = (int)((pa.y - loy) * inv),
                               cz = (int)((pa.z - loz) * inv);
@@ -349,7 +349,11 @@ __global__ void __launch_bounds__(NT, NT >= 1024 ? 1 : NT >= 512 ? 2 : NT >= 384
                     // follow each other in the array are merged (always, when the fast axis has <= 3 cells).
                     // Built before the candidate loop so that lanes with one merged run stay converged.
                     int ab = 0, ae = 0, bb = 0, be = 0, cb = 0, ce = 0;
-                    {
+                    if (flo == 0 && fhi == nf - 1) {
+                        // whole rows: the cells of rows cm-1 .. cm+1 are one contiguous range (two lookups)
+                        const int first = (sl * nm + max(cm - 1, 0)) * nf, last = (sl * nm + min(cm + 1, nm - 1)) * nf + nf - 1;
+                        ab = first ? (int)cellB[first - 1] : 0; ae = (int)cellB[last];
+                    } else {
                         const int row1 = (sl * nm + cm) * nf;
                         if (cm > 0) {
                             const int row0 = row1 - nf;
