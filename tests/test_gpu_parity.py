@@ -504,3 +504,52 @@ def test_sparse_fold_equals_dense_fold_and_host_sums():
     assert ent.size == np.count_nonzero(host[:, 0]) and np.all(np.diff(ent["key"].astype(np.int64)) > 0)
     k = ent["key"].astype(np.int64)
     np.testing.assert_allclose(np.stack([ent["score"], ent["bb1"], ent["bb2"], ent["hbframes"]], 1), host[k], rtol=1e-12)
+
+
+def test_session_file_from_a_gpu_analysis(rpn11, golden_ab, tmp_path):
+    """core/DataHandler.py:20-28 on a live analysis: the lazy, array-backed containers of the GPU path are
+    expanded into the reference's session layout; re-imported, the session reproduces the pinned numbers of
+    tests/test_basic.py:38-43 and the golden per-contact data."""
+    from pycontact_b200.core.DataHandler import DataHandler
+    an = Analyzer("rpn11_ubq.psf", "rpn11_ubq.dcd", 5.0, 2.5, 120, "segid RN11", "segid UBQ",
+                  topology=rpn11.topology, frames=rpn11.coords)
+    an.runFrameScan(1)
+    an.runContactAnalysis([0, 0, 1, 1, 0], [0, 0, 1, 1, 0], 1)
+    path = str(tmp_path / "gpu.session")
+    DataHandler.writeSessionToFile(path, an)
+    assert b"pycontact_b200" not in open(path, "rb").read()
+    contacts, arguments, trajArgs, maps, contactResults = DataHandler.importSessionFromFile(path)
+    assert len(contacts) == 148 and sum(c.hbond_percentage() for c in contacts) == 676.0
+    assert arguments == ["rpn11_ubq.psf", "rpn11_ubq.dcd", 5.0, 2.5, 120, "segid RN11", "segid UBQ"]
+    assert maps == [[0, 0, 1, 1, 0], [0, 0, 1, 1, 0]] and len(trajArgs) == 7
+    assert [len(f) for f in contactResults] == np.diff(golden_ab["frame_ptr"]).tolist()
+    flat = [c for f in contactResults for c in f]
+    assert [c.idx1 for c in flat] == golden_ab["idx1"].tolist() and [c.idx2 for c in flat] == golden_ab["idx2"].tolist()
+    np.testing.assert_allclose([c.distance for c in flat], golden_ab["distance"], rtol=RTOL)
+    np.testing.assert_allclose([c.weight for c in flat], golden_ab["weight"], rtol=RTOL)
+    assert sum(len(c.hbondinfo) for c in flat) == 457
+    _check_accumulated(contacts, golden_ab)
+
+
+def test_scripting_job_on_files(tmp_path):
+    """core/Scripting.py:28-41: PyContactJob.runJob + writeSessionToFile on PSF/DCD files."""
+    from pycontact_b200.core.DataHandler import DataHandler
+    from pycontact_b200.core.Scripting import JobConfig, PyContactJob
+    from tests.test_io_cpu import _write_dcd, _write_psf
+    s = synth.make_system("tiny")
+    coords = synth.frames_host(s, range(5))
+    psf, dcd = str(tmp_path / "tiny.psf"), str(tmp_path / "tiny.dcd")
+    _write_psf(psf, s.topology)
+    _write_dcd(dcd, coords)
+    job = PyContactJob(psf, dcd, str(tmp_path / "tinyjob"), JobConfig(5.0, 2.5, 120, s.maps[0], s.maps[1], s.sel1text, s.sel2text))
+    job.runJob(1)
+    job.writeSessionToFile()
+    contacts, arguments, trajArgs, maps, contactResults = DataHandler.importSessionFromFile(str(tmp_path / "tinyjob.session"))
+    t = s.topology
+    ora = frame_oracle.scan_frames([coords[f, s.sel1] for f in range(5)], [coords[f, s.sel2] for f in range(5)],
+                                   s.sel1, s.sel2, 5.0, 2.5, 120, t.names, t.types, t.bonds)
+    oacc = frame_oracle.accumulate(ora, s.maps[0], s.maps[1], t.names, t.resids, t.resnames, t.segids, s.backbone)
+    assert [a.key1 for a in contacts] == oacc["key1"] and [a.key2 for a in contacts] == oacc["key2"]
+    np.testing.assert_allclose(np.asarray([a.scoreArray for a in contacts], float), oacc["score"], rtol=RTOL, atol=1e-12)
+    assert [len(f) for f in contactResults] == [len(f["idx1"]) for f in ora]
+    assert arguments[:2] == [psf, dcd] and maps == [s.maps[0], s.maps[1]]
