@@ -147,6 +147,17 @@ int pc_accumulate(pc_ctx *ctx, void *stream);
  * hbond_percentage, core/Biochemistry.py:150-186, core/ContactAnalyzer.py:588-591). */
 int pc_fold_rows(pc_ctx *ctx, double *d_totals, int64_t n_keys, void *stream);
 
+/* Per-key statistics over the (keys x frames) score matrix, all keys in one launch (one CTA per key):
+ * d_out[n_keys][8] = mean score, median score, hbond_percentage, total_time, mean_life_time,
+ * median_life_time, number of life-time entries, frames above the threshold -- AccumulatedContact.mean_score /
+ * median_score / hbond_percentage / total_time / mean_life_time / median_life_time
+ * (core/Biochemistry.py:150-213) for every contact at once, which is what the reference's filters and
+ * sorts (core/ContactFilters.py:185-287) recompute per object.  d_scores is row-major float64
+ * [n_keys][n_frames] (scoreArray of each key); d_hbonds (may be NULL) holds the H-bonds per (key, frame)
+ * (hbondFramesScan).  n_frames <= 16384 per call. */
+int pc_key_stats(int device, const double *d_scores, const uint32_t *d_hbonds, int64_t n_keys, int32_t n_frames,
+                 double ns_per_frame, double threshold, double *d_out, void *stream);
+
 /* The same aggregation for key spaces too large for a dense table: a per-context open-addressing table
  * (key -> sum score, sum bb1, sum bb2, frames with an H-bond) that lives across batches.
  * pc_fold_sparse_init sizes it (entries, rounded up to a power of two) and clears it;

@@ -16,6 +16,7 @@
 #include "pc_order.cuh"
 #include "pc_search.cuh"
 #include "pc_synth.cuh"
+#include "pc_stats.cuh"
 
 static thread_local std::string g_err;
 static unsigned long long g_launches = 0;      // kernels launched by this library (bench.py's gpu_launches)
@@ -527,6 +528,29 @@ extern "C" int pc_fold_rows(pc_ctx *c, double *d_totals, int64_t n_keys, void *s
     CUDA_TRY(cudaSetDevice(c->device));
     pc_fold_rows_kernel<<<2 * c->num_sms, 256, 0, (cudaStream_t)stream>>>(c->rows.p, c->counters.p, c->cap_rows, d_totals,
                                                                          (unsigned long long)n_keys);
+    CUDA_TRY(cudaGetLastError());
+    g_launches += 1;
+    return PC_OK;
+}
+
+extern "C" int pc_key_stats(int device, const double *d_scores, const uint32_t *d_hbonds, int64_t n_keys, int32_t n_frames,
+                            double ns_per_frame, double threshold, double *d_out, void *stream) {
+    if (!d_scores || !d_out || n_keys < 0 || n_frames < 0) return fail(PC_ERR_INVALID, "pc_key_stats: bad arguments");
+    if (n_frames > PC_STATS_MAX_FRAMES)
+        return fail(PC_ERR_INVALID, "pc_key_stats: more than 16384 frames per call (split the frame range)");
+    if (n_keys == 0) return PC_OK;
+    CUDA_TRY(cudaSetDevice(device));
+    int fpad = 2, rpad = 2;
+    while (fpad < n_frames) fpad <<= 1;
+    while (rpad < n_frames / 2 + 2) rpad <<= 1;
+    const size_t smem = sizeof(double) * (size_t)fpad + sizeof(unsigned int) * (size_t)rpad;
+    CUDA_TRY(cudaFuncSetAttribute(pc_key_stats_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int sms = 0;
+    CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));
+    const int per_sm = smem > 100 * 1024 ? 1 : 2;
+    const int grid = (int)std::min<int64_t>(n_keys, (int64_t)per_sm * sms);
+    pc_key_stats_kernel<<<grid, PC_STATS_NT, smem, (cudaStream_t)stream>>>(d_scores, d_hbonds, (long long)n_keys, n_frames, fpad,
+                                                                        rpad, ns_per_frame, threshold, d_out);
     CUDA_TRY(cudaGetLastError());
     g_launches += 1;
     return PC_OK;

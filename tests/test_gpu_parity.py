@@ -5,6 +5,8 @@ Everything goes through the C ABI (ctypes -> libpycontact_b200.so).  The bar
 the reference's in-frame order; distances, weights, angles and scores within 1e-5
 relative (the device stores float32 records, the reference float64).
 """
+import os
+
 import numpy as np
 import pytest
 
@@ -553,3 +555,122 @@ def test_scripting_job_on_files(tmp_path):
     np.testing.assert_allclose(np.asarray([a.scoreArray for a in contacts], float), oacc["score"], rtol=RTOL, atol=1e-12)
     assert [len(f) for f in contactResults] == [len(f["idx1"]) for f in ora]
     assert arguments[:2] == [psf, dcd] and maps == [s.maps[0], s.maps[1]]
+
+
+# ---- per-contact statistics and filters on the device ---------------------------------
+STATS_RTOL = 1e-12      # float64 sums in a different order / count * ns instead of repeated addition
+
+
+def _check_stats(st, ora, exact_counts=True):
+    for k in ("mean", "median", "hbond_percentage", "total_time", "mean_life_time", "median_life_time"):
+        np.testing.assert_allclose(st[k], ora[k], rtol=STATS_RTOL, atol=1e-300, err_msg=k)
+    assert np.array_equal(st["life_entries"], ora["life_entries"])
+    assert np.array_equal(st["frames_above"], ora["frames_above"])
+
+
+@pytest.mark.parametrize("tag", ["a", "b"])
+def test_key_stats_against_reference_golden(tag):
+    """pc_key_stats vs the values the reference's AccumulatedContact methods give on its golden session."""
+    from pycontact_b200 import stats
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "rpn11_ubq_stats_golden.npz"))
+    ns, thr = g["params_" + tag]
+    st = stats.key_statistics(g["score"], g["hbonds"], ns, thr)
+    np.testing.assert_allclose(st["mean"], g["mean"], rtol=STATS_RTOL)
+    assert np.array_equal(st["median"], g["median"])
+    assert np.array_equal(st["hbond_percentage"], g["hbond_percentage"]) and st["hbond_percentage"].sum() == 676.0
+    np.testing.assert_allclose(st["total_time"], g["total_time_" + tag], rtol=STATS_RTOL)
+    np.testing.assert_allclose(st["mean_life_time"], g["mean_life_time_" + tag], rtol=STATS_RTOL)
+    np.testing.assert_allclose(st["median_life_time"], g["median_life_time_" + tag], rtol=STATS_RTOL)
+    assert np.array_equal(st["life_entries"], g["life_entries_" + tag])
+
+
+def _random_scores(K, F, seed):
+    rng = np.random.default_rng(seed)
+    sc = rng.random((K, F))
+    # on/off episodes of random length so that runs of every size occur
+    gate = np.repeat(rng.random((K, F // 7 + 1)) > 0.45, 7, axis=1)[:, :F]
+    sc = sc * gate
+    sc[0] = 0.0
+    if K > 1:
+        sc[1] = 0.9
+    hb = (rng.random((K, F)) > 0.8).astype(np.int64) * rng.integers(1, 4, (K, F)) * (sc > 0)
+    return sc, hb
+
+
+@pytest.mark.parametrize("F", [1, 2, 3, 50, 777, 4096])
+def test_key_stats_against_oracle(F):
+    from oracle import stats_oracle
+    from pycontact_b200 import stats
+    sc, hb = _random_scores(37, F, 100 + F)
+    for ns, thr in ((1, 0), (0.02, 0.5)):
+        _check_stats(stats.key_statistics(sc, hb, ns, thr), stats_oracle.key_statistics(sc, hb, ns, thr))
+
+
+def test_key_stats_full_size_and_limits():
+    """C2's 10^4 frames (and the 16384-frame limit): oracle on a sample of keys, array identities on all."""
+    from oracle import stats_oracle
+    from pycontact_b200 import stats
+    for K, F in ((600, 10000), (9, 16384)):
+        sc, hb = _random_scores(K, F, 7)
+        st = stats.key_statistics(sc, hb, 0.02, 0.5)
+        sample = np.unique(np.r_[0, 1, np.random.default_rng(1).integers(0, K, 6)])
+        ora = stats_oracle.key_statistics(sc[sample], hb[sample], 0.02, 0.5)
+        _check_stats({k: v[sample] for k, v in st.items()}, ora)
+        above = sc > 0.5
+        assert np.array_equal(st["frames_above"], above.sum(1))
+        np.testing.assert_allclose(st["mean"], sc.mean(1), rtol=1e-12)
+        assert np.array_equal(st["median"], np.median(sc, axis=1))
+        assert np.array_equal(st["hbond_percentage"], (hb > 0).sum(1) / F * 100)
+        starts = above[:, :1].sum(1) + (above[:, 1:] & ~above[:, :-1]).sum(1)          # maximal runs
+        assert np.array_equal(st["life_entries"], starts + (~above[:, -1]).astype(int))
+        np.testing.assert_allclose(st["mean_life_time"] * st["life_entries"], st["total_time"], rtol=1e-12)
+    with pytest.raises(ValueError):
+        stats.key_statistics(np.zeros((2, 16385)), None)
+    empty = stats.key_statistics(np.zeros((0, 10)), None)
+    assert all(v.shape == (0,) for v in empty.values())
+    nohb = stats.key_statistics(np.ones((3, 5)), None, 1, 0)
+    assert nohb["hbond_percentage"].tolist() == [0, 0, 0] and nohb["median_life_time"].tolist() == [5, 5, 5]
+
+
+def test_filters_and_sorting_on_device():
+    """core/ContactFilters.py:187-287: the criteria come from pc_key_stats; expectations from the oracle."""
+    from oracle import stats_oracle
+    from pycontact_b200.core import Biochemistry as bio
+    from pycontact_b200.core import ContactFilters as cf
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "rpn11_ubq_stats_golden.npz"))
+    gold = np.load(os.path.join(os.path.dirname(__file__), "golden", "rpn11_ubq_golden.npz"))
+
+    def contacts():
+        out = []
+        for k in range(len(g["score"])):
+            c = bio.AccumulatedContact(list(gold["acc_key1"][k]), list(gold["acc_key2"][k]))
+            c.scoreArray = g["score"][k].tolist()
+            c.contributingAtoms = [[] for _ in range(g["score"].shape[1])]
+            c.hbondFrames = g["hbonds"][k].tolist()
+            c.hbondFramesScan = (lambda h: (lambda: h))(g["hbonds"][k].tolist())
+            out.append(c)
+        return out
+
+    ora = stats_oracle.key_statistics(g["score"], g["hbonds"], 1, 0)
+    titles = lambda cs: [c.title for c in cs]
+    base = contacts()
+    assert titles(cf.TotalTimeFilter("t", u"greater", 25).filterContacts(contacts())) == \
+        [c.title for c, v in zip(base, ora["total_time"]) if v > 25]
+    assert titles(cf.ScoreFilter("s", u"smaller", 0.3, u"Mean").filterContacts(contacts())) == \
+        [c.title for c, v in zip(base, g["mean"]) if v < 0.3]
+    assert titles(cf.ScoreFilter("s", u"greater", 0.1, u"Median").filterContacts(contacts())) == \
+        [c.title for c, v in zip(base, g["median"]) if v > 0.1]
+    assert titles(cf.ScoreFilter("s", u"greater", 10.0, u"HB %").filterContacts(contacts())) == \
+        [c.title for c, v in zip(base, g["hbond_percentage"]) if v > 10.0]
+    assert titles(cf.OnlyFilter("o", "hbonds", 0).filterContacts(contacts())) == \
+        [c.title for c, v in zip(base, g["hbond_percentage"]) if v > 0]
+    ns, thr = g["params_b"]
+    for key, col in ((u"total time", "total_time_b"), (u"mean lifetime", "mean_life_time_b"),
+                     (u"median lifetime", "median_life_time_b")):
+        s = cf.Sorting("x", key, True)
+        s.setThresholdAndNsPerFrame(thr, ns)
+        got = s.sortContacts(contacts())
+        vals = [getattr(c, {"total time": "ttime", "mean lifetime": "meanLifeTime", "median lifetime": "medianLifeTime"}[key])
+                for c in got]
+        assert vals == sorted(vals, reverse=True)
+        np.testing.assert_allclose(sorted(vals), np.sort(g[col]), rtol=STATS_RTOL)
