@@ -724,11 +724,11 @@ extern "C" int pc_last_status(pc_ctx *c, uint64_t *status, int64_t *need_contact
 
 #ifdef PC_PHASE_CLOCKS
 // profiling build only: cycles per phase of the last scan (valid after pc_batch_totals)
-extern "C" int pc_phase_clocks(pc_ctx *c, unsigned long long *out16) {
-    for (int i = 0; i < 14; i++) out16[i] = c->h_counters[PC_CNT_PHASE + i];
+extern "C" int pc_phase_clocks(pc_ctx *c, unsigned long long *out24) {
+    for (int i = 0; i < 24; i++) out24[i] = c->h_counters[PC_CNT_PHASE + i];
     unsigned int retried = 0;                    // frames the fast plan handed to the full plan
     if (c->retry.p) CUDA_TRY(cudaMemcpy(&retried, c->retry.p, sizeof(retried), cudaMemcpyDeviceToHost));
-    out16[14] = retried; out16[15] = (unsigned long long)c->last_small_ctas;
+    out24[14] = retried; out24[15] = (unsigned long long)c->last_small_ctas;
     return PC_OK;
 }
 #endif

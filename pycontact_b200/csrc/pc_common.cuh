@@ -19,7 +19,7 @@
 #ifdef PC_PHASE_CLOCKS
 // profiling build only (tools/phase_clocks.py): cycles per phase of the small-frame kernel, summed over CTAs
 enum { PC_CNT_CONTACTS = 0, PC_CNT_HBONDS = 1, PC_CNT_STATUS = 2, PC_CNT_EVALS = 3, PC_CNT_ROWS = 4,
-       PC_CNT_WORK = 5, PC_CNT_PHASE = 8, PC_CNT_COUNT = 24 };
+       PC_CNT_WORK = 5, PC_CNT_PHASE = 8, PC_CNT_COUNT = 32 };
 #define PC_PHASE_BEGIN() long long pc_t_prev = clock64()
 #define PC_PHASE_MARK(i) do { if (threadIdx.x == 0) { const long long pc_t = clock64(); \
         atomicAdd(&a.counters[PC_CNT_PHASE + (i)], (unsigned long long)(pc_t - pc_t_prev)); pc_t_prev = pc_t; } } while (0)

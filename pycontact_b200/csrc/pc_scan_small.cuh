@@ -300,6 +300,13 @@ __global__ void __launch_bounds__(NT, NT >= 1024 ? 1 : NT >= 512 ? 2 : NT >= 384
             __syncthreads();
             PC_PHASE_MARK(2);
             nInA = (int)s_nA; nInB = self ? nInA : (int)s_nB;
+#ifdef PC_PHASE_CLOCKS
+            if (tid == 0) {
+                atomicAdd(&a.counters[PC_CNT_PHASE + 16], (unsigned long long)(nInA + (self ? 0 : nInB)));
+                atomicMax(&a.counters[PC_CNT_PHASE + 17], (unsigned long long)(nInA + (self ? 0 : nInB)));
+                atomicAdd(&a.counters[PC_CNT_PHASE + 18], 1ull);
+            }
+#endif
             if (nInA + (self ? 0 : nInB) > capCand) {
                 staged = false;
             } else {
@@ -435,6 +442,9 @@ __global__ void __launch_bounds__(NT, NT >= 1024 ? 1 : NT >= 512 ? 2 : NT >= 384
         unsigned nh = s_nhits;
         if (!staged || nh > (unsigned)a.capHits) {
             if (fl.retry_list != nullptr) {
+#ifdef PC_PHASE_CLOCKS
+                if (tid == 0) atomicAdd(&a.counters[PC_CNT_PHASE + (staged ? 13 : 12)], 1ull);   // why frames are handed on
+#endif
                 if (tid == 0) fl.retry_list[atomicAdd(fl.retry_count, 1u)] = f;
                 __syncthreads();
                 continue;

@@ -42,13 +42,13 @@ gen1 = device_synth.DeviceTrajectory(s, 0, s.sel1); d1 = DeviceBuffer(F * n1 * 1
 gen2 = device_synth.DeviceTrajectory(s, 0, s.sel2); d2 = DeviceBuffer(F * n2 * 12, 0); gen2.generate(d2.ptr, 0, F)
 check(lib.pc_device_sync(0))
 lib.pc_phase_clocks.argtypes = [ctypes.c_void_p, ctypes.POINTER(ctypes.c_ulonglong)]
-for ctas in (0, 3, 1):
+for ctas in [int(x) for x in (args[2].split(',') if len(args) > 2 else ['0', '1'])]:
     eng = ContactEngine(s1, s2, 5.0, 2.5, 120, device=0, slots=1)
     eng.set_maps(gm1.gid, gm2.gid, gm2.n_groups)
     lib.pc_set_small_ctas(eng.slots[0].ctx, ctas)
     for rep in range(3):
         tot = eng.scan_device(d1.ptr, d2.ptr, F, accumulate=True)
-    out = (ctypes.c_ulonglong * 16)()
+    out = (ctypes.c_ulonglong * 24)()
     lib.pc_phase_clocks(eng.slots[0].ctx, out)
     v = list(out)[:12]
     t = float(sum(v)) or 1.0
@@ -56,4 +56,6 @@ for ctas in (0, 3, 1):
     for nm, x in zip(NAMES, v):
         print("  %-52s %12d cycles  %5.1f%%  %8.0f cycles/frame" % (nm, x, 100.0 * x / t, x / F))
     print("  %-52s %12d cycles          %8.0f cycles/frame" % ("sum", sum(v), sum(v) / F))
+    print("  frames handed to the full plan: %d for staging (in-grid atoms), %d for the hit queue" % (out[12], out[13]))
+    print("  atoms inside the grid per frame: mean %.0f, max %d (%d frame passes)" % (out[16] / max(out[18], 1), out[17], out[18]))
     eng.close()
