@@ -234,6 +234,42 @@ int pc_find_contacts(int device, const float *h_xyz1, int32_t n1, const float *h
                      double cutoff, int64_t *h_row_ptr, int32_t **h_cols);
 void pc_free_host(void *p);
 
+/* ---- SASA and "within" (the other two routines of the reference's cy_modules) ---- */
+
+/* The sphere points all atoms share (sasa_grid, cy_modules/src/gridsearch.C:453-484): pointstyle != 0 ->
+ * random points from the reference's fixed seed (srandom(38572111) / random()), 0 -> its spiral.
+ * h_pts receives 3 * npts floats.  Host-only (no GPU needed). */
+int pc_sasa_points(int32_t npts, int32_t pointstyle, float *h_pts);
+
+/* cy_sasa(npcoords, natoms, pairdist, 0, -1, nprad, surfacePoints, probeRadius, pointstyle, restricted,
+ * restrictedList)  (cy_modules/cy_gridsearch.pyx:14-22 -> sasa_grid, gridsearch.C:430-529) for a BATCH of
+ * frames of one selection -- the loop of calculate_sasa_parallel (gui/SasaWidgets.py:27-49) in one call.
+ * h_xyz: nframes x natoms x 3 float32; h_radius[natoms]; h_restricted[natoms] is read only when
+ * restricted != 0.  h_total[nframes] = the reference's float32 total per frame (same summation order);
+ * h_exposed (may be NULL) = nframes x natoms exposed sphere points per atom (0 for atoms outside the
+ * restriction).  Host pointers; synchronous. */
+int pc_sasa(int device, const float *h_xyz, int32_t nframes, int32_t natoms, const float *h_radius,
+            float pairdist, int32_t npts, double srad, int32_t pointstyle, int32_t restricted,
+            const int32_t *h_restricted, float *h_total, int32_t *h_exposed);
+
+/* The same for frames resident in HBM (pitch = floats between frames); outputs in device memory;
+ * d_evals (may be NULL) is incremented by the number of point-sphere tests done.  Asynchronous on `stream`;
+ * scratch memory is stream-ordered (cudaMallocAsync).  radius / restriction are host arrays. */
+int pc_sasa_device(int device, const float *d_xyz, int32_t nframes, int32_t natoms, int64_t pitch,
+                   const float *h_radius, float pairdist, int32_t npts, double srad, int32_t pointstyle,
+                   int32_t restricted, const int32_t *h_restricted, float *d_total, int32_t *d_exposed,
+                   uint64_t *d_evals, void *stream);
+
+/* cy_find_within(xyz, flgs, others, num, r)  (cy_modules/cy_gridsearch.pyx:24-29 -> find_within,
+ * gridsearch.C:595-713) for a batch of frames: h_result[f][i] = 1 iff flgs[i] and some atom j with others[j]
+ * has ((dx*dx) + (dy*dy)) + (dz*dz) < r*r in float32 (strict) -- the geometric core of an "around"
+ * selection (core/ContactAnalyzer.py:321-324 re-evaluates those per frame).  flgs / others are per-atom
+ * 0/1 int32 arrays shared by all frames.  Host pointers; synchronous. */
+int pc_find_within(int device, const float *h_xyz, int32_t nframes, int32_t num, const int32_t *h_flgs,
+                   const int32_t *h_others, float r, int32_t *h_result);
+int pc_within_device(int device, const float *d_xyz, int32_t nframes, int32_t num, int64_t pitch,
+                     const int32_t *d_flgs, const int32_t *d_others, float r, int32_t *d_result, void *stream);
+
 /* Synthetic trajectory generator used by bench.py: frame f =
  * base + amp[res]*sin(2*pi*f/period[res] + phase[res]) + N(0, sigma) jitter from a
  * counter-based generator keyed (seed, frame, atom).  Writes nframes frames in `layout`. */

@@ -39,3 +39,19 @@ extern "C" int ref_find_contacts_csr(const float *pos1, int n1, const float *pos
 }
 
 extern "C" void ref_free(void *p) { free(p); }
+
+// sasa_grid (gridsearch.C:430-529) and find_within (gridsearch.C:595-713), reached the way
+// cy_gridsearch.pyx:14-31 reaches them (allow_double_counting = 0, maxpairs = -1).
+extern "C" double ref_sasa_grid(const float *pos, int natoms, float pairdist, const float *radius, int npts,
+                                double srad, int pointstyle, int restricted, const int *restrictedList) {
+    // cy_sasa stores the double in a C float before returning it (cy_gridsearch.pyx:21-22)
+    const float sasa = (float)sasa_grid(pos, natoms, pairdist, 0, -1, radius, npts, srad, pointstyle, restricted,
+                                        restrictedList);
+    return (double)sasa;
+}
+
+extern "C" void ref_find_within(const float *xyz, int *flgs, int *others, int num, float r, int *result_out) {
+    int *res = find_within(xyz, flgs, others, num, r);
+    for (int i = 0; i < num; i++) result_out[i] = res[i];
+    delete[] res;
+}

@@ -63,6 +63,7 @@ EXPORTS = [
     "pc_host_free", "pc_load_records", "pc_stream_create", "pc_stream_sync", "pc_stream_destroy",
     "pc_device_alloc", "pc_device_free", "pc_memcpy", "pc_memset", "pc_device_sync",
     "pc_launch_count", "pc_event_create", "pc_event_record", "pc_event_elapsed_ms", "pc_event_destroy", "pc_fold_rows", "pc_fetch_packed_rows", "pc_pack_rows", "pc_set_pack_format", "pc_fold_sparse_init", "pc_fold_rows_sparse", "pc_fold_sparse_fetch", "pc_fold_sparse_share", "pc_set_probe", "pc_key_stats",
+    "pc_sasa_points", "pc_sasa", "pc_sasa_device", "pc_find_within", "pc_within_device",
 ]
 
 _lib = None
@@ -132,6 +133,12 @@ def load():
     lib.pc_set_pack_format.argtypes = [vp, ctypes.c_int]
     lib.pc_set_probe.argtypes = [vp, vp, vp]
     lib.pc_fold_rows.argtypes = [vp, vp, i64, vp]
+    f32 = ctypes.c_float
+    lib.pc_sasa_points.argtypes = [i32, i32, vp]
+    lib.pc_sasa.argtypes = [ctypes.c_int, vp, i32, i32, vp, f32, i32, f64, i32, i32, vp, vp, vp]
+    lib.pc_sasa_device.argtypes = [ctypes.c_int, vp, i32, i32, i64, vp, f32, i32, f64, i32, i32, vp, vp, vp, vp, vp]
+    lib.pc_find_within.argtypes = [ctypes.c_int, vp, i32, i32, vp, vp, f32, vp]
+    lib.pc_within_device.argtypes = [ctypes.c_int, vp, i32, i32, i64, vp, vp, f32, vp, vp]
     lib.pc_host_alloc.argtypes = [P(vp), i64]
     lib.pc_host_free.argtypes = [vp]
     lib.pc_host_free.restype = None

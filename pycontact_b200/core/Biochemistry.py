@@ -15,6 +15,17 @@ from __future__ import annotations
 import numpy as np
 
 
+# CHARMM radii as VMD has them (core/Biochemistry.py:10-24); keyed by the FIRST character of the atom name
+# at the only call site (gui/SasaWidgets.py:185, 190), so "Mg" is never hit -- kept for fidelity.
+vdwRadii = {"H": 1.0, "C": 1.5, "N": 1.399999976158142, "O": 1.2999999523162842, "F": 1.47, "Mg": 1.73, "P": 1.8,
+            "S": 1.899999976158142}
+
+
+def vdwRadius(atomType):
+    """van der Waals radius of an atom type; 1.5 A when unknown."""
+    return vdwRadii.get(atomType, 1.5)
+
+
 class HydrogenBondAtoms:
     atoms = ["O", "N", "S"]
 

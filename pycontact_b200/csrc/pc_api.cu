@@ -17,6 +17,7 @@
 #include "pc_search.cuh"
 #include "pc_synth.cuh"
 #include "pc_stats.cuh"
+#include "pc_sasa.cuh"
 
 static thread_local std::string g_err;
 static unsigned long long g_launches = 0;      // kernels launched by this library (bench.py's gpu_launches)
@@ -934,3 +935,246 @@ extern "C" int pc_host_alloc(void **out, int64_t bytes) {
     return PC_OK;
 }
 extern "C" void pc_host_free(void *p) { if (p) cudaFreeHost(p); }
+
+// ---- SASA and "within" (kernels in pc_sasa.cuh) ----------------------------------------------
+
+// glibc's random() after srandom(seed) (the additive-feedback TYPE_3 generator: r[i] = r[i-31] + r[i-3], 310
+// outputs discarded, top 31 bits returned), written out so that the library neither depends on nor disturbs
+// the process-wide generator the reference reseeds through vmd_srandom (gridsearch.C:32-45).
+static void glibc_random_sequence(unsigned seed, int count, long *out) {
+    std::vector<int32_t> r(344 + (size_t)count);
+    r[0] = seed ? (int32_t)seed : 1;
+    for (int i = 1; i < 31; i++) {
+        const long long hi = r[i - 1] / 127773, lo = r[i - 1] % 127773;
+        long long w = 16807 * lo - 2836 * hi;
+        if (w < 0) w += 2147483647;
+        r[i] = (int32_t)w;
+    }
+    for (int i = 31; i < 34; i++) r[i] = r[i - 31];
+    for (size_t i = 34; i < r.size(); i++) r[i] = (int32_t)((uint32_t)r[i - 31] + (uint32_t)r[i - 3]);
+    for (int k = 0; k < count; k++) out[k] = (long)((uint32_t)r[344 + k] >> 1);
+}
+
+// The sphere points every atom shares (gridsearch.C:453-484): pointstyle != 0 -> random points from the fixed
+// seed 38572111, 0 -> the spiral (whose k-1 indexing makes the first point NaN: it never counts as buried).
+extern "C" int pc_sasa_points(int32_t npts, int32_t pointstyle, float *h_pts) {
+    if (npts < 1 || !h_pts) return fail(PC_ERR_INVALID, "pc_sasa_points: bad arguments");
+    if (pointstyle) {
+        const float rand_max_inv = 1.0f / (float)2147483647L;
+        std::vector<long> rnd(2 * (size_t)npts);
+        glibc_random_sequence(38572111u, 2 * npts, rnd.data());
+        for (int i = 0; i < npts; i++) {
+            const float u1 = (float)rnd[2 * i], u2 = (float)rnd[2 * i + 1];
+            const float z = 2.0f * u1 * rand_max_inv - 1.0f;
+            const float phi = (float)((double)2.0f * M_PI * (double)u2 * (double)rand_max_inv);
+            const float R = sqrtf(1.0f - z * z);
+            h_pts[3 * i] = R * cosf(phi);
+            h_pts[3 * i + 1] = R * sinf(phi);
+            h_pts[3 * i + 2] = z;
+        }
+    } else {
+        for (int k = 0; k < npts; k++) {
+            const float h = (float)(2.0 * (k - 1.0) / (npts - 1.0) - 1.0);
+            const float theta = acosf(h);
+            float phi = 0.f;
+            if (!(k == 1 || k == npts))
+                phi = (float)fmod((double)phi + 3.6 / (double)sqrtf((float)npts * (1.0f - h * h)), 2.0 * M_PI);
+            h_pts[3 * k] = cosf(phi) * sinf(theta);
+            h_pts[3 * k + 1] = sinf(phi) * sinf(theta);
+            h_pts[3 * k + 2] = cosf(theta);
+        }
+    }
+    return PC_OK;
+}
+
+namespace {
+struct StreamBuf {            // stream-ordered scratch: released behind the work that uses it
+    void *p = nullptr;
+    cudaStream_t s = 0;
+    ~StreamBuf() { if (p) cudaFreeAsync(p, s); }
+    cudaError_t alloc(size_t bytes, cudaStream_t stream) {
+        s = stream;
+        return cudaMallocAsync(&p, std::max<size_t>(bytes, 16), stream);
+    }
+    template <typename T> T *as() const { return reinterpret_cast<T *>(p); }
+};
+
+struct GridWork {             // cell list of a sub-batch of frames
+    StreamBuf bbox, geom, cellcnt, cellid, rank, sidx, sorted;
+    int cap_cells = 0, cell_pitch = 0;
+    static size_t bytes_per_frame(int n, int cap_cells) {
+        return (size_t)n * (16 + 4 + 4 + 4) + ((size_t)cap_cells + 1) * 4 + 6 * 4 + sizeof(PcGridGeom);
+    }
+    cudaError_t alloc(int fb, int n, int cap, cudaStream_t s) {
+        cap_cells = cap; cell_pitch = cap + 1;
+        cudaError_t e;
+        if ((e = bbox.alloc((size_t)fb * 6 * 4, s)) != cudaSuccess) return e;
+        if ((e = geom.alloc((size_t)fb * sizeof(PcGridGeom), s)) != cudaSuccess) return e;
+        if ((e = cellcnt.alloc((size_t)fb * cell_pitch * 4, s)) != cudaSuccess) return e;
+        if ((e = cellid.alloc((size_t)fb * n * 4, s)) != cudaSuccess) return e;
+        if ((e = rank.alloc((size_t)fb * n * 4, s)) != cudaSuccess) return e;
+        if ((e = sidx.alloc((size_t)fb * n * 4, s)) != cudaSuccess) return e;
+        return sorted.alloc((size_t)fb * n * 16, s);
+    }
+};
+
+int grid_cap_cells(int n) { return std::min(std::max(4096, n), 1 << 22); }
+int grid_chunks(int n) { return std::min(std::max((n + 1023) / 1024, 1), 1024); }
+// cell edge a hair above the search distance: relative slack for the float32 cell coordinate, absolute slack
+// for the rounding of large coordinates (0.01 A covers |x| up to ~5e4 A)
+float grid_edge(float dist) { return std::max(dist * 1.001f, dist + 0.01f); }
+
+// bbox -> geometry -> count -> scan -> scatter for frames [0, fb) at xyz
+cudaError_t grid_build(GridWork &g, const float *xyz, long long pitch, int fb, int n, const int *d_mask, const float *d_w,
+                       float dist, cudaStream_t s, unsigned long long &launches) {
+    const dim3 cg(grid_chunks(n), fb);
+    pcg_init_kernel<<<(fb * 6 + 255) / 256, 256, 0, s>>>(g.bbox.as<unsigned>(), fb);
+    cudaError_t e = cudaMemsetAsync(g.cellcnt.p, 0, (size_t)fb * g.cell_pitch * 4, s);
+    if (e != cudaSuccess) return e;
+    pcg_bbox_kernel<<<cg, 256, 0, s>>>(xyz, pitch, n, d_mask, g.bbox.as<unsigned>());
+    pcg_geom_kernel<<<(fb + 127) / 128, 128, 0, s>>>(g.bbox.as<unsigned>(), fb, grid_edge(dist), g.cap_cells,
+                                                     g.geom.as<PcGridGeom>());
+    pcg_count_kernel<<<cg, 256, 0, s>>>(xyz, pitch, n, d_mask, g.geom.as<PcGridGeom>(), g.cell_pitch, g.cellcnt.as<int>(),
+                                        g.cellid.as<int>(), g.rank.as<int>());
+    pcg_scan_kernel<<<fb, 1024, 0, s>>>(g.geom.as<PcGridGeom>(), g.cell_pitch, g.cellcnt.as<int>());
+    pcg_scatter_kernel<<<cg, 256, 0, s>>>(xyz, pitch, n, d_w, g.cell_pitch, g.cellcnt.as<int>(), g.cellid.as<int>(),
+                                          g.rank.as<int>(), g.sorted.as<float4>(), g.sidx.as<int>());
+    launches += 6;
+    return cudaGetLastError();
+}
+
+const size_t kGridBudget = 1536ull << 20;     // scratch per sub-batch of frames
+}  // namespace
+
+extern "C" int pc_sasa_device(int device, const float *d_xyz, int32_t nframes, int32_t natoms, int64_t pitch,
+                              const float *h_radius, float pairdist, int32_t npts, double srad, int32_t pointstyle,
+                              int32_t restricted, const int32_t *h_restricted, float *d_total, int32_t *d_exposed,
+                              uint64_t *d_evals, void *stream) {
+    if (nframes < 0 || natoms < 0 || !d_total || (natoms && (!d_xyz || !h_radius)) || pitch < 3ll * natoms)
+        return fail(PC_ERR_INVALID, "pc_sasa_device: bad arguments");
+    if (npts < 1 || npts > PCS_MAX_POINTS) return fail(PC_ERR_INVALID, "pc_sasa_device: 1 <= surface points <= 1024");
+    if (!(pairdist > 0)) return fail(PC_ERR_INVALID, "pc_sasa_device: pairdist must be positive");
+    if (restricted && !h_restricted) return fail(PC_ERR_INVALID, "pc_sasa_device: restricted without a restriction list");
+    if (nframes == 0) return PC_OK;
+    CUDA_TRY(cudaSetDevice(device));
+    cudaStream_t s = (cudaStream_t)stream;
+    if (natoms == 0) { CUDA_TRY(cudaMemsetAsync(d_total, 0, (size_t)nframes * 4, s)); return PC_OK; }
+
+    std::vector<float> radp((size_t)natoms), pts(3 * (size_t)npts);
+    for (int i = 0; i < natoms; i++) radp[i] = (float)((double)h_radius[i] + srad);     // float rad = radius[i]+srad (:497)
+    int rc = pc_sasa_points(npts, pointstyle, pts.data());
+    if (rc != PC_OK) return rc;
+    const float prefac = (float)(4 * M_PI / npts);
+    const float sqdist = pairdist * pairdist;
+
+    StreamBuf d_radp, d_pts, d_rl, d_area;
+    CUDA_TRY(d_radp.alloc((size_t)natoms * 4, s));
+    CUDA_TRY(d_pts.alloc(pts.size() * 4, s));
+    CUDA_TRY(cudaMemcpyAsync(d_radp.p, radp.data(), (size_t)natoms * 4, cudaMemcpyHostToDevice, s));
+    CUDA_TRY(cudaMemcpyAsync(d_pts.p, pts.data(), pts.size() * 4, cudaMemcpyHostToDevice, s));
+    if (restricted) {
+        CUDA_TRY(d_rl.alloc((size_t)natoms * 4, s));
+        CUDA_TRY(cudaMemcpyAsync(d_rl.p, h_restricted, (size_t)natoms * 4, cudaMemcpyHostToDevice, s));
+    }
+    const int cap = grid_cap_cells(natoms);
+    const size_t per_frame = GridWork::bytes_per_frame(natoms, cap) + (size_t)natoms * 4;
+    const int fb = (int)std::min<size_t>(std::min<size_t>(std::max<size_t>(kGridBudget / per_frame, 1), 32768), (size_t)nframes);
+    GridWork g;
+    CUDA_TRY(g.alloc(fb, natoms, cap, s));
+    CUDA_TRY(d_area.alloc((size_t)fb * natoms * 4, s));
+    for (int f0 = 0; f0 < nframes; f0 += fb) {
+        const int nf = std::min(fb, nframes - f0);
+        const float *xyz = d_xyz + (long long)f0 * pitch;
+        CUDA_TRY(grid_build(g, xyz, pitch, nf, natoms, nullptr, d_radp.as<float>(), pairdist, s, g_launches));
+        pc_sasa_atoms_kernel<<<dim3((natoms + PCS_WARPS - 1) / PCS_WARPS, nf), PCS_WARPS * 32, 3 * (size_t)npts * 4, s>>>(
+            g.sorted.as<float4>(), g.sidx.as<int>(), g.cellcnt.as<int>(), g.geom.as<PcGridGeom>(), natoms, g.cell_pitch,
+            d_pts.as<float>(), npts, sqdist, restricted, d_rl.as<int>(), prefac, d_area.as<float>(),
+            d_exposed ? d_exposed + (long long)f0 * natoms : nullptr, (unsigned long long *)d_evals);
+        pc_sasa_sum_kernel<<<nf, 256, 0, s>>>(d_area.as<float>(), natoms, d_total + f0);
+        CUDA_TRY(cudaGetLastError());
+        g_launches += 2;
+    }
+    return PC_OK;
+}
+
+extern "C" int pc_sasa(int device, const float *h_xyz, int32_t nframes, int32_t natoms, const float *h_radius,
+                       float pairdist, int32_t npts, double srad, int32_t pointstyle, int32_t restricted,
+                       const int32_t *h_restricted, float *h_total, int32_t *h_exposed) {
+    if (nframes < 0 || natoms < 0 || !h_total || (nframes && natoms && !h_xyz))
+        return fail(PC_ERR_INVALID, "pc_sasa: bad arguments");
+    if (nframes == 0) return PC_OK;
+    CUDA_TRY(cudaSetDevice(device));
+    const size_t frame_bytes = (size_t)natoms * 12;
+    const int fb = (int)std::min<size_t>(std::max<size_t>((1ull << 30) / std::max<size_t>(frame_bytes, 1), 1), (size_t)nframes);
+    DevBuf<float> d_xyz, d_total;
+    DevBuf<int32_t> d_exp;
+    CUDA_TRY(d_xyz.ensure((size_t)fb * natoms * 3));
+    CUDA_TRY(d_total.ensure((size_t)fb));
+    if (h_exposed) CUDA_TRY(d_exp.ensure((size_t)fb * natoms));
+    for (int f0 = 0; f0 < nframes; f0 += fb) {
+        const int nf = std::min(fb, nframes - f0);
+        if (natoms) CUDA_TRY(cudaMemcpyAsync(d_xyz.p, h_xyz + (size_t)f0 * natoms * 3, (size_t)nf * frame_bytes, cudaMemcpyHostToDevice, 0));
+        const int rc = pc_sasa_device(device, d_xyz.p, nf, natoms, 3ll * natoms, h_radius, pairdist, npts, srad, pointstyle,
+                                      restricted, h_restricted, d_total.p, h_exposed ? d_exp.p : nullptr, nullptr, nullptr);
+        if (rc != PC_OK) return rc;
+        CUDA_TRY(cudaMemcpyAsync(h_total + f0, d_total.p, (size_t)nf * 4, cudaMemcpyDeviceToHost, 0));
+        if (h_exposed && natoms)
+            CUDA_TRY(cudaMemcpyAsync(h_exposed + (size_t)f0 * natoms, d_exp.p, (size_t)nf * natoms * 4, cudaMemcpyDeviceToHost, 0));
+        CUDA_TRY(cudaStreamSynchronize(0));
+    }
+    return PC_OK;
+}
+
+extern "C" int pc_within_device(int device, const float *d_xyz, int32_t nframes, int32_t num, int64_t pitch,
+                                const int32_t *d_flgs, const int32_t *d_others, float r, int32_t *d_result, void *stream) {
+    if (nframes < 0 || num < 0 || (nframes && num && (!d_xyz || !d_flgs || !d_others || !d_result)) || pitch < 3ll * num)
+        return fail(PC_ERR_INVALID, "pc_within_device: bad arguments");
+    if (!(r > 0)) return fail(PC_ERR_INVALID, "pc_within_device: r must be positive");
+    if (nframes == 0 || num == 0) return PC_OK;
+    CUDA_TRY(cudaSetDevice(device));
+    cudaStream_t s = (cudaStream_t)stream;
+    const int cap = grid_cap_cells(num);
+    const size_t per_frame = GridWork::bytes_per_frame(num, cap);
+    const int fb = (int)std::min<size_t>(std::min<size_t>(std::max<size_t>(kGridBudget / per_frame, 1), 32768), (size_t)nframes);
+    GridWork g;
+    CUDA_TRY(g.alloc(fb, num, cap, s));
+    const float r2 = r * r;                                   // const float r2 = (float)(r*r)  (gridsearch.C:677)
+    for (int f0 = 0; f0 < nframes; f0 += fb) {
+        const int nf = std::min(fb, nframes - f0);
+        const float *xyz = d_xyz + (long long)f0 * pitch;
+        CUDA_TRY(grid_build(g, xyz, pitch, nf, num, d_others, nullptr, r, s, g_launches));
+        pc_within_kernel<<<dim3(grid_chunks(num), nf), 256, 0, s>>>(xyz, pitch, num, d_flgs, g.sorted.as<float4>(),
+                                                                     g.cellcnt.as<int>(), g.geom.as<PcGridGeom>(), g.cell_pitch,
+                                                                     r2, d_result + (long long)f0 * num);
+        CUDA_TRY(cudaGetLastError());
+        g_launches += 1;
+    }
+    return PC_OK;
+}
+
+extern "C" int pc_find_within(int device, const float *h_xyz, int32_t nframes, int32_t num, const int32_t *h_flgs,
+                              const int32_t *h_others, float r, int32_t *h_result) {
+    if (nframes < 0 || num < 0 || (nframes && num && (!h_xyz || !h_flgs || !h_others || !h_result)))
+        return fail(PC_ERR_INVALID, "pc_find_within: bad arguments");
+    if (nframes == 0 || num == 0) return PC_OK;
+    CUDA_TRY(cudaSetDevice(device));
+    const size_t frame_bytes = (size_t)num * 12;
+    const int fb = (int)std::min<size_t>(std::max<size_t>((1ull << 30) / frame_bytes, 1), (size_t)nframes);
+    DevBuf<float> d_xyz;
+    DevBuf<int32_t> d_f, d_o, d_res;
+    CUDA_TRY(d_xyz.ensure((size_t)fb * num * 3));
+    CUDA_TRY(d_f.ensure((size_t)num));
+    CUDA_TRY(d_o.ensure((size_t)num));
+    CUDA_TRY(d_res.ensure((size_t)fb * num));
+    CUDA_TRY(cudaMemcpyAsync(d_f.p, h_flgs, (size_t)num * 4, cudaMemcpyHostToDevice, 0));
+    CUDA_TRY(cudaMemcpyAsync(d_o.p, h_others, (size_t)num * 4, cudaMemcpyHostToDevice, 0));
+    for (int f0 = 0; f0 < nframes; f0 += fb) {
+        const int nf = std::min(fb, nframes - f0);
+        CUDA_TRY(cudaMemcpyAsync(d_xyz.p, h_xyz + (size_t)f0 * num * 3, (size_t)nf * frame_bytes, cudaMemcpyHostToDevice, 0));
+        const int rc = pc_within_device(device, d_xyz.p, nf, num, 3ll * num, d_f.p, d_o.p, r, d_res.p, nullptr);
+        if (rc != PC_OK) return rc;
+        CUDA_TRY(cudaMemcpyAsync(h_result + (size_t)f0 * num, d_res.p, (size_t)nf * num * 4, cudaMemcpyDeviceToHost, 0));
+        CUDA_TRY(cudaStreamSynchronize(0));
+    }
+    return PC_OK;
+}

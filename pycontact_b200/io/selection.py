@@ -10,13 +10,17 @@ Grammar (case-sensitive keywords, like MDAnalysis)::
     primary:= 'all' | 'protein' | 'backbone' | 'nucleic' (unsupported)
             | 'segid' V+ | 'resname' V+ | 'name' V+ | 'type' V+
             | 'resid' R+ | 'resnum' R+ | 'index' R+ | 'bynum' R+
+            | 'around' NUMBER factor | 'same' 'residue' 'as' factor
     V      := string with optional '*' / '?' wildcards
     R      := N | N:M | N-M        (inclusive ranges)
 
-``around`` (a per-frame geometric selection, re-evaluated inside the frame loop
-at core/ContactAnalyzer.py:321-324) is SURVEY.md row f-4 ("next") and raises
-NotImplementedError.  The result is a sorted array of unique 0-based atom
-indices, like ``AtomGroup.indices`` of an MDAnalysis selection.
+``around R sel`` and ``same residue as sel`` need the positions of one frame
+(``select_atoms(topo, text, positions=frame)``): ``around`` = atoms NOT in ``sel`` with an atom of
+``sel`` closer than R, decided on the GPU by ``pc_find_within`` with the arithmetic of the reference's
+own ``find_within`` (cy_modules/src/gridsearch.C:595-826: float32, strict ``<``).  The reference
+re-evaluates such selections per frame (core/ContactAnalyzer.py:321-324); without positions they raise
+NotImplementedError.  The result is a sorted array of unique 0-based atom indices, like
+``AtomGroup.indices`` of an MDAnalysis selection.
 """
 from __future__ import annotations
 
@@ -40,7 +44,7 @@ NPHE NPRO NSER NTHR NTRP NTYR NVAL CLEU CME DALA GLYM HYP NORL PGLU QLN TRPO TYR
 BACKBONE_NAMES = frozenset(["N", "CA", "C", "O"])
 
 _KEYWORDS = {"and", "or", "not", "(", ")", "all", "protein", "backbone", "segid", "resname",
-             "name", "type", "resid", "resnum", "index", "bynum", "around", "self"}
+             "name", "type", "resid", "resnum", "index", "bynum", "around", "same", "self"}
 
 
 class SelectionError(Exception):
@@ -52,11 +56,13 @@ def _tokenize(text: str) -> List[str]:
 
 
 class _Parser:
-    def __init__(self, text, topo):
+    def __init__(self, text, topo, positions=None, device=0):
         self.tok = _tokenize(text)
         self.pos = 0
         self.topo = topo
         self.n = topo.n_atoms
+        self.positions = positions
+        self.device = device
 
     def peek(self):
         return self.tok[self.pos] if self.pos < len(self.tok) else None
@@ -151,14 +157,33 @@ class _Parser:
         if t == "bynum":
             return self._match_ranges(np.arange(1, self.n + 1), self.values())
         if t == "around":
-            raise NotImplementedError("'around' selections are per-frame geometric selections "
-                                      "(SURVEY.md f-4) and are not implemented yet")
+            try:
+                r = float(self.take())
+            except (TypeError, ValueError):
+                raise SelectionError("'around' needs a distance")
+            inner = self.factor()
+            if self.positions is None:
+                raise NotImplementedError("'around' is a per-frame geometric selection: pass positions= "
+                                          "(one frame, (natoms, 3)) to select_atoms")
+            from ..cy_modules.cy_gridsearch import find_within_frames
+            pos = np.ascontiguousarray(self.positions, np.float32).reshape(1, self.n, 3)
+            hit = find_within_frames(pos, (~inner).astype(np.int32), inner.astype(np.int32), r, device=self.device)
+            return hit[0].astype(bool)
+        if t == "same":
+            if self.take() != "residue" or self.take() != "as":
+                raise SelectionError("only 'same residue as' is supported")
+            inner = self.factor()
+            seg = np.asarray(topo.segids, dtype=object)
+            res = np.asarray(topo.resids)
+            keys = set(zip(seg[inner].tolist(), res[inner].tolist()))
+            return np.fromiter(((a, b) in keys for a, b in zip(seg.tolist(), res.tolist())), bool, self.n)
         raise SelectionError("unknown selection token %r" % t)
 
 
-def select_atoms(topo, text: str) -> np.ndarray:
-    """Indices (sorted, unique, int64) of the atoms of ``topo`` matching ``text``."""
-    p = _Parser(text, topo)
+def select_atoms(topo, text: str, positions=None, device=0) -> np.ndarray:
+    """Indices (sorted, unique, int64) of the atoms of ``topo`` matching ``text``.  ``positions`` (one frame,
+    (natoms, 3)) is needed by the geometric keyword ``around`` only."""
+    p = _Parser(text, topo, positions, device)
     mask = p.expr()
     if p.peek() is not None:
         raise SelectionError("trailing tokens in selection: %r" % p.tok[p.pos:])
