@@ -1044,6 +1044,20 @@ cudaError_t grid_build(GridWork &g, const float *xyz, long long pitch, int fb, i
 }
 
 const size_t kGridBudget = 1536ull << 20;     // scratch per sub-batch of frames
+
+// The stream-ordered scratch comes from the device's default memory pool; by default the pool hands its memory
+// back to the driver at every synchronisation, so each call would pay for fresh allocations.  Keep it.
+cudaError_t grid_pool_keep(int device) {
+    static bool done[64] = {};
+    if (device < 0 || device >= 64 || done[device]) return cudaSuccess;
+    cudaMemPool_t pool;
+    cudaError_t e = cudaDeviceGetDefaultMemPool(&pool, device);
+    if (e != cudaSuccess) return e;
+    uint64_t keep = ~0ull;
+    e = cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+    if (e == cudaSuccess) done[device] = true;
+    return e;
+}
 }  // namespace
 
 extern "C" int pc_sasa_device(int device, const float *d_xyz, int32_t nframes, int32_t natoms, int64_t pitch,
@@ -1057,6 +1071,7 @@ extern "C" int pc_sasa_device(int device, const float *d_xyz, int32_t nframes, i
     if (restricted && !h_restricted) return fail(PC_ERR_INVALID, "pc_sasa_device: restricted without a restriction list");
     if (nframes == 0) return PC_OK;
     CUDA_TRY(cudaSetDevice(device));
+    CUDA_TRY(grid_pool_keep(device));
     cudaStream_t s = (cudaStream_t)stream;
     if (natoms == 0) { CUDA_TRY(cudaMemsetAsync(d_total, 0, (size_t)nframes * 4, s)); return PC_OK; }
 
@@ -1076,6 +1091,7 @@ extern "C" int pc_sasa_device(int device, const float *d_xyz, int32_t nframes, i
         CUDA_TRY(d_rl.alloc((size_t)natoms * 4, s));
         CUDA_TRY(cudaMemcpyAsync(d_rl.p, h_restricted, (size_t)natoms * 4, cudaMemcpyHostToDevice, s));
     }
+    CUDA_TRY(cudaFuncSetAttribute(pc_sasa_atoms_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pc_sasa_smem(PCS_MAX_POINTS)));
     const int cap = grid_cap_cells(natoms);
     const size_t per_frame = GridWork::bytes_per_frame(natoms, cap) + (size_t)natoms * 4;
     const int fb = (int)std::min<size_t>(std::min<size_t>(std::max<size_t>(kGridBudget / per_frame, 1), 32768), (size_t)nframes);
@@ -1086,7 +1102,7 @@ extern "C" int pc_sasa_device(int device, const float *d_xyz, int32_t nframes, i
         const int nf = std::min(fb, nframes - f0);
         const float *xyz = d_xyz + (long long)f0 * pitch;
         CUDA_TRY(grid_build(g, xyz, pitch, nf, natoms, nullptr, d_radp.as<float>(), pairdist, s, g_launches));
-        pc_sasa_atoms_kernel<<<dim3((natoms + PCS_WARPS - 1) / PCS_WARPS, nf), PCS_WARPS * 32, 3 * (size_t)npts * 4, s>>>(
+        pc_sasa_atoms_kernel<<<dim3((natoms + PCS_WARPS - 1) / PCS_WARPS, nf), PCS_WARPS * 32, pc_sasa_smem(npts), s>>>(
             g.sorted.as<float4>(), g.sidx.as<int>(), g.cellcnt.as<int>(), g.geom.as<PcGridGeom>(), natoms, g.cell_pitch,
             d_pts.as<float>(), npts, sqdist, restricted, d_rl.as<int>(), prefac, d_area.as<float>(),
             d_exposed ? d_exposed + (long long)f0 * natoms : nullptr, (unsigned long long *)d_evals);
@@ -1132,6 +1148,7 @@ extern "C" int pc_within_device(int device, const float *d_xyz, int32_t nframes,
     if (!(r > 0)) return fail(PC_ERR_INVALID, "pc_within_device: r must be positive");
     if (nframes == 0 || num == 0) return PC_OK;
     CUDA_TRY(cudaSetDevice(device));
+    CUDA_TRY(grid_pool_keep(device));
     cudaStream_t s = (cudaStream_t)stream;
     const int cap = grid_cap_cells(num);
     const size_t per_frame = GridWork::bytes_per_frame(num, cap);

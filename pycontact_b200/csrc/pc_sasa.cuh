@@ -155,20 +155,34 @@ __global__ void __launch_bounds__(256) pcg_scatter_kernel(const float *xyz, long
 
 #define PCS_WARPS 8
 #define PCS_LIST 192          // neighbour spheres staged per warp between two passes over the sphere points
+#define PCS_STEP 16           // neighbour spheres of phase 1 (lanes own points)
+#define PCS_SWITCH 12         // phase 1 runs only while more points than this are live
 #define PCS_MAX_POINTS 1024
 
-// grid (ceil(n / PCS_WARPS), frames); dynamic shared memory: 3 * npts floats (the shared sphere points).
-// sorted[].w = radius + probe radius (float32, formed like gridsearch.C:497).
+// rows of the 27-cell neighbourhood, the atom's own row first: near spheres bury most points, so the live list
+// shrinks early
+__constant__ signed char PCS_ROW_DZ[9] = {0, 0, 0, -1, 1, -1, -1, 1, 1};
+__constant__ signed char PCS_ROW_DY[9] = {0, -1, 1, 0, 0, -1, 1, -1, 1};
+
+static inline size_t pc_sasa_smem(int npts) {       // dynamic shared memory of pc_sasa_atoms_kernel
+    return 3 * (size_t)npts * 4 + (size_t)PCS_WARPS * (((size_t)npts + 31) & ~(size_t)31) * 2;
+}
+
+// grid (ceil(n / PCS_WARPS), frames); dynamic shared memory: the 3 * npts shared sphere points + one list of
+// live (not yet buried) point indices per warp.  sorted[].w = radius + probe radius (float32, formed like
+// gridsearch.C:497).  A warp owns one atom and keeps a compacted list of its live points (see flush below):
+// the per-point early exit of gridsearch.C:506-516 without its divergence.
 __global__ void __launch_bounds__(PCS_WARPS * 32) pc_sasa_atoms_kernel(
         const float4 *sorted, const int *sidx, const int *cellstart, const PcGridGeom *geom, int n, int cell_pitch,
         const float *pts, int npts, float sqdist, int restricted, const int *rlist, float prefac, float *area,
         int *exposed, unsigned long long *evals) {
     __shared__ float4 s_list[PCS_WARPS][PCS_LIST];
-    __shared__ unsigned s_buried[PCS_WARPS][PCS_MAX_POINTS / 32];
     extern __shared__ float s_pts[];
-    for (int i = threadIdx.x; i < 3 * npts; i += blockDim.x) s_pts[i] = pts[i];
     const int f = blockIdx.y, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    s_buried[warp][lane] = 0u;
+    const int npad = (npts + 31) & ~31;
+    unsigned short *s_live = reinterpret_cast<unsigned short *>(s_pts + 3 * npts) + warp * npad;
+    for (int i = threadIdx.x; i < 3 * npts; i += blockDim.x) s_pts[i] = pts[i];
+    for (int i = lane; i < npts; i += 32) s_live[i] = (unsigned short)i;
     __syncthreads();
     const PcGridGeom g = geom[f];
     if (!g.ncell) return;
@@ -182,30 +196,72 @@ __global__ void __launch_bounds__(PCS_WARPS * 32) pc_sasa_atoms_kernel(
         if (lane == 0) { area[(long long)f * n + orig] = 0.f; if (exposed) exposed[(long long)f * n + orig] = 0; }
         return;
     }
-    const int nwords = (npts + 31) >> 5;
     const unsigned lt = (1u << lane) - 1u;
     unsigned long long my_evals = 0;
+    int nlive = npts;                                       // same value in every lane
 
-    // one pass of this warp's sphere points over the staged neighbour spheres (gridsearch.C:500-521)
+    // the live points against the staged neighbour spheres (gridsearch.C:500-521), in two phases:
+    //  1. lanes own points, the first PCS_STEP spheres (the nearest rows come first): most buried points die here;
+    //  2. the survivors one at a time, lanes own the remaining spheres 32 at a time (warp-uniform control flow;
+    //     a point leaves at the first 32-sphere chunk that buries it) -- a handful of long-lived points no
+    //     longer drags the whole warp down the list one sphere per iteration.
     auto flush = [&](int cnt) {
         __syncwarp();
-        for (int pc = 0; pc < nwords; pc++) {
-            const int p = pc * 32 + lane;
-            const unsigned old = s_buried[warp][pc];
-            bool bur = false;
-            if (p < npts && !((old >> lane) & 1u)) {
+        int k0 = 0;
+        if (nlive > PCS_SWITCH) {
+            k0 = min(cnt, PCS_STEP);
+            int w = 0;
+            for (int c = 0; c < nlive; c += 32) {
+                const int idx = c + lane;
+                bool live = false;
+                int p = 0;
+                if (idx < nlive) {
+                    p = s_live[idx];
+                    const float sx = __fadd_rn(me.x, __fmul_rn(me.w, s_pts[3 * p]));
+                    const float sy = __fadd_rn(me.y, __fmul_rn(me.w, s_pts[3 * p + 1]));
+                    const float sz = __fadd_rn(me.z, __fmul_rn(me.w, s_pts[3 * p + 2]));
+                    live = true;
+                    int k = 0;
+                    for (; k < k0; k++) {
+                        const float4 q = s_list[warp][k];
+                        if (dist2_exact(sx, sy, sz, q.x, q.y, q.z) <= q.w) { live = false; break; }
+                    }
+                    my_evals += (unsigned long long)(k + (live ? 0 : 1));
+                }
+                // every entry of this chunk has been read by its lane before the ballot; the survivors go to
+                // positions <= their old ones
+                const unsigned m = __ballot_sync(PC_FULL_MASK, live);
+                __syncwarp();
+                if (live) s_live[w + __popc(m & lt)] = (unsigned short)p;
+                w += __popc(m);
+                __syncwarp();
+            }
+            nlive = w;
+        }
+        if (k0 < cnt && nlive) {
+            int w = 0;
+            for (int i = 0; i < nlive; i++) {
+                const int p = s_live[i];
                 const float sx = __fadd_rn(me.x, __fmul_rn(me.w, s_pts[3 * p]));
                 const float sy = __fadd_rn(me.y, __fmul_rn(me.w, s_pts[3 * p + 1]));
                 const float sz = __fadd_rn(me.z, __fmul_rn(me.w, s_pts[3 * p + 2]));
-                int k = 0;
-                for (; k < cnt; k++) {
-                    const float4 q = s_list[warp][k];
-                    if (dist2_exact(sx, sy, sz, q.x, q.y, q.z) <= q.w) { bur = true; break; }
+                bool bur = false;
+                for (int kb = k0; kb < cnt; kb += 32) {
+                    const int k = kb + lane;
+                    bool hit = false;
+                    if (k < cnt) {
+                        const float4 q = s_list[warp][k];
+                        hit = dist2_exact(sx, sy, sz, q.x, q.y, q.z) <= q.w;
+                        my_evals++;
+                    }
+                    if (__any_sync(PC_FULL_MASK, hit)) { bur = true; break; }
                 }
-                my_evals += (unsigned long long)(k + (bur ? 1 : 0));
+                if (!bur) {                                 // w <= i: that entry has been consumed
+                    if (lane == 0) s_live[w] = (unsigned short)p;
+                    w++;
+                }
             }
-            const unsigned m = __ballot_sync(PC_FULL_MASK, bur);
-            if (lane == 0) s_buried[warp][pc] = old | m;
+            nlive = w;
         }
         __syncwarp();
     };
@@ -215,44 +271,37 @@ __global__ void __launch_bounds__(PCS_WARPS * 32) pc_sasa_atoms_kernel(
     cx = min(max(cx, 0), g.nx - 1); cy = min(max(cy, 0), g.ny - 1); cz = min(max(cz, 0), g.nz - 1);
     const int x0 = max(cx - 1, 0), x1 = min(cx + 1, g.nx - 1);
     int cnt = 0;
-    for (int dz = -1; dz <= 1; dz++) {
-        const int z = cz + dz;
-        if (z < 0 || z >= g.nz) continue;
-        for (int dy = -1; dy <= 1; dy++) {
-            const int y = cy + dy;
-            if (y < 0 || y >= g.ny) continue;
-            const int row = (z * g.ny + y) * g.nx;
-            const int b = cs[row + x0], e = cs[row + x1 + 1];
-            for (int j0 = b; j0 < e; j0 += 32) {
-                const int j = j0 + lane;
-                bool ok = false;
-                float4 q = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (j < e) {
-                    q = fs[j];
-                    const float d2 = dist2_exact(me.x, me.y, me.z, q.x, q.y, q.z);
-                    // the reference's neighbour list (:363-368).  A sphere further away than the two radii (plus a
-                    // margin 1000x the float32 rounding of the point test) cannot bury any point of this atom.
-                    const float rs = me.w + q.w;
-                    ok = d2 >= 0.001f && d2 <= sqdist && d2 <= rs * rs * 1.001f;
-                }
-                const unsigned m = __ballot_sync(PC_FULL_MASK, ok);
-                const int add = __popc(m);
-                if (cnt + add > PCS_LIST) { flush(cnt); cnt = 0; }
-                if (ok) s_list[warp][cnt + __popc(m & lt)] = make_float4(q.x, q.y, q.z, __fmul_rn(q.w, q.w));
-                cnt += add;
+    for (int r = 0; r < 9 && nlive; r++) {
+        const int z = cz + PCS_ROW_DZ[r], y = cy + PCS_ROW_DY[r];
+        if (z < 0 || z >= g.nz || y < 0 || y >= g.ny) continue;
+        const int row = (z * g.ny + y) * g.nx;
+        const int b = cs[row + x0], e = cs[row + x1 + 1];
+        for (int j0 = b; j0 < e; j0 += 32) {
+            const int j = j0 + lane;
+            bool ok = false;
+            float4 q = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (j < e) {
+                q = fs[j];
+                const float d2 = dist2_exact(me.x, me.y, me.z, q.x, q.y, q.z);
+                // the reference's neighbour list (:363-368).  A sphere further away than the two radii (plus a
+                // margin 1000x the float32 rounding of the point test) cannot bury any point of this atom.
+                const float rs = me.w + q.w;
+                ok = d2 >= 0.001f && d2 <= sqdist && d2 <= rs * rs * 1.001f;
             }
+            const unsigned m = __ballot_sync(PC_FULL_MASK, ok);
+            const int add = __popc(m);
+            if (cnt + add > PCS_LIST) { flush(cnt); cnt = 0; }
+            if (ok) s_list[warp][cnt + __popc(m & lt)] = make_float4(q.x, q.y, q.z, __fmul_rn(q.w, q.w));
+            cnt += add;
         }
     }
-    flush(cnt);
-    int bur = lane < nwords ? __popc(s_buried[warp][lane]) : 0;
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) bur += __shfl_xor_sync(PC_FULL_MASK, bur, o);
+    if (nlive) flush(cnt);
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) my_evals += __shfl_xor_sync(PC_FULL_MASK, my_evals, o);
     if (lane == 0) {
-        const int surfpts = npts - bur;
-        area[(long long)f * n + orig] = __fmul_rn(__fmul_rn(__fmul_rn(prefac, me.w), me.w), (float)surfpts);
-        if (exposed) exposed[(long long)f * n + orig] = surfpts;
+        // nlive = surfpts of gridsearch.C:499-521
+        area[(long long)f * n + orig] = __fmul_rn(__fmul_rn(__fmul_rn(prefac, me.w), me.w), (float)nlive);
+        if (exposed) exposed[(long long)f * n + orig] = nlive;
         if (evals) atomicAdd(evals, my_evals);
     }
 }

@@ -78,7 +78,9 @@ __device__ __forceinline__ int pc_large_cell_of(const PcLargeFrame &F, float x, 
 // ---- L1 / L3: streaming kernels -----------------------------------------------------------------
 #define PC_STREAM_NT 512
 #define PC_STREAM_CHUNK 24576            // 2048 atoms per chunk
+#ifndef PC_STREAM_STAGES
 #define PC_STREAM_STAGES 3
+#endif
 #define PC_STREAM_HINFO (PC_STREAM_CHUNK / 12 * 4 + 32)      // a chunk's slice of the heavy-atom list
 #define PC_STREAM_SLOT (PC_STREAM_CHUNK + 16 + PC_STREAM_HINFO)
 #define PC_STREAM_SMEM (PC_STREAM_STAGES * PC_STREAM_SLOT + PC_STREAM_STAGES * 8 + 16)
