@@ -36,7 +36,9 @@ def build(force: bool = False) -> None:
     if force or not os.path.exists(_ORACLE_SO) or \
             os.path.getmtime(_ORACLE_SO) < os.path.getmtime(os.path.join(_HERE, "gridsearch_oracle.c")):
         subprocess.check_call(["make", "-s", "-C", _HERE, os.path.join(_HERE, "liboracle.so")])
-    if force or not os.path.exists(_REF_SO):
+    shim = os.path.join(_HERE, "ref_shim.cpp")
+    if force or not os.path.exists(_REF_SO) or os.path.getmtime(_REF_SO) < os.path.getmtime(shim):
+        # the Makefile keeps a prebuilt _ref when /root/reference is absent (the GPU box)
         subprocess.check_call(["make", "-s", "-C", _HERE, "ref"])
 
 

@@ -227,7 +227,7 @@ class Analyzer(object):
         self.segids = list(topo.segids)
         self.backbone = [int(i) for i in select_atoms(topo, "backbone")]
         if "around" in sel1text or "around" in sel2text:
-            raise NotImplementedError("'around' selections are not implemented (SURVEY.md f-4)")
+            return self._scan_dynamic_selections(topo, dcd, cutoff, hbondcutoff, hbondcutangle, sel1text, sel2text)
         self_mode = sel2text == "self"
         idx1 = select_atoms(topo, sel1text)
         idx2 = idx1 if self_mode else select_atoms(topo, sel2text)
@@ -257,6 +257,96 @@ class Analyzer(object):
         stats["seconds"] = time.time() - start
         self.scanStats = stats
         self.currentFrameNumber = max(0, source.n_frames - 1)
+        self._traj = traj
+        return LazyContactResults(traj)
+
+    def _all_frames(self, dcd, natoms):
+        """(F, natoms, 3) float32 of the whole trajectory (the reference's serial loop walks u.trajectory)."""
+        if self._frames is not None:
+            arr = np.asarray(self._frames)
+            if arr.ndim != 3 or arr.shape[1] != natoms:
+                raise ValueError("selections with 'around' need frames= as (F, natoms, 3) over ALL atoms")
+            return np.ascontiguousarray(arr, np.float32)
+        from ..io.dcd import DCDReader
+        if not str(dcd).lower().endswith(".dcd"):
+            raise NotImplementedError("only DCD trajectories are read natively; pass frames= for other formats")
+        rd = DCDReader(dcd)
+        out = np.empty((len(rd), natoms, 3), np.float32)
+        for f in range(len(rd)):
+            out[f] = rd.frame(f)
+        return out
+
+    def _scan_dynamic_selections(self, topo, dcd, cutoff, hbondcutoff, hbondcutangle, sel1text, sel2text):
+        """Selections containing ``around`` are re-evaluated on every frame (:319-331): the atoms, their local
+        indices and the search grid change per frame.  All frames of every ``around`` are evaluated on the GPU in
+        one ``pc_find_within`` call; runs of frames with identical atom sets are then scanned with a topology of
+        their own, and their records are re-indexed into the UNION of the per-frame selections, which is what
+        the accumulation and the result views work on (results carry global atom indices either way)."""
+        from ..io.selection import select_atoms_frames
+        from ..scheduler import ArraySource
+        self_mode = sel2text == "self"
+        dev = (self._devices or [0])[0]
+        coords = self._all_frames(dcd, topo.n_atoms)
+        F = len(coords)
+        per1 = select_atoms_frames(topo, sel1text, coords, device=dev)
+        per2 = per1 if self_mode else select_atoms_frames(topo, sel2text, coords, device=dev)
+        if F == 0 or len(per1[0]) == 0 or len(per2[0]) == 0:
+            raise Exception("empty atom selection")                      # :312-313 (selections of the first frame)
+        hcsr = prepare.hydrogen_csr_from_bond_table(topo.names, topo.types, topo.bonds)
+        bb = np.zeros(topo.n_atoms, bool)
+        bb[self.backbone] = True
+        seg_codes = prepare.string_codes(topo.segids)
+        prep = lambda idx: prepare.prepare_selection(idx, topo.names, topo.resids, seg_codes, bb, hcsr)
+        u1 = np.unique(np.concatenate(per1))
+        S1 = prep(u1)
+        if self_mode:
+            u2, S2 = u1, S1
+        else:
+            u2 = np.unique(np.concatenate(per2))
+            S2 = prep(u2)
+        self._sel = (S1, S2)
+        self.totalFrameNumber = F
+        traj = TrajectoryContacts(S1, S2, hbondcutoff, hbondcutangle)
+        stats = dict(frames=F, contacts=0, hbonds=0, pair_evals=0, batches=0, path=0, selection_runs=0)
+        start = time.time()
+        empty_i, empty_f = np.zeros(0, np.int64), np.zeros(0)
+        f = 0
+        while f < F:
+            g = f + 1
+            while g < F and np.array_equal(per1[g], per1[f]) and (self_mode or np.array_equal(per2[g], per2[f])):
+                g += 1
+            i1, i2 = per1[f], per2[f]
+            stats["selection_runs"] += 1
+            if len(i1) == 0 or len(i2) == 0:
+                part = dict(frame_counts=np.zeros(g - f, np.int64), li=empty_i, lj=empty_i, idx1=empty_i, idx2=empty_i,
+                            distance=empty_f, weight=empty_f, hb_count=empty_i, hb_donor=empty_i, hb_acceptor=empty_i,
+                            hb_hydrogen=empty_i, hb_side=np.zeros(0, np.int8), hb_distance=empty_f, hb_angle=empty_f)
+            else:
+                s1 = prep(i1)
+                s2 = s1 if self_mode else prep(i2)
+                eng = ContactEngine(s1, None if self_mode else s2, cutoff, hbondcutoff, hbondcutangle, device=dev)
+                try:
+                    src = ArraySource(np.ascontiguousarray(coords[f:g][:, i1]),
+                                      None if self_mode else np.ascontiguousarray(coords[f:g][:, i2]))
+                    t, _, st = run_scan([eng], src, batch_frames=self._batch_frames, order_keys=True, accumulate=False,
+                                        keep_contacts=True)
+                finally:
+                    eng.close()
+                for k in ("contacts", "hbonds", "pair_evals", "batches"):
+                    stats[k] += st[k]
+                stats["path"] = st["path"]
+                part = dict(frame_counts=np.diff(t.frame_ptr), li=np.searchsorted(u1, t.idx1), lj=np.searchsorted(u2, t.idx2),
+                            idx1=t.idx1, idx2=t.idx2, distance=t.distance, weight=t.weight, hb_count=np.diff(t.hb_ptr),
+                            hb_donor=t.hb_donor, hb_acceptor=t.hb_acceptor, hb_hydrogen=t.hb_hydrogen, hb_side=t.hb_side,
+                            hb_distance=t.hb_distance, hb_angle=t.hb_angle)
+            traj._parts.append(part)
+            traj.frame_numbers.extend(range(f, g))
+            f = g
+            self.currentFrameNumber = g - 1
+            self.frameUpdate.emit(float(g) / float(F))
+        traj.finalize()
+        stats["seconds"] = time.time() - start
+        self.scanStats = stats
         self._traj = traj
         return LazyContactResults(traj)
 

@@ -61,6 +61,12 @@ class _Parser:
         self.pos = 0
         self.topo = topo
         self.n = topo.n_atoms
+        if positions is not None:
+            positions = np.ascontiguousarray(positions, np.float32)
+            if positions.ndim == 2:
+                positions = positions[None]
+            if positions.ndim != 3 or positions.shape[1:] != (self.n, 3):
+                raise ValueError("positions must be (natoms, 3) or (frames, natoms, 3)")
         self.positions = positions
         self.device = device
 
@@ -166,25 +172,64 @@ class _Parser:
                 raise NotImplementedError("'around' is a per-frame geometric selection: pass positions= "
                                           "(one frame, (natoms, 3)) to select_atoms")
             from ..cy_modules.cy_gridsearch import find_within_frames
-            pos = np.ascontiguousarray(self.positions, np.float32).reshape(1, self.n, 3)
-            hit = find_within_frames(pos, (~inner).astype(np.int32), inner.astype(np.int32), r, device=self.device)
-            return hit[0].astype(bool)
+            pos = self.positions                                   # (F, natoms, 3)
+            if inner.ndim == 1:                                    # one call for all frames
+                hit = find_within_frames(pos, (~inner).astype(np.int32), inner.astype(np.int32), r, device=self.device)
+            else:                                                  # the inner selection changes per frame itself
+                hit = np.stack([find_within_frames(pos[f:f + 1], (~inner[f]).astype(np.int32), inner[f].astype(np.int32),
+                                                   r, device=self.device)[0] for f in range(len(pos))])
+            return hit.astype(bool)
         if t == "same":
             if self.take() != "residue" or self.take() != "as":
                 raise SelectionError("only 'same residue as' is supported")
             inner = self.factor()
             seg = np.asarray(topo.segids, dtype=object)
             res = np.asarray(topo.resids)
-            keys = set(zip(seg[inner].tolist(), res[inner].tolist()))
-            return np.fromiter(((a, b) in keys for a, b in zip(seg.tolist(), res.tolist())), bool, self.n)
+            # residues = runs of equal (segid, resid); a residue is in when any of its atoms is
+            change = np.ones(self.n, bool)
+            change[1:] = (seg[1:] != seg[:-1]) | (res[1:] != res[:-1])
+            rid = np.cumsum(change) - 1
+            nres = int(rid[-1]) + 1 if self.n else 0
+            if inner.ndim == 1:
+                has = np.zeros(nres, bool)
+                has[rid[inner]] = True
+                return has[rid]
+            out = np.zeros(inner.shape, bool)
+            for f in range(inner.shape[0]):
+                has = np.zeros(nres, bool)
+                has[rid[inner[f]]] = True
+                out[f] = has[rid]
+            return out
         raise SelectionError("unknown selection token %r" % t)
+
+
+def _mask(topo, text, positions, device):
+    p = _Parser(text, topo, positions, device)
+    mask = p.expr()
+    if p.peek() is not None:
+        raise SelectionError("trailing tokens in selection: %r" % p.tok[p.pos:])
+    return mask
 
 
 def select_atoms(topo, text: str, positions=None, device=0) -> np.ndarray:
     """Indices (sorted, unique, int64) of the atoms of ``topo`` matching ``text``.  ``positions`` (one frame,
     (natoms, 3)) is needed by the geometric keyword ``around`` only."""
-    p = _Parser(text, topo, positions, device)
-    mask = p.expr()
-    if p.peek() is not None:
-        raise SelectionError("trailing tokens in selection: %r" % p.tok[p.pos:])
+    if positions is not None and np.ndim(positions) != 2:
+        raise ValueError("select_atoms takes one frame; use select_atoms_frames for (frames, natoms, 3)")
+    mask = _mask(topo, text, positions, device)
+    if mask.ndim == 2:
+        mask = mask[0]
     return np.nonzero(mask)[0].astype(np.int64)
+
+
+def select_atoms_frames(topo, text: str, frames, device=0) -> List[np.ndarray]:
+    """The selection re-evaluated on every frame of ``frames`` ((F, natoms, 3)), as the reference's serial frame
+    loop does for selections containing ``around`` (core/ContactAnalyzer.py:321-324): a list of F index arrays.
+    All frames of an ``around`` go to the GPU in one ``pc_find_within`` call."""
+    frames = np.asarray(frames)
+    F = frames.shape[0]
+    mask = _mask(topo, text, frames, device) if F else np.zeros(topo.n_atoms, bool)
+    if mask.ndim == 1:
+        idx = np.nonzero(mask)[0].astype(np.int64)
+        return [idx for _ in range(F)]
+    return [np.nonzero(mask[f])[0].astype(np.int64) for f in range(F)]

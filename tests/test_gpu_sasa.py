@@ -137,3 +137,45 @@ def test_around_selection_on_a_frame(rpn11):
     for f in (0, 17):
         idx = select_atoms(rpn11.topology, "segid UBQ and around 5.0 (segid RN11)", positions=rpn11.coords[f])
         assert np.array_equal(idx, np.nonzero(want[f])[0])
+
+
+def test_analyzer_with_around_selection_rescans_every_frame(rpn11):
+    """core/ContactAnalyzer.py:319-331: a selection containing `around` is re-evaluated on every frame, so atoms,
+    local indices and the search grid change per frame.  Expected values: the oracle run frame by frame on that
+    frame's own selection (find_within oracle + residue expansion in numpy)."""
+    from oracle import frame_oracle
+    from pycontact_b200.core.ContactAnalyzer import Analyzer
+    from tests.test_gpu_parity import _compare_traj, RTOL
+    topo = rpn11.topology
+    F = 12
+    coords = rpn11.coords[:F]
+    sel2 = "segid UBQ and same residue as around 4.0 (segid RN11)"
+    an = Analyzer("x.psf", "x.dcd", 5.0, 2.5, 120, "segid RN11", sel2, topology=topo, frames=coords)
+    an.runFrameScan(1)
+    assert len(an.contactResults) == F
+    seg, res = np.asarray(topo.segids), np.asarray(topo.resids)
+    idx1 = np.nonzero(seg == "RN11")[0]
+    inner = (seg == "RN11")
+    expected, sizes = [], []
+    for f in range(F):
+        hit = so.find_within(coords[f], (~inner).astype(np.int32), inner.astype(np.int32), 4.0).astype(bool)
+        resset = set(zip(seg[hit].tolist(), res[hit].tolist()))
+        whole = np.fromiter(((a, b) in resset for a, b in zip(seg.tolist(), res.tolist())), bool, len(seg))
+        idx2 = np.nonzero(whole & (seg == "UBQ"))[0]
+        sizes.append(len(idx2))
+        expected += frame_oracle.scan_frames([coords[f][idx1]], [coords[f][idx2]], idx1, idx2, 5.0, 2.5, 120,
+                                             topo.names, topo.types, topo.bonds)
+    assert len(set(sizes)) > 1                       # the selection really changes over the frames
+    _compare_traj(an.contactResults.traj, expected)
+    assert an.scanStats["selection_runs"] > 1
+    acc = an.runContactAnalysis([0, 0, 1, 1, 0], [0, 0, 1, 1, 0], 1)
+    ora = frame_oracle.accumulate(expected, [0, 0, 1, 1, 0], [0, 0, 1, 1, 0], an.name_array, an.resid_array,
+                                  an.resname_array, an.segids, an.backbone)
+    assert [a.key1 for a in acc] == ora["key1"] and [a.key2 for a in acc] == ora["key2"]
+    np.testing.assert_allclose(np.asarray([a.scoreArray for a in acc], float), ora["score"], rtol=RTOL, atol=1e-12)
+    assert np.array_equal(np.asarray([a.hbondFramesScan() for a in acc]), ora["hbonds"])
+    # the first frame's selection decides whether the analysis starts at all (:312-313)
+    an0 = Analyzer("x.psf", "x.dcd", 5.0, 2.5, 120, "segid RN11", "segid UBQ and around 0.01 (segid RN11)",
+                   topology=topo, frames=coords)
+    with pytest.raises(Exception):
+        an0.runFrameScan(1)
