@@ -303,31 +303,92 @@ __device__ __forceinline__ long long pc_gacc_find(const PcGlobalTable &t, unsign
     return -1;
 }
 
+// one (frame, key) update of the global table: `cnt` contacts with weight sum w (backbone parts b1, b2) and
+// smallest order key `first`
+__device__ __forceinline__ void pc_gacc_apply(const PcAccArgs &a, const PcGlobalTable &t, int f, unsigned long long key,
+                                              double w, double b1, double b2, unsigned int cnt, unsigned long long first,
+                                              unsigned int &status) {
+    bool fresh;
+    const long long s = pc_gacc_find(t, (unsigned long long)f * t.nkeys + key, true, fresh);
+    if (s < 0) { status |= (unsigned)PC_ST_TABLE_OVERFLOW; return; }
+    if (fresh) {
+        t.e[s].rowidx = atomicAdd(&a.frame_rcount[f], 1u);
+        const unsigned long long q = atomicAdd(t.nfresh, 1ull);
+        if ((long long)q < a.cap_rows) t.fresh[q] = (unsigned int)s;
+    }
+    PcGlobalEntry *e = t.e + s;
+    atomicAdd(&e->score, w);
+    if (b1 != 0.0) atomicAdd(&e->bb1, b1);
+    if (b2 != 0.0) atomicAdd(&e->bb2, b2);
+    atomicAdd(&e->ncont, cnt);
+    atomicMin(&e->first, first);
+}
+
+// Contacts reach the table in the order the pair search found them: neighbouring records share their A atoms'
+// residues and the B residues next to them, so a tile of PC_GACC_TILE consecutive contacts holds only a few
+// hundred distinct keys.  Each CTA therefore folds a tile into a small shared-memory table first and sends ONE
+// update per distinct key to the global table.  The tile sums are 2^-40 fixed point, exact and order-independent,
+// so score and its backbone parts stay consistent (sc = score - bb is formed by the caller and must not see two
+// differently rounded float sums); each is kept as two 32-bit halves (bits 20.. and 0..19 of the 41-bit weight,
+// neither half overflows over 2048 weights <= 1) because 32-bit shared-memory atomics are native while 64-bit
+// ones are CAS loops -- the L2 atomics, which bound this kernel, drop by the tile's contacts-per-key ratio.  A
+// contact that finds no slot within 16 probes goes to the global table directly.
+#define PC_GACC_TILE 2048
+#define PC_GACC_SLOTS 1024
+#define PC_GACC_FIX 1099511627776.0     // 2^40
 __global__ void __launch_bounds__(256) pc_gacc_insert_kernel(const PcAccArgs a, PcGlobalTable t) {
-    const int f = blockIdx.y;
+    __shared__ unsigned long long s_key[PC_GACC_SLOTS], s_first[PC_GACC_SLOTS];
+    __shared__ unsigned int s_hi[3][PC_GACC_SLOTS], s_lo[3][PC_GACC_SLOTS];      // score, bb1, bb2
+    __shared__ unsigned int s_cnt[PC_GACC_SLOTS];
+    const int f = blockIdx.y, tid = threadIdx.x;
     const uint32_t c0 = a.frame_cstart[f], cn = a.frame_ccount[f];
     unsigned int status = 0;
-    for (uint32_t c = blockIdx.x * blockDim.x + threadIdx.x; c < cn; c += gridDim.x * blockDim.x) {
-        const pc_contact rec = a.contacts[c0 + c];
-        const unsigned long long key =
-            (unsigned long long)__ldg(a.lgid1 + rec.i) * a.ngroups2 + (unsigned long long)__ldg(a.lgid2 + rec.j);
-        bool fresh;
-        const long long s = pc_gacc_find(t, (unsigned long long)f * t.nkeys + key, true, fresh);
-        if (s < 0) { status |= (unsigned)PC_ST_TABLE_OVERFLOW; continue; }
-        if (fresh) {
-            t.e[s].rowidx = atomicAdd(&a.frame_rcount[f], 1u);
-            const unsigned long long q = atomicAdd(t.nfresh, 1ull);
-            if ((long long)q < a.cap_rows) t.fresh[q] = (unsigned int)s;
+    for (uint32_t base = blockIdx.x * (uint32_t)PC_GACC_TILE; base < cn; base += gridDim.x * (uint32_t)PC_GACC_TILE) {
+        for (int s = tid; s < PC_GACC_SLOTS; s += 256) {
+            s_key[s] = PC_EMPTY_KEY; s_first[s] = PC_EMPTY_KEY;
+            s_hi[0][s] = s_hi[1][s] = s_hi[2][s] = 0u; s_lo[0][s] = s_lo[1][s] = s_lo[2][s] = 0u; s_cnt[s] = 0u;
         }
-        const double w = (double)rec.weight;
-        PcGlobalEntry *e = t.e + s;
-        atomicAdd(&e->score, w);
-        if (__ldg(a.lflag1 + rec.i) & PC_ATOM_BACKBONE) atomicAdd(&e->bb1, w);
-        if (__ldg(a.lflag2 + rec.j) & PC_ATOM_BACKBONE) atomicAdd(&e->bb2, w);
-        atomicAdd(&e->ncont, 1u);
-        const unsigned long long ok = a.order_keys ? a.order_keys[c0 + c]
-                                                   : (((unsigned long long)(unsigned)rec.i << 32) | (unsigned)rec.j);
-        atomicMin(&e->first, ok);
+        __syncthreads();
+        const uint32_t end = min(cn, base + (uint32_t)PC_GACC_TILE);
+        for (uint32_t c = base + tid; c < end; c += 256) {
+            const pc_contact rec = a.contacts[c0 + c];
+            const unsigned long long key =
+                (unsigned long long)__ldg(a.lgid1 + rec.i) * a.ngroups2 + (unsigned long long)__ldg(a.lgid2 + rec.j);
+            const bool bk1 = __ldg(a.lflag1 + rec.i) & PC_ATOM_BACKBONE, bk2 = __ldg(a.lflag2 + rec.j) & PC_ATOM_BACKBONE;
+            const unsigned long long ok = a.order_keys ? a.order_keys[c0 + c]
+                                                       : (((unsigned long long)(unsigned)rec.i << 32) | (unsigned)rec.j);
+            unsigned int h = (unsigned int)(pc_hash64(key) & (PC_GACC_SLOTS - 1));
+            int slot = -1;
+#pragma unroll 1
+            for (int p = 0; p < 16; p++) {
+                unsigned long long prev = s_key[h];
+                if (prev == PC_EMPTY_KEY) prev = atomicCAS(&s_key[h], PC_EMPTY_KEY, key);
+                if (prev == PC_EMPTY_KEY || prev == key) { slot = (int)h; break; }
+                h = (h + 1) & (PC_GACC_SLOTS - 1);
+            }
+            if (slot >= 0) {
+                const unsigned long long wq = __double2ull_rn((double)fminf(rec.weight, 1.0f) * PC_GACC_FIX);
+                const unsigned int hi = (unsigned int)(wq >> 20), lo = (unsigned int)(wq & 0xfffffu);
+                atomicAdd(&s_hi[0][slot], hi); atomicAdd(&s_lo[0][slot], lo);
+                if (bk1) { atomicAdd(&s_hi[1][slot], hi); atomicAdd(&s_lo[1][slot], lo); }
+                if (bk2) { atomicAdd(&s_hi[2][slot], hi); atomicAdd(&s_lo[2][slot], lo); }
+                atomicAdd(&s_cnt[slot], 1u);
+                if (ok < s_first[slot]) atomicMin(&s_first[slot], ok);     // a CAS loop: only when it can lower the minimum
+            } else {
+                pc_gacc_apply(a, t, f, key, (double)rec.weight, bk1 ? (double)rec.weight : 0.0,
+                              bk2 ? (double)rec.weight : 0.0, 1u, ok, status);
+            }
+        }
+        __syncthreads();
+        for (int s = tid; s < PC_GACC_SLOTS; s += 256)
+            if (s_key[s] != PC_EMPTY_KEY) {
+                double v[3];
+#pragma unroll
+                for (int k = 0; k < 3; k++)
+                    v[k] = (double)(((unsigned long long)s_hi[k][s] << 20) + (unsigned long long)s_lo[k][s]) * (1.0 / PC_GACC_FIX);
+                pc_gacc_apply(a, t, f, s_key[s], v[0], v[1], v[2], s_cnt[s], s_first[s], status);
+            }
+        __syncthreads();
     }
     status = __reduce_or_sync(PC_FULL_MASK, status);
     if ((threadIdx.x & 31) == 0 && status) atomicOr(&a.counters[PC_CNT_STATUS], (unsigned long long)status);

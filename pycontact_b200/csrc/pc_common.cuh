@@ -65,6 +65,7 @@ struct PcScanArgs {
     double hb_cutoff, hb_angle;
     int capCells, capHits, capHb;      // shared-memory capacities (small-frame path)
     int fuse_acc;                      // small-frame path: accumulate (frame, key) rows inside the scan kernel
+    int dense_mode;                    // large-frame path: 0 = pair kernel chosen per frame, 1 = thread per atom, 2 = warp per cell
     pc_row *rows;
     long long cap_rows;
     uint32_t *frame_rstart, *frame_rcount;

@@ -349,8 +349,9 @@ struct PcLargeOut {
 // Which pair kernel searches a frame: with a few B atoms per cell on average every B atom is a candidate
 // of several A atoms, and loading it once per A CELL (warp per cell, lanes over B) beats loading it once
 // per A ATOM (thread per atom).
-__device__ __forceinline__ bool pc_large_is_dense(const PcLargeFrame &F, bool self) {
+__device__ __forceinline__ bool pc_large_is_dense(const PcLargeFrame &F, bool self, int mode = 0) {
     const unsigned nB = self ? F.nA_in : F.nB_in;
+    if (mode) return F.ncell > 0 && mode == 2;
     return F.ncell > 0 && (unsigned long long)nB * 2ull >= 5ull * (unsigned long long)F.ncell;      // >= 2.5 per cell
 }
 
@@ -379,7 +380,7 @@ __global__ void __launch_bounds__(256) pc_large_pair_kernel(const PcScanArgs a, 
     pc_contact *slice = a.contacts + (long long)f * o.cap_c_frame;
     const int nx = F.nx, ny = F.ny, nz = F.nz;
     const long long items = 3ll * F.nA_in;
-    if (pc_large_is_dense(F, self)) return;          // dense frames are searched by pc_large_pair_dense_kernel
+    if (pc_large_is_dense(F, self, a.dense_mode)) return;          // dense frames are searched by pc_large_pair_dense_kernel
     for (long long tile = blockIdx.x * (long long)blockDim.x; tile < items; tile += (long long)gridDim.x * blockDim.x) {
         if (threadIdx.x == 0) qn = 0;
         __syncthreads();
@@ -515,7 +516,7 @@ __global__ void __launch_bounds__(256) pc_large_pair_dense_kernel(const PcScanAr
     if (threadIdx.x == 0) F = fr[fb];
     __syncthreads();
     const bool self = a.self_mode != 0;
-    if (!pc_large_is_dense(F, self)) return;
+    if (!pc_large_is_dense(F, self, a.dense_mode)) return;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
     uint2 *wq = q[warp];
     unsigned wn = 0;                      // entries in this warp's queue (same value in every lane)
