@@ -330,24 +330,34 @@ __device__ __forceinline__ void pc_gacc_apply(const PcAccArgs &a, const PcGlobal
 // update per distinct key to the global table.  The tile sums are 2^-40 fixed point, exact and order-independent,
 // so score and its backbone parts stay consistent (sc = score - bb is formed by the caller and must not see two
 // differently rounded float sums); each is kept as two 32-bit halves (bits 20.. and 0..19 of the 41-bit weight,
-// neither half overflows over 2048 weights <= 1) because 32-bit shared-memory atomics are native while 64-bit
+// neither half overflows over 4096 weights <= 1) because 32-bit shared-memory atomics are native while 64-bit
 // ones are CAS loops -- the L2 atomics, which bound this kernel, drop by the tile's contacts-per-key ratio.  A
 // contact that finds no slot within 16 probes goes to the global table directly.
+#ifndef PC_GACC_TILE
 #define PC_GACC_TILE 2048
+#endif
+#ifndef PC_GACC_SLOTS
 #define PC_GACC_SLOTS 1024
+#endif
 #define PC_GACC_FIX 1099511627776.0     // 2^40
+// dynamic shared memory: key, first (u64 each), 4 classes x (hi, lo), count
+#define PC_GACC_SMEM (PC_GACC_SLOTS * (8 + 8 + 4 * 2 * 4 + 4))
+// Every contact belongs to exactly ONE of four classes (atom 1 backbone?, atom 2 backbone?), so it costs three
+// shared-memory atomics (its class's two halves + the count) instead of up to seven; score = sum of the classes,
+// bb1 = classes 2 + 3, bb2 = classes 1 + 3, in exact integer arithmetic at flush time.
 __global__ void __launch_bounds__(256) pc_gacc_insert_kernel(const PcAccArgs a, PcGlobalTable t) {
-    __shared__ unsigned long long s_key[PC_GACC_SLOTS], s_first[PC_GACC_SLOTS];
-    __shared__ unsigned int s_hi[3][PC_GACC_SLOTS], s_lo[3][PC_GACC_SLOTS];      // score, bb1, bb2
-    __shared__ unsigned int s_cnt[PC_GACC_SLOTS];
+    extern __shared__ __align__(16) unsigned char gacc_smem[];
+    unsigned long long *s_key = reinterpret_cast<unsigned long long *>(gacc_smem);
+    unsigned long long *s_first = s_key + PC_GACC_SLOTS;
+    unsigned int *s_hi = reinterpret_cast<unsigned int *>(s_first + PC_GACC_SLOTS);      // [4][SLOTS]
+    unsigned int *s_lo = s_hi + 4 * PC_GACC_SLOTS;                                       // [4][SLOTS]
+    unsigned int *s_cnt = s_lo + 4 * PC_GACC_SLOTS;
     const int f = blockIdx.y, tid = threadIdx.x;
     const uint32_t c0 = a.frame_cstart[f], cn = a.frame_ccount[f];
     unsigned int status = 0;
     for (uint32_t base = blockIdx.x * (uint32_t)PC_GACC_TILE; base < cn; base += gridDim.x * (uint32_t)PC_GACC_TILE) {
-        for (int s = tid; s < PC_GACC_SLOTS; s += 256) {
-            s_key[s] = PC_EMPTY_KEY; s_first[s] = PC_EMPTY_KEY;
-            s_hi[0][s] = s_hi[1][s] = s_hi[2][s] = 0u; s_lo[0][s] = s_lo[1][s] = s_lo[2][s] = 0u; s_cnt[s] = 0u;
-        }
+        for (int s = tid; s < PC_GACC_SLOTS; s += 256) { s_key[s] = PC_EMPTY_KEY; s_first[s] = PC_EMPTY_KEY; s_cnt[s] = 0u; }
+        for (int s = tid; s < 8 * PC_GACC_SLOTS; s += 256) s_hi[s] = 0u;                 // s_hi and s_lo are adjacent
         __syncthreads();
         const uint32_t end = min(cn, base + (uint32_t)PC_GACC_TILE);
         for (uint32_t c = base + tid; c < end; c += 256) {
@@ -368,10 +378,9 @@ __global__ void __launch_bounds__(256) pc_gacc_insert_kernel(const PcAccArgs a, 
             }
             if (slot >= 0) {
                 const unsigned long long wq = __double2ull_rn((double)fminf(rec.weight, 1.0f) * PC_GACC_FIX);
-                const unsigned int hi = (unsigned int)(wq >> 20), lo = (unsigned int)(wq & 0xfffffu);
-                atomicAdd(&s_hi[0][slot], hi); atomicAdd(&s_lo[0][slot], lo);
-                if (bk1) { atomicAdd(&s_hi[1][slot], hi); atomicAdd(&s_lo[1][slot], lo); }
-                if (bk2) { atomicAdd(&s_hi[2][slot], hi); atomicAdd(&s_lo[2][slot], lo); }
+                const int cls = (bk1 ? 2 : 0) + (bk2 ? 1 : 0);
+                atomicAdd(&s_hi[cls * PC_GACC_SLOTS + slot], (unsigned int)(wq >> 20));
+                atomicAdd(&s_lo[cls * PC_GACC_SLOTS + slot], (unsigned int)(wq & 0xfffffu));
                 atomicAdd(&s_cnt[slot], 1u);
                 if (ok < s_first[slot]) atomicMin(&s_first[slot], ok);     // a CAS loop: only when it can lower the minimum
             } else {
@@ -382,11 +391,13 @@ __global__ void __launch_bounds__(256) pc_gacc_insert_kernel(const PcAccArgs a, 
         __syncthreads();
         for (int s = tid; s < PC_GACC_SLOTS; s += 256)
             if (s_key[s] != PC_EMPTY_KEY) {
-                double v[3];
+                unsigned long long v[4];
 #pragma unroll
-                for (int k = 0; k < 3; k++)
-                    v[k] = (double)(((unsigned long long)s_hi[k][s] << 20) + (unsigned long long)s_lo[k][s]) * (1.0 / PC_GACC_FIX);
-                pc_gacc_apply(a, t, f, s_key[s], v[0], v[1], v[2], s_cnt[s], s_first[s], status);
+                for (int k = 0; k < 4; k++)
+                    v[k] = ((unsigned long long)s_hi[k * PC_GACC_SLOTS + s] << 20) + (unsigned long long)s_lo[k * PC_GACC_SLOTS + s];
+                pc_gacc_apply(a, t, f, s_key[s], (double)(v[0] + v[1] + v[2] + v[3]) * (1.0 / PC_GACC_FIX),
+                              (double)(v[2] + v[3]) * (1.0 / PC_GACC_FIX), (double)(v[1] + v[3]) * (1.0 / PC_GACC_FIX), s_cnt[s],
+                              s_first[s], status);
             }
         __syncthreads();
     }

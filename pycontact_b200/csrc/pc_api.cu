@@ -516,7 +516,8 @@ extern "C" int pc_accumulate(pc_ctx *c, void *stream) {
     const int per_frame_blocks = std::max(1, 4 * c->num_sms / a.nframes);
     const unsigned long long avg = ncontacts / a.nframes + 1;
     const int blocks = (int)std::max<unsigned long long>(1, std::min<unsigned long long>((avg * 2 + 255) / 256, per_frame_blocks));
-    pc_gacc_insert_kernel<<<dim3(blocks, a.nframes), 256, 0, s>>>(a, t);
+    CUDA_TRY(cudaFuncSetAttribute(pc_gacc_insert_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, PC_GACC_SMEM));
+    pc_gacc_insert_kernel<<<dim3(blocks, a.nframes), 256, PC_GACC_SMEM, s>>>(a, t);
     pc_gacc_hbond_kernel<<<dim3(std::max(1, blocks / 4), a.nframes), 256, 0, s>>>(a, t);
     pc_gacc_offsets_kernel<<<1, 1024, 0, s>>>(a, c->gacc_cursor.p);
     pc_gacc_emit_kernel<<<4 * c->num_sms, 256, 0, s>>>(a, t, c->gacc_cursor.p);
