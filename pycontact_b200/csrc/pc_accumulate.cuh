@@ -55,6 +55,9 @@ __global__ void __launch_bounds__(NT) pc_accumulate_kernel(const PcAccArgs a) {
         __syncthreads();
         const uint32_t c0 = a.frame_cstart[f], cn = a.frame_ccount[f];
         for (uint32_t c = tid; c < cn; c += NT) {
+            // a full table makes every further key walk 256 slots, and the batch is redone on the global table
+            // anyway (PC_ST_TABLE_OVERFLOW): stop at the first overflow instead of finishing the frame
+            if (*(volatile unsigned int *)&s_status & (unsigned)PC_ST_TABLE_OVERFLOW) break;
             const pc_contact rec = a.contacts[c0 + c];
             const unsigned long long key =
                 (unsigned long long)__ldg(a.lgid1 + rec.i) * a.ngroups2 + (unsigned long long)__ldg(a.lgid2 + rec.j);
@@ -179,6 +182,9 @@ __global__ void __launch_bounds__(NT) pc_accumulate_compact_kernel(const PcAccAr
         __syncthreads();
         const uint32_t c0 = a.frame_cstart[f], cn = a.frame_ccount[f];
         for (uint32_t c = tid; c < cn; c += NT) {
+            // a full table makes every further key walk 256 slots, and the batch is redone on the global table
+            // anyway (PC_ST_TABLE_OVERFLOW): stop at the first overflow instead of finishing the frame
+            if (*(volatile unsigned int *)&s_status & (unsigned)PC_ST_TABLE_OVERFLOW) break;
             const pc_contact rec = a.contacts[c0 + c];
             const unsigned long long key =
                 (unsigned long long)__ldg(a.lgid1 + rec.i) * a.ngroups2 + (unsigned long long)__ldg(a.lgid2 + rec.j);

@@ -178,3 +178,30 @@ __device__ __forceinline__ bool pair_within(float ax, float ay, float az, float 
     if (d2f > sqdist_hi) return false;
     return !(dist2_exact(ax, ay, az, bx, by, bz) > sqdist);
 }
+
+// Self-interaction filter on a hit mask (core/multi_trajectory.py:93-95: a pair is dropped when
+// (resid1 - resid2) < 5, signed, and both atoms are in the same segment).  word(k) = packed atom word of
+// candidate k.  Four hits per round with all their topology loads issued before the first test: written as
+// `a && b` per hit, the segment load waited for the residue load, and each hit for the previous one.
+template <typename WordOf>
+__device__ __forceinline__ unsigned pc_self_filter(unsigned m, int ares, int aseg, const int *lres, const int *lseg, WordOf word) {
+    unsigned t = m;
+    while (t) {
+        int k[4], r[4], g[4];
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+            k[u] = t ? __ffs(t) - 1 : k[0];
+            t &= t - 1;                                    // 0 stays 0
+        }
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+            const int lj = PC_W_INDEX(word(k[u]));
+            r[u] = __ldg(lres + lj); g[u] = __ldg(lseg + lj);
+        }
+#pragma unroll
+        for (int u = 0; u < 4; u++)
+            if ((ares - r[u]) < 5 && aseg == g[u]) m &= ~(1u << k[u]);
+    }
+    return m;
+}
+

@@ -423,16 +423,9 @@ __global__ void __launch_bounds__(256) pc_large_pair_kernel(const PcScanArgs a, 
                             const float4 pb = __ldg(sB + jb + k);
                             m |= (unsigned)pair_within(pa.x, pa.y, pa.z, pb.x, pb.y, pb.z, sqdist, sqdist_hi) << k;
                         }
-                        if (self && m) {
-                            // (resid1 - resid2) < 5 and same segment -> dropped (core/multi_trajectory.py:93-95)
-                            unsigned t = m;
-                            while (t) {
-                                const int k = __ffs(t) - 1;
-                                t &= t - 1;
-                                const int lj = PC_W_INDEX(__float_as_uint(__ldg(sB + jb + k).w));
-                                if ((ares - __ldg(a.t.lres1 + lj)) < 5 && aseg == __ldg(a.t.lseg1 + lj)) m &= ~(1u << k);
-                            }
-                        }
+                        if (self && m)
+                            m = pc_self_filter(m, ares, aseg, a.t.lres1, a.t.lseg1,
+                                               [&](int k) { return __float_as_uint(__ldg(&sB[jb + k].w)); });
                         if (!m) continue;
                         unsigned p = atomicAdd(&qn, (unsigned)__popc(m));
                         while (m) {

@@ -403,16 +403,9 @@ __global__ void __launch_bounds__(NT, NT >= 1024 ? 1 : NT >= 512 ? 2 : NT >= 384
 #pragma unroll 1
                             for (; k0 < cnt; k0++)
                                 if (pair_within_packed(nxy, naz, sortB[jb + k0], sqdist)) m |= 1u << k0;
-                            if (self && m) {
-                                // (resid1 - resid2) < 5 and same segment -> dropped (core/multi_trajectory.py:93-95)
-                                unsigned t = m;
-                                while (t) {
-                                    const int k = __ffs(t) - 1;
-                                    t &= t - 1;
-                                    const int lj = PC_W_INDEX(__float_as_uint(sortB[jb + k].w));
-                                    if ((ares - __ldg(a.t.lres1 + lj)) < 5 && aseg == __ldg(a.t.lseg1 + lj)) m &= ~(1u << k);
-                                }
-                            }
+                            if (self && m)
+                                m = pc_self_filter(m, ares, aseg, a.t.lres1, a.t.lseg1,
+                                                   [&](int k) { return __float_as_uint(sortB[jb + k].w); });
                             if (!m) continue;
                             unsigned p = atomicAdd(&s_nhits, (unsigned)__popc(m));
                             while (m) {

@@ -1,10 +1,12 @@
 OUT=gpurun_out; mkdir -p $OUT
-timeout 600 python -m pytest tests -m gpu -q -x -k "synthetic or fused or edge or sparse or packed" > $OUT/c4v_pytest.log 2>&1; echo "pytest rc=$?"; tail -3 $OUT/c4v_pytest.log
+timeout 600 python -m pytest tests -m gpu -q -x -k "synthetic or fused or edge or sparse or packed or self or golden" > $OUT/c4v_pytest.log 2>&1; echo "pytest rc=$?"; tail -3 $OUT/c4v_pytest.log
 for lib in $1; do
-PYCONTACT_B200_LIB=pycontact_b200/$lib timeout 300 python bench.py --workload c4 --steps 2 --warmup 3 --no-cpu 2>$OUT/c4v.err | python -c "
+for wl in c4 c4s; do
+PYCONTACT_B200_LIB=pycontact_b200/$lib timeout 300 python bench.py --workload $wl --steps 2 --warmup 3 --no-cpu 2>$OUT/c4v.err | python -c "
 import sys,json
 for l in sys.stdin:
     if l.startswith('{'):
-        j=json.loads(l); print('$lib value %.1f ms/step %.3f scanseq %.3f'%(j['value'],j['ms_per_step'],j['roofline'].get('scan_sequence_ms_per_batch',0)))
+        j=json.loads(l); print('$lib $wl value %.1f ms/step %.3f scanseq %.3f'%(j['value'],j['ms_per_step'],j['roofline'].get('scan_sequence_ms_per_batch',0)))
 "
+done
 done
