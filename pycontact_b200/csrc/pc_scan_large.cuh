@@ -359,6 +359,10 @@ __device__ __forceinline__ bool pc_large_is_dense(const PcLargeFrame &F, bool se
 // atomic per tile of 256 work items: in dense systems (a hit every ~6 candidates) a global atomic per
 // hit would make every hit an L2 round trip inside the candidate loop.
 #define PC_PAIR_Q 4096
+#ifndef PC_PAIR_UNROLL
+#define PC_PAIR_UNROLL 4
+#endif
+constexpr int pc_pair_unroll = PC_PAIR_UNROLL;
 __global__ void __launch_bounds__(256) pc_large_pair_kernel(const PcScanArgs a, PcLargeFrame *fr, int f0,
                                                             const uint32_t *cellsA, const uint32_t *cellsB, int capCells,
                                                             const float4 *sortA, const float4 *sortB, int n1h_alloc,
@@ -418,7 +422,7 @@ __global__ void __launch_bounds__(256) pc_large_pair_kernel(const PcScanArgs a, 
                     for (int jb = b0[dy]; jb < b1[dy]; jb += 32) {
                         const int cnt = min(32, b1[dy] - jb);
                         unsigned m = 0;
-#pragma unroll 4
+#pragma unroll pc_pair_unroll
                         for (int k = 0; k < cnt; k++) {
                             const float4 pb = __ldg(sB + jb + k);
                             m |= (unsigned)pair_within(pa.x, pa.y, pa.z, pb.x, pb.y, pb.z, sqdist, sqdist_hi) << k;
