@@ -355,8 +355,8 @@ __device__ __forceinline__ bool pc_large_is_dense(const PcLargeFrame &F, bool se
     return F.ncell > 0 && (unsigned long long)nB * 2ull >= 5ull * (unsigned long long)F.ncell;      // >= 2.5 per cell
 }
 
-// Hits are staged in a per-CTA queue in shared memory and appended to the frame's slice with ONE global
-// atomic per tile of 256 work items: in dense systems (a hit every ~6 candidates) a global atomic per
+// Hits are staged in per-WARP queues in shared memory and appended to the frame's slice with ONE global
+// atomic per 32 work items (a CTA-wide queue cost a barrier per tile, 31 % of this kernel's stall samples on c3): in dense systems (a hit every ~6 candidates) a global atomic per
 // hit would make every hit an L2 round trip inside the candidate loop.
 #define PC_PAIR_Q 4096
 #ifndef PC_PAIR_UNROLL
@@ -368,13 +368,14 @@ __global__ void __launch_bounds__(256) pc_large_pair_kernel(const PcScanArgs a, 
                                                             const float4 *sortA, const float4 *sortB, int n1h_alloc,
                                                             int n2h_alloc, PcLargeOut o) {
     __shared__ PcLargeFrame F;
-    __shared__ uint2 q[PC_PAIR_Q];
-    __shared__ unsigned int qn, qbase;
+    __shared__ uint2 q[8][PC_PAIR_Q / 8];          // one queue per warp: no CTA barrier inside the tile loop
+    __shared__ unsigned int qn[8];
     const int fb = blockIdx.y, f = f0 + fb;
     if (threadIdx.x == 0) F = fr[fb];
     __syncthreads();
     const bool self = a.self_mode != 0;
-    const int lane = threadIdx.x & 31;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    uint2 *wq = q[warp];
     unsigned long long evals = 0;
     unsigned int status = 0;
     const float sqdist = a.sqdist, sqdist_hi = a.sqdist * 1.00000095367431640625f;   // 1 + 2^-20
@@ -385,10 +386,10 @@ __global__ void __launch_bounds__(256) pc_large_pair_kernel(const PcScanArgs a, 
     const int nx = F.nx, ny = F.ny, nz = F.nz;
     const long long items = 3ll * F.nA_in;
     if (pc_large_is_dense(F, self, a.dense_mode)) return;          // dense frames are searched by pc_large_pair_dense_kernel
-    for (long long tile = blockIdx.x * (long long)blockDim.x; tile < items; tile += (long long)gridDim.x * blockDim.x) {
-        if (threadIdx.x == 0) qn = 0;
-        __syncthreads();
-        const long long w = tile + threadIdx.x;
+    for (long long tile = (blockIdx.x * 8ll + warp) * 32; tile < items; tile += (long long)gridDim.x * 256) {
+        if (lane == 0) qn[warp] = 0;
+        __syncwarp();
+        const long long w = tile + lane;
         if (w < items) {
             // layer-major items: a warp holds 32 neighbouring atoms (A is cell-sorted) on the same layer,
             // so its lanes walk the same or adjacent B runs (few distinct cache lines per load)
@@ -431,12 +432,12 @@ __global__ void __launch_bounds__(256) pc_large_pair_kernel(const PcScanArgs a, 
                             m = pc_self_filter(m, ares, aseg, a.t.lres1, a.t.lseg1,
                                                [&](int k) { return __float_as_uint(__ldg(&sB[jb + k].w)); });
                         if (!m) continue;
-                        unsigned p = atomicAdd(&qn, (unsigned)__popc(m));
+                        unsigned p = atomicAdd(&qn[warp], (unsigned)__popc(m));
                         while (m) {
                             const int j = jb + __ffs(m) - 1;
                             m &= m - 1;
-                            if (p < PC_PAIR_Q) {
-                                q[p] = make_uint2((unsigned)ia, (unsigned)j);
+                            if (p < PC_PAIR_Q / 8) {
+                                wq[p] = make_uint2((unsigned)ia, (unsigned)j);
                             } else {
                                 // queue full (very long cutoffs): this hit goes straight to the slice
                                 const unsigned slot = atomicAdd(&fr[fb].ccursor, 1u);
@@ -454,21 +455,22 @@ __global__ void __launch_bounds__(256) pc_large_pair_kernel(const PcScanArgs a, 
                 }
             }
         }
-        __syncthreads();
-        const unsigned n = min(qn, (unsigned)PC_PAIR_Q);
-        if (threadIdx.x == 0 && n) qbase = atomicAdd(&fr[fb].ccursor, n);
-        __syncthreads();
-        for (unsigned k = threadIdx.x; k < n; k += blockDim.x) {
+        __syncwarp();
+        const unsigned n = min(qn[warp], (unsigned)(PC_PAIR_Q / 8));
+        unsigned qbase = 0;
+        if (lane == 0 && n) qbase = atomicAdd(&fr[fb].ccursor, n);
+        qbase = __shfl_sync(PC_FULL_MASK, qbase, 0);
+        for (unsigned k = lane; k < n; k += 32) {
             const long long slot = (long long)qbase + k;
             if (slot < o.cap_c_frame) {
                 pc_contact rec;
-                rec.i = (int)q[k].x; rec.j = (int)q[k].y; rec.distance = 0.f; rec.weight = 0.f;
+                rec.i = (int)wq[k].x; rec.j = (int)wq[k].y; rec.distance = 0.f; rec.weight = 0.f;
                 slice[slot] = rec;
             } else {
                 status |= (unsigned)PC_ST_OUT_OVERFLOW;
             }
         }
-        __syncthreads();
+        __syncwarp();
     }
 #pragma unroll
     for (int s = 16; s > 0; s >>= 1) evals += __shfl_xor_sync(PC_FULL_MASK, evals, s);
