@@ -1124,16 +1124,17 @@ extern "C" int pc_sasa(int device, const float *h_xyz, int32_t nframes, int32_t 
     CUDA_TRY(cudaSetDevice(device));
     const size_t frame_bytes = (size_t)natoms * 12;
     const int fb = (int)std::min<size_t>(std::max<size_t>((1ull << 30) / std::max<size_t>(frame_bytes, 1), 1), (size_t)nframes);
-    DevBuf<float> d_xyz, d_total;
-    DevBuf<int32_t> d_exp;
-    CUDA_TRY(d_xyz.ensure((size_t)fb * natoms * 3));
-    CUDA_TRY(d_total.ensure((size_t)fb));
-    if (h_exposed) CUDA_TRY(d_exp.ensure((size_t)fb * natoms));
+    CUDA_TRY(grid_pool_keep(device));
+    StreamBuf d_xyz, d_total, d_exp;                  // stream-ordered like the kernels' scratch (same pool, no cudaMalloc)
+    CUDA_TRY(d_xyz.alloc((size_t)fb * natoms * 12, 0));
+    CUDA_TRY(d_total.alloc((size_t)fb * 4, 0));
+    if (h_exposed) CUDA_TRY(d_exp.alloc((size_t)fb * natoms * 4, 0));
     for (int f0 = 0; f0 < nframes; f0 += fb) {
         const int nf = std::min(fb, nframes - f0);
         if (natoms) CUDA_TRY(cudaMemcpyAsync(d_xyz.p, h_xyz + (size_t)f0 * natoms * 3, (size_t)nf * frame_bytes, cudaMemcpyHostToDevice, 0));
-        const int rc = pc_sasa_device(device, d_xyz.p, nf, natoms, 3ll * natoms, h_radius, pairdist, npts, srad, pointstyle,
-                                      restricted, h_restricted, d_total.p, h_exposed ? d_exp.p : nullptr, nullptr, nullptr);
+        const int rc = pc_sasa_device(device, d_xyz.as<float>(), nf, natoms, 3ll * natoms, h_radius, pairdist, npts, srad, pointstyle,
+                                      restricted, h_restricted, d_total.as<float>(), h_exposed ? d_exp.as<int32_t>() : nullptr, nullptr,
+                                      nullptr);
         if (rc != PC_OK) return rc;
         CUDA_TRY(cudaMemcpyAsync(h_total + f0, d_total.p, (size_t)nf * 4, cudaMemcpyDeviceToHost, 0));
         if (h_exposed && natoms)
@@ -1179,18 +1180,19 @@ extern "C" int pc_find_within(int device, const float *h_xyz, int32_t nframes, i
     CUDA_TRY(cudaSetDevice(device));
     const size_t frame_bytes = (size_t)num * 12;
     const int fb = (int)std::min<size_t>(std::max<size_t>((1ull << 30) / frame_bytes, 1), (size_t)nframes);
-    DevBuf<float> d_xyz;
-    DevBuf<int32_t> d_f, d_o, d_res;
-    CUDA_TRY(d_xyz.ensure((size_t)fb * num * 3));
-    CUDA_TRY(d_f.ensure((size_t)num));
-    CUDA_TRY(d_o.ensure((size_t)num));
-    CUDA_TRY(d_res.ensure((size_t)fb * num));
+    CUDA_TRY(grid_pool_keep(device));
+    StreamBuf d_xyz, d_f, d_o, d_res;
+    CUDA_TRY(d_xyz.alloc((size_t)fb * num * 12, 0));
+    CUDA_TRY(d_f.alloc((size_t)num * 4, 0));
+    CUDA_TRY(d_o.alloc((size_t)num * 4, 0));
+    CUDA_TRY(d_res.alloc((size_t)fb * num * 4, 0));
     CUDA_TRY(cudaMemcpyAsync(d_f.p, h_flgs, (size_t)num * 4, cudaMemcpyHostToDevice, 0));
     CUDA_TRY(cudaMemcpyAsync(d_o.p, h_others, (size_t)num * 4, cudaMemcpyHostToDevice, 0));
     for (int f0 = 0; f0 < nframes; f0 += fb) {
         const int nf = std::min(fb, nframes - f0);
         CUDA_TRY(cudaMemcpyAsync(d_xyz.p, h_xyz + (size_t)f0 * num * 3, (size_t)nf * frame_bytes, cudaMemcpyHostToDevice, 0));
-        const int rc = pc_within_device(device, d_xyz.p, nf, num, 3ll * num, d_f.p, d_o.p, r, d_res.p, nullptr);
+        const int rc = pc_within_device(device, d_xyz.as<float>(), nf, num, 3ll * num, d_f.as<int32_t>(), d_o.as<int32_t>(), r,
+                                        d_res.as<int32_t>(), nullptr);
         if (rc != PC_OK) return rc;
         CUDA_TRY(cudaMemcpyAsync(h_result + (size_t)f0 * num, d_res.p, (size_t)nf * num * 4, cudaMemcpyDeviceToHost, 0));
         CUDA_TRY(cudaStreamSynchronize(0));

@@ -47,7 +47,11 @@ ms = timed(lambda: check(lib.pc_sasa_device(0, d_xyz.ptr, F, n, 3 * n, _lib.ptr(
 launches = (lib.pc_launch_count() - k0) // 5
 evals = int(d_ev.download(np.uint64, 1)[0]) // 5
 tot = d_tot.download(np.float32, F)
-t0 = time.perf_counter(); api = sasa_frames(coords, rad, PAIRDIST, 50, 1.4, 1, 0, rl); t_api = (time.perf_counter() - t0) * 1e3
+t_apis = []
+for _ in range(3):
+    t0 = time.perf_counter(); api = sasa_frames(coords, rad, PAIRDIST, 50, 1.4, 1, 0, rl); t_apis.append((time.perf_counter() - t0) * 1e3)
+t_api = min(t_apis)
+print('sasa_frames calls: ' + ', '.join('%.1f ms' % t for t in t_apis))
 assert np.array_equal(api, tot)
 ns = max(1, min(F, int(2e5 // max(n, 1)) + 1))
 t0 = time.perf_counter()
