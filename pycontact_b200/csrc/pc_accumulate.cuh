@@ -377,8 +377,7 @@ __global__ void __launch_bounds__(256) pc_gacc_insert_kernel(const PcAccArgs a, 
             int slot = -1;
 #pragma unroll 1
             for (int p = 0; p < 16; p++) {
-                unsigned long long prev = s_key[h];
-                if (prev == PC_EMPTY_KEY) prev = atomicCAS(&s_key[h], PC_EMPTY_KEY, key);
+                const unsigned long long prev = atomicCAS(&s_key[h], PC_EMPTY_KEY, key);
                 if (prev == PC_EMPTY_KEY || prev == key) { slot = (int)h; break; }
                 h = (h + 1) & (PC_GACC_SLOTS - 1);
             }
