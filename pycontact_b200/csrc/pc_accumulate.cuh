@@ -21,6 +21,7 @@ struct PcAccArgs {
     const uint32_t *frame_cstart, *frame_ccount, *frame_hstart, *frame_hcount;
     const int *lgid1, *lgid2;               // per local index
     const uint8_t *lflag1, *lflag2;
+    const uint32_t *lgb1, *lgb2;            // group id | backbone << 31 per local index (one load instead of two)
     unsigned long long ngroups2;
     int nframes, cap;                       // cap = table slots, power of two
     pc_row *rows;
@@ -309,13 +310,24 @@ __device__ __forceinline__ long long pc_gacc_find(const PcGlobalTable &t, unsign
     return -1;
 }
 
+// group id and backbone flag of every selection atom in one word (pc_set_maps)
+__global__ void pc_pack_gid_flag_kernel(const int *gid, const uint8_t *flag, int n, uint32_t *out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = (uint32_t)gid[i] | ((flag[i] & PC_ATOM_BACKBONE) ? 0x80000000u : 0u);
+}
+
 // one (frame, key) update of the global table: `cnt` contacts with weight sum w (backbone parts b1, b2) and
 // smallest order key `first`
-__device__ __forceinline__ void pc_gacc_apply(const PcAccArgs &a, const PcGlobalTable &t, int f, unsigned long long key,
-                                              double w, double b1, double b2, unsigned int cnt, unsigned long long first,
-                                              unsigned int &status) {
-    bool fresh;
-    const long long s = pc_gacc_find(t, (unsigned long long)f * t.nkeys + key, true, fresh);
+__device__ __forceinline__ unsigned long long pc_gacc_home(const PcGlobalTable &t, unsigned long long ck) {
+    unsigned long long h = ck;
+    h ^= h >> 33; h *= 0xff51afd7ed558ccdull; h ^= h >> 33; h *= 0xc4ceb9fe1a85ec53ull; h ^= h >> 33;
+    return h & (t.cap - 1ull);
+}
+
+// the update behind a probe: s = slot of the key (< 0: table overflow), fresh = this call inserted it
+__device__ __forceinline__ void pc_gacc_update(const PcAccArgs &a, const PcGlobalTable &t, int f, long long s, bool fresh,
+                                               double w, double b1, double b2, unsigned int cnt, unsigned long long first,
+                                               unsigned int &status) {
     if (s < 0) { status |= (unsigned)PC_ST_TABLE_OVERFLOW; return; }
     if (fresh) {
         t.e[s].rowidx = atomicAdd(&a.frame_rcount[f], 1u);
@@ -328,6 +340,14 @@ __device__ __forceinline__ void pc_gacc_apply(const PcAccArgs &a, const PcGlobal
     if (b2 != 0.0) atomicAdd(&e->bb2, b2);
     atomicAdd(&e->ncont, cnt);
     atomicMin(&e->first, first);
+}
+
+__device__ __forceinline__ void pc_gacc_apply(const PcAccArgs &a, const PcGlobalTable &t, int f, unsigned long long key,
+                                              double w, double b1, double b2, unsigned int cnt, unsigned long long first,
+                                              unsigned int &status) {
+    bool fresh;
+    const long long s = pc_gacc_find(t, (unsigned long long)f * t.nkeys + key, true, fresh);
+    pc_gacc_update(a, t, f, s, fresh, w, b1, b2, cnt, first, status);
 }
 
 // Contacts reach the table in the order the pair search found them: neighbouring records share their A atoms'
@@ -368,9 +388,9 @@ __global__ void __launch_bounds__(256) pc_gacc_insert_kernel(const PcAccArgs a, 
         const uint32_t end = min(cn, base + (uint32_t)PC_GACC_TILE);
         for (uint32_t c = base + tid; c < end; c += 256) {
             const pc_contact rec = a.contacts[c0 + c];
-            const unsigned long long key =
-                (unsigned long long)__ldg(a.lgid1 + rec.i) * a.ngroups2 + (unsigned long long)__ldg(a.lgid2 + rec.j);
-            const bool bk1 = __ldg(a.lflag1 + rec.i) & PC_ATOM_BACKBONE, bk2 = __ldg(a.lflag2 + rec.j) & PC_ATOM_BACKBONE;
+            const uint32_t g1 = __ldg(a.lgb1 + rec.i), g2 = __ldg(a.lgb2 + rec.j);
+            const unsigned long long key = (unsigned long long)(g1 & 0x7fffffffu) * a.ngroups2 + (unsigned long long)(g2 & 0x7fffffffu);
+            const bool bk1 = g1 >> 31, bk2 = g2 >> 31;
             const unsigned long long ok = a.order_keys ? a.order_keys[c0 + c]
                                                        : (((unsigned long long)(unsigned)rec.i << 32) | (unsigned)rec.j);
             unsigned int h = (unsigned int)(pc_hash64(key) & (PC_GACC_SLOTS - 1));
@@ -394,16 +414,49 @@ __global__ void __launch_bounds__(256) pc_gacc_insert_kernel(const PcAccArgs a, 
             }
         }
         __syncthreads();
-        for (int s = tid; s < PC_GACC_SLOTS; s += 256)
-            if (s_key[s] != PC_EMPTY_KEY) {
+        // flush: the global probe is a CAS that returns (an L2 round trip), and a thread owns SLOTS / 256 slots --
+        // the first probes of all of them are issued before any is consumed (this loop was 48 % of the kernel's
+        // stall samples when each slot waited for the previous one)
+        {
+            constexpr int PER = PC_GACC_SLOTS / 256;
+            unsigned long long ck[PER], home[PER], prev[PER];
+#pragma unroll
+            for (int u = 0; u < PER; u++) {
+                const int s = tid + u * 256;
+                ck[u] = s_key[s];
+                if (ck[u] != PC_EMPTY_KEY) {
+                    ck[u] += (unsigned long long)f * t.nkeys;
+                    home[u] = pc_gacc_home(t, ck[u]);
+                    prev[u] = atomicCAS(&t.e[home[u]].key, PC_EMPTY_KEY, ck[u]);
+                } else {
+                    ck[u] = PC_EMPTY_KEY; home[u] = 0; prev[u] = 0;
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < PER; u++) {
+                const int s = tid + u * 256;
+                if (ck[u] == PC_EMPTY_KEY) continue;
+                long long gs = (long long)home[u];
+                bool fresh = prev[u] == PC_EMPTY_KEY;
+                if (!fresh && prev[u] != ck[u]) {                    // collision at home: the ordinary probe sequence from the next slot
+                    gs = -1;
+                    unsigned long long p = (home[u] + 1) & (t.cap - 1ull);
+                    for (unsigned long long probes = 1; probes < 512 && probes < t.cap; probes++) {
+                        const unsigned long long pv = atomicCAS(&t.e[p].key, PC_EMPTY_KEY, ck[u]);
+                        if (pv == PC_EMPTY_KEY) { fresh = true; gs = (long long)p; break; }
+                        if (pv == ck[u]) { gs = (long long)p; break; }
+                        p = (p + 1) & (t.cap - 1ull);
+                    }
+                }
                 unsigned long long v[4];
 #pragma unroll
                 for (int k = 0; k < 4; k++)
                     v[k] = ((unsigned long long)s_hi[k * PC_GACC_SLOTS + s] << 20) + (unsigned long long)s_lo[k * PC_GACC_SLOTS + s];
-                pc_gacc_apply(a, t, f, s_key[s], (double)(v[0] + v[1] + v[2] + v[3]) * (1.0 / PC_GACC_FIX),
-                              (double)(v[2] + v[3]) * (1.0 / PC_GACC_FIX), (double)(v[1] + v[3]) * (1.0 / PC_GACC_FIX), s_cnt[s],
-                              s_first[s], status);
+                pc_gacc_update(a, t, f, gs, fresh, (double)(v[0] + v[1] + v[2] + v[3]) * (1.0 / PC_GACC_FIX),
+                               (double)(v[2] + v[3]) * (1.0 / PC_GACC_FIX), (double)(v[1] + v[3]) * (1.0 / PC_GACC_FIX), s_cnt[s],
+                               s_first[s], status);
             }
+        }
         __syncthreads();
     }
     status = __reduce_or_sync(PC_FULL_MASK, status);

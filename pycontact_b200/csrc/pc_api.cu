@@ -62,6 +62,7 @@ struct pc_ctx {
     DevBuf<uint32_t> hinfo1, hinfo2, hmask1, hmask2, hpre1, hpre2, linfo1, linfo2;
     DevBuf<int> lres1, lseg1, lres2, lseg2, lhptr1, lhidx1, lhptr2, lhidx2, lgid1, lgid2;
     DevBuf<uint8_t> lflag1, lflag2;
+    DevBuf<uint32_t> lgb1, lgb2;      // group id | backbone << 31 (pc_set_maps)
     unsigned long long ngroups1 = 0, ngroups2 = 0;
     // limits (0 = automatic)
     int lim_hits = 0, lim_hb = 0, lim_cells = 0, lim_table = 0;
@@ -241,6 +242,11 @@ extern "C" int pc_set_maps(pc_ctx *c, const int32_t *gid1, const int32_t *gid2, 
     CUDA_TRY(cudaSetDevice(c->device));
     CUDA_TRY(c->lgid1.upload(std::vector<int>(gid1, gid1 + c->n1)));
     CUDA_TRY(c->lgid2.upload(std::vector<int>(gid2, gid2 + c->n2)));
+    CUDA_TRY(c->lgb1.ensure((size_t)c->n1));
+    CUDA_TRY(c->lgb2.ensure((size_t)c->n2));
+    if (c->n1) pc_pack_gid_flag_kernel<<<(c->n1 + 255) / 256, 256>>>(c->lgid1.p, c->lflag1.p, c->n1, c->lgb1.p);
+    if (c->n2) pc_pack_gid_flag_kernel<<<(c->n2 + 255) / 256, 256>>>(c->lgid2.p, c->self_mode ? c->lflag1.p : c->lflag2.p, c->n2, c->lgb2.p);
+    CUDA_TRY(cudaGetLastError());
     CUDA_TRY(cudaDeviceSynchronize());
     c->ngroups2 = (unsigned long long)ngroups2;
     int g1max = 0;
@@ -443,6 +449,7 @@ extern "C" int pc_accumulate(pc_ctx *c, void *stream) {
     a.frame_cstart = meta(c, 0); a.frame_ccount = meta(c, 1); a.frame_hstart = meta(c, 2); a.frame_hcount = meta(c, 3);
     a.lgid1 = c->lgid1.p; a.lgid2 = c->lgid2.p;
     a.lflag1 = c->lflag1.p; a.lflag2 = c->self_mode ? c->lflag1.p : c->lflag2.p;
+    a.lgb1 = c->lgb1.p; a.lgb2 = c->lgb2.p;
     a.ngroups2 = c->ngroups2;
     a.nframes = c->last_nframes;
     int cap = c->lim_table > 0 ? c->lim_table : 1024;
