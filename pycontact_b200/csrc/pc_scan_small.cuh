@@ -49,7 +49,7 @@ __host__ inline PcSmallSmem pc_small_layout(int self_mode, int capCells, int cap
     o = 0;
     L.off_hits = take(4 * capHits);
     L.off_hb = take((int)sizeof(pc_hbond) * capHb);
-    L.off_tab = take(36 * capTab);
+    L.off_tab = take(40 * capTab);
     o = o > end_early ? o : end_early;
     L.off_sort = take(16 * capCand);
     L.off_cellA = take(4 * (capCells + 1));
@@ -135,10 +135,11 @@ __global__ void __launch_bounds__(NT, NT >= 1024 ? 1 : NT >= 512 ? 2 : NT >= 384
     // few dozen float32 weights stays within ~1e-7 relative of the float64 sum (the parity bar is 1e-5)
     unsigned long long *tkey = reinterpret_cast<unsigned long long *>(smem + L.off_tab);
     unsigned long long *tfirst = tkey + capTab;
-    float *tscore = reinterpret_cast<float *>(tfirst + capTab);
-    float *tbb1 = tscore + capTab;
-    float *tbb2 = tbb1 + capTab;
-    unsigned int *tncont = reinterpret_cast<unsigned int *>(tbb2 + capTab);
+    // every contact belongs to ONE class (atom 1 backbone ? 2 : 0) + (atom 2 backbone ? 1 : 0) and adds its weight to
+    // that class only: one float atomic per hit instead of one to three (score, bb1, bb2); the row's score is the
+    // sum of the four classes, bb1 = classes 2 + 3, bb2 = classes 1 + 3
+    float *tcls = reinterpret_cast<float *>(tfirst + capTab);            // [4][capTab]
+    unsigned int *tncont = reinterpret_cast<unsigned int *>(tcls + 4 * capTab);
     unsigned int *tnhb = tncont + capTab;
 
     __shared__ float red[NT / 32][12];
@@ -424,7 +425,7 @@ __global__ void __launch_bounds__(NT, NT >= 1024 ? 1 : NT >= 512 ? 2 : NT >= 384
         // warp that gets here is past the barrier that ended phase 5 (or skipped the grid).
         if (fuse)
             for (int s = tid; s < capTab; s += NT) {
-                tkey[s] = PC_EMPTY_KEY; tscore[s] = 0.f; tbb1[s] = 0.f; tbb2[s] = 0.f;
+                tkey[s] = PC_EMPTY_KEY; tcls[s] = 0.f; tcls[capTab + s] = 0.f; tcls[2 * capTab + s] = 0.f; tcls[3 * capTab + s] = 0.f;
                 tfirst[s] = PC_EMPTY_KEY; tncont[s] = 0; tnhb[s] = 0;
             }
         __syncthreads();
@@ -537,9 +538,8 @@ __global__ void __launch_bounds__(NT, NT >= 1024 ? 1 : NT >= 512 ? 2 : NT >= 384
                 }
                 if (slot == 0xffffffffu) atomicOr(&s_status, (unsigned)PC_ST_TABLE_OVERFLOW);
                 else {
-                    atomicAdd(&tscore[slot], wgt);
-                    if (wa & PC_W_BACKBONE) atomicAdd(&tbb1[slot], wgt);
-                    if (wb & PC_W_BACKBONE) atomicAdd(&tbb2[slot], wgt);
+                    const int cls = ((wa & PC_W_BACKBONE) ? 2 : 0) + ((wb & PC_W_BACKBONE) ? 1 : 0);
+                    atomicAdd(&tcls[cls * capTab + slot], wgt);
                     atomicAdd(&tncont[slot], 1u);
                     // the minimum only ever decreases: a (possibly stale) read that is already smaller settles it
                     const unsigned long long mine = ((unsigned long long)(unsigned)li << 32) | (unsigned)lj;
@@ -609,7 +609,8 @@ __global__ void __launch_bounds__(NT, NT >= 1024 ? 1 : NT >= 512 ? 2 : NT >= 384
             for (int s = tb; s < te; s++) {
                 if (tkey[s] == PC_EMPTY_KEY) continue;
                 pc_row r;
-                r.key = tkey[s]; r.score = (double)tscore[s]; r.bb1 = (double)tbb1[s]; r.bb2 = (double)tbb2[s];
+                const double c0 = tcls[s], c1 = tcls[capTab + s], c2 = tcls[2 * capTab + s], c3 = tcls[3 * capTab + s];
+                r.key = tkey[s]; r.score = (c0 + c1) + (c2 + c3); r.bb1 = c2 + c3; r.bb2 = c1 + c3;
                 r.ncontacts = tncont[s]; r.nhbonds = tnhb[s]; r.first = tfirst[s];
                 a.rows[o++] = r;
             }

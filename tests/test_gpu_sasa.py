@@ -179,3 +179,14 @@ def test_analyzer_with_around_selection_rescans_every_frame(rpn11):
                    topology=topo, frames=coords)
     with pytest.raises(Exception):
         an0.runFrameScan(1)
+
+
+def test_sasa_and_within_large_frame_equal_reference():
+    """300 000 atoms in one frame: many CTAs per frame, cell budget = atoms, one long running sum."""
+    from pycontact_b200.cy_modules.cy_gridsearch import sasa_frames, find_within_frames
+    pos, rad, rl = _cloud(300000, 77)
+    got = sasa_frames(pos[None], rad, PAIRDIST, 50, 1.4, 1, 1, rl)
+    assert got[0] == so.ref_sasa(pos, rad, PAIRDIST, 50, 1.4, 1, 1, rl)
+    f = rl
+    o = (1 - rl).astype(np.int32)
+    assert np.array_equal(find_within_frames(pos[None], f, o, 3.0)[0], so.ref_find_within(pos, f, o, 3.0))
