@@ -187,8 +187,9 @@ __global__ void __launch_bounds__(NT) pc_accumulate_compact_kernel(const PcAccAr
             // anyway (PC_ST_TABLE_OVERFLOW): stop at the first overflow instead of finishing the frame
             if (*(volatile unsigned int *)&s_status & (unsigned)PC_ST_TABLE_OVERFLOW) break;
             const pc_contact rec = a.contacts[c0 + c];
-            const unsigned long long key =
-                (unsigned long long)__ldg(a.lgid1 + rec.i) * a.ngroups2 + (unsigned long long)__ldg(a.lgid2 + rec.j);
+            // group id and backbone flag of an atom in one word: two random loads per contact, not four
+            const uint32_t g1 = __ldg(a.lgb1 + rec.i), g2 = __ldg(a.lgb2 + rec.j);
+            const unsigned long long key = (unsigned long long)(g1 & 0x7fffffffu) * a.ngroups2 + (unsigned long long)(g2 & 0x7fffffffu);
             unsigned s = pc_hash64(key) & mask;
             int probes = 0;
             for (;;) {
@@ -199,8 +200,8 @@ __global__ void __launch_bounds__(NT) pc_accumulate_compact_kernel(const PcAccAr
             }
             if (s == 0xffffffffu) { atomicOr(&s_status, (unsigned)PC_ST_TABLE_OVERFLOW); continue; }
             atomicAdd(&score[s], rec.weight);
-            if (__ldg(a.lflag1 + rec.i) & PC_ATOM_BACKBONE) atomicAdd(&bb1[s], rec.weight);
-            if (__ldg(a.lflag2 + rec.j) & PC_ATOM_BACKBONE) atomicAdd(&bb2[s], rec.weight);
+            if (g1 >> 31) atomicAdd(&bb1[s], rec.weight);
+            if (g2 >> 31) atomicAdd(&bb2[s], rec.weight);
             atomicAdd(&cnt[s], 1u);
         }
         __syncthreads();
