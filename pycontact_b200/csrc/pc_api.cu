@@ -1035,13 +1035,13 @@ float grid_edge(float dist) { return std::max(dist * 1.001f, dist + 0.01f); }
 
 // bbox -> geometry -> count -> scan -> scatter for frames [0, fb) at xyz
 cudaError_t grid_build(GridWork &g, const float *xyz, long long pitch, int fb, int n, const int *d_mask, const float *d_w,
-                       float dist, cudaStream_t s, unsigned long long &launches) {
+                       float edge, cudaStream_t s, unsigned long long &launches) {
     const dim3 cg(grid_chunks(n), fb);
     pcg_init_kernel<<<(fb * 6 + 255) / 256, 256, 0, s>>>(g.bbox.as<unsigned>(), fb);
     cudaError_t e = cudaMemsetAsync(g.cellcnt.p, 0, (size_t)fb * g.cell_pitch * 4, s);
     if (e != cudaSuccess) return e;
     pcg_bbox_kernel<<<cg, 256, 0, s>>>(xyz, pitch, n, d_mask, g.bbox.as<unsigned>());
-    pcg_geom_kernel<<<(fb + 127) / 128, 128, 0, s>>>(g.bbox.as<unsigned>(), fb, grid_edge(dist), g.cap_cells,
+    pcg_geom_kernel<<<(fb + 127) / 128, 128, 0, s>>>(g.bbox.as<unsigned>(), fb, edge, g.cap_cells,
                                                      g.geom.as<PcGridGeom>());
     pcg_count_kernel<<<cg, 256, 0, s>>>(xyz, pitch, n, d_mask, g.geom.as<PcGridGeom>(), g.cell_pitch, g.cellcnt.as<int>(),
                                         g.cellid.as<int>(), g.rank.as<int>());
@@ -1090,6 +1090,9 @@ extern "C" int pc_sasa_device(int device, const float *d_xyz, int32_t nframes, i
     if (rc != PC_OK) return rc;
     const float prefac = (float)(4 * M_PI / npts);
     const float sqdist = pairdist * pairdist;
+    // candidate rows are kept while their gap to the atom is within `reach`: pairdist plus slack for the float32 cell
+    // coordinates (relative) and for the rounding of large coordinates (absolute); cells are half of it wide
+    const float reach = pairdist * 1.001f + 0.02f;
 
     StreamBuf d_radp, d_pts, d_rl, d_area;
     CUDA_TRY(d_radp.alloc((size_t)natoms * 4, s));
@@ -1110,10 +1113,10 @@ extern "C" int pc_sasa_device(int device, const float *d_xyz, int32_t nframes, i
     for (int f0 = 0; f0 < nframes; f0 += fb) {
         const int nf = std::min(fb, nframes - f0);
         const float *xyz = d_xyz + (long long)f0 * pitch;
-        CUDA_TRY(grid_build(g, xyz, pitch, nf, natoms, nullptr, d_radp.as<float>(), pairdist, s, g_launches));
+        CUDA_TRY(grid_build(g, xyz, pitch, nf, natoms, nullptr, d_radp.as<float>(), 0.5f * reach * 1.0001f, s, g_launches));
         pc_sasa_atoms_kernel<<<dim3((natoms + PCS_WARPS - 1) / PCS_WARPS, nf), PCS_WARPS * 32, pc_sasa_smem(npts), s>>>(
             g.sorted.as<float4>(), g.sidx.as<int>(), g.cellcnt.as<int>(), g.geom.as<PcGridGeom>(), natoms, g.cell_pitch,
-            d_pts.as<float>(), npts, sqdist, restricted, d_rl.as<int>(), prefac, d_area.as<float>(),
+            d_pts.as<float>(), npts, sqdist, reach, restricted, d_rl.as<int>(), prefac, d_area.as<float>(),
             d_exposed ? d_exposed + (long long)f0 * natoms : nullptr, (unsigned long long *)d_evals);
         pc_sasa_sum_kernel<<<nf, 256, 0, s>>>(d_area.as<float>(), natoms, d_total + f0);
         CUDA_TRY(cudaGetLastError());
@@ -1169,7 +1172,7 @@ extern "C" int pc_within_device(int device, const float *d_xyz, int32_t nframes,
     for (int f0 = 0; f0 < nframes; f0 += fb) {
         const int nf = std::min(fb, nframes - f0);
         const float *xyz = d_xyz + (long long)f0 * pitch;
-        CUDA_TRY(grid_build(g, xyz, pitch, nf, num, d_others, nullptr, r, s, g_launches));
+        CUDA_TRY(grid_build(g, xyz, pitch, nf, num, d_others, nullptr, grid_edge(r), s, g_launches));
         pc_within_kernel<<<dim3(grid_chunks(num), nf), 256, 0, s>>>(xyz, pitch, num, d_flgs, g.sorted.as<float4>(),
                                                                      g.cellcnt.as<int>(), g.geom.as<PcGridGeom>(), g.cell_pitch,
                                                                      r2, d_result + (long long)f0 * num);
