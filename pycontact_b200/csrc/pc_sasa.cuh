@@ -155,8 +155,12 @@ __global__ void __launch_bounds__(256) pcg_scatter_kernel(const float *xyz, long
 
 #define PCS_WARPS 8
 #define PCS_LIST 192          // neighbour spheres staged per warp between two passes over the sphere points
+#ifndef PCS_STEP
 #define PCS_STEP 16           // neighbour spheres of phase 1 (lanes own points)
+#endif
+#ifndef PCS_SWITCH
 #define PCS_SWITCH 12         // phase 1 runs only while more points than this are live
+#endif
 #define PCS_MAX_POINTS 1024
 
 // rows of the 5 x 5 x 5 half-size-cell neighbourhood, the atom's own row first: near spheres bury most points, so the
