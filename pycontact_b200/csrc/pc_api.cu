@@ -369,7 +369,7 @@ extern "C" int pc_scan_device(pc_ctx *c, const float *d_xyz1, const float *d_xyz
     // key (an order key) is not asked for; pc_accumulate then has nothing left to do for this batch
     const bool fuse_acc = c->want_fused_acc && c->have_maps && !order_keys && c->lim_table <= 2048;
     a.fuse_acc = 0;
-    { const char *dm = getenv("PC_DENSE_MODE"); a.dense_mode = dm ? atoi(dm) : 0; }   // experiment switch
+    a.dense_mode = 0;                  // pair kernel chosen per frame on the device (pc_large_is_dense)
     a.rows = c->rows.p; a.cap_rows = c->cap_rows; a.frame_rstart = meta(c, 4); a.frame_rcount = meta(c, 5);
     PcSmallSmem L2;
     int cells1 = 0, hits1 = 0, hb1 = 0, cells2 = 0, hits2 = 0, hb2 = 0;
