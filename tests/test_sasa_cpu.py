@@ -104,3 +104,41 @@ def test_selection_same_residue_and_around_need_positions(rpn11):
     assert np.array_equal(a, np.nonzero((seg == "UBQ") & (res >= 5) & (res <= 7))[0])
     with pytest.raises(NotImplementedError):
         select_atoms(topo, "segid UBQ and around 5.0 (segid RN11)")
+
+
+def test_select_atoms_frames_host_logic_with_the_oracle_standing_in_for_the_kernel(rpn11, monkeypatch):
+    """Parser logic of per-frame selections (boolean operators over (frames x atoms) masks, nested `around`,
+    `same residue as` of a per-frame selection) with the find_within ORACLE in place of the CUDA call -- the kernel
+    itself is compared with the reference in tests/test_gpu_sasa.py."""
+    from pycontact_b200.cy_modules import cy_gridsearch
+    from pycontact_b200.io.selection import select_atoms, select_atoms_frames
+
+    def fake(coords, flgs, others, r, device=0):
+        return np.stack([so.find_within(c, flgs, others, r) for c in coords])
+    monkeypatch.setattr(cy_gridsearch, "find_within_frames", fake)
+    topo = rpn11.topology
+    frames = rpn11.coords[:3]
+    seg, res = np.asarray(topo.segids), np.asarray(topo.resids)
+    rn11 = seg == "RN11"
+    per = select_atoms_frames(topo, "segid UBQ and around 4.0 (segid RN11)", frames)
+    assert len(per) == 3
+    for f in range(3):
+        want = so.find_within(frames[f], (~rn11).astype(np.int32), rn11.astype(np.int32), 4.0).astype(bool) & (seg == "UBQ")
+        assert np.array_equal(per[f], np.nonzero(want)[0])
+        assert np.array_equal(select_atoms(topo, "segid UBQ and around 4.0 (segid RN11)", positions=frames[f]), per[f])
+    # a static selection comes back once per frame
+    stat = select_atoms_frames(topo, "segid UBQ and name CA", frames)
+    assert len(stat) == 3 and all(np.array_equal(s, stat[0]) for s in stat)
+    # whole residues of a per-frame selection, negation, and an `around` of a per-frame selection
+    whole = select_atoms_frames(topo, "same residue as (segid UBQ and around 4.0 (segid RN11))", frames)
+    nested = select_atoms_frames(topo, "segid RN11 and not around 3.0 (segid UBQ and around 4.0 (segid RN11))", frames)
+    for f in range(3):
+        keys = set(zip(seg[per[f]].tolist(), res[per[f]].tolist()))
+        want = np.fromiter(((a, b) in keys for a, b in zip(seg.tolist(), res.tolist())), bool, len(seg))
+        assert np.array_equal(whole[f], np.nonzero(want)[0])
+        inner = np.zeros(len(seg), bool)
+        inner[per[f]] = True
+        near = so.find_within(frames[f], (~inner).astype(np.int32), inner.astype(np.int32), 3.0).astype(bool)
+        assert np.array_equal(nested[f], np.nonzero(rn11 & ~near)[0])
+    with pytest.raises(ValueError):
+        select_atoms(topo, "all", positions=frames)            # one frame only
