@@ -23,16 +23,13 @@ from typing import List, Optional, Tuple
 import numpy as np
 
 from . import _lib
-from .scheduler import chunks
+from .scheduler import worker_slices
 
 
 def frame_slice(n_frames: int, rank: int, world: int) -> Tuple[int, int]:
-    """[lo, hi) of the frames rank ``rank`` analyses -- the reference's chunk rule."""
-    parts = chunks(list(range(n_frames)), world)
-    parts += [[]] * (world - len(parts))
-    if not parts[rank]:
-        return 0, 0
-    return parts[rank][0], parts[rank][-1] + 1
+    """[lo, hi) of the frames rank ``rank`` analyses -- the reference's chunk rule, made lossless
+    (scheduler.worker_slices: every frame belongs to exactly one rank)."""
+    return worker_slices(n_frames, world)[rank]
 
 
 def aggregate_rows(rows: np.ndarray, n_keys: int) -> np.ndarray:

@@ -28,6 +28,35 @@ def chunks(seq, num):
     return out
 
 
+def worker_slices(n_items: int, num: int):
+    """``num`` contiguous [lo, hi) ranges that cover range(n_items) exactly once.
+
+    ``chunks`` keeps the reference's float stepping, which for many (n, num) pairs yields num + 1
+    non-empty slices (8 frames over 6 workers: 7 slices).  The reference runs every slice as its
+    own pool task and loses nothing (core/multi_trajectory.py:434-451); a fixed set of GPUs / ranks
+    cannot, so the boundaries of the first ``num`` chunks are kept and whatever ``chunks`` puts
+    beyond them is folded into the last worker's range."""
+    if num < 1:
+        raise ValueError("need at least one worker")
+    parts = [p for p in chunks(range(n_items), num) if len(p)]
+    out = []
+    for w in range(num):
+        if w < len(parts) and w < num - 1:
+            out.append((parts[w][0], parts[w][-1] + 1))
+        elif w == num - 1 and len(parts) > w:
+            out.append((parts[w][0], n_items))
+        else:
+            out.append((0, 0))
+    # consecutive, disjoint, complete
+    pos = 0
+    for lo, hi in out:
+        if hi > lo:
+            assert lo == pos, (n_items, num, out)
+            pos = hi
+    assert pos == n_items, (n_items, num, out)
+    return out
+
+
 def default_batch_frames(n1: int, n2: int, target_bytes: int = 96 << 20) -> int:
     per_frame = max(1, (n1 + n2) * 12)
     return int(max(1, min(4096, target_bytes // per_frame)))
@@ -79,7 +108,7 @@ def run_scan(engines: Sequence[ContactEngine], source, *, batch_frames: Optional
     if batch_frames is None:
         batch_frames = default_batch_frames(eng0.n1, eng0.n2)
     labels = list(range(F)) if frame_numbers is None else list(frame_numbers)
-    slices = [s for s in chunks(list(range(F)), len(engines)) if len(s)]
+    slices = [range(lo, hi) for lo, hi in worker_slices(F, len(engines)) if hi > lo]
     traj = TrajectoryContacts(eng0.sel1, eng0.sel2, eng0.hbondcutoff, eng0.hbondcutangle) if keep_contacts else None
     table = AccumulationTable(F, *group_maps) if accumulate else None
 

@@ -16,7 +16,7 @@ from pycontact_b200.core.Biochemistry import AccumulatedContact, AtomContact, Hy
 from pycontact_b200.core.ContactAnalyzer import Analyzer
 from pycontact_b200.engine import BatchResult
 from pycontact_b200.results import AccumulationTable, LazyContactResults, TrajectoryContacts
-from pycontact_b200.scheduler import chunks, default_batch_frames
+from pycontact_b200.scheduler import chunks, default_batch_frames, worker_slices
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
@@ -35,6 +35,22 @@ def test_library_exports_every_declared_symbol():
 
 def test_record_layouts_match_header():
     assert _lib.contact_dtype.itemsize == 16 and _lib.hbond_dtype.itemsize == 20 and _lib.row_dtype.itemsize == 48
+
+
+def test_worker_slices_assign_every_frame_exactly_once():
+    """chunks() keeps the reference's float stepping (num + 1 slices for e.g. 8 frames over 6 workers);
+    the scheduler and the rank slicing must still hand every frame to exactly one worker."""
+    from pycontact_b200 import distributed
+    assert len([c for c in chunks(list(range(8)), 6) if len(c)]) == 7          # the case that used to drop frame 7
+    for F in list(range(0, 400)) + [712, 999, 1000, 2999, 3000, 10000]:
+        for world in range(1, 17):
+            sl = worker_slices(F, world)
+            assert len(sl) == world
+            assert [f for lo, hi in sl for f in range(lo, hi)] == list(range(F)), (F, world, sl)
+            assert [distributed.frame_slice(F, r, world) for r in range(world)] == sl
+            ref = [c for c in chunks(list(range(F)), world) if len(c)]
+            if len(ref) == world:              # where the reference's rule yields one slice per worker, it is kept
+                assert [(c[0], c[-1] + 1) for c in ref] == [x for x in sl if x[1] > x[0]]
 
 
 def test_chunks_rule():
