@@ -34,6 +34,9 @@ extern "C" {
                                      (core/ContactAnalyzer.py:432, core/multi_trajectory.py:158) */
 #define PC_ERR_NOMEM         -5
 #define PC_ST_STAGE_OVERFLOW_BIT 64 /* pc_last_status: small-frame staging too small -> use pc_set_path(ctx, 2) */
+#define PC_ST_TAIL_OVERFLOW_BIT 128 /* large-frame path: a frame does not fit the fused tail kernel -> pc_set_tail(ctx, 0) */
+#define PC_ST_PRECISION_BIT     256 /* a (frame, key) cell has > 1024 contacts: float32 cell sums would leave the 1e-5
+                                       bar -> pc_set_limits(..., table_slots = 16384) selects the exact global table */
 
 /* per-atom flag bits (pc_set_topology) */
 #define PC_ATOM_HYDROGEN   1u   /* name starts with "H"   (core/ContactAnalyzer.py:360)      */
@@ -125,6 +128,17 @@ int pc_set_path(pc_ctx *ctx, int path);
  * 3 x 384 / 4 x 256 threads per SM, then the full plan. */
 int pc_set_small_ctas(pc_ctx *ctx, int ctas);
 
+/* Large-frame path, what follows the streaming kernels: on != 0 (default) = one fused kernel, a CTA per frame
+ * (cell sort, pair search, records, H-bond test and -- with maps, without order keys -- the accumulation, all out
+ * of shared memory); 0 = the multi-kernel sequence, which has no limit on a frame's in-grid atoms.  A batch whose
+ * frames do not fit the fused kernel reports PC_ERR_CAPACITY with status bit 128; callers then switch it off and
+ * re-run (ContactEngine does).  Same records either way (vmd_gridsearch3, cy_modules/src/gridsearch.C:1111-1142). */
+int pc_set_tail(pc_ctx *ctx, int on);
+
+/* Multi-kernel sequence only, for tests: which pair kernel searches a frame -- 0 = chosen per frame on the device
+ * by B atoms per cell, 1 = thread per (A atom, layer), 2 = warp per (A cell, layer) with the B runs in lanes. */
+int pc_set_dense_mode(pc_ctx *ctx, int mode);
+
 /* Output capacities for one batch (totals over the batch, not per frame). */
 int pc_reserve(pc_ctx *ctx, int32_t max_frames, int64_t cap_contacts, int64_t cap_hbonds, int64_t cap_rows);
 
@@ -171,6 +185,13 @@ int pc_fold_rows_sparse(pc_ctx *ctx, void *stream);
  * adds its rows to owner's table (owner = NULL undoes it).  Synchronise ctx's stream before fetching. */
 int pc_fold_sparse_share(pc_ctx *ctx, pc_ctx *owner);
 int pc_fold_sparse_fetch(pc_ctx *ctx, void *stream, pc_fold_entry *h_entries, int64_t max_entries, int64_t *n_entries);
+/* Frame-sharded runs (one rank per GPU, core/multi_trajectory.py:423-451 with ranks for pool workers): the
+ * ranks' sparse maps meet in ONE all-gather of fixed-size buffers.  export writes the table's occupied entries,
+ * compacted, into d_out[0 .. max_entries) and pads the rest with key = 2^64-1 (more entries than that: the
+ * overflow flag that pc_fold_sparse_fetch reports); import folds such a buffer (of another rank) into this
+ * context's table.  Asynchronous on `stream`; device pointers. */
+int pc_fold_sparse_export(pc_ctx *ctx, void *stream, pc_fold_entry *d_out, int64_t max_entries);
+int pc_fold_sparse_import(pc_ctx *ctx, void *stream, const pc_fold_entry *d_in, int64_t n_entries);
 
 /* Analyzer.runContactAnalysis(map1, map2) may be called again with other maps on the SAME
  * contactResults (core/ContactAnalyzer.py:64-70): loads previously fetched records of `nframes`
@@ -305,6 +326,11 @@ void pc_event_destroy(void *event);
  * kernel -- the streaming bin of selection 2, or of selection 1 in self mode -- for the first
  * sub-batch of every pc_scan_device call.  NULL, NULL switches it off. */
 int pc_set_probe(pc_ctx *ctx, void *start_event, void *end_event);
+
+/* Measurement helpers of bench.py: the GPU's FP32 issue rate from chains of independent FFMAs (instructions per
+ * second over all SMs; synchronous, default stream) and the device's free / total memory. */
+int pc_fp32_peak(int device, int32_t iters, double *ffma_per_s);
+int pc_mem_info(int device, int64_t *free_bytes, int64_t *total_bytes);
 
 /* Pinned host memory helpers for the Python layer (cudaHostAlloc / cudaFreeHost). */
 int pc_host_alloc(void **out, int64_t bytes);

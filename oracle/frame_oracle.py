@@ -265,3 +265,70 @@ def hbond_percentage(acc):
     """AccumulatedContact.hbond_percentage per key (core/Biochemistry.py:150-158)."""
     hb = acc["hbonds"]
     return (hb > 0).sum(axis=1) / float(hb.shape[1]) * 100.0
+
+
+# ---------------------------------------------------------------------------------------
+# the same accumulation on arrays (frames with 10^4 .. 10^7 contacts, where the per-contact Python
+# loop above takes hours).  tests/test_oracle.py checks it against accumulate() on the fixtures.
+# ---------------------------------------------------------------------------------------
+def atom_key_codes(amap, n_atoms, names, resids, resnames, segids):
+    """int64 code per GLOBAL atom index: equal codes <=> equal key arrays under ``amap``
+    (makeKeyArraysFromMaps, core/ContactAnalyzer.py:107-158; the key compares as a string, Q7)."""
+    amap = [int(bool(v)) for v in amap]
+    cols = []
+    if amap[0]:
+        cols.append(np.arange(n_atoms, dtype=np.int64))
+    for on, vals in ((amap[1], names), (amap[2], resids), (amap[3], resnames), (amap[4], segids)):
+        if on:
+            _, inv = np.unique(np.asarray([str(v) for v in vals[:n_atoms]], dtype=object).astype(str), return_inverse=True)
+            cols.append(inv.astype(np.int64))
+    if not cols:
+        return np.zeros(n_atoms, np.int64)
+    code = np.zeros(n_atoms, np.int64)
+    for c in cols:
+        _, inv = np.unique(np.stack([code, c], 1), axis=0, return_inverse=True)
+        code = inv.reshape(-1).astype(np.int64)
+    return code
+
+
+def accumulate_arrays(frames, code1, code2, backbone, n_atoms):
+    """Per frame, the (key -> fscore, bb1score, bb2score, hbonds, contributing contacts) cells of
+    core/ContactAnalyzer.py:527-559 as arrays sorted by (code of atom1's key, code of atom2's key)."""
+    bb = np.zeros(n_atoms, bool)
+    bb[np.asarray(list(backbone), np.int64)] = True
+    m2 = int(code2.max()) + 1 if len(code2) else 1
+    out = []
+    for fr in frames:
+        a, b = np.asarray(fr["idx1"], np.int64), np.asarray(fr["idx2"], np.int64)
+        k = code1[a] * m2 + code2[b]
+        uk, inv = np.unique(k, return_inverse=True)
+        w = np.asarray(fr["weight"], np.float64)
+        n = uk.size
+        out.append({
+            "k1": uk // m2, "k2": uk % m2,
+            "score": np.bincount(inv, weights=w, minlength=n),
+            "bb1": np.bincount(inv, weights=w * bb[a], minlength=n),
+            "bb2": np.bincount(inv, weights=w * bb[b], minlength=n),
+            "nhb": np.bincount(inv, weights=np.diff(fr["hb_ptr"]), minlength=n).astype(np.int64),
+            "ncont": np.bincount(inv, minlength=n).astype(np.int64)})
+    return out
+
+
+def heavy_only_search(is_h1, is_h2, search=None):
+    """A ``search`` for frame_contacts that runs the neighbour search on the heavy atoms only.
+
+    Every pair with a hydrogen is dropped right after the search (core/multi_trajectory.py:89), so the
+    contact SET is the same; the order inside an atom's row can differ from the reference's (the grid's
+    origin is the bounding box of the atoms searched).  For unordered comparisons on frames whose raw
+    pair list (10^8 pairs at 3 M atoms) would not fit the host."""
+    search = search or (native.ref_find_contacts if native.have_reference() else native.oracle_find_contacts)
+    h1 = np.nonzero(~np.asarray(is_h1, bool))[0]
+    h2 = np.nonzero(~np.asarray(is_h2, bool))[0]
+
+    def run(xyz1, xyz2, cutoff):
+        rp, cols = search(np.ascontiguousarray(xyz1[h1]), np.ascontiguousarray(xyz2[h2]), cutoff)
+        row_ptr = np.zeros(xyz1.shape[0] + 1, np.int64)
+        row_ptr[h1 + 1] = np.diff(rp)
+        np.cumsum(row_ptr, out=row_ptr)
+        return row_ptr, h2[cols]
+    return run

@@ -35,6 +35,8 @@ ST_MISSING_H = 8
 ST_BAD_COORDS = 16
 ST_TABLE_OVERFLOW = 32
 ST_STAGE_OVERFLOW = 64
+ST_TAIL_OVERFLOW = 128
+ST_PRECISION = 256
 
 # numpy mirrors of the C records
 contact_dtype = np.dtype([("i", "<i4"), ("j", "<i4"), ("distance", "<f4"), ("weight", "<f4")])
@@ -57,12 +59,12 @@ class PcError(Exception):
 
 # every symbol include/pycontact_b200.h declares (tests check the library exports all of them)
 EXPORTS = [
-    "pc_last_error", "pc_version", "pc_device_count", "pc_create", "pc_destroy", "pc_set_topology", "pc_set_maps", "pc_set_limits", "pc_set_path", "pc_set_fused_accumulate", "pc_set_small_ctas",
+    "pc_last_error", "pc_version", "pc_device_count", "pc_create", "pc_destroy", "pc_set_topology", "pc_set_maps", "pc_set_limits", "pc_set_path", "pc_set_fused_accumulate", "pc_set_small_ctas", "pc_set_tail", "pc_set_dense_mode",
     "pc_reserve", "pc_scan_device", "pc_accumulate", "pc_scan_host", "pc_batch_totals", "pc_last_status",
     "pc_device_outputs", "pc_fetch", "pc_find_contacts", "pc_free_host", "pc_synth_frames", "pc_host_alloc",
     "pc_host_free", "pc_load_records", "pc_stream_create", "pc_stream_sync", "pc_stream_destroy",
     "pc_device_alloc", "pc_device_free", "pc_memcpy", "pc_memset", "pc_device_sync",
-    "pc_launch_count", "pc_event_create", "pc_event_record", "pc_event_elapsed_ms", "pc_event_destroy", "pc_fold_rows", "pc_fetch_packed_rows", "pc_pack_rows", "pc_set_pack_format", "pc_fold_sparse_init", "pc_fold_rows_sparse", "pc_fold_sparse_fetch", "pc_fold_sparse_share", "pc_set_probe", "pc_key_stats",
+    "pc_launch_count", "pc_event_create", "pc_event_record", "pc_event_elapsed_ms", "pc_event_destroy", "pc_fold_rows", "pc_fetch_packed_rows", "pc_pack_rows", "pc_set_pack_format", "pc_fold_sparse_init", "pc_fold_rows_sparse", "pc_fold_sparse_fetch", "pc_fold_sparse_share", "pc_set_probe", "pc_key_stats", "pc_fold_sparse_export", "pc_fold_sparse_import", "pc_fp32_peak", "pc_mem_info",
     "pc_sasa_points", "pc_sasa", "pc_sasa_device", "pc_find_within", "pc_within_device",
 ]
 
@@ -93,6 +95,8 @@ def load():
     lib.pc_set_path.argtypes = [vp, ctypes.c_int]
     lib.pc_set_fused_accumulate.argtypes = [vp, ctypes.c_int]
     lib.pc_set_small_ctas.argtypes = [vp, ctypes.c_int]
+    lib.pc_set_tail.argtypes = [vp, ctypes.c_int]
+    lib.pc_set_dense_mode.argtypes = [vp, ctypes.c_int]
     lib.pc_reserve.argtypes = [vp, i32, i64, i64, i64]
     lib.pc_scan_device.argtypes = [vp, vp, vp, i32, i32, i64, i64, i32, vp]
     lib.pc_accumulate.argtypes = [vp, vp]
@@ -132,6 +136,10 @@ def load():
     lib.pc_pack_rows.argtypes = [vp, vp]
     lib.pc_set_pack_format.argtypes = [vp, ctypes.c_int]
     lib.pc_set_probe.argtypes = [vp, vp, vp]
+    lib.pc_fold_sparse_export.argtypes = [vp, vp, vp, ctypes.c_int64]
+    lib.pc_fold_sparse_import.argtypes = [vp, vp, vp, ctypes.c_int64]
+    lib.pc_fp32_peak.argtypes = [ctypes.c_int, ctypes.c_int32, ctypes.POINTER(ctypes.c_double)]
+    lib.pc_mem_info.argtypes = [ctypes.c_int, ctypes.POINTER(ctypes.c_int64), ctypes.POINTER(ctypes.c_int64)]
     lib.pc_fold_rows.argtypes = [vp, vp, i64, vp]
     f32 = ctypes.c_float
     lib.pc_sasa_points.argtypes = [i32, i32, vp]

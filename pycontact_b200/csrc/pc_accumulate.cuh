@@ -141,8 +141,7 @@ __global__ void __launch_bounds__(256) pc_fold_rows_kernel(const pc_row *rows, c
                                                            long long cap_rows, double *totals,
                                                            unsigned long long n_keys) {
     // a batch that overflowed a buffer is re-run by the caller: do not fold its partial rows
-    if (counters[PC_CNT_STATUS] & (PC_ST_HITS_OVERFLOW | PC_ST_HB_OVERFLOW | PC_ST_OUT_OVERFLOW | PC_ST_TABLE_OVERFLOW |
-                                   PC_ST_STAGE_OVERFLOW)) return;
+    if (counters[PC_CNT_STATUS] & PC_ST_RERUN_MASK) return;
     const long long n = min((long long)counters[PC_CNT_ROWS], cap_rows);
     for (long long r = blockIdx.x * (long long)blockDim.x + threadIdx.x; r < n; r += (long long)gridDim.x * blockDim.x) {
         const pc_row row = rows[r];
@@ -157,102 +156,113 @@ __global__ void __launch_bounds__(256) pc_fold_rows_kernel(const pc_row *rows, c
 
 // ---------------------------------------------------------------------------------------------------
 // Mid-size frames (thousands of keys per frame, e.g. protein vs. solvent at 1 M atoms): still one CTA
-// per frame and a shared-memory table, but with 24-byte slots -- key, three float32 sums, packed
-// counts -- so that 8192 slots fit one SM.  float32 sums of a handful of float32 weights stay within
-// ~1e-7 relative of the float64 sum (the parity bar is 1e-5).  No first-appearance key: only used when
-// no order keys were requested.
+// per frame and a shared-memory table, but with 28-byte slots -- key, three float32 sums, two 32-bit
+// counts -- so that 8192 slots fit one SM.  float32 sums stay within ~1e-6 relative of the float64 sum
+// while a (frame, key) cell holds at most PC_FLOAT_SUM_MAX contacts; a cell that grows beyond it (coarse
+// maps on large frames) raises PC_ST_PRECISION and the caller redoes the batch on the global-table path,
+// whose sums are exact.  No first-appearance key: only used when no order keys were requested.
+// pc_compact_frame is the body for one frame; the large-frame tail kernel (pc_scan_tail.cuh) runs it on
+// the frame it has just searched.
 // ---------------------------------------------------------------------------------------------------
+#define PC_COMPACT_SLOTS 8192
+#define PC_COMPACT_SLOT_BYTES 28
+#define PC_COMPACT_SMEM (PC_COMPACT_SLOTS * PC_COMPACT_SLOT_BYTES)
+
 template <int NT>
-__global__ void __launch_bounds__(NT) pc_accumulate_compact_kernel(const PcAccArgs a) {
-    extern __shared__ __align__(16) unsigned char smem[];
-    const int cap = a.cap;
+__device__ __forceinline__ void pc_compact_frame(const PcAccArgs &a, const int f, unsigned char *smem, uint32_t *wsum,
+                                                 long long *s_base, unsigned int *s_status) {
+    constexpr int cap = PC_COMPACT_SLOTS;
     unsigned long long *keys = reinterpret_cast<unsigned long long *>(smem);
     float *score = reinterpret_cast<float *>(keys + cap);
     float *bb1 = score + cap;
     float *bb2 = bb1 + cap;
-    unsigned int *cnt = reinterpret_cast<unsigned int *>(bb2 + cap);       // contacts | hbonds << 16 (saturating on emit)
+    unsigned int *ncont = reinterpret_cast<unsigned int *>(bb2 + cap);
+    unsigned int *nhb = ncont + cap;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    constexpr unsigned mask = (unsigned)cap - 1u;
+    for (int s = tid; s < cap; s += NT) { keys[s] = PC_EMPTY_KEY; score[s] = 0.f; bb1[s] = 0.f; bb2[s] = 0.f; ncont[s] = 0u; nhb[s] = 0u; }
+    if (tid == 0) *s_status = 0;
+    __syncthreads();
+    const uint32_t c0 = a.frame_cstart[f], cn = a.frame_ccount[f];
+    for (uint32_t c = tid; c < cn; c += NT) {
+        // a full table makes every further key walk 256 slots, and the batch is redone on the global table
+        // anyway (PC_ST_TABLE_OVERFLOW): stop at the first overflow instead of finishing the frame
+        if (*(volatile unsigned int *)s_status & (unsigned)PC_ST_TABLE_OVERFLOW) break;
+        const pc_contact rec = a.contacts[c0 + c];
+        // group id and backbone flag of an atom in one word: two random loads per contact, not four
+        const uint32_t g1 = __ldg(a.lgb1 + rec.i), g2 = __ldg(a.lgb2 + rec.j);
+        const unsigned long long key = (unsigned long long)(g1 & 0x7fffffffu) * a.ngroups2 + (unsigned long long)(g2 & 0x7fffffffu);
+        unsigned s = pc_hash64(key) & mask;
+        int probes = 0;
+        for (;;) {
+            const unsigned long long prev = atomicCAS(&keys[s], PC_EMPTY_KEY, key);
+            if (prev == PC_EMPTY_KEY || prev == key) break;
+            s = (s + 1) & mask;
+            if (++probes >= 256) { s = 0xffffffffu; break; }
+        }
+        if (s == 0xffffffffu) { atomicOr(s_status, (unsigned)PC_ST_TABLE_OVERFLOW); continue; }
+        atomicAdd(&score[s], rec.weight);
+        if (g1 >> 31) atomicAdd(&bb1[s], rec.weight);
+        if (g2 >> 31) atomicAdd(&bb2[s], rec.weight);
+        if (atomicAdd(&ncont[s], 1u) == PC_FLOAT_SUM_MAX) atomicOr(s_status, (unsigned)PC_ST_PRECISION);
+    }
+    __syncthreads();
+    const uint32_t h0 = a.frame_hstart[f], hn = a.frame_hcount[f];
+    for (uint32_t h = tid; h < hn; h += NT) {
+        const pc_hbond rec = a.hbonds[h0 + h];
+        const unsigned long long key =
+            (unsigned long long)__ldg(a.lgid1 + rec.i) * a.ngroups2 + (unsigned long long)__ldg(a.lgid2 + rec.j);
+        unsigned s = pc_hash64(key) & mask;
+        for (int probes = 0; probes < 256; probes++) {
+            const unsigned long long k = keys[s];
+            if (k == key) { atomicAdd(&nhb[s], 1u); break; }
+            if (k == PC_EMPTY_KEY) break;
+            s = (s + 1) & mask;
+        }
+    }
+    __syncthreads();
+    constexpr int ch = (cap + NT - 1) / NT;
+    const int b = min(tid * ch, cap), e = min(b + ch, cap);
+    uint32_t n = 0;
+    for (int s = b; s < e; s++) n += keys[s] != PC_EMPTY_KEY;
+    const uint32_t incl = warp_incl_scan(n, lane);
+    if (lane == 31) wsum[warp] = incl;
+    __syncthreads();
+    if (warp == 0) {
+        const uint32_t v = lane < NT / 32 ? wsum[lane] : 0;
+        const uint32_t vi = warp_incl_scan(v, lane);
+        wsum[lane] = vi - v;
+        const uint32_t total = __shfl_sync(PC_FULL_MASK, vi, 31);
+        if (lane == 0) {
+            long long base = (long long)atomicAdd(&a.counters[PC_CNT_ROWS], (unsigned long long)total);
+            if (base + total > a.cap_rows) { atomicOr(s_status, (unsigned)PC_ST_OUT_OVERFLOW); base = -1; }
+            *s_base = base;
+            a.frame_rstart[f] = (uint32_t)(base < 0 ? 0 : base);
+            a.frame_rcount[f] = base < 0 ? 0u : total;
+        }
+    }
+    __syncthreads();
+    if (*s_base >= 0) {
+        long long o = *s_base + wsum[warp] + incl - n;
+        for (int s = b; s < e; s++) {
+            if (keys[s] == PC_EMPTY_KEY) continue;
+            pc_row r;
+            r.key = keys[s]; r.score = (double)score[s]; r.bb1 = (double)bb1[s]; r.bb2 = (double)bb2[s];
+            r.ncontacts = ncont[s]; r.nhbonds = nhb[s]; r.first = keys[s];
+            a.rows[o++] = r;
+        }
+    }
+    if (tid == 0 && *s_status) atomicOr(&a.counters[PC_CNT_STATUS], (unsigned long long)*s_status);
+    __syncthreads();
+}
+
+template <int NT>
+__global__ void __launch_bounds__(NT) pc_accumulate_compact_kernel(const PcAccArgs a) {
+    extern __shared__ __align__(16) unsigned char smem[];
     __shared__ uint32_t wsum[32];
     __shared__ long long s_base;
     __shared__ unsigned int s_status;
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const unsigned mask = (unsigned)cap - 1u;
-
-    for (int f = blockIdx.x; f < a.nframes; f += gridDim.x) {
-        for (int s = tid; s < cap; s += NT) { keys[s] = PC_EMPTY_KEY; score[s] = 0.f; bb1[s] = 0.f; bb2[s] = 0.f; cnt[s] = 0u; }
-        if (tid == 0) s_status = 0;
-        __syncthreads();
-        const uint32_t c0 = a.frame_cstart[f], cn = a.frame_ccount[f];
-        for (uint32_t c = tid; c < cn; c += NT) {
-            // a full table makes every further key walk 256 slots, and the batch is redone on the global table
-            // anyway (PC_ST_TABLE_OVERFLOW): stop at the first overflow instead of finishing the frame
-            if (*(volatile unsigned int *)&s_status & (unsigned)PC_ST_TABLE_OVERFLOW) break;
-            const pc_contact rec = a.contacts[c0 + c];
-            // group id and backbone flag of an atom in one word: two random loads per contact, not four
-            const uint32_t g1 = __ldg(a.lgb1 + rec.i), g2 = __ldg(a.lgb2 + rec.j);
-            const unsigned long long key = (unsigned long long)(g1 & 0x7fffffffu) * a.ngroups2 + (unsigned long long)(g2 & 0x7fffffffu);
-            unsigned s = pc_hash64(key) & mask;
-            int probes = 0;
-            for (;;) {
-                const unsigned long long prev = atomicCAS(&keys[s], PC_EMPTY_KEY, key);
-                if (prev == PC_EMPTY_KEY || prev == key) break;
-                s = (s + 1) & mask;
-                if (++probes >= 256) { s = 0xffffffffu; break; }
-            }
-            if (s == 0xffffffffu) { atomicOr(&s_status, (unsigned)PC_ST_TABLE_OVERFLOW); continue; }
-            atomicAdd(&score[s], rec.weight);
-            if (g1 >> 31) atomicAdd(&bb1[s], rec.weight);
-            if (g2 >> 31) atomicAdd(&bb2[s], rec.weight);
-            atomicAdd(&cnt[s], 1u);
-        }
-        __syncthreads();
-        const uint32_t h0 = a.frame_hstart[f], hn = a.frame_hcount[f];
-        for (uint32_t h = tid; h < hn; h += NT) {
-            const pc_hbond rec = a.hbonds[h0 + h];
-            const unsigned long long key =
-                (unsigned long long)__ldg(a.lgid1 + rec.i) * a.ngroups2 + (unsigned long long)__ldg(a.lgid2 + rec.j);
-            unsigned s = pc_hash64(key) & mask;
-            for (int probes = 0; probes < 256; probes++) {
-                const unsigned long long k = keys[s];
-                if (k == key) { atomicAdd(&cnt[s], 65536u); break; }
-                if (k == PC_EMPTY_KEY) break;
-                s = (s + 1) & mask;
-            }
-        }
-        __syncthreads();
-        const int ch = (cap + NT - 1) / NT;
-        const int b = min(tid * ch, cap), e = min(b + ch, cap);
-        uint32_t n = 0;
-        for (int s = b; s < e; s++) n += keys[s] != PC_EMPTY_KEY;
-        const uint32_t incl = warp_incl_scan(n, lane);
-        if (lane == 31) wsum[warp] = incl;
-        __syncthreads();
-        if (warp == 0) {
-            const uint32_t v = lane < NT / 32 ? wsum[lane] : 0;
-            const uint32_t vi = warp_incl_scan(v, lane);
-            wsum[lane] = vi - v;
-            const uint32_t total = __shfl_sync(PC_FULL_MASK, vi, 31);
-            if (lane == 0) {
-                long long base = (long long)atomicAdd(&a.counters[PC_CNT_ROWS], (unsigned long long)total);
-                if (base + total > a.cap_rows) { atomicOr(&s_status, (unsigned)PC_ST_OUT_OVERFLOW); base = -1; }
-                s_base = base;
-                a.frame_rstart[f] = (uint32_t)(base < 0 ? 0 : base);
-                a.frame_rcount[f] = base < 0 ? 0u : total;
-            }
-        }
-        __syncthreads();
-        if (s_base >= 0) {
-            long long o = s_base + wsum[warp] + incl - n;
-            for (int s = b; s < e; s++) {
-                if (keys[s] == PC_EMPTY_KEY) continue;
-                pc_row r;
-                r.key = keys[s]; r.score = (double)score[s]; r.bb1 = (double)bb1[s]; r.bb2 = (double)bb2[s];
-                r.ncontacts = cnt[s] & 0xffffu; r.nhbonds = cnt[s] >> 16; r.first = keys[s];
-                a.rows[o++] = r;
-            }
-        }
-        if (tid == 0 && s_status) atomicOr(&a.counters[PC_CNT_STATUS], (unsigned long long)s_status);
-        __syncthreads();
-    }
+    for (int f = blockIdx.x; f < a.nframes; f += gridDim.x) pc_compact_frame<NT>(a, f, smem, wsum, &s_base, &s_status);
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -558,8 +568,7 @@ __global__ void __launch_bounds__(256) pc_fold_sparse_clear_kernel(pc_fold_entry
 __global__ void __launch_bounds__(256) pc_fold_sparse_kernel(const pc_row *rows, const unsigned long long *counters,
                                                              long long cap_rows, pc_fold_entry *tab, unsigned long long cap,
                                                              unsigned long long *meta) {
-    if (counters[PC_CNT_STATUS] & (PC_ST_HITS_OVERFLOW | PC_ST_HB_OVERFLOW | PC_ST_OUT_OVERFLOW | PC_ST_TABLE_OVERFLOW |
-                                   PC_ST_STAGE_OVERFLOW)) return;
+    if (counters[PC_CNT_STATUS] & PC_ST_RERUN_MASK) return;
     const long long n = min((long long)counters[PC_CNT_ROWS], cap_rows);
     const unsigned long long mask = cap - 1ull;
     for (long long r = blockIdx.x * (long long)blockDim.x + threadIdx.x; r < n; r += (long long)gridDim.x * blockDim.x) {
@@ -591,5 +600,57 @@ __global__ void __launch_bounds__(256) pc_fold_sparse_compact_kernel(const pc_fo
         if (e.key == PC_EMPTY_KEY) continue;
         const unsigned long long p = atomicAdd(&meta[1], 1ull);
         if (p < max_out) out[p] = e;
+    }
+}
+
+// ---- exchange of sparse aggregated maps between ranks (frame-sharded runs) ---------------------
+// export: the table's occupied entries, compacted into a FIXED-capacity buffer (rest padded with empty keys) so that
+// every rank contributes the same number of bytes to one all-gather; import: another rank's buffer folded into
+// this table.  meta[0] = overflow flag, meta[1] = compaction cursor (cleared by the caller).
+__global__ void __launch_bounds__(256) pc_fold_sparse_export_kernel(const pc_fold_entry *tab, unsigned long long cap,
+                                                                    pc_fold_entry *out, unsigned long long max_out,
+                                                                    unsigned long long *meta) {
+    for (unsigned long long s = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x; s < cap;
+         s += (unsigned long long)gridDim.x * blockDim.x) {
+        const pc_fold_entry e = tab[s];
+        if (e.key == PC_EMPTY_KEY) continue;
+        const unsigned long long p = atomicAdd(&meta[1], 1ull);
+        if (p < max_out) out[p] = e;
+        else meta[0] = 1ull;
+    }
+}
+
+__global__ void __launch_bounds__(256) pc_fold_sparse_pad_kernel(pc_fold_entry *out, unsigned long long max_out,
+                                                                 const unsigned long long *meta) {
+    pc_fold_entry e;
+    e.key = PC_EMPTY_KEY; e.score = 0.0; e.bb1 = 0.0; e.bb2 = 0.0; e.hbframes = 0.0;
+    for (unsigned long long s = min(meta[1], max_out) + blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x; s < max_out;
+         s += (unsigned long long)gridDim.x * blockDim.x)
+        out[s] = e;
+}
+
+__global__ void __launch_bounds__(256) pc_fold_sparse_import_kernel(const pc_fold_entry *in, unsigned long long n,
+                                                                    pc_fold_entry *tab, unsigned long long cap,
+                                                                    unsigned long long *meta) {
+    const unsigned long long mask = cap - 1ull;
+    for (unsigned long long r = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x; r < n;
+         r += (unsigned long long)gridDim.x * blockDim.x) {
+        const pc_fold_entry row = in[r];
+        if (row.key == PC_EMPTY_KEY) continue;
+        unsigned long long h = row.key;
+        h ^= h >> 33; h *= 0xff51afd7ed558ccdull; h ^= h >> 33; h *= 0xc4ceb9fe1a85ec53ull; h ^= h >> 33;
+        unsigned long long s = h & mask;
+        bool found = false;
+        for (int probes = 0; probes < 512; probes++) {
+            const unsigned long long prev = atomicCAS(reinterpret_cast<unsigned long long *>(&tab[s].key), PC_EMPTY_KEY,
+                                                       (unsigned long long)row.key);
+            if (prev == PC_EMPTY_KEY || prev == row.key) { found = true; break; }
+            s = (s + 1) & mask;
+        }
+        if (!found) { meta[0] = 1ull; continue; }
+        atomicAdd(&tab[s].score, row.score);
+        if (row.bb1 != 0.0) atomicAdd(&tab[s].bb1, row.bb1);
+        if (row.bb2 != 0.0) atomicAdd(&tab[s].bb2, row.bb2);
+        if (row.hbframes != 0.0) atomicAdd(&tab[s].hbframes, row.hbframes);
     }
 }

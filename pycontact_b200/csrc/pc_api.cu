@@ -13,11 +13,13 @@
 #include "pc_scan_small.cuh"
 #include "pc_scan_large.cuh"
 #include "pc_accumulate.cuh"
+#include "pc_scan_tail.cuh"
 #include "pc_order.cuh"
 #include "pc_search.cuh"
 #include "pc_synth.cuh"
 #include "pc_stats.cuh"
 #include "pc_sasa.cuh"
+#include "pc_peak.cuh"
 
 static thread_local std::string g_err;
 static unsigned long long g_launches = 0;      // kernels launched by this library (bench.py's gpu_launches)
@@ -67,6 +69,8 @@ struct pc_ctx {
     // limits (0 = automatic)
     int lim_hits = 0, lim_hb = 0, lim_cells = 0, lim_table = 0;
     int force_path = 0;               // 0 = automatic, 1 = small-frame kernel, 2 = large-frame path
+    int tail_mode = 1;                // large-frame path: 1 = fused per-frame tail kernel, 0 = multi-kernel sequence
+    int dense_mode = 0;               // multi-kernel sequence: pair kernel 0 = per frame on the device, 1 = thread per atom, 2 = warp per cell
     // batch outputs
     int max_frames = 0;
     long long cap_contacts = 0, cap_hbonds = 0, cap_rows = 0;
@@ -151,6 +155,18 @@ extern "C" int pc_set_path(pc_ctx *c, int path) {
     return PC_OK;
 }
 
+extern "C" int pc_set_tail(pc_ctx *c, int on) {
+    if (!c) return fail(PC_ERR_INVALID, "pc_set_tail: ctx is NULL");
+    c->tail_mode = on ? 1 : 0;
+    return PC_OK;
+}
+
+extern "C" int pc_set_dense_mode(pc_ctx *c, int mode) {
+    if (!c || mode < 0 || mode > 2) return fail(PC_ERR_INVALID, "pc_set_dense_mode: 0 (per frame), 1 (thread per atom) or 2 (warp per cell)");
+    c->dense_mode = mode;
+    return PC_OK;
+}
+
 extern "C" int pc_set_probe(pc_ctx *c, void *start_event, void *end_event) {
     if (!c) return fail(PC_ERR_INVALID, "pc_set_probe: ctx is NULL");
     c->probe[0] = start_event; c->probe[1] = end_event;
@@ -206,8 +222,9 @@ static cudaError_t upload_side(int n, const uint8_t *flags, const int32_t *resid
     if ((e = b.lseg->upload(seg)) != cudaSuccess) return e;
     if ((e = b.lhptr->upload(ptr)) != cudaSuccess) return e;
     if ((e = b.lhidx->upload(idx)) != cudaSuccess) return e;
-    if ((e = b.lflag->upload(std::vector<uint8_t>(flags, flags + n))) != cudaSuccess) return e;
-    return cudaDeviceSynchronize();      // the host vectors die with this frame
+    const std::vector<uint8_t> fl(flags, flags + n);
+    if ((e = b.lflag->upload(fl)) != cudaSuccess) return e;
+    return cudaDeviceSynchronize();      // every host vector above outlives this synchronisation
 }
 
 extern "C" int pc_set_topology(pc_ctx *c, int32_t n1, int32_t n2, const uint8_t *f1, const uint8_t *f2,
@@ -240,8 +257,9 @@ extern "C" int pc_set_maps(pc_ctx *c, const int32_t *gid1, const int32_t *gid2, 
     if (!c || !c->have_topology) return fail(PC_ERR_INVALID, "pc_set_maps: set the topology first");
     if (!gid1 || !gid2 || ngroups2 <= 0) return fail(PC_ERR_INVALID, "pc_set_maps: bad arguments");
     CUDA_TRY(cudaSetDevice(c->device));
-    CUDA_TRY(c->lgid1.upload(std::vector<int>(gid1, gid1 + c->n1)));
-    CUDA_TRY(c->lgid2.upload(std::vector<int>(gid2, gid2 + c->n2)));
+    const std::vector<int> g1v(gid1, gid1 + c->n1), g2v(gid2, gid2 + c->n2);      // alive until the synchronisation below
+    CUDA_TRY(c->lgid1.upload(g1v));
+    CUDA_TRY(c->lgid2.upload(g2v));
     CUDA_TRY(c->lgb1.ensure((size_t)c->n1));
     CUDA_TRY(c->lgb2.ensure((size_t)c->n2));
     if (c->n1) pc_pack_gid_flag_kernel<<<(c->n1 + 255) / 256, 256>>>(c->lgid1.p, c->lflag1.p, c->n1, c->lgb1.p);
@@ -335,6 +353,22 @@ static bool plan_small_cfg(const pc_ctx *c, bool fuse_acc, int ctas, int &capCel
     return true;
 }
 
+static PcAccArgs acc_args(pc_ctx *c, bool order_keys, int nframes) {
+    PcAccArgs a;
+    memset(&a, 0, sizeof a);
+    a.contacts = c->contacts.p; a.hbonds = c->hbonds.p;
+    a.order_keys = order_keys ? c->order_keys.p : nullptr;
+    a.frame_cstart = meta(c, 0); a.frame_ccount = meta(c, 1); a.frame_hstart = meta(c, 2); a.frame_hcount = meta(c, 3);
+    a.lgid1 = c->lgid1.p; a.lgid2 = c->lgid2.p;
+    a.lflag1 = c->lflag1.p; a.lflag2 = c->self_mode ? c->lflag1.p : c->lflag2.p;
+    a.lgb1 = c->lgb1.p; a.lgb2 = c->lgb2.p;
+    a.ngroups2 = c->ngroups2;
+    a.nframes = nframes;
+    a.rows = c->rows.p; a.cap_rows = c->cap_rows; a.counters = c->counters.p;
+    a.frame_rstart = meta(c, 4); a.frame_rcount = meta(c, 5);
+    return a;
+}
+
 extern "C" int pc_scan_device(pc_ctx *c, const float *d_xyz1, const float *d_xyz2, int32_t nframes,
                               int32_t layout, int64_t pitch1, int64_t pitch2, int32_t order_keys, void *stream) {
     if (!c || !c->have_topology) return fail(PC_ERR_INVALID, "pc_scan_device: set the topology first");
@@ -369,7 +403,7 @@ extern "C" int pc_scan_device(pc_ctx *c, const float *d_xyz1, const float *d_xyz
     // key (an order key) is not asked for; pc_accumulate then has nothing left to do for this batch
     const bool fuse_acc = c->want_fused_acc && c->have_maps && !order_keys && c->lim_table <= 2048;
     a.fuse_acc = 0;
-    a.dense_mode = 0;                  // pair kernel chosen per frame on the device (pc_large_is_dense)
+    a.dense_mode = c->dense_mode;      // 0: pair kernel chosen per frame on the device (pc_large_is_dense)
     a.rows = c->rows.p; a.cap_rows = c->cap_rows; a.frame_rstart = meta(c, 4); a.frame_rcount = meta(c, 5);
     PcSmallSmem L2;
     int cells1 = 0, hits1 = 0, hb1 = 0, cells2 = 0, hits2 = 0, hb2 = 0;
@@ -415,9 +449,16 @@ extern "C" int pc_scan_device(pc_ctx *c, const float *d_xyz1, const float *d_xyz
         c->last_fused = fuse_acc;
         c->last_path = 1;
     } else {
-        int rc = pc_large_scan(c->large, a, c->num_sms, s, g_err, &g_launches, (cudaEvent_t)c->probe[0], (cudaEvent_t)c->probe[1]);
+        // the fused tail kernel also accumulates when the maps are known, no order keys are asked for and the
+        // frame's keys are expected to fit its shared-memory table (pc_set_limits' table_slots <= 8192)
+        const bool tail = c->tail_mode && !c->self_mode;
+        const bool tail_acc = tail && c->want_fused_acc && c->have_maps && !order_keys && c->lim_table <= PC_COMPACT_SLOTS;
+        PcAccArgs acc = acc_args(c, false, nframes);
+        int rc = pc_large_scan(c->large, a, c->num_sms, s, g_err, &g_launches, (cudaEvent_t)c->probe[0], (cudaEvent_t)c->probe[1],
+                               tail ? 1 : 0, tail_acc ? &acc : nullptr);
         if (rc != PC_OK) return rc;
         c->last_path = 2;
+        c->last_fused = tail_acc;
     }
     if (order_keys) {
         if (c->n1 >= (1 << 27)) return fail(PC_ERR_INVALID, "pc_scan_device: order keys need n1 < 2^27");
@@ -443,20 +484,10 @@ extern "C" int pc_accumulate(pc_ctx *c, void *stream) {
     c->packed_valid = false;
     CUDA_TRY(cudaSetDevice(c->device));
     cudaStream_t s = (cudaStream_t)stream;
-    PcAccArgs a;
-    a.contacts = c->contacts.p; a.hbonds = c->hbonds.p;
-    a.order_keys = c->last_order_keys ? c->order_keys.p : nullptr;
-    a.frame_cstart = meta(c, 0); a.frame_ccount = meta(c, 1); a.frame_hstart = meta(c, 2); a.frame_hcount = meta(c, 3);
-    a.lgid1 = c->lgid1.p; a.lgid2 = c->lgid2.p;
-    a.lflag1 = c->lflag1.p; a.lflag2 = c->self_mode ? c->lflag1.p : c->lflag2.p;
-    a.lgb1 = c->lgb1.p; a.lgb2 = c->lgb2.p;
-    a.ngroups2 = c->ngroups2;
-    a.nframes = c->last_nframes;
+    PcAccArgs a = acc_args(c, c->last_order_keys, c->last_nframes);
     int cap = c->lim_table > 0 ? c->lim_table : 1024;
     int p2 = 64; while (p2 < cap) p2 <<= 1;
     a.cap = p2;
-    a.rows = c->rows.p; a.cap_rows = c->cap_rows; a.counters = c->counters.p;
-    a.frame_rstart = meta(c, 4); a.frame_rcount = meta(c, 5);
     const size_t smem = (size_t)a.cap * 48;
     const size_t smem_max = (c->smem_optin ? c->smem_optin : 232448) - 1024;
     // one CTA per frame with the table in shared memory while a frame's keys fit (<= 2048 slots);
@@ -471,10 +502,10 @@ extern "C" int pc_accumulate(pc_ctx *c, void *stream) {
         g_launches += 1;
         return PC_OK;
     }
-    // Thousands of keys per frame, no order keys: compact 24-byte slots, 8192 of them in one SM's shared memory
+    // Thousands of keys per frame, no order keys: compact 28-byte slots, 8192 of them in one SM's shared memory
     if (!c->last_order_keys && c->lim_table <= 8192) {
-        a.cap = 8192;
-        const size_t sm2 = (size_t)a.cap * 24;
+        a.cap = PC_COMPACT_SLOTS;
+        const size_t sm2 = PC_COMPACT_SMEM;
         auto kern = pc_accumulate_compact_kernel<1024>;
         CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm2));
         kern<<<std::min(a.nframes, c->num_sms), 1024, sm2, s>>>(a);
@@ -494,7 +525,8 @@ extern "C" int pc_accumulate(pc_ctx *c, void *stream) {
         CUDA_TRY(cudaMemcpyAsync(c->h_counters, c->counters.p, PC_CNT_COUNT * sizeof(unsigned long long),
                                  cudaMemcpyDeviceToHost, s));
         CUDA_TRY(cudaStreamSynchronize(s));
-        if (c->h_counters[PC_CNT_STATUS] & (PC_ST_OUT_OVERFLOW | PC_ST_HITS_OVERFLOW | PC_ST_HB_OVERFLOW | PC_ST_STAGE_OVERFLOW))
+        if (c->h_counters[PC_CNT_STATUS] & (PC_ST_OUT_OVERFLOW | PC_ST_HITS_OVERFLOW | PC_ST_HB_OVERFLOW | PC_ST_STAGE_OVERFLOW |
+                                            PC_ST_TAIL_OVERFLOW))
             return PC_OK;                    // the scan overflowed; pc_batch_totals reports it and the caller rescans
         ncontacts = std::min<unsigned long long>(c->h_counters[PC_CNT_CONTACTS], c->cap_contacts);
         c->gacc_retry = false;
@@ -623,6 +655,67 @@ extern "C" int pc_fold_sparse_fetch(pc_ctx *c, void *stream, pc_fold_entry *h_en
     return PC_OK;
 }
 
+extern "C" int pc_fold_sparse_export(pc_ctx *c, void *stream, pc_fold_entry *d_out, int64_t max_entries) {
+    if (!c || !c->fold_cap || !d_out || max_entries <= 0) return fail(PC_ERR_INVALID, "pc_fold_sparse_export: bad arguments");
+    CUDA_TRY(cudaSetDevice(c->device));
+    cudaStream_t s = (cudaStream_t)stream;
+    CUDA_TRY(cudaMemsetAsync(c->fold_meta.p + 1, 0, sizeof(unsigned long long), s));
+    pc_fold_sparse_export_kernel<<<4 * c->num_sms, 256, 0, s>>>(c->fold_tab.p, c->fold_cap, d_out, (unsigned long long)max_entries,
+                                                                c->fold_meta.p);
+    pc_fold_sparse_pad_kernel<<<2 * c->num_sms, 256, 0, s>>>(d_out, (unsigned long long)max_entries, c->fold_meta.p);
+    CUDA_TRY(cudaGetLastError());
+    g_launches += 2;
+    return PC_OK;
+}
+
+extern "C" int pc_fold_sparse_import(pc_ctx *c, void *stream, const pc_fold_entry *d_in, int64_t n_entries) {
+    if (!c || !c->fold_cap || !d_in || n_entries < 0) return fail(PC_ERR_INVALID, "pc_fold_sparse_import: bad arguments");
+    if (n_entries == 0) return PC_OK;
+    CUDA_TRY(cudaSetDevice(c->device));
+    pc_fold_sparse_import_kernel<<<2 * c->num_sms, 256, 0, (cudaStream_t)stream>>>(d_in, (unsigned long long)n_entries, c->fold_tab.p,
+                                                                                   c->fold_cap, c->fold_meta.p);
+    CUDA_TRY(cudaGetLastError());
+    g_launches += 1;
+    return PC_OK;
+}
+
+extern "C" int pc_fp32_peak(int device, int32_t iters, double *ffma_per_s) {
+    if (!ffma_per_s || iters <= 0) return fail(PC_ERR_INVALID, "pc_fp32_peak: bad arguments");
+    CUDA_TRY(cudaSetDevice(device));
+    int sms = 0;
+    CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));
+    float *d = nullptr;
+    CUDA_TRY(cudaMalloc(&d, 64));
+    cudaEvent_t e0, e1;
+    CUDA_TRY(cudaEventCreate(&e0));
+    CUDA_TRY(cudaEventCreate(&e1));
+    const int ctas = sms * 8;                      // 2048 threads per SM
+    double best = 0.0;
+    for (int rep = 0; rep < 4; rep++) {            // first pass warms up
+        CUDA_TRY(cudaEventRecord(e0, 0));
+        pc_ffma_chain_kernel<<<ctas, 256>>>(d, iters, 0.999f, 1e-3f);
+        CUDA_TRY(cudaEventRecord(e1, 0));
+        CUDA_TRY(cudaEventSynchronize(e1));
+        float ms = 0.f;
+        CUDA_TRY(cudaEventElapsedTime(&ms, e0, e1));
+        const double rate = (double)ctas * 256.0 * 64.0 * (double)iters / ((double)ms * 1e-3);
+        if (rep > 0 && rate > best) best = rate;
+    }
+    cudaEventDestroy(e0); cudaEventDestroy(e1); cudaFree(d);
+    g_launches += 4;
+    *ffma_per_s = best;
+    return PC_OK;
+}
+
+extern "C" int pc_mem_info(int device, int64_t *free_bytes, int64_t *total_bytes) {
+    CUDA_TRY(cudaSetDevice(device));
+    size_t f = 0, t = 0;
+    CUDA_TRY(cudaMemGetInfo(&f, &t));
+    if (free_bytes) *free_bytes = (int64_t)f;
+    if (total_bytes) *total_bytes = (int64_t)t;
+    return PC_OK;
+}
+
 extern "C" int pc_load_records(pc_ctx *c, const pc_contact *h_contacts, const uint64_t *h_order_keys,
                                const pc_hbond *h_hbonds, int32_t nframes, const uint32_t *cs, const uint32_t *cc,
                                const uint32_t *hs, const uint32_t *hc, void *stream) {
@@ -708,11 +801,11 @@ extern "C" int pc_batch_totals(pc_ctx *c, void *stream, int64_t *n_contacts, int
     if (st & PC_ST_BAD_COORDS) return fail(PC_ERR_INVALID, "non-finite coordinates in a frame");
     if (st & PC_ST_MISSING_H)
         return fail(PC_ERR_MISSING_H, "a hydrogen bonded to a selected N/O/S atom is not part of that selection");
-    if (st & (PC_ST_HITS_OVERFLOW | PC_ST_HB_OVERFLOW | PC_ST_OUT_OVERFLOW | PC_ST_TABLE_OVERFLOW | PC_ST_STAGE_OVERFLOW)) {
-        char buf[256];
+    if (st & PC_ST_RERUN_MASK) {
+        char buf[320];
         snprintf(buf, sizeof buf,
                  "capacity exceeded (status 0x%llx: 1=hits/frame 2=hbonds/frame 4=batch buffers 32=accumulation table "
-                 "64=small-frame staging); "
+                 "64=small-frame staging 128=large-frame tail staging 256=float32 cell sums); "
                  "needed contacts=%llu hbonds=%llu rows=%llu",
                  st, c->h_counters[PC_CNT_CONTACTS], c->h_counters[PC_CNT_HBONDS], c->h_counters[PC_CNT_ROWS]);
         g_err = buf;

@@ -15,6 +15,17 @@
 #define PC_ST_BAD_COORDS     16ull   // non-finite coordinates
 #define PC_ST_TABLE_OVERFLOW 32ull   // accumulation hash table too small
 #define PC_ST_STAGE_OVERFLOW 64ull   // small-frame path: more atoms inside the grid than the staging arrays hold
+#define PC_ST_TAIL_OVERFLOW 128ull   // large-frame path: a frame's in-grid atoms do not fit the fused per-frame tail kernel
+#define PC_ST_PRECISION     256ull   // a (frame, key) cell holds more contacts than a float32 sum keeps within the 1e-5 bar
+
+// any of these: the batch's outputs are incomplete and the caller re-runs it with larger buffers / another path
+#define PC_ST_RERUN_MASK (PC_ST_HITS_OVERFLOW | PC_ST_HB_OVERFLOW | PC_ST_OUT_OVERFLOW | PC_ST_TABLE_OVERFLOW | \
+                          PC_ST_STAGE_OVERFLOW | PC_ST_TAIL_OVERFLOW | PC_ST_PRECISION)
+
+// float32 per-cell sums (small-frame kernel's fused table, compact table): up to this many weights <= 1 per cell the
+// rounding of the running sum stays ~sqrt(n) * 6e-8 relative (<= 2e-6); cells beyond it are redone in float64 /
+// exact fixed point on the global-table path
+#define PC_FLOAT_SUM_MAX 1024u
 
 #ifdef PC_PHASE_CLOCKS
 // profiling build only (tools/phase_clocks.py): cycles per phase of the small-frame kernel, summed over CTAs
@@ -35,6 +46,25 @@ enum { PC_CNT_CONTACTS = 0, PC_CNT_HBONDS = 1, PC_CNT_STATUS = 2, PC_CNT_EVALS =
 // below 3e-5 cells for extents up to 1000 A, so with 2e-4 of slack two such atoms always
 // land in the same or adjacent cells (DESIGN.md "grid exactness").
 #define PC_EDGE_SCALE 1.0002f
+
+// Cells per axis of a grid over a box of extent (ex, ey, ez): edge `edge`, grown x1.26 until the grid fits `cap`
+// cells (the reference grows its boxes the same way, gridsearch.C:969-985).  Guard of the slack argument above: a
+// cell coordinate u = (x - lo) * inv carries up to 2 * u * 2^-23 cells of float32 rounding, which the 2e-4 of
+// PC_EDGE_SCALE covers up to ~800 cells per axis (4000 A at a 5 A cutoff); grids with a longer axis get cells
+// wider by 5e-7 per cell of that axis, so accepted pairs still always sit in the same or adjacent cells.
+__device__ __forceinline__ void pc_grid_dims(const float ex, const float ey, const float ez, const float edge, const long long cap,
+                                             int &nx, int &ny, int &nz, float &inv) {
+    float e = edge;
+    bool widened = false;
+    for (;;) {
+        inv = 1.0f / e;
+        const long long cx = (long long)(ex * inv) + 1, cy = (long long)(ey * inv) + 1, cz = (long long)(ez * inv) + 1;
+        const long long longest = cx > cy ? (cx > cz ? cx : cz) : (cy > cz ? cy : cz);
+        if (!widened && longest > 512) { e = e * (1.0f + 5e-7f * (float)longest); widened = true; continue; }
+        if (cx * cy * cz <= cap) { nx = (int)cx; ny = (int)cy; nz = (int)cz; return; }
+        e *= 1.26f;
+    }
+}
 
 // Packed atom word carried in the .w of staged float4 coordinates and in PcTopoDev::hinfo:
 //   bits 0..26 local index in the selection, bit 30 backbone, bit 31 name[0] in {O,N,S}

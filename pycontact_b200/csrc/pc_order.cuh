@@ -85,9 +85,15 @@ __global__ void __launch_bounds__(NT) pc_order_kernel(const PcScanArgs a) {
                 if (bj >= g.nb[k]) bj = g.nb[k] - 1;
                 d[k] = bj - bi;
             }
-            // a pair inside the cutoff is always in adjacent boxes of the reference grid (it was found there)
+            // A pair the reference finds sits in adjacent boxes of ITS grid.  The scan's own cells are 2e-4 wider than
+            // the cutoff, so it can in principle accept a pair whose reference boxes are two apart on one axis: that
+            // needs |dx| within ~1e-6 (relative) of the cutoff, dy and dz ~ 0 and the two box coordinates rounding to
+            // opposite sides of two box boundaries -- a pair the reference's stencil would not visit.  Never observed
+            // (the parity tests compare pair SETS with the reference on every fixture and synthetic system); such a
+            // pair gets rank 31, so it sorts behind its atom's real partners instead of aliasing another offset's rank.
+            const bool adjacent = d[0] >= -1 && d[0] <= 1 && d[1] >= -1 && d[1] <= 1 && d[2] >= -1 && d[2] <= 1;
             const int si = (d[0] + 1) + 3 * (d[1] + 1) + 9 * (d[2] + 1);
-            const unsigned rank = (si >= 0 && si < 27) ? PC_STENCIL_RANK[si] : 31u;
+            const unsigned rank = adjacent ? PC_STENCIL_RANK[si] : 31u;
             a.order_out[c0 + c] = ((unsigned long long)(unsigned)rec.i << 37) | ((unsigned long long)rank << 32) |
                                   (unsigned long long)(unsigned)rec.j;
         }

@@ -244,16 +244,7 @@ __global__ void __launch_bounds__(256) pc_large_grid_kernel(const PcScanArgs a, 
         if (bad && !empty) { atomicOr(&a.counters[PC_CNT_STATUS], PC_ST_BAD_COORDS); empty = true; }
         int nx = 0, ny = 0, nz = 0;
         float inv = 0.f;
-        if (!empty) {
-            float e = a.edge;
-            for (;;) {
-                inv = 1.0f / e;
-                const long long lx = (long long)(ext[0] * inv) + 1, ly = (long long)(ext[1] * inv) + 1,
-                                lz = (long long)(ext[2] * inv) + 1;
-                if (lx * ly * lz <= (long long)capCells) { nx = (int)lx; ny = (int)ly; nz = (int)lz; break; }
-                e *= 1.26f;
-            }
-        }
+        if (!empty) pc_grid_dims(ext[0], ext[1], ext[2], a.edge, (long long)capCells, nx, ny, nz, inv);
         F.lo[0] = lo[0]; F.lo[1] = lo[1]; F.lo[2] = lo[2]; F.inv = inv;
         F.nx = nx; F.ny = ny; F.nz = nz; F.ncell = nx * ny * nz;
         s_ncell = F.ncell;
@@ -709,110 +700,3 @@ __global__ void pc_large_finish_kernel(const PcScanArgs a, PcLargeFrame *fr, int
     atomicMax(&a.counters[7], (unsigned long long)fr[fb].hcursor);
 }
 
-static inline int pc_large_fail(std::string &err, const char *what, cudaError_t e) {
-    err = std::string(what) + ": " + cudaGetErrorString(e);
-    return PC_ERR_CUDA;
-}
-#define PCL_TRY(expr) do { cudaError_t _e = (expr); if (_e != cudaSuccess) return pc_large_fail(err, #expr, _e); } while (0)
-
-// CTAs per frame of a streaming kernel over n atoms: about eight waves of resident CTAs (2 per SM)
-// over the nfb frames of the launch, so the last, partly filled wave costs little, but every CTA
-// walks at least four chunks; atom ranges start on multiples of 32.
-static inline void pc_stream_geom(int n, int nfb, int num_sms, int &ctas, int &per) {
-    const int atoms_chunk = PC_STREAM_CHUNK / 12;
-    const int want = std::max(1, (16 * num_sms + nfb - 1) / nfb);
-    const int most = std::max(1, n / (4 * atoms_chunk));
-    ctas = std::min(want, most);
-    per = ((n + ctas - 1) / ctas + 31) & ~31;
-    ctas = (n + per - 1) / per;
-}
-
-static inline int pc_large_scan(PcLargeWork &W, const PcScanArgs &a, int num_sms, cudaStream_t s, std::string &err,
-                                unsigned long long *launches, cudaEvent_t probe0 = nullptr, cudaEvent_t probe1 = nullptr) {
-    const int n1 = a.t.n1, n2 = a.self_mode ? a.t.n1 : a.t.n2;
-    const int n1h = a.t.n1h, n2h = a.self_mode ? a.t.n1h : a.t.n2h;
-    const bool self = a.self_mode != 0;
-    if (a.stride != 3) { err = "the large-frame path reads packed xyz (PC_LAYOUT_XYZ) only"; return PC_ERR_INVALID; }
-    if ((((uintptr_t)a.xyz1 | (uintptr_t)a.xyz2) & 3) != 0) { err = "coordinates must be 4-byte aligned"; return PC_ERR_INVALID; }
-    // cells per frame: a few per atom of the smaller side, bounded like the reference's MAXBOXES
-    long long cc = 8ll * std::min(n1h, n2h);
-    cc = std::max(4096ll, std::min(cc, 4000000ll));
-    const int capCells = (int)cc;
-    const int a1 = std::max(n1h, 1), a2 = std::max(n2h, 1);
-    // frames in flight: bound the work memory to ~6 GB
-    const size_t per_frame = (size_t)(capCells + 1) * 4 * (self ? 1 : 2) + (size_t)a1 * 36 + (self ? 0 : (size_t)a2 * 36);
-    int FB = (int)std::max<size_t>(1, std::min<size_t>(256, (6ull << 30) / std::max<size_t>(per_frame, 1)));
-    FB = std::min(FB, a.nframes);
-    if (W.FB < FB || W.capCells != capCells || W.n1h != n1h || W.n2h != n2h || W.self_mode != a.self_mode) {
-        W.release();
-        PCL_TRY(cudaMalloc(&W.frames, sizeof(PcLargeFrame) * FB));
-        PCL_TRY(cudaMalloc(&W.cellA, (size_t)FB * (capCells + 1) * 4));
-        PCL_TRY(cudaMalloc(&W.candA, (size_t)FB * a1 * sizeof(float4)));
-        PCL_TRY(cudaMalloc(&W.ccellA, (size_t)FB * a1 * 4));
-        PCL_TRY(cudaMalloc(&W.sortA, (size_t)FB * a1 * sizeof(float4)));
-        if (!self) {
-            PCL_TRY(cudaMalloc(&W.cellB, (size_t)FB * (capCells + 1) * 4));
-            PCL_TRY(cudaMalloc(&W.candB, (size_t)FB * a2 * sizeof(float4)));
-            PCL_TRY(cudaMalloc(&W.ccellB, (size_t)FB * a2 * 4));
-            PCL_TRY(cudaMalloc(&W.sortB, (size_t)FB * a2 * sizeof(float4)));
-            PCL_TRY(cudaMalloc(&W.occ, (size_t)FB * capCells));
-        }
-        W.FB = FB; W.capCells = capCells; W.n1h = n1h; W.n2h = n2h; W.self_mode = a.self_mode;
-        PCL_TRY(cudaFuncSetAttribute(pc_large_stream_kernel<PC_MODE_BBOX>, cudaFuncAttributeMaxDynamicSharedMemorySize, PC_STREAM_SMEM));
-        PCL_TRY(cudaFuncSetAttribute(pc_large_stream_kernel<PC_MODE_BIN>, cudaFuncAttributeMaxDynamicSharedMemorySize, PC_STREAM_SMEM));
-    }
-    FB = W.FB;
-    PcLargeOut o;
-    o.cap_c_frame = a.cap_contacts / a.nframes;
-    o.cap_h_frame = a.cap_hbonds / a.nframes;
-    if (o.cap_c_frame < 1 || o.cap_h_frame < 1) { err = "pc_reserve: capacities smaller than the number of frames"; return PC_ERR_INVALID; }
-    const int use_bboxB = (!self && (long long)n2h <= 4ll * n1h) ? 1 : 0;
-    for (int f0 = 0; f0 < a.nframes; f0 += FB) {
-        const int nfb = std::min(FB, a.nframes - f0);
-        int ctasA, perA, ctasB = 0, perB = 0;
-        pc_stream_geom(n1, nfb, num_sms, ctasA, perA);
-        if (!self) pc_stream_geom(n2, nfb, num_sms, ctasB, perB);
-        pc_large_reset_kernel<<<(nfb + 63) / 64, 64, 0, s>>>(W.frames, nfb);
-        pc_large_stream_kernel<PC_MODE_BBOX><<<dim3(ctasA, nfb), PC_STREAM_NT, PC_STREAM_SMEM, s>>>(
-            a, W.frames, f0, 0, 0, perA, nullptr, 0, nullptr, nullptr, 0, nullptr);
-        if (use_bboxB)
-            pc_large_stream_kernel<PC_MODE_BBOX><<<dim3(ctasB, nfb), PC_STREAM_NT, PC_STREAM_SMEM, s>>>(
-                a, W.frames, f0, 1, 6, perB, nullptr, 0, nullptr, nullptr, 0, nullptr);
-        pc_large_grid_kernel<<<nfb, 256, 0, s>>>(a, W.frames, capCells, use_bboxB, W.cellA, W.cellB);
-        if (!self) {
-            // B first: its cell counts tell which A atoms can have a partner at all
-            if (probe0 && f0 == 0) cudaEventRecord(probe0, s);
-            pc_large_stream_kernel<PC_MODE_BIN><<<dim3(ctasB, nfb), PC_STREAM_NT, PC_STREAM_SMEM, s>>>(
-                a, W.frames, f0, 1, 0, perB, W.cellB, capCells, W.candB, W.ccellB, a2, nullptr);
-            if (probe1 && f0 == 0) cudaEventRecord(probe1, s);
-            pc_large_occ_kernel<<<dim3(std::max(1, std::min((capCells + 255) / 256, 4 * num_sms / nfb + 1)), nfb), 256, 0, s>>>(
-                W.frames, W.cellB, capCells, W.occ);
-        }
-        if (self && probe0 && f0 == 0) cudaEventRecord(probe0, s);
-        pc_large_stream_kernel<PC_MODE_BIN><<<dim3(ctasA, nfb), PC_STREAM_NT, PC_STREAM_SMEM, s>>>(
-            a, W.frames, f0, 0, 0, perA, W.cellA, capCells, W.candA, W.ccellA, a1, self ? nullptr : W.occ);
-        if (self && probe1 && f0 == 0) cudaEventRecord(probe1, s);
-        pc_large_scan_kernel<<<dim3(nfb, self ? 1 : 2), 1024, 0, s>>>(W.frames, W.cellA, W.cellB, capCells);
-        const int per_frame_blocks = std::max(1, 4 * num_sms / nfb);
-        const int blocksA = std::max(1, std::min((n1h + 255) / 256, per_frame_blocks));
-        const int blocksB = std::max(1, std::min((n2h + 255) / 256, per_frame_blocks));
-        pc_large_scatter_kernel<<<dim3(blocksA, nfb), 256, 0, s>>>(W.frames, 0, W.cellA, capCells, W.candA, W.ccellA, W.sortA, a1);
-        if (!self)
-            pc_large_scatter_kernel<<<dim3(blocksB, nfb), 256, 0, s>>>(W.frames, 1, W.cellB, capCells, W.candB, W.ccellB, W.sortB, a2);
-        // the number of in-grid A atoms is only known on the device: launch for the worst case, surplus CTAs exit
-        const int pblocks = (int)std::max<long long>(1, std::min<long long>((3ll * n1h + 255) / 256, std::max(64, 2 * per_frame_blocks)));
-        pc_large_pair_kernel<<<dim3(pblocks, nfb), 256, 0, s>>>(a, W.frames, f0, W.cellA, W.cellB, capCells, W.sortA, W.sortB,
-                                                               a1, a2, o);
-        // every frame is searched by exactly one of the two kernels (pc_large_is_dense, decided on the device)
-        const int dper = 8 * 4;
-        const int dblocks_pair = (int)std::max<long long>(1, std::min<long long>((3ll * capCells + dper - 1) / dper, std::max(64, 2 * per_frame_blocks)));
-        pc_large_pair_dense_kernel<<<dim3(dblocks_pair, nfb), 256, 0, s>>>(a, W.frames, f0, W.cellA, W.cellB, capCells, W.sortA,
-                                                                          W.sortB, a1, a2, o);
-        const int dblocks = (int)std::max<long long>(1, std::min<long long>((o.cap_c_frame + 255) / 256, per_frame_blocks));
-        pc_large_drain_kernel<<<dim3(dblocks, nfb), 256, 0, s>>>(a, W.frames, f0, W.sortA, W.sortB, a1, a2, o);
-        pc_large_finish_kernel<<<(nfb + 63) / 64, 64, 0, s>>>(a, W.frames, f0, nfb, o);
-        PCL_TRY(cudaGetLastError());
-        *launches += 9 + (use_bboxB ? 1 : 0) + (self ? 0 : 3);
-    }
-    return PC_OK;
-}

@@ -220,16 +220,7 @@ __global__ void __launch_bounds__(NT, NT >= 1024 ? 1 : NT >= 512 ? 2 : NT >= 384
                 if (bm && !empty) { atomicOr(&s_status, (unsigned)PC_ST_BAD_COORDS); empty = true; }
                 int nx = 0, ny = 0, nz = 0;
                 float inv = 0.f;
-                if (!empty) {
-                    float e = a.edge;
-                    for (;;) {
-                        inv = 1.0f / e;
-                        const long long cx = (long long)(ex * inv) + 1, cy = (long long)(ey * inv) + 1,
-                                        cz = (long long)(ez * inv) + 1;
-                        if (cx * cy * cz <= (long long)a.capCells) { nx = (int)cx; ny = (int)cy; nz = (int)cz; break; }
-                        e *= 1.26f;
-                    }
-                }
+                if (!empty) pc_grid_dims(ex, ey, ez, a.edge, (long long)a.capCells, nx, ny, nz, inv);
                 g.lo[0] = lx; g.lo[1] = ly; g.lo[2] = lz;
                 g.inv = inv; g.nx = nx; g.ny = ny; g.nz = nz; g.ncell = nx * ny * nz;
                 // axes by cell count, ascending (ties keep x < y < z)
@@ -540,7 +531,8 @@ __global__ void __launch_bounds__(NT, NT >= 1024 ? 1 : NT >= 512 ? 2 : NT >= 384
                 else {
                     const int cls = ((wa & PC_W_BACKBONE) ? 2 : 0) + ((wb & PC_W_BACKBONE) ? 1 : 0);
                     atomicAdd(&tcls[cls * capTab + slot], wgt);
-                    atomicAdd(&tncont[slot], 1u);
+                    // float32 class sums: a cell with more contacts than PC_FLOAT_SUM_MAX is redone exactly (global table)
+                    if (atomicAdd(&tncont[slot], 1u) == PC_FLOAT_SUM_MAX) atomicOr(&s_status, (unsigned)PC_ST_PRECISION);
                     // the minimum only ever decreases: a (possibly stale) read that is already smaller settles it
                     const unsigned long long mine = ((unsigned long long)(unsigned)li << 32) | (unsigned)lj;
                     if (*(volatile unsigned long long *)&tfirst[slot] > mine) atomicMin(&tfirst[slot], mine);

@@ -1,0 +1,371 @@
+// pc_scan_tail.cuh -- large-frame path, everything behind the streaming kernels in ONE kernel per batch.
+//
+// A 1 M-atom frame (protein vs. lipid + water) is 12 MB of coordinates of which a few
+// thousand atoms per selection can have a partner: the streaming kernels of pc_scan_large.cuh (the HBM-bound
+// part) compact exactly those -- B atoms inside the grid around selection A, A atoms whose 27-cell
+// neighbourhood holds a B atom -- into small float4 arrays that stay in L2.  Everything after that
+// (cell sort, pair search of gridsearch.C:1111-1142, filters, distance + weight of
+// core/multi_trajectory.py:98-107, the H-bond test of :112-209 and the per-frame accumulation of
+// core/ContactAnalyzer.py:527-559) used to be eight more launches over all frames, each latency-bound on a few
+// thousand atoms per frame.  Here ONE CTA owns one frame and does all of it out of shared memory:
+//   T1  the frame's B cell counts (left in global memory by the bin kernel) -> shared memory, exclusive scan
+//   T2  compacted B atoms -> cell order in shared memory (float4: x, y, z, packed atom word)
+//   T3  pair search + drain, warp-autonomous: a warp takes 32 (A atom, stencil z-layer) items at a time (A atoms
+//       come straight from the compacted array in L2, already in residue order), tests the layer's three B runs
+//       out of shared memory with the reference's exact float32 expression (pair_within_packed), queues its
+//       hits in its own shared-memory queue and, whenever >= 96 are queued, turns them into contact records
+//       (float64 distance, weight; one coalesced run of 16-byte records per round).  No CTA barrier inside.
+//   T3b N/O/S pairs queued by the drain: one thread per (pair, side) runs the donor-H...acceptor test
+//   T4  (maps set, no order keys) the frame's records are grouped by key in the compact shared-memory table of
+//       pc_accumulate.cuh (pc_compact_frame), laid over the memory T1-T3 used
+// Frames whose in-grid B atoms + cell offsets do not fit the pool raise PC_ST_TAIL_OVERFLOW; the caller then
+// re-runs the batch on the multi-kernel sequence (pc_set_tail(ctx, 0)), which has no such limit.
+#pragma once
+#include "pc_scan_large.cuh"
+#include "pc_accumulate.cuh"
+
+#define PC_TAIL_NT 1024
+#define PC_TAIL_WQ 256                   // hits per warp queue
+#define PC_TAIL_DRAIN_AT 96              // a warp drains its queue once this many hits wait (>= 3 full rounds of lanes)
+#define PC_TAIL_GATE 4096                // N/O/S pairs per frame queued for the H-bond pass (more are tested in place)
+#define PC_TAIL_SMEM PC_COMPACT_SMEM     // dynamic shared memory: the accumulation table of T4 is the larger tenant
+#define PC_TAIL_POOL (PC_TAIL_SMEM - (PC_TAIL_NT / 32) * PC_TAIL_WQ * 4 - PC_TAIL_GATE * 4)   // cell offsets + sorted B
+
+__global__ void __launch_bounds__(PC_TAIL_NT, 1) pc_large_tail_kernel(const PcScanArgs a, const PcLargeFrame *fr, const int f0,
+                                                                      const int nfb, const uint32_t *cellsB, const int capCells,
+                                                                      const float4 *candA, const float4 *candB,
+                                                                      const uint32_t *ccellB, const int n1h_alloc,
+                                                                      const int n2h_alloc, const PcLargeOut o, const PcAccArgs acc,
+                                                                      const int fuse_acc) {
+    constexpr int NT = PC_TAIL_NT, NW = NT / 32;
+    extern __shared__ __align__(16) unsigned char smem[];
+    uint32_t *wq = reinterpret_cast<uint32_t *>(smem);                 // [NW][PC_TAIL_WQ]
+    uint32_t *gateq = wq + NW * PC_TAIL_WQ;                            // [PC_TAIL_GATE]
+    unsigned char *pool = reinterpret_cast<unsigned char *>(gateq + PC_TAIL_GATE);
+    __shared__ PcLargeFrame F;
+    __shared__ uint32_t wsum[32];
+    __shared__ unsigned int wqn[NW];
+    __shared__ unsigned int s_next, s_ccur, s_hcur, s_ngate, s_status;
+    __shared__ long long s_base;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const float sqdist = a.sqdist;
+    unsigned long long evals = 0;
+    uint32_t *mywq = wq + warp * PC_TAIL_WQ;
+    volatile unsigned int *vqn = wqn;
+
+    for (int fb = blockIdx.x; fb < nfb; fb += gridDim.x) {
+        const int f = f0 + fb;
+        if (tid == 0) { F = fr[fb]; s_next = 0; s_ccur = 0; s_hcur = 0; s_ngate = 0; s_status = 0; }
+        if (tid < NW) wqn[tid] = 0;
+        __syncthreads();
+        const int ncell = F.ncell, nA = (int)F.nA_in, nB = (int)F.nB_in;
+        const size_t cell_bytes = ((size_t)(ncell + 1) * 4 + 15) & ~(size_t)15;
+        const bool fits = nA <= 65535 && nB <= 65535 && cell_bytes + 16ull * (size_t)nB <= (size_t)PC_TAIL_POOL;
+        uint32_t *cellB_s = reinterpret_cast<uint32_t *>(pool);
+        float4 *sortB = reinterpret_cast<float4 *>(pool + cell_bytes);
+        const float4 *cA = candA + (size_t)fb * n1h_alloc;
+        pc_contact *slice = a.contacts + (long long)f * o.cap_c_frame;
+        pc_hbond *hslice = a.hbonds + (long long)f * o.cap_h_frame;
+        const float *fr1 = a.xyz1 + (long long)f * a.pitch1;
+        const float *fr2 = a.xyz2 + (long long)f * a.pitch2;
+
+        // One donor-H...acceptor side of a gated pair (core/multi_trajectory.py:112-209).
+        // side 0: donor = atom1, acceptor = atom2; side 1: donor = atom2, acceptor = atom1
+        auto hbond_side = [&](const unsigned u, const int side) {
+            const float4 pa = __ldg(cA + (u >> 16)), pb = sortB[u & 0xffffu];
+            const int li = PC_W_INDEX(__float_as_uint(pa.w)), lj = PC_W_INDEX(__float_as_uint(pb.w));
+            const int *hptr = side == 0 ? a.t.lhptr1 : a.t.lhptr2;
+            const int *hidx = side == 0 ? a.t.lhidx1 : a.t.lhidx2;
+            const int heavy = side == 0 ? li : lj;
+            const int p0 = __ldg(hptr + heavy), p1 = __ldg(hptr + heavy + 1);
+            if (p0 == p1) return;
+            const double ax = pa.x, ay = pa.y, az = pa.z, bx = pb.x, by = pb.y, bz = pb.z;
+            for (int p = p0; p < p1; p++) {
+                const int hl = __ldg(hidx + p);
+                if (hl < 0) { atomicOr(&s_status, (unsigned)PC_ST_MISSING_H); continue; }
+                float hxf, hyf, hzf;
+                load_xyz(side == 0 ? fr1 : fr2, hl, a.stride, hxf, hyf, hzf);
+                double d = 0, ang = 0;
+                const bool ok = side == 0
+                    ? hbond_test(hxf, hyf, hzf, ax, ay, az, bx, by, bz, a.hb_cutoff, a.hb_angle, d, ang)
+                    : hbond_test(hxf, hyf, hzf, bx, by, bz, ax, ay, az, a.hb_cutoff, a.hb_angle, d, ang);
+                if (!ok) continue;
+                const unsigned hq = atomicAdd(&s_hcur, 1u);
+                if ((long long)hq < o.cap_h_frame) {
+                    pc_hbond r;
+                    r.i = li; r.j = lj; r.hyd = (uint32_t)hl | (side ? 0x80000000u : 0u);
+                    r.distance = (float)d; r.angle = (float)ang;
+                    hslice[hq] = r;
+                } else {
+                    atomicOr(&s_status, (unsigned)PC_ST_OUT_OVERFLOW);
+                }
+            }
+        };
+        // one hit -> contact record `slot` of the frame's slice; N/O/S pairs are queued for T3b
+        auto emit = [&](const unsigned u, const long long slot) {
+            const float4 pa = __ldg(cA + (u >> 16)), pb = sortB[u & 0xffffu];
+            const unsigned wa = __float_as_uint(pa.w), wb = __float_as_uint(pb.w);
+            const double dx = (double)pa.x - (double)pb.x, dy = (double)pa.y - (double)pb.y, dz = (double)pa.z - (double)pb.z;
+            const double dist = sqrt(dx * dx + dy * dy + dz * dz);
+            if (slot < o.cap_c_frame) {
+                pc_contact rec;
+                rec.i = PC_W_INDEX(wa); rec.j = PC_W_INDEX(wb); rec.distance = (float)dist; rec.weight = contact_weight_f32(dist);
+                slice[slot] = rec;
+            } else {
+                atomicOr(&s_status, (unsigned)PC_ST_OUT_OVERFLOW);
+            }
+            if (wa & wb & PC_W_HBCLASS) {
+                const unsigned q = atomicAdd(&s_ngate, 1u);
+                if (q < (unsigned)PC_TAIL_GATE) gateq[q] = u;
+                else { hbond_side(u, 0); hbond_side(u, 1); }         // queue full: tested in place
+            }
+        };
+        // the warp's queued hits -> records (lanes over hits, one claim of the frame's cursor per call)
+        auto drain_queue = [&]() {
+            __syncwarp();
+            const unsigned n = min(vqn[warp], (unsigned)PC_TAIL_WQ);
+            if (n) {
+                unsigned base = 0;
+                if (lane == 0) base = atomicAdd(&s_ccur, n);
+                base = __shfl_sync(PC_FULL_MASK, base, 0);
+                for (unsigned k = lane; k < n; k += 32) emit(mywq[k], (long long)base + k);
+            }
+            __syncwarp();
+            if (lane == 0) wqn[warp] = 0;
+            __syncwarp();
+        };
+
+        if (!fits) {
+            if (tid == 0) atomicOr(&s_status, (unsigned)PC_ST_TAIL_OVERFLOW);
+        } else if (ncell > 0 && nA > 0 && nB > 0) {
+            // ---- T1: B cell counts -> shared memory, exclusive scan -------------------------------------------
+            const uint32_t *gB = cellsB + (size_t)fb * (capCells + 1);
+            for (int c = tid; c < ncell; c += NT) cellB_s[c] = __ldg(gB + c);
+            __syncthreads();
+            block_excl_scan_inplace<NT>(cellB_s, ncell, wsum);
+            // ---- T2: compacted B atoms -> cell order; afterwards cellB_s[c] == END of cell c -----------------
+            const float4 *cB = candB + (size_t)fb * n2h_alloc;
+            const uint32_t *ccB = ccellB + (size_t)fb * n2h_alloc;
+            for (int p = tid; p < nB; p += NT) sortB[atomicAdd(&cellB_s[__ldg(ccB + p)], 1u)] = __ldg(cB + p);
+            __syncthreads();
+            // ---- T3: pair search + drain, warp-autonomous -----------------------------------------------------
+            const int nx = F.nx, ny = F.ny, nz = F.nz;
+            const float lox = F.lo[0], loy = F.lo[1], loz = F.lo[2], inv = F.inv;
+            const int nitems = 3 * nA;
+            for (;;) {
+                int w = 0;
+                if (lane == 0) w = (int)atomicAdd(&s_next, 32u);
+                w = __shfl_sync(PC_FULL_MASK, w, 0);
+                if (w >= nitems) break;
+                w += lane;
+                if (w < nitems) {
+                    // layer-major items: the lanes of a warp hold consecutive A atoms (compaction keeps the
+                    // selection's order, i.e. neighbours along the chain) on the same stencil layer
+                    const int layer = (w >= nA) + (w >= 2 * nA), ia = w - layer * nA;
+                    const float4 pa = __ldg(cA + ia);
+                    const int cx = (int)((pa.x - lox) * inv), cy = (int)((pa.y - loy) * inv), cz = (int)((pa.z - loz) * inv);
+                    const int z = cz + layer - 1;
+                    if (z >= 0 && z < nz) {
+                        const int xlo = max(cx - 1, 0), xhi = min(cx + 1, nx - 1);
+                        int b0[3], b1[3];
+#pragma unroll
+                        for (int dy = 0; dy < 3; dy++) {
+                            const int y = cy + dy - 1;
+                            if (y < 0 || y >= ny) { b0[dy] = 0; b1[dy] = 0; continue; }
+                            const int row = (z * ny + y) * nx;
+                            b0[dy] = (row + xlo) ? (int)cellB_s[row + xlo - 1] : 0;
+                            b1[dy] = (int)cellB_s[row + xhi];
+                        }
+                        const float2 nxy = make_float2(-pa.x, -pa.y);
+                        const float naz = -pa.z;
+#pragma unroll
+                        for (int dy = 0; dy < 3; dy++) {
+                            evals += (unsigned)(b1[dy] - b0[dy]);
+                            for (int jb = b0[dy]; jb < b1[dy]; jb += 32) {
+                                const int cnt = min(32, b1[dy] - jb);
+                                unsigned m = 0;
+                                int k0 = 0;
+#pragma unroll 1
+                                for (; k0 + 4 <= cnt; k0 += 4) {
+                                    unsigned m4 = 0;
+#pragma unroll
+                                    for (int u = 0; u < 4; u++)
+                                        if (pair_within_packed(nxy, naz, sortB[jb + k0 + u], sqdist)) m4 |= 1u << u;
+                                    m |= m4 << k0;
+                                }
+#pragma unroll 1
+                                for (; k0 < cnt; k0++)
+                                    if (pair_within_packed(nxy, naz, sortB[jb + k0], sqdist)) m |= 1u << k0;
+                                if (!m) continue;
+                                unsigned p = atomicAdd(&wqn[warp], (unsigned)__popc(m));
+                                while (m) {
+                                    const unsigned u = ((unsigned)ia << 16) | (unsigned)(jb + __ffs(m) - 1);
+                                    m &= m - 1;
+                                    if (p < (unsigned)PC_TAIL_WQ) mywq[p] = u;
+                                    else emit(u, (long long)atomicAdd(&s_ccur, 1u));     // queue full: this lane drains its own hit
+                                    p++;
+                                }
+                            }
+                        }
+                    }
+                }
+                __syncwarp();
+                if (vqn[warp] >= (unsigned)PC_TAIL_DRAIN_AT) drain_queue();
+            }
+            drain_queue();
+            __syncthreads();
+            // ---- T3b: donor-H...acceptor tests, one thread per (gated pair, side) ------------------------------
+            const unsigned ngate = min(s_ngate, (unsigned)PC_TAIL_GATE);
+            for (unsigned it = tid; it < 2u * ngate; it += NT) hbond_side(gateq[it >> 1], (int)(it & 1u));
+        }
+        __syncthreads();
+        // ---- per-frame counts and totals (what pc_large_finish_kernel does on the multi-kernel sequence) -----------
+        if (tid == 0) {
+            const unsigned cc = s_ccur, hc = s_hcur;
+            a.frame_cstart[f] = (uint32_t)((long long)f * o.cap_c_frame);
+            a.frame_ccount[f] = (uint32_t)min((long long)cc, o.cap_c_frame);
+            a.frame_hstart[f] = (uint32_t)((long long)f * o.cap_h_frame);
+            a.frame_hcount[f] = (uint32_t)min((long long)hc, o.cap_h_frame);
+            // the totals report what WOULD be needed so the host can re-reserve after an overflow
+            if (cc) atomicAdd(&a.counters[PC_CNT_CONTACTS], (unsigned long long)cc);
+            if (hc) atomicAdd(&a.counters[PC_CNT_HBONDS], (unsigned long long)hc);
+            atomicMax(&a.counters[6], (unsigned long long)cc);
+            atomicMax(&a.counters[7], (unsigned long long)hc);
+            if (s_status) atomicOr(&a.counters[PC_CNT_STATUS], (unsigned long long)s_status);
+            if (fuse_acc && cc == 0) { acc.frame_rstart[f] = 0; acc.frame_rcount[f] = 0; }
+        }
+        __syncthreads();
+        // ---- T4: per-frame accumulation of the records just written (they are in L2) -----------------------------
+        const bool have = fuse_acc && s_ccur != 0;
+        const bool do_acc = have && !(s_status & (unsigned)(PC_ST_OUT_OVERFLOW | PC_ST_TAIL_OVERFLOW));
+        __syncthreads();                   // pc_compact_frame reuses s_status
+        if (do_acc) pc_compact_frame<NT>(acc, f, smem, wsum, &s_base, &s_status);
+        else if (have && tid == 0) { acc.frame_rstart[f] = 0; acc.frame_rcount[f] = 0; }
+        __syncthreads();
+    }
+#pragma unroll
+    for (int s = 16; s > 0; s >>= 1) evals += __shfl_xor_sync(PC_FULL_MASK, evals, s);
+    if (lane == 0 && evals) atomicAdd(&a.counters[PC_CNT_EVALS], evals);
+}
+
+// ---- host side of the large-frame path --------------------------------------------------------------------------
+static inline int pc_large_fail(std::string &err, const char *what, cudaError_t e) {
+    err = std::string(what) + ": " + cudaGetErrorString(e);
+    return PC_ERR_CUDA;
+}
+#define PCL_TRY(expr) do { cudaError_t _e = (expr); if (_e != cudaSuccess) return pc_large_fail(err, #expr, _e); } while (0)
+
+// CTAs per frame of a streaming kernel over n atoms: about eight waves of resident CTAs (2 per SM)
+// over the nfb frames of the launch, so the last, partly filled wave costs little, but every CTA
+// walks at least four chunks; atom ranges start on multiples of 32.
+static inline void pc_stream_geom(int n, int nfb, int num_sms, int &ctas, int &per) {
+    const int atoms_chunk = PC_STREAM_CHUNK / 12;
+    const int want = std::max(1, (16 * num_sms + nfb - 1) / nfb);
+    const int most = std::max(1, n / (4 * atoms_chunk));
+    ctas = std::min(want, most);
+    per = ((n + ctas - 1) / ctas + 31) & ~31;
+    ctas = (n + per - 1) / per;
+}
+
+// tail != 0: the fused per-frame tail kernel (two selections only); acc != nullptr with it: rows are produced too.
+static inline int pc_large_scan(PcLargeWork &W, const PcScanArgs &a, int num_sms, cudaStream_t s, std::string &err,
+                                unsigned long long *launches, cudaEvent_t probe0, cudaEvent_t probe1, int tail,
+                                const PcAccArgs *acc) {
+    const int n1 = a.t.n1, n2 = a.self_mode ? a.t.n1 : a.t.n2;
+    const int n1h = a.t.n1h, n2h = a.self_mode ? a.t.n1h : a.t.n2h;
+    const bool self = a.self_mode != 0;
+    if (a.stride != 3) { err = "the large-frame path reads packed xyz (PC_LAYOUT_XYZ) only"; return PC_ERR_INVALID; }
+    if ((((uintptr_t)a.xyz1 | (uintptr_t)a.xyz2) & 3) != 0) { err = "coordinates must be 4-byte aligned"; return PC_ERR_INVALID; }
+    if (self) tail = 0;
+    // cells per frame: a few per atom of the smaller side, bounded like the reference's MAXBOXES
+    long long cc = 8ll * std::min(n1h, n2h);
+    cc = std::max(4096ll, std::min(cc, 4000000ll));
+    const int capCells = (int)cc;
+    const int a1 = std::max(n1h, 1), a2 = std::max(n2h, 1);
+    // frames in flight: bound the work memory to ~6 GB
+    const size_t per_frame = (size_t)(capCells + 1) * 4 * (self ? 1 : 2) + (size_t)a1 * 36 + (self ? 0 : (size_t)a2 * 36);
+    int FB = (int)std::max<size_t>(1, std::min<size_t>(296, (6ull << 30) / std::max<size_t>(per_frame, 1)));
+    FB = std::min(FB, a.nframes);
+    if (W.FB < FB || W.capCells != capCells || W.n1h != n1h || W.n2h != n2h || W.self_mode != a.self_mode) {
+        W.release();
+        PCL_TRY(cudaMalloc(&W.frames, sizeof(PcLargeFrame) * FB));
+        PCL_TRY(cudaMalloc(&W.cellA, (size_t)FB * (capCells + 1) * 4));
+        PCL_TRY(cudaMalloc(&W.candA, (size_t)FB * a1 * sizeof(float4)));
+        PCL_TRY(cudaMalloc(&W.ccellA, (size_t)FB * a1 * 4));
+        PCL_TRY(cudaMalloc(&W.sortA, (size_t)FB * a1 * sizeof(float4)));
+        if (!self) {
+            PCL_TRY(cudaMalloc(&W.cellB, (size_t)FB * (capCells + 1) * 4));
+            PCL_TRY(cudaMalloc(&W.candB, (size_t)FB * a2 * sizeof(float4)));
+            PCL_TRY(cudaMalloc(&W.ccellB, (size_t)FB * a2 * 4));
+            PCL_TRY(cudaMalloc(&W.sortB, (size_t)FB * a2 * sizeof(float4)));
+            PCL_TRY(cudaMalloc(&W.occ, (size_t)FB * capCells));
+        }
+        W.FB = FB; W.capCells = capCells; W.n1h = n1h; W.n2h = n2h; W.self_mode = a.self_mode;
+        PCL_TRY(cudaFuncSetAttribute(pc_large_stream_kernel<PC_MODE_BBOX>, cudaFuncAttributeMaxDynamicSharedMemorySize, PC_STREAM_SMEM));
+        PCL_TRY(cudaFuncSetAttribute(pc_large_stream_kernel<PC_MODE_BIN>, cudaFuncAttributeMaxDynamicSharedMemorySize, PC_STREAM_SMEM));
+        PCL_TRY(cudaFuncSetAttribute(pc_large_tail_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, PC_TAIL_SMEM));
+    }
+    FB = W.FB;
+    PcLargeOut o;
+    o.cap_c_frame = a.cap_contacts / a.nframes;
+    o.cap_h_frame = a.cap_hbonds / a.nframes;
+    if (o.cap_c_frame < 1 || o.cap_h_frame < 1) { err = "pc_reserve: capacities smaller than the number of frames"; return PC_ERR_INVALID; }
+    const int use_bboxB = (!self && (long long)n2h <= 4ll * n1h) ? 1 : 0;
+    for (int f0 = 0; f0 < a.nframes; f0 += FB) {
+        const int nfb = std::min(FB, a.nframes - f0);
+        int ctasA, perA, ctasB = 0, perB = 0;
+        pc_stream_geom(n1, nfb, num_sms, ctasA, perA);
+        if (!self) pc_stream_geom(n2, nfb, num_sms, ctasB, perB);
+        pc_large_reset_kernel<<<(nfb + 63) / 64, 64, 0, s>>>(W.frames, nfb);
+        pc_large_stream_kernel<PC_MODE_BBOX><<<dim3(ctasA, nfb), PC_STREAM_NT, PC_STREAM_SMEM, s>>>(
+            a, W.frames, f0, 0, 0, perA, nullptr, 0, nullptr, nullptr, 0, nullptr);
+        if (use_bboxB)
+            pc_large_stream_kernel<PC_MODE_BBOX><<<dim3(ctasB, nfb), PC_STREAM_NT, PC_STREAM_SMEM, s>>>(
+                a, W.frames, f0, 1, 6, perB, nullptr, 0, nullptr, nullptr, 0, nullptr);
+        pc_large_grid_kernel<<<nfb, 256, 0, s>>>(a, W.frames, capCells, use_bboxB, W.cellA, W.cellB);
+        if (!self) {
+            // B first: its cell counts tell which A atoms can have a partner at all
+            if (probe0 && f0 == 0) cudaEventRecord(probe0, s);
+            pc_large_stream_kernel<PC_MODE_BIN><<<dim3(ctasB, nfb), PC_STREAM_NT, PC_STREAM_SMEM, s>>>(
+                a, W.frames, f0, 1, 0, perB, W.cellB, capCells, W.candB, W.ccellB, a2, nullptr);
+            if (probe1 && f0 == 0) cudaEventRecord(probe1, s);
+            pc_large_occ_kernel<<<dim3(std::max(1, std::min((capCells + 255) / 256, 4 * num_sms / nfb + 1)), nfb), 256, 0, s>>>(
+                W.frames, W.cellB, capCells, W.occ);
+        }
+        if (self && probe0 && f0 == 0) cudaEventRecord(probe0, s);
+        pc_large_stream_kernel<PC_MODE_BIN><<<dim3(ctasA, nfb), PC_STREAM_NT, PC_STREAM_SMEM, s>>>(
+            a, W.frames, f0, 0, 0, perA, W.cellA, capCells, W.candA, W.ccellA, a1, self ? nullptr : W.occ);
+        if (self && probe1 && f0 == 0) cudaEventRecord(probe1, s);
+        if (tail) {
+            PcAccArgs none;
+            memset(&none, 0, sizeof none);
+            pc_large_tail_kernel<<<std::min(nfb, num_sms), PC_TAIL_NT, PC_TAIL_SMEM, s>>>(
+                a, W.frames, f0, nfb, W.cellB, capCells, W.candA, W.candB, W.ccellB, a1, a2, o, acc ? *acc : none, acc ? 1 : 0);
+            PCL_TRY(cudaGetLastError());
+            *launches += 7 + (use_bboxB ? 1 : 0);
+            continue;
+        }
+        pc_large_scan_kernel<<<dim3(nfb, self ? 1 : 2), 1024, 0, s>>>(W.frames, W.cellA, W.cellB, capCells);
+        const int per_frame_blocks = std::max(1, 4 * num_sms / nfb);
+        const int blocksA = std::max(1, std::min((n1h + 255) / 256, per_frame_blocks));
+        const int blocksB = std::max(1, std::min((n2h + 255) / 256, per_frame_blocks));
+        pc_large_scatter_kernel<<<dim3(blocksA, nfb), 256, 0, s>>>(W.frames, 0, W.cellA, capCells, W.candA, W.ccellA, W.sortA, a1);
+        if (!self)
+            pc_large_scatter_kernel<<<dim3(blocksB, nfb), 256, 0, s>>>(W.frames, 1, W.cellB, capCells, W.candB, W.ccellB, W.sortB, a2);
+        // the number of in-grid A atoms is only known on the device: launch for the worst case, surplus CTAs exit
+        const int pblocks = (int)std::max<long long>(1, std::min<long long>((3ll * n1h + 255) / 256, std::max(64, 2 * per_frame_blocks)));
+        pc_large_pair_kernel<<<dim3(pblocks, nfb), 256, 0, s>>>(a, W.frames, f0, W.cellA, W.cellB, capCells, W.sortA, W.sortB,
+                                                               a1, a2, o);
+        // every frame is searched by exactly one of the two kernels (pc_large_is_dense, decided on the device)
+        const int dper = 8 * 4;
+        const int dblocks_pair = (int)std::max<long long>(1, std::min<long long>((3ll * capCells + dper - 1) / dper, std::max(64, 2 * per_frame_blocks)));
+        pc_large_pair_dense_kernel<<<dim3(dblocks_pair, nfb), 256, 0, s>>>(a, W.frames, f0, W.cellA, W.cellB, capCells, W.sortA,
+                                                                          W.sortB, a1, a2, o);
+        const int dblocks = (int)std::max<long long>(1, std::min<long long>((o.cap_c_frame + 255) / 256, per_frame_blocks));
+        pc_large_drain_kernel<<<dim3(dblocks, nfb), 256, 0, s>>>(a, W.frames, f0, W.sortA, W.sortB, a1, a2, o);
+        pc_large_finish_kernel<<<(nfb + 63) / 64, 64, 0, s>>>(a, W.frames, f0, nfb, o);
+        PCL_TRY(cudaGetLastError());
+        *launches += 9 + (use_bboxB ? 1 : 0) + (self ? 0 : 3);
+    }
+    return PC_OK;
+}

@@ -121,6 +121,7 @@ class ContactEngine:
         self.launches = 0
         self.forced_path = 0
         self.pack_bytes = 24
+        self.tail = True
 
     # ------------------------------------------------------------------------------------------
     def close(self):
@@ -177,12 +178,37 @@ class ContactEngine:
         ent = buf[:n.value]
         return ent[np.argsort(ent["key"], kind="stable")]
 
+    def fold_sparse_export(self, d_out, max_entries: int):
+        """The table's occupied entries -> d_out[0 .. max_entries) on the device (compacted, padded with empty
+        keys): one rank's contribution to the all-gather of a frame-sharded run.  Asynchronous on slot 0's stream;
+        the other slots must have finished folding (their streams are synchronised here)."""
+        for s in self.slots[1:]:
+            check(self.lib.pc_stream_sync(s.stream))
+        s0 = self.slots[0]
+        check(self.lib.pc_fold_sparse_export(s0.ctx, s0.stream, d_out, int(max_entries)))
+
+    def fold_sparse_import(self, d_in, n_entries: int):
+        """Fold another rank's exported buffer into this engine's table (slot 0's stream)."""
+        s0 = self.slots[0]
+        check(self.lib.pc_fold_sparse_import(s0.ctx, s0.stream, d_in, int(n_entries)))
+
     def set_pack_format(self, bytes_per_row: int):
         """Transfer format of packed rows: 24 (pc_row_packed) or 12 (pc_row_slim: 32-bit key, score, counts;
         the per-key bb sums then come from the aggregated table of pc_fold_rows)."""
         for s in self.slots:
             check(self.lib.pc_set_pack_format(s.ctx, int(bytes_per_row)))
         self.pack_bytes = int(bytes_per_row)
+
+    def set_tail(self, on: bool):
+        """Large-frame path: fused per-frame tail kernel (default) or the multi-kernel sequence."""
+        self.tail = bool(on)
+        for s in self.slots:
+            check(self.lib.pc_set_tail(s.ctx, int(self.tail)))
+
+    def set_dense_mode(self, mode: int):
+        """Multi-kernel sequence, tests: 0 = pair kernel chosen per frame, 1 = thread per atom, 2 = warp per cell."""
+        for s in self.slots:
+            check(self.lib.pc_set_dense_mode(s.ctx, int(mode)))
 
     def set_path(self, path: int):
         """0 = automatic, 1 = small-frame kernel, 2 = large-frame path (tests cover both)."""
@@ -203,6 +229,12 @@ class ContactEngine:
             self.lim[0] = max(8192, 2 * (self.lim[0] or 4096))
         if st & _lib.ST_HB_OVERFLOW:
             self.lim[1] = max(1024, 2 * (self.lim[1] or 256))
+        if st & _lib.ST_TAIL_OVERFLOW:
+            # a frame's in-grid atoms do not fit the fused per-frame tail kernel: multi-kernel sequence from now on
+            self.set_tail(False)
+        if st & _lib.ST_PRECISION:
+            # a (frame, key) cell with more contacts than a float32 sum carries within 1e-5: exact global table
+            self.lim[3] = 16384
         if st & _lib.ST_TABLE_OVERFLOW:
             # beyond 2048 slots the library switches to compact shared-memory slots (<= 8192), then to its
             # global-memory table

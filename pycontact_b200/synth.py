@@ -231,14 +231,20 @@ def _finish(name, seed, b, sel1, sel2, s1t, s2t, rng, n_frames, maps=None, meta=
     return s
 
 
-def _two_chain(name, seed, nres_chain, n_water, n_frames):
+def _two_chain(name, seed, nres_chain, n_water, n_frames, interleave=False):
     rng = np.random.default_rng(seed)
     b = _Builder(rng)
     nx = max(1, int(round(nres_chain ** (1 / 3) * 0.6)))
     ny = int(np.ceil(np.sqrt(nres_chain / nx)))
     nz = int(np.ceil(nres_chain / (nx * ny)))
-    sa = _snake_sites(nx, ny, nz, SPACING, (-nx * SPACING + SPACING / 2, 0, 0))[:nres_chain]
-    sb = _snake_sites(nx, ny, nz, SPACING, (SPACING / 2, 0, 0))[:nres_chain]
+    if interleave:
+        # both chains on ONE lattice, residues alternating: the selections' bounding boxes coincide and every
+        # atom has partners (the case the bounding-box prefilter of the scan kernels cannot thin out)
+        both = _snake_sites(2 * nx, ny, nz, SPACING, (-nx * SPACING + SPACING / 2, 0, 0))[:2 * nres_chain]
+        sa, sb = both[0::2], both[1::2]
+    else:
+        sa = _snake_sites(nx, ny, nz, SPACING, (-nx * SPACING + SPACING / 2, 0, 0))[:nres_chain]
+        sb = _snake_sites(nx, ny, nz, SPACING, (SPACING / 2, 0, 0))[:nres_chain]
     a = b.add_protein(sa, "PA")
     c = b.add_protein(sb, "PB")
     lo = np.minimum(sa.min(0), sb.min(0)) - 3.0
@@ -254,13 +260,17 @@ def _two_chain(name, seed, nres_chain, n_water, n_frames):
 
 
 def make_system(name: str, seed: int = None) -> SynthSystem:
-    """name in {"tiny", "small", "c2", "c3", "c4", "c3_small"}  (SURVEY.md §8 configs)."""
+    """name in {"tiny", "small", "small_i", "c2", "c2i", "c3", "c3_small", "c4", "c4_small"}  (SURVEY.md §8 configs)."""
     if name == "tiny":          # CPU tests / golden vectors: 2 x 24 residues + 120 waters = 1128 atoms
         return _two_chain(name, 7 if seed is None else seed, 24, 120, 6)
     if name == "small":         # GPU parity at oracle-friendly size: 2 x 120 residues + 1000 waters
         return _two_chain(name, 11 if seed is None else seed, 120, 1000, 64)
     if name == "c2":            # 100 032 atoms: 2 x 375 residues (6000 atoms each) + 29 344 waters
         return _two_chain(name, 1002 if seed is None else seed, 375, 29344, 10000)
+    if name == "c2i":           # c2 with the two chains interdigitated (every selected atom inside the search grid)
+        return _two_chain(name, 1002 if seed is None else seed, 375, 29344, 10000, interleave=True)
+    if name == "small_i":       # the same at test size
+        return _two_chain(name, 11 if seed is None else seed, 120, 1000, 64, interleave=True)
     if name in ("c3", "c3_small"):
         seed = 1003 if seed is None else seed
         rng = np.random.default_rng(seed)

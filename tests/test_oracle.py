@@ -104,6 +104,35 @@ def test_frame_oracle_reproduces_golden_session(rpn11, golden_ab):
     assert frame_oracle.hbond_percentage(acc).sum() == 676.0                   # tests/test_basic.py:43
 
 
+def test_array_accumulation_oracle_equals_the_loop_oracle(rpn11, golden_ab):
+    """accumulate_arrays (what the full-size GPU tests use) gives the cells of the reference's golden session."""
+    s1, s2 = golden_ab["sel1"].astype(np.int64), golden_ab["sel2"].astype(np.int64)
+    res = _scan(rpn11, s1, s2, range(50), False)
+    t = rpn11.topology
+    for m1, m2 in ((golden_ab["map1"], golden_ab["map2"]), ([0, 1, 1, 1, 1], [0, 0, 0, 0, 1]), ([1, 0, 0, 0, 0], [0, 0, 1, 0, 0])):
+        acc = frame_oracle.accumulate(res, m1, m2, t.names, t.resids, t.resnames, t.segids, rpn11.backbone)
+        c1 = frame_oracle.atom_key_codes(m1, t.n_atoms, t.names, t.resids, t.resnames, t.segids)
+        c2 = frame_oracle.atom_key_codes(m2, t.n_atoms, t.names, t.resids, t.resnames, t.segids)
+        arr = frame_oracle.accumulate_arrays(res, c1, c2, rpn11.backbone, t.n_atoms)
+        # code pair -> key strings through any contact that carries it
+        name_of = {}
+        for fr in res:
+            for a, b in zip(fr["idx1"].tolist(), fr["idx2"].tolist()):
+                name_of.setdefault((int(c1[a]), int(c2[b])), frame_oracle._key_string(
+                    frame_oracle._key_arrays([int(bool(v)) for v in m1], a, t.names, t.resids, t.resnames, t.segids),
+                    frame_oracle._key_arrays([int(bool(v)) for v in m2], b, t.names, t.resids, t.resnames, t.segids)))
+        row = {k: i for i, k in enumerate(acc["keys"])}
+        assert len(set(name_of.values())) == len(name_of) == len(acc["keys"])
+        bb1 = np.zeros(len(row))
+        for f, fr in enumerate(arr):
+            ks = [row[name_of[(int(a), int(b))]] for a, b in zip(fr["k1"], fr["k2"])]
+            assert sorted(ks) == np.nonzero(acc["ncontrib"][:, f])[0].tolist()
+            np.testing.assert_allclose(fr["score"], acc["score"][ks, f], rtol=1e-12)
+            assert np.array_equal(fr["nhb"], acc["hbonds"][ks, f]) and np.array_equal(fr["ncont"], acc["ncontrib"][ks, f])
+            np.add.at(bb1, ks, fr["bb1"])
+        np.testing.assert_allclose(bb1, acc["bb1"], rtol=1e-12, atol=1e-12)
+
+
 def test_frame_oracle_self_mode(rpn11, golden_self):
     s1 = golden_self["sel1"].astype(np.int64)
     frames = golden_self["full_frames"].tolist()
