@@ -442,6 +442,8 @@ def run_gpu(args):
 
     eng = ContactEngine(s1, s2, CUTOFF, HB_CUTOFF, HB_ANGLE, device=local, slots=args.slots)
     eng.set_maps(gm1.gid, gm2.gid, gm2.n_groups)
+    if os.environ.get("PC_NO_TAIL"):                       # experiments: the multi-kernel sequence of the large-frame path
+        eng.set_tail(False)
     n_keys = gm1.n_groups * gm2.n_groups
     dense = n_keys <= (1 << 20) and not args.sparse_fold   # aggregated maps as a dense [n_keys][4] table (32 MB at most)
     sparse = not dense                                     # ... or as a hash table keyed by the 64-bit key
