@@ -442,8 +442,8 @@ def run_gpu(args):
 
     eng = ContactEngine(s1, s2, CUTOFF, HB_CUTOFF, HB_ANGLE, device=local, slots=args.slots)
     eng.set_maps(gm1.gid, gm2.gid, gm2.n_groups)
-    if os.environ.get("PC_NO_TAIL"):                       # experiments: the multi-kernel sequence of the large-frame path
-        eng.set_tail(False)
+    if os.environ.get("PC_TAIL"):                          # experiments: 0 = multi-kernel sequence, 1 = tail kernel v1, 2 = walk
+        eng.set_tail(int(os.environ["PC_TAIL"]))
     n_keys = gm1.n_groups * gm2.n_groups
     dense = n_keys <= (1 << 20) and not args.sparse_fold   # aggregated maps as a dense [n_keys][4] table (32 MB at most)
     sparse = not dense                                     # ... or as a hash table keyed by the 64-bit key
@@ -833,7 +833,7 @@ def run_gpu(args):
             "config": {"workload": "%s: %s" % (args.workload, w["desc"]), "frames_per_step": F_all,
                        "frames_per_gpu_per_step": F, "trajectory_frames": F_total, "clipped": clipped,
                        "atoms_sel1": n1, "atoms_sel2": n2, "batch_frames": batch, "batches_per_gpu_per_step": nb,
-                       "kernel_path": "large-frame (streaming bin + fused per-frame tail kernel)" if large and eng.tail else
+                       "kernel_path": "large-frame (streaming bin of the larger selection + fused per-frame kernel, tail mode %d)" % eng.tail if large and eng.tail else
                                       "large-frame (multi-kernel sequence)" if large else "small-frame (one CTA per frame)",
                        "l2": "inputs (%.1f GB per GPU and step, read once) exceed the 126 MB L2" % (F * in_bytes_frame / 1e9),
                        "results": "per-frame records (contacts, H-bonds, (frame, key) cells) stay in HBM; time-aggregated maps ("

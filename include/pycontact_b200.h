@@ -128,12 +128,14 @@ int pc_set_path(pc_ctx *ctx, int path);
  * 3 x 384 / 4 x 256 threads per SM, then the full plan. */
 int pc_set_small_ctas(pc_ctx *ctx, int ctas);
 
-/* Large-frame path, what follows the streaming kernels: on != 0 (default) = one fused kernel, a CTA per frame
- * (cell sort, pair search, records, H-bond test and -- with maps, without order keys -- the accumulation, all out
- * of shared memory); 0 = the multi-kernel sequence, which has no limit on a frame's in-grid atoms.  A batch whose
- * frames do not fit the fused kernel reports PC_ERR_CAPACITY with status bit 128; callers then switch it off and
- * re-run (ContactEngine does).  Same records either way (vmd_gridsearch3, cy_modules/src/gridsearch.C:1111-1142). */
-int pc_set_tail(pc_ctx *ctx, int on);
+/* Large-frame path, what follows the streaming kernels.  mode 2 (default) and 1: ONE fused kernel, a CTA per frame
+ * (cell sort, pair search, records, H-bond test and -- with maps, without order keys -- the accumulation, all out of
+ * shared memory); 2 reads selection 1 straight from the frame and balances the pair search inside the warp, 1 works on
+ * the compacted atoms of both selections.  0 = the multi-kernel sequence, which has no limit on a frame's in-grid
+ * atoms.  A batch whose frames do not fit a fused kernel reports PC_ERR_CAPACITY with status bit 128; callers then
+ * select 0 and re-run (ContactEngine does).  Same records either way (vmd_gridsearch3,
+ * cy_modules/src/gridsearch.C:1111-1142). */
+int pc_set_tail(pc_ctx *ctx, int mode);
 
 /* Multi-kernel sequence only, for tests: which pair kernel searches a frame -- 0 = chosen per frame on the device
  * by B atoms per cell, 1 = thread per (A atom, layer), 2 = warp per (A cell, layer) with the B runs in lanes. */

@@ -69,7 +69,8 @@ struct pc_ctx {
     // limits (0 = automatic)
     int lim_hits = 0, lim_hb = 0, lim_cells = 0, lim_table = 0;
     int force_path = 0;               // 0 = automatic, 1 = small-frame kernel, 2 = large-frame path
-    int tail_mode = 1;                // large-frame path: 1 = fused per-frame tail kernel, 0 = multi-kernel sequence
+    int tail_mode = 2;                // large-frame path: 2 = walk kernel (A from the frame), 1 = fused tail kernel on compacted A and B,
+                                      // 0 = multi-kernel sequence
     int dense_mode = 0;               // multi-kernel sequence: pair kernel 0 = per frame on the device, 1 = thread per atom, 2 = warp per cell
     // batch outputs
     int max_frames = 0;
@@ -157,7 +158,8 @@ extern "C" int pc_set_path(pc_ctx *c, int path) {
 
 extern "C" int pc_set_tail(pc_ctx *c, int on) {
     if (!c) return fail(PC_ERR_INVALID, "pc_set_tail: ctx is NULL");
-    c->tail_mode = on ? 1 : 0;
+    if (on < 0 || on > 2) return fail(PC_ERR_INVALID, "pc_set_tail: 0 (multi-kernel sequence), 1 (fused tail kernel) or 2 (walk kernel)");
+    c->tail_mode = on;
     return PC_OK;
 }
 
@@ -451,11 +453,11 @@ extern "C" int pc_scan_device(pc_ctx *c, const float *d_xyz1, const float *d_xyz
     } else {
         // the fused tail kernel also accumulates when the maps are known, no order keys are asked for and the
         // frame's keys are expected to fit its shared-memory table (pc_set_limits' table_slots <= 8192)
-        const bool tail = c->tail_mode && !c->self_mode;
+        const int tail = c->self_mode ? 0 : c->tail_mode;
         const bool tail_acc = tail && c->want_fused_acc && c->have_maps && !order_keys && c->lim_table <= PC_COMPACT_SLOTS;
         PcAccArgs acc = acc_args(c, false, nframes);
         int rc = pc_large_scan(c->large, a, c->num_sms, s, g_err, &g_launches, (cudaEvent_t)c->probe[0], (cudaEvent_t)c->probe[1],
-                               tail ? 1 : 0, tail_acc ? &acc : nullptr);
+                               tail, tail_acc ? &acc : nullptr);
         if (rc != PC_OK) return rc;
         c->last_path = 2;
         c->last_fused = tail_acc;
@@ -806,8 +808,9 @@ extern "C" int pc_batch_totals(pc_ctx *c, void *stream, int64_t *n_contacts, int
         snprintf(buf, sizeof buf,
                  "capacity exceeded (status 0x%llx: 1=hits/frame 2=hbonds/frame 4=batch buffers 32=accumulation table "
                  "64=small-frame staging 128=large-frame tail staging 256=float32 cell sums); "
-                 "needed contacts=%llu hbonds=%llu rows=%llu",
-                 st, c->h_counters[PC_CNT_CONTACTS], c->h_counters[PC_CNT_HBONDS], c->h_counters[PC_CNT_ROWS]);
+                 "needed contacts=%llu hbonds=%llu rows=%llu detail=0x%llx",
+                 st, c->h_counters[PC_CNT_CONTACTS], c->h_counters[PC_CNT_HBONDS], c->h_counters[PC_CNT_ROWS],
+                 c->h_counters[PC_CNT_WORK]);
         g_err = buf;
         return PC_ERR_CAPACITY;
     }

@@ -33,6 +33,7 @@ struct PcLargeFrame {
 
 struct PcLargeWork {
     int FB = 0, capCells = 0, n1h = 0, n2h = 0, self_mode = 0;
+    bool clean = false;                               // every frame slot is in its reset state (the walk kernel leaves it so)
     PcLargeFrame *frames = nullptr;
     uint32_t *cellA = nullptr, *cellB = nullptr;      // FB x (capCells + 1)
     float4 *candA = nullptr, *candB = nullptr;        // FB x n_h   (compacted, unsorted)

@@ -248,6 +248,338 @@ __global__ void __launch_bounds__(PC_TAIL_NT, 1) pc_large_tail_kernel(const PcSc
     if (lane == 0 && evals) atomicAdd(&a.counters[PC_CNT_EVALS], evals);
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// Tail kernel, second form ("walk"): same job, but selection A is read straight from the frame (no streaming bin, no
+// occupancy kernel for A) and the pair search is load-balanced inside the warp.
+//
+// In the kernel above a lane owns an (A atom, stencil layer) item and walks that item's three B runs; runs hold 0..8
+// atoms, so a warp spends its time on the longest run of its 32 lanes and on loop control (ncu: 80 % of the kernel's
+// instructions in the search, 15 of 32 lanes active).  Here a warp takes 32 consecutive heavy A atoms and
+//   setup  every lane looks its atom's (up to) nine rows up in a per-cell table of x-triples (start | length of the
+//          B atoms in cells cx-1..cx+1 of a row: ONE shared-memory load per row) -- atoms whose 27-cell neighbourhood is
+//          empty are skipped by a bit of the dilated occupancy map -- and the non-empty runs of all 32 atoms are
+//          written, compacted, to the warp's run list (warp prefix sums, no atomics);
+//   walk   the W candidates of the batch are cut into 32 equal ranges: a lane finds the start of its range (binary search
+//          over the lanes' prefix sums by shuffle, then over the owner's runs) and walks it -- one B atom from shared
+//          memory, the reference's float32 test, ballot-compacted append to the warp's hit queue -- moving to the next
+//          run / owner atom (coordinates parked in shared memory) as it goes.  Every lane does W / 32 evaluations.
+// Hits are drained like above, except that the A atom of a hit is re-read through the heavy-atom list (L1 / L2).
+// ---------------------------------------------------------------------------------------------------------------------
+#define PC_WALK_NT 1024
+#define PC_WALK_WQ 128
+#define PC_WALK_DRAIN_AT 96
+#define PC_WALK_GATE 1024
+#define PC_WALK_RUNS 160                      // run list of a round; 16 atoms x 9 rows always fit (rounds with more runs go in two halves)
+#define PC_WALK_FIXED ((PC_WALK_NT / 32) * (PC_WALK_WQ * 4 + PC_WALK_RUNS * 4 + 32 * 12) + PC_WALK_GATE * 4)
+#define PC_WALK_POOL (PC_TAIL_SMEM - PC_WALK_FIXED)     // occupancy bits + cell offsets / x-triples + sorted B
+#define PC_WALK_MAXRUN 2047u                  // a run's length has 11 bits in the run record
+
+__global__ void __launch_bounds__(PC_WALK_NT, 1) pc_large_walk_kernel(const PcScanArgs a, PcLargeFrame *fr, const int f0, const int nfb,
+                                                                      const uint32_t *cellsB, const int capCells,
+                                                                      const float4 *candB, const uint32_t *ccellB,
+                                                                      const int n2h_alloc, const PcLargeOut o, const PcAccArgs acc,
+                                                                      const int fuse_acc, const int reset_frames) {
+    constexpr int NT = PC_WALK_NT, NW = NT / 32;
+    extern __shared__ __align__(16) unsigned char smem[];
+    float *apos_all = reinterpret_cast<float *>(smem);                                     // [NW][3][32]: x, y, z of a round's atoms
+    uint32_t *wq = reinterpret_cast<uint32_t *>(apos_all + NW * 96);                       // [NW][PC_WALK_WQ]
+    uint32_t *runs_all = wq + NW * PC_WALK_WQ;                                             // [NW][PC_WALK_RUNS]
+    uint32_t *gateq = runs_all + NW * PC_WALK_RUNS;                                        // [PC_WALK_GATE]
+    unsigned char *pool = reinterpret_cast<unsigned char *>(gateq + PC_WALK_GATE);
+    __shared__ PcLargeFrame F;
+    __shared__ uint32_t wsum[32];
+    __shared__ unsigned int s_next, s_ccur, s_hcur, s_ngate, s_status;
+    __shared__ unsigned int s_keep[2];
+    __shared__ long long s_base;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const unsigned lt_mask = (1u << lane) - 1u;
+    const float sqdist = a.sqdist;
+    unsigned long long evals = 0;
+    uint32_t *mywq = wq + warp * PC_WALK_WQ;
+    uint32_t *runs = runs_all + warp * PC_WALK_RUNS;
+    float *apos = apos_all + warp * 96;
+    const int n1h = a.t.n1h;
+    const uint32_t *hinfo1 = a.t.hinfo1;
+
+    for (int fb = blockIdx.x; fb < nfb; fb += gridDim.x) {
+        const int f = f0 + fb;
+        if (tid == 0) { F = fr[fb]; s_next = 0; s_ccur = 0; s_hcur = 0; s_ngate = 0; s_status = 0; }
+        __syncthreads();
+        const int ncell = F.ncell, nB = (int)F.nB_in;
+        const size_t occ_bytes = ((size_t)((ncell + 31) / 32) * 4 + 15) & ~(size_t)15;
+        const size_t cell_bytes = ((size_t)(ncell + 1) * 4 + 15) & ~(size_t)15;
+        const bool fits = n1h <= 65535 && nB <= 65535 && occ_bytes + cell_bytes + 16ull * (size_t)nB <= (size_t)PC_WALK_POOL;
+        uint32_t *occ = reinterpret_cast<uint32_t *>(pool);
+        uint32_t *cellB_s = reinterpret_cast<uint32_t *>(pool + occ_bytes);      // counts -> offsets -> ends -> x-triples
+        uint32_t *tri = cellB_s;
+        float4 *sortB = reinterpret_cast<float4 *>(pool + occ_bytes + cell_bytes);
+        pc_contact *slice = a.contacts + (long long)f * o.cap_c_frame;
+        pc_hbond *hslice = a.hbonds + (long long)f * o.cap_h_frame;
+        const float *fr1 = a.xyz1 + (long long)f * a.pitch1;
+        const float *fr2 = a.xyz2 + (long long)f * a.pitch2;
+
+        // A atom of a hit: heavy ordinal -> packed word -> coordinates (the warp read them a moment ago: L1 / L2)
+        auto load_a = [&](const unsigned ka) -> float4 {
+            const uint32_t info = __ldg(hinfo1 + ka);
+            const float *p = fr1 + 3ll * PC_W_INDEX(info);
+            return make_float4(__ldg(p), __ldg(p + 1), __ldg(p + 2), __uint_as_float(info));
+        };
+        auto hbond_side = [&](const unsigned u, const int side) {
+            const float4 pa = load_a(u >> 16), pb = sortB[u & 0xffffu];
+            const int li = PC_W_INDEX(__float_as_uint(pa.w)), lj = PC_W_INDEX(__float_as_uint(pb.w));
+            const int *hptr = side == 0 ? a.t.lhptr1 : a.t.lhptr2;
+            const int *hidx = side == 0 ? a.t.lhidx1 : a.t.lhidx2;
+            const int heavy = side == 0 ? li : lj;
+            const int p0 = __ldg(hptr + heavy), p1 = __ldg(hptr + heavy + 1);
+            if (p0 == p1) return;
+            const double ax = pa.x, ay = pa.y, az = pa.z, bx = pb.x, by = pb.y, bz = pb.z;
+            for (int p = p0; p < p1; p++) {
+                const int hl = __ldg(hidx + p);
+                if (hl < 0) { atomicOr(&s_status, (unsigned)PC_ST_MISSING_H); continue; }
+                float hxf, hyf, hzf;
+                load_xyz(side == 0 ? fr1 : fr2, hl, a.stride, hxf, hyf, hzf);
+                double d = 0, ang = 0;
+                const bool ok = side == 0
+                    ? hbond_test(hxf, hyf, hzf, ax, ay, az, bx, by, bz, a.hb_cutoff, a.hb_angle, d, ang)
+                    : hbond_test(hxf, hyf, hzf, bx, by, bz, ax, ay, az, a.hb_cutoff, a.hb_angle, d, ang);
+                if (!ok) continue;
+                const unsigned hq = atomicAdd(&s_hcur, 1u);
+                if ((long long)hq < o.cap_h_frame) {
+                    pc_hbond r;
+                    r.i = li; r.j = lj; r.hyd = (uint32_t)hl | (side ? 0x80000000u : 0u);
+                    r.distance = (float)d; r.angle = (float)ang;
+                    hslice[hq] = r;
+                } else {
+                    atomicOr(&s_status, (unsigned)PC_ST_OUT_OVERFLOW);
+                }
+            }
+        };
+        auto emit = [&](const unsigned u, const long long slot) {
+            const float4 pa = load_a(u >> 16), pb = sortB[u & 0xffffu];
+            const unsigned wa = __float_as_uint(pa.w), wb = __float_as_uint(pb.w);
+            const double dx = (double)pa.x - (double)pb.x, dy = (double)pa.y - (double)pb.y, dz = (double)pa.z - (double)pb.z;
+            const double dist = sqrt(dx * dx + dy * dy + dz * dz);
+            if (slot < o.cap_c_frame) {
+                pc_contact rec;
+                rec.i = PC_W_INDEX(wa); rec.j = PC_W_INDEX(wb); rec.distance = (float)dist; rec.weight = contact_weight_f32(dist);
+                slice[slot] = rec;
+            } else {
+                atomicOr(&s_status, (unsigned)PC_ST_OUT_OVERFLOW);
+            }
+            if (wa & wb & PC_W_HBCLASS) {
+                const unsigned q = atomicAdd(&s_ngate, 1u);
+                if (q < (unsigned)PC_WALK_GATE) gateq[q] = u;
+                else { hbond_side(u, 0); hbond_side(u, 1); }         // queue full: tested in place
+            }
+        };
+
+        if (!fits) {
+            if (tid == 0) {
+                atomicOr(&s_status, (unsigned)PC_ST_TAIL_OVERFLOW);
+                atomicMax(&a.counters[PC_CNT_WORK], (1ull << 56) | (unsigned long long)(occ_bytes + cell_bytes + 16ull * (size_t)nB));
+            }
+        } else if (ncell > 0 && n1h > 0 && nB > 0) {
+            const int nx = F.nx, ny = F.ny, nz = F.nz;
+            const float lox = F.lo[0], loy = F.lo[1], loz = F.lo[2], inv = F.inv;
+            // ---- T1: B cell counts -> shared memory, exclusive scan; T2: compacted B atoms -> cell order -----------
+            const uint32_t *gB = cellsB + (size_t)fb * (capCells + 1);
+            for (int c = tid; c < ncell; c += NT) cellB_s[c] = __ldg(gB + c);
+            __syncthreads();
+            block_excl_scan_inplace<NT>(cellB_s, ncell, wsum);
+            const float4 *cB = candB + (size_t)fb * n2h_alloc;
+            const uint32_t *ccB = ccellB + (size_t)fb * n2h_alloc;
+            for (int p = tid; p < nB; p += NT) sortB[atomicAdd(&cellB_s[__ldg(ccB + p)], 1u)] = __ldg(cB + p);
+            __syncthreads();                                        // cellB_s[c] == END of cell c from here on
+            // x-triples, in place: cell c's END becomes start | length << 16 of the B atoms in cells cx-1 .. cx+1 of c's
+            // row.  NT cells at a time, lowest first; the two ends just below a chunk are kept aside, because the chunk
+            // before has already overwritten them (a triple reads the ends of cells c-2 .. c+1).
+            if (tid < 2) s_keep[tid] = 0u;
+            __syncthreads();
+            for (int lo = 0; lo < ncell; lo += NT) {
+                const int c = lo + tid;
+                unsigned j0 = 0, j1 = 0, mine = 0;
+                if (c < ncell) {
+                    const int cx = c % nx, row = c - cx;
+                    const int i0 = row + max(cx - 1, 0) - 1;
+                    j0 = i0 < 0 ? 0u : (i0 >= lo ? cellB_s[i0] : s_keep[i0 - (lo - 2)]);
+                    j1 = cellB_s[row + min(cx + 1, nx - 1)];
+                    mine = cellB_s[c];
+                }
+                __syncthreads();
+                if (c < ncell) {
+                    if (j1 - j0 > PC_WALK_MAXRUN) {
+                        atomicOr(&s_status, (unsigned)PC_ST_TAIL_OVERFLOW);
+                        atomicMax(&a.counters[PC_CNT_WORK], (2ull << 56) | ((unsigned long long)(unsigned)c << 32) | (unsigned long long)(j1 - j0));
+                    }
+                    cellB_s[c] = j0 | ((j1 - j0) << 16);
+                    if (tid >= NT - 2) s_keep[tid - (NT - 2)] = mine;
+                }
+                __syncthreads();
+            }
+            // dilated occupancy: bit c = some B atom in the 27 cells around c (nine x-triples)
+            for (int c0 = warp * 32; c0 < ncell; c0 += NT) {
+                const int c = c0 + lane;
+                bool any = false;
+                if (c < ncell) {
+                    const int cx = c % nx, cy = (c / nx) % ny, cz = c / (nx * ny);
+                    for (int z = max(cz - 1, 0); z <= min(cz + 1, nz - 1); z++)
+                        for (int y = max(cy - 1, 0); y <= min(cy + 1, ny - 1); y++)
+                            any |= (tri[(z * ny + y) * nx + cx] >> 16) != 0u;
+                }
+                const unsigned bal = __ballot_sync(PC_FULL_MASK, any);
+                if (lane == 0) occ[c0 >> 5] = bal;
+            }
+            __syncthreads();
+            if (!(s_status & (unsigned)PC_ST_TAIL_OVERFLOW)) {
+            // ---- T3: pair search, 32 heavy A atoms per warp and round ---------------------------------------------
+            unsigned wn = 0;                                        // hits in this warp's queue (uniform)
+            auto drain_queue = [&]() {
+                __syncwarp();
+                unsigned base = 0;
+                if (lane == 0) base = atomicAdd(&s_ccur, wn);
+                base = __shfl_sync(PC_FULL_MASK, base, 0);
+                for (unsigned k = lane; k < wn; k += 32) emit(mywq[k], (long long)base + k);
+                wn = 0;
+                __syncwarp();
+            };
+            for (;;) {
+                int k0 = 0;
+                if (lane == 0) k0 = (int)atomicAdd(&s_next, 32u);
+                k0 = __shfl_sync(PC_FULL_MASK, k0, 0);
+                if (k0 >= n1h) break;
+                const int k = k0 + lane;
+                // -- setup: this lane's atom, its cell, its non-empty rows
+                float x = 0.f, y = 0.f, z = 0.f;
+                int cx = 0, cy = 0, cz = 0;
+                bool has = false;
+                if (k < n1h) {
+                    const uint32_t info = __ldg(hinfo1 + k);
+                    const float *p = fr1 + 3ll * PC_W_INDEX(info);
+                    x = __ldg(p); y = __ldg(p + 1); z = __ldg(p + 2);
+                    const float ux = (x - lox) * inv, uy = (y - loy) * inv, uz = (z - loz) * inv;
+                    if (ux >= 0.f && uy >= 0.f && uz >= 0.f) {
+                        cx = (int)ux; cy = (int)uy; cz = (int)uz;
+                        if (cx < nx && cy < ny && cz < nz) {
+                            const int c = (cz * ny + cy) * nx + cx;
+                            has = (occ[c >> 5] >> (c & 31)) & 1u;
+                        }
+                    }
+                }
+                if (!__ballot_sync(PC_FULL_MASK, has)) continue;    // 32 atoms without any B atom around them
+                unsigned nr = 0, T = 0;
+                if (has) {
+                    for (int zz = max(cz - 1, 0); zz <= min(cz + 1, nz - 1); zz++)
+                        for (int yy = max(cy - 1, 0); yy <= min(cy + 1, ny - 1); yy++) {
+                            const unsigned len = tri[(zz * ny + yy) * nx + cx] >> 16;
+                            nr += len != 0u; T += len;
+                        }
+                }
+                apos[lane] = x; apos[32 + lane] = y; apos[64 + lane] = z;
+                const unsigned nr_all = __reduce_add_sync(PC_FULL_MASK, nr);
+                const int nparts = nr_all > (unsigned)PC_WALK_RUNS ? 2 : 1;        // 16 atoms have at most 144 runs
+                for (int part = 0; part < nparts; part++) {
+                const bool mine = has && (nparts == 1 || (lane >> 4) == part);
+                const unsigned nrp = mine ? nr : 0u, Tp = mine ? T : 0u;
+                const unsigned rincl = warp_incl_scan(nrp, lane), tincl = warp_incl_scan(Tp, lane);
+                const unsigned W = __shfl_sync(PC_FULL_MASK, tincl, 31);
+                const unsigned off = tincl - Tp;                    // candidates of the lanes before this one
+                unsigned rpos = rincl - nrp;
+                const unsigned roff = rpos;
+                __syncwarp();                                       // the previous part's walk has left the run list
+                if (mine) {
+                    for (int zz = max(cz - 1, 0); zz <= min(cz + 1, nz - 1); zz++)
+                        for (int yy = max(cy - 1, 0); yy <= min(cy + 1, ny - 1); yy++) {
+                            const unsigned t3 = tri[(zz * ny + yy) * nx + cx];
+                            if (t3 >> 16) runs[rpos++] = t3 | ((unsigned)lane << 27);     // start 16 | length 11 | owner 5
+                        }
+                }
+                __syncwarp();
+                // -- walk: lane l evaluates candidates [l * per, (l + 1) * per) of the W candidates
+                const unsigned per = (W + 31u) >> 5;
+                const unsigned lo = min((unsigned)lane * per, W), hi = min(lo + per, W);
+                evals += hi - lo;
+                unsigned L = 0;
+#pragma unroll
+                for (int sft = 16; sft > 0; sft >>= 1) {
+                    const unsigned cand = L + (unsigned)sft;
+                    const unsigned v = __shfl_sync(PC_FULL_MASK, off, cand & 31u);
+                    if (cand < 32u && v <= lo) L = cand;
+                }
+                unsigned ri = __shfl_sync(PC_FULL_MASK, roff, L);
+                unsigned rem = lo - __shfl_sync(PC_FULL_MASK, off, L);
+                unsigned j = 0, jend = 0, ka = 0;
+                float2 nxy = make_float2(0.f, 0.f);
+                float naz = 0.f;
+                if (lo < hi) {
+                    unsigned rec = runs[ri], len = (rec >> 16) & 0x7ffu;
+                    while (rem >= len) { rem -= len; rec = runs[++ri]; len = (rec >> 16) & 0x7ffu; }
+                    j = (rec & 0xffffu) + rem; jend = (rec & 0xffffu) + len; L = rec >> 27;
+                    nxy = make_float2(-apos[L], -apos[32 + L]); naz = -apos[64 + L]; ka = (unsigned)k0 + L;
+                }
+                for (unsigned it = 0; it < per; it++) {
+                    const bool act = lo + it < hi;
+                    bool hit = false;
+                    if (act) hit = pair_within_packed(nxy, naz, sortB[j], sqdist);
+                    const unsigned bal = __ballot_sync(PC_FULL_MASK, hit);
+                    if (bal) {
+                        if (hit) mywq[wn + __popc(bal & lt_mask)] = (ka << 16) | j;
+                        wn += __popc(bal);
+                    }
+                    if (act && ++j == jend && lo + it + 1 < hi) {
+                        const unsigned rec = runs[++ri];
+                        j = rec & 0xffffu; jend = j + ((rec >> 16) & 0x7ffu);
+                        if ((rec >> 27) != L) {
+                            L = rec >> 27;
+                            nxy = make_float2(-apos[L], -apos[32 + L]); naz = -apos[64 + L]; ka = (unsigned)k0 + L;
+                        }
+                    }
+                    if (wn > (unsigned)(PC_WALK_WQ - 32)) drain_queue();
+                }
+                }
+                if (wn >= (unsigned)PC_WALK_DRAIN_AT) drain_queue();
+                __syncwarp();
+            }
+            drain_queue();
+            }
+            __syncthreads();
+            // ---- T3b: donor-H...acceptor tests, one thread per (gated pair, side) ------------------------------
+            const unsigned ngate = min(s_ngate, (unsigned)PC_WALK_GATE);
+            for (unsigned it = tid; it < 2u * ngate; it += NT) hbond_side(gateq[it >> 1], (int)(it & 1u));
+        }
+        __syncthreads();
+        // ---- per-frame counts and totals; the frame's work slot is made ready for the next batch -----------------
+        if (tid == 0) {
+            const unsigned cc = s_ccur, hc = s_hcur;
+            a.frame_cstart[f] = (uint32_t)((long long)f * o.cap_c_frame);
+            a.frame_ccount[f] = (uint32_t)min((long long)cc, o.cap_c_frame);
+            a.frame_hstart[f] = (uint32_t)((long long)f * o.cap_h_frame);
+            a.frame_hcount[f] = (uint32_t)min((long long)hc, o.cap_h_frame);
+            if (cc) atomicAdd(&a.counters[PC_CNT_CONTACTS], (unsigned long long)cc);
+            if (hc) atomicAdd(&a.counters[PC_CNT_HBONDS], (unsigned long long)hc);
+            atomicMax(&a.counters[6], (unsigned long long)cc);
+            atomicMax(&a.counters[7], (unsigned long long)hc);
+            if (s_status) atomicOr(&a.counters[PC_CNT_STATUS], (unsigned long long)s_status);
+            if (fuse_acc && cc == 0) { acc.frame_rstart[f] = 0; acc.frame_rcount[f] = 0; }
+            if (reset_frames) {
+                PcLargeFrame &G = fr[fb];
+                for (int k = 0; k < 3; k++) { G.bbox[k] = 0xffffffffu; G.bbox[3 + k] = 0u; G.bbox[6 + k] = 0xffffffffu; G.bbox[9 + k] = 0u; }
+                G.nA_in = G.nB_in = 0; G.ccursor = G.hcursor = 0; G.ncell = 0; G.pad[0] = 0;
+            }
+        }
+        __syncthreads();
+        // ---- T4: per-frame accumulation of the records just written (they are in L2) -----------------------------
+        const bool have = fuse_acc && s_ccur != 0;
+        const bool do_acc = have && !(s_status & (unsigned)(PC_ST_OUT_OVERFLOW | PC_ST_TAIL_OVERFLOW));
+        __syncthreads();                   // pc_compact_frame reuses s_status
+        if (do_acc) pc_compact_frame<NT>(acc, f, smem, wsum, &s_base, &s_status);
+        else if (have && tid == 0) { acc.frame_rstart[f] = 0; acc.frame_rcount[f] = 0; }
+        __syncthreads();
+    }
+#pragma unroll
+    for (int sft = 16; sft > 0; sft >>= 1) evals += __shfl_xor_sync(PC_FULL_MASK, evals, sft);
+    if (lane == 0 && evals) atomicAdd(&a.counters[PC_CNT_EVALS], evals);
+}
+
 // ---- host side of the large-frame path --------------------------------------------------------------------------
 static inline int pc_large_fail(std::string &err, const char *what, cudaError_t e) {
     err = std::string(what) + ": " + cudaGetErrorString(e);
@@ -267,7 +599,8 @@ static inline void pc_stream_geom(int n, int nfb, int num_sms, int &ctas, int &p
     ctas = (n + per - 1) / per;
 }
 
-// tail != 0: the fused per-frame tail kernel (two selections only); acc != nullptr with it: rows are produced too.
+// tail: 0 = multi-kernel sequence, 1 = fused tail kernel on the compacted A and B atoms, 2 = walk kernel (A read from the
+// frame); two selections only.  acc != nullptr with a tail kernel: rows are produced too.
 static inline int pc_large_scan(PcLargeWork &W, const PcScanArgs &a, int num_sms, cudaStream_t s, std::string &err,
                                 unsigned long long *launches, cudaEvent_t probe0, cudaEvent_t probe1, int tail,
                                 const PcAccArgs *acc) {
@@ -304,6 +637,8 @@ static inline int pc_large_scan(PcLargeWork &W, const PcScanArgs &a, int num_sms
         PCL_TRY(cudaFuncSetAttribute(pc_large_stream_kernel<PC_MODE_BBOX>, cudaFuncAttributeMaxDynamicSharedMemorySize, PC_STREAM_SMEM));
         PCL_TRY(cudaFuncSetAttribute(pc_large_stream_kernel<PC_MODE_BIN>, cudaFuncAttributeMaxDynamicSharedMemorySize, PC_STREAM_SMEM));
         PCL_TRY(cudaFuncSetAttribute(pc_large_tail_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, PC_TAIL_SMEM));
+        PCL_TRY(cudaFuncSetAttribute(pc_large_walk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, PC_TAIL_SMEM));
+        W.clean = false;
     }
     FB = W.FB;
     PcLargeOut o;
@@ -316,7 +651,11 @@ static inline int pc_large_scan(PcLargeWork &W, const PcScanArgs &a, int num_sms
         int ctasA, perA, ctasB = 0, perB = 0;
         pc_stream_geom(n1, nfb, num_sms, ctasA, perA);
         if (!self) pc_stream_geom(n2, nfb, num_sms, ctasB, perB);
-        pc_large_reset_kernel<<<(nfb + 63) / 64, 64, 0, s>>>(W.frames, nfb);
+        if (!(tail == 2 && W.clean)) {
+            pc_large_reset_kernel<<<(W.FB + 63) / 64, 64, 0, s>>>(W.frames, W.FB);
+            *launches += 1;
+        }
+        W.clean = tail == 2;
         pc_large_stream_kernel<PC_MODE_BBOX><<<dim3(ctasA, nfb), PC_STREAM_NT, PC_STREAM_SMEM, s>>>(
             a, W.frames, f0, 0, 0, perA, nullptr, 0, nullptr, nullptr, 0, nullptr);
         if (use_bboxB)
@@ -329,6 +668,15 @@ static inline int pc_large_scan(PcLargeWork &W, const PcScanArgs &a, int num_sms
             pc_large_stream_kernel<PC_MODE_BIN><<<dim3(ctasB, nfb), PC_STREAM_NT, PC_STREAM_SMEM, s>>>(
                 a, W.frames, f0, 1, 0, perB, W.cellB, capCells, W.candB, W.ccellB, a2, nullptr);
             if (probe1 && f0 == 0) cudaEventRecord(probe1, s);
+            if (tail == 2) {
+                PcAccArgs none;
+                memset(&none, 0, sizeof none);
+                pc_large_walk_kernel<<<std::min(nfb, num_sms), PC_WALK_NT, PC_TAIL_SMEM, s>>>(
+                    a, W.frames, f0, nfb, W.cellB, capCells, W.candB, W.ccellB, a2, o, acc ? *acc : none, acc ? 1 : 0, 1);
+                PCL_TRY(cudaGetLastError());
+                *launches += 4 + (use_bboxB ? 1 : 0);
+                continue;
+            }
             pc_large_occ_kernel<<<dim3(std::max(1, std::min((capCells + 255) / 256, 4 * num_sms / nfb + 1)), nfb), 256, 0, s>>>(
                 W.frames, W.cellB, capCells, W.occ);
         }
@@ -342,7 +690,7 @@ static inline int pc_large_scan(PcLargeWork &W, const PcScanArgs &a, int num_sms
             pc_large_tail_kernel<<<std::min(nfb, num_sms), PC_TAIL_NT, PC_TAIL_SMEM, s>>>(
                 a, W.frames, f0, nfb, W.cellB, capCells, W.candA, W.candB, W.ccellB, a1, a2, o, acc ? *acc : none, acc ? 1 : 0);
             PCL_TRY(cudaGetLastError());
-            *launches += 7 + (use_bboxB ? 1 : 0);
+            *launches += 6 + (use_bboxB ? 1 : 0);
             continue;
         }
         pc_large_scan_kernel<<<dim3(nfb, self ? 1 : 2), 1024, 0, s>>>(W.frames, W.cellA, W.cellB, capCells);
@@ -365,7 +713,7 @@ static inline int pc_large_scan(PcLargeWork &W, const PcScanArgs &a, int num_sms
         pc_large_drain_kernel<<<dim3(dblocks, nfb), 256, 0, s>>>(a, W.frames, f0, W.sortA, W.sortB, a1, a2, o);
         pc_large_finish_kernel<<<(nfb + 63) / 64, 64, 0, s>>>(a, W.frames, f0, nfb, o);
         PCL_TRY(cudaGetLastError());
-        *launches += 9 + (use_bboxB ? 1 : 0) + (self ? 0 : 3);
+        *launches += 8 + (use_bboxB ? 1 : 0) + (self ? 0 : 3);
     }
     return PC_OK;
 }

@@ -121,7 +121,7 @@ class ContactEngine:
         self.launches = 0
         self.forced_path = 0
         self.pack_bytes = 24
-        self.tail = True
+        self.tail = 2
 
     # ------------------------------------------------------------------------------------------
     def close(self):
@@ -199,11 +199,12 @@ class ContactEngine:
             check(self.lib.pc_set_pack_format(s.ctx, int(bytes_per_row)))
         self.pack_bytes = int(bytes_per_row)
 
-    def set_tail(self, on: bool):
-        """Large-frame path: fused per-frame tail kernel (default) or the multi-kernel sequence."""
-        self.tail = bool(on)
+    def set_tail(self, mode):
+        """Large-frame path: 2 / True = walk kernel (default), 1 = fused tail kernel on compacted atoms,
+        0 / False = multi-kernel sequence."""
+        self.tail = 2 if mode is True else int(mode)
         for s in self.slots:
-            check(self.lib.pc_set_tail(s.ctx, int(self.tail)))
+            check(self.lib.pc_set_tail(s.ctx, self.tail))
 
     def set_dense_mode(self, mode: int):
         """Multi-kernel sequence, tests: 0 = pair kernel chosen per frame, 1 = thread per atom, 2 = warp per cell."""
@@ -231,7 +232,10 @@ class ContactEngine:
             self.lim[1] = max(1024, 2 * (self.lim[1] or 256))
         if st & _lib.ST_TAIL_OVERFLOW:
             # a frame's in-grid atoms do not fit the fused per-frame tail kernel: multi-kernel sequence from now on
-            self.set_tail(False)
+            import os
+            if os.environ.get("PC_DEBUG"):
+                print("pycontact_b200: tail kernel handed a batch over:", self.lib.pc_last_error().decode(), flush=True)
+            self.set_tail(0)
         if st & _lib.ST_PRECISION:
             # a (frame, key) cell with more contacts than a float32 sum carries within 1e-5: exact global table
             self.lim[3] = 16384
