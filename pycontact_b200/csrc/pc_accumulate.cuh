@@ -184,27 +184,37 @@ __device__ __forceinline__ void pc_compact_frame(const PcAccArgs &a, const int f
     if (tid == 0) *s_status = 0;
     __syncthreads();
     const uint32_t c0 = a.frame_cstart[f], cn = a.frame_ccount[f];
-    for (uint32_t c = tid; c < cn; c += NT) {
+    // four contacts per thread and round: their records, then their eight group words, are loaded back to back (a
+    // thread's contacts used to wait for each other's L2 round trips: two dependent loads per contact)
+    for (uint32_t cb = tid; cb < cn; cb += 4 * NT) {
         // a full table makes every further key walk 256 slots, and the batch is redone on the global table
         // anyway (PC_ST_TABLE_OVERFLOW): stop at the first overflow instead of finishing the frame
         if (*(volatile unsigned int *)s_status & (unsigned)PC_ST_TABLE_OVERFLOW) break;
-        const pc_contact rec = a.contacts[c0 + c];
-        // group id and backbone flag of an atom in one word: two random loads per contact, not four
-        const uint32_t g1 = __ldg(a.lgb1 + rec.i), g2 = __ldg(a.lgb2 + rec.j);
-        const unsigned long long key = (unsigned long long)(g1 & 0x7fffffffu) * a.ngroups2 + (unsigned long long)(g2 & 0x7fffffffu);
-        unsigned s = pc_hash64(key) & mask;
-        int probes = 0;
-        for (;;) {
-            const unsigned long long prev = atomicCAS(&keys[s], PC_EMPTY_KEY, key);
-            if (prev == PC_EMPTY_KEY || prev == key) break;
-            s = (s + 1) & mask;
-            if (++probes >= 256) { s = 0xffffffffu; break; }
+        pc_contact rec[4];
+        uint32_t g1[4], g2[4];
+#pragma unroll
+        for (int u = 0; u < 4; u++) rec[u] = a.contacts[c0 + min(cb + (uint32_t)u * NT, cn - 1u)];
+#pragma unroll
+        for (int u = 0; u < 4; u++) { g1[u] = __ldg(a.lgb1 + rec[u].i); g2[u] = __ldg(a.lgb2 + rec[u].j); }
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+            if (cb + (uint32_t)u * NT >= cn) break;
+            // group id and backbone flag of an atom in one word: two random loads per contact, not four
+            const unsigned long long key = (unsigned long long)(g1[u] & 0x7fffffffu) * a.ngroups2 + (unsigned long long)(g2[u] & 0x7fffffffu);
+            unsigned s = pc_hash64(key) & mask;
+            int probes = 0;
+            for (;;) {
+                const unsigned long long prev = atomicCAS(&keys[s], PC_EMPTY_KEY, key);
+                if (prev == PC_EMPTY_KEY || prev == key) break;
+                s = (s + 1) & mask;
+                if (++probes >= 256) { s = 0xffffffffu; break; }
+            }
+            if (s == 0xffffffffu) { atomicOr(s_status, (unsigned)PC_ST_TABLE_OVERFLOW); continue; }
+            atomicAdd(&score[s], rec[u].weight);
+            if (g1[u] >> 31) atomicAdd(&bb1[s], rec[u].weight);
+            if (g2[u] >> 31) atomicAdd(&bb2[s], rec[u].weight);
+            if (atomicAdd(&ncont[s], 1u) == PC_FLOAT_SUM_MAX) atomicOr(s_status, (unsigned)PC_ST_PRECISION);
         }
-        if (s == 0xffffffffu) { atomicOr(s_status, (unsigned)PC_ST_TABLE_OVERFLOW); continue; }
-        atomicAdd(&score[s], rec.weight);
-        if (g1 >> 31) atomicAdd(&bb1[s], rec.weight);
-        if (g2 >> 31) atomicAdd(&bb2[s], rec.weight);
-        if (atomicAdd(&ncont[s], 1u) == PC_FLOAT_SUM_MAX) atomicOr(s_status, (unsigned)PC_ST_PRECISION);
     }
     __syncthreads();
     const uint32_t h0 = a.frame_hstart[f], hn = a.frame_hcount[f];
@@ -257,7 +267,7 @@ __device__ __forceinline__ void pc_compact_frame(const PcAccArgs &a, const int f
 }
 
 template <int NT>
-__global__ void __launch_bounds__(NT) pc_accumulate_compact_kernel(const PcAccArgs a) {
+__global__ void __launch_bounds__(NT, 1) pc_accumulate_compact_kernel(const PcAccArgs a) {
     extern __shared__ __align__(16) unsigned char smem[];
     __shared__ uint32_t wsum[32];
     __shared__ long long s_base;

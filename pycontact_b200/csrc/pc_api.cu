@@ -69,7 +69,7 @@ struct pc_ctx {
     // limits (0 = automatic)
     int lim_hits = 0, lim_hb = 0, lim_cells = 0, lim_table = 0;
     int force_path = 0;               // 0 = automatic, 1 = small-frame kernel, 2 = large-frame path
-    int tail_mode = 2;                // large-frame path: 2 = walk kernel (A from the frame), 1 = fused tail kernel on compacted A and B,
+    int tail_mode = 1;                // large-frame path: 2 = walk kernel (A from the frame), 1 = fused tail kernel on compacted A and B,
                                       // 0 = multi-kernel sequence
     int dense_mode = 0;               // multi-kernel sequence: pair kernel 0 = per frame on the device, 1 = thread per atom, 2 = warp per cell
     // batch outputs

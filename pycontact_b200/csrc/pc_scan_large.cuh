@@ -28,7 +28,7 @@ struct PcLargeFrame {
     int nx, ny, nz, ncell;
     unsigned int nA_in, nB_in;        // atoms inside the grid
     unsigned int ccursor, hcursor;    // records written into this frame's slices
-    unsigned int pad[2];
+    unsigned int pad[2];              // CTAs of the frame that have finished the bbox pass / the bin pass of selection B
 };
 
 struct PcLargeWork {
@@ -40,11 +40,12 @@ struct PcLargeWork {
     uint32_t *ccellA = nullptr, *ccellB = nullptr;    // FB x n_h   cell id of each compacted atom
     float4 *sortA = nullptr, *sortB = nullptr;        // FB x n_h   (cell order)
     uint8_t *occ = nullptr;                           // FB x capCells: cell has a B atom in its 27-cell neighbourhood
+    uint8_t *occ2 = nullptr;                          // FB x capCells: scratch of the separable dilation
     void release() {
-        void *ps[] = {frames, cellA, cellB, candA, candB, ccellA, ccellB, sortA, sortB, occ};
+        void *ps[] = {frames, cellA, cellB, candA, candB, ccellA, ccellB, sortA, sortB, occ, occ2};
         for (void *p : ps) if (p) cudaFree(p);
         frames = nullptr; cellA = cellB = nullptr; candA = candB = sortA = sortB = nullptr;
-        ccellA = ccellB = nullptr; occ = nullptr; FB = 0;
+        ccellA = ccellB = nullptr; occ = occ2 = nullptr; FB = 0;
     }
     ~PcLargeWork() { release(); }
 };
@@ -66,6 +67,7 @@ __global__ void pc_large_reset_kernel(PcLargeFrame *fr, int nfb) {
         fr[f].bbox[6 + k] = 0xffffffffu; fr[f].bbox[9 + k] = 0u;
     }
     fr[f].nA_in = fr[f].nB_in = 0; fr[f].ccursor = fr[f].hcursor = 0; fr[f].ncell = 0;
+    fr[f].pad[0] = fr[f].pad[1] = 0;          // arrival counters of the streaming kernels' epilogues
 }
 
 __device__ __forceinline__ int pc_large_cell_of(const PcLargeFrame &F, float x, float y, float z) {
@@ -76,12 +78,79 @@ __device__ __forceinline__ int pc_large_cell_of(const PcLargeFrame &F, float x, 
     return (cz * F.ny + cy) * F.nx + cx;
 }
 
+// ---- L2: grid geometry + zeroed cell counters (one CTA per frame) -----------------------------------
+// All threads of a CTA call this for frame fb; thread 0 reads the frame's bounding boxes (through L2: other CTAs
+// wrote them with atomics) and fixes the geometry.  Returns the number of cells.
+__device__ __forceinline__ int pc_large_grid_frame(const PcScanArgs &a, PcLargeFrame *fr, const int fb, const int capCells,
+                                                   const int use_bboxB, uint32_t *cellsA, uint32_t *cellsB, int *s_ncell) {
+    if (threadIdx.x == 0) {
+        PcLargeFrame &F = fr[fb];
+        bool empty = false, bad = false;
+        float lo[3], ext[3];
+        for (int k = 0; k < 3; k++) {
+            const float minA = pc_dec_float(__ldcg(&F.bbox[k])), maxA = pc_dec_float(__ldcg(&F.bbox[3 + k]));
+            float l = minA - a.edge, h = maxA + a.edge;
+            if (!a.self_mode && use_bboxB) {
+                const float minB = pc_dec_float(__ldcg(&F.bbox[6 + k])), maxB = pc_dec_float(__ldcg(&F.bbox[9 + k]));
+                l = fmaxf(minA, minB) - a.edge; h = fminf(maxA, maxB) + a.edge;
+            }
+            if (!(l <= h)) empty = true;
+            else if (!isfinite(l) || !isfinite(h)) bad = true;
+            lo[k] = l; ext[k] = h - l;
+        }
+        if (bad && !empty) { atomicOr(&a.counters[PC_CNT_STATUS], PC_ST_BAD_COORDS); empty = true; }
+        int nx = 0, ny = 0, nz = 0;
+        float inv = 0.f;
+        if (!empty) pc_grid_dims(ext[0], ext[1], ext[2], a.edge, (long long)capCells, nx, ny, nz, inv);
+        F.lo[0] = lo[0]; F.lo[1] = lo[1]; F.lo[2] = lo[2]; F.inv = inv;
+        F.nx = nx; F.ny = ny; F.nz = nz; F.ncell = nx * ny * nz;
+        *s_ncell = F.ncell;
+    }
+    __syncthreads();
+    const int ncell = *s_ncell;
+    uint32_t *cA = cellsA + (size_t)fb * (capCells + 1);
+    uint32_t *cB = a.self_mode ? nullptr : cellsB + (size_t)fb * (capCells + 1);
+    for (int c = threadIdx.x; c <= ncell; c += blockDim.x) { cA[c] = 0; if (cB) cB[c] = 0; }
+    return ncell;
+}
+
+// Dilated B occupancy of one frame by ONE CTA (the streaming bin's last CTA of the frame): separable -- x, then y, then z,
+// three loads per cell and pass instead of 27 -- through L2 (the counts were written by other CTAs' atomics, the
+// intermediate bytes by this CTA's other threads).
+__device__ __forceinline__ void pc_large_occ_frame(const int nx, const int ny, const int nz, const uint32_t *cB, uint8_t *o, uint8_t *t) {
+    const int ncell = nx * ny * nz, nxy = nx * ny;
+    for (int c = threadIdx.x; c < ncell; c += blockDim.x) {
+        const int cx = c % nx;
+        unsigned v = __ldcg(cB + c);
+        if (cx > 0) v |= __ldcg(cB + c - 1);
+        if (cx + 1 < nx) v |= __ldcg(cB + c + 1);
+        o[c] = v ? 1 : 0;
+    }
+    __syncthreads();
+    for (int c = threadIdx.x; c < ncell; c += blockDim.x) {
+        const int cy = (c / nx) % ny;
+        unsigned v = __ldcg(o + c);
+        if (cy > 0) v |= __ldcg(o + c - nx);
+        if (cy + 1 < ny) v |= __ldcg(o + c + nx);
+        t[c] = (uint8_t)v;
+    }
+    __syncthreads();
+    for (int c = threadIdx.x; c < ncell; c += blockDim.x) {
+        const int cz = c / nxy;
+        unsigned v = __ldcg(t + c);
+        if (cz > 0) v |= __ldcg(t + c - nxy);
+        if (cz + 1 < nz) v |= __ldcg(t + c + nxy);
+        o[c] = (uint8_t)v;
+    }
+}
+
 // ---- L1 / L3: streaming kernels -----------------------------------------------------------------
 #define PC_STREAM_NT 512
 #define PC_STREAM_CHUNK 24576            // 2048 atoms per chunk
 #ifndef PC_STREAM_STAGES
 #define PC_STREAM_STAGES 3
 #endif
+#define PC_STREAM_MAXCH 256                                  // chunk boundaries whose heavy ordinals are looked up ahead of the loop
 #define PC_STREAM_HINFO (PC_STREAM_CHUNK / 12 * 4 + 32)      // a chunk's slice of the heavy-atom list
 #define PC_STREAM_SLOT (PC_STREAM_CHUNK + 16 + PC_STREAM_HINFO)
 #define PC_STREAM_SMEM (PC_STREAM_STAGES * PC_STREAM_SLOT + PC_STREAM_STAGES * 8 + 16)
@@ -90,11 +159,21 @@ struct PcStreamDesc { int cnt, hoff, off0, abase; };          // per ring slot, 
 
 enum { PC_MODE_BBOX = 0, PC_MODE_BIN = 1 };
 
+// What the LAST CTA of a frame does when it leaves a streaming kernel (one launch less per batch each):
+//   PC_EPI_GRID  after the bbox pass of selection A: the frame's grid geometry + zeroed cell counters
+//   PC_EPI_OCC   after the bin pass of selection B: the dilated B occupancy that the bin pass of A filters with
+enum { PC_EPI_NONE = 0, PC_EPI_GRID = 1, PC_EPI_OCC = 2 };
+struct PcStreamEpi {
+    int what, capCells, use_bboxB;
+    uint32_t *cellsA, *cellsB;
+    uint8_t *occ, *occ2;
+};
+
 template <int MODE>
 __global__ void __launch_bounds__(PC_STREAM_NT) pc_large_stream_kernel(const PcScanArgs a, PcLargeFrame *fr, int f0, int side,
                                                                        int slot0, int atoms_per_cta, uint32_t *cells,
                                                                        int capCells, float4 *cand, uint32_t *ccell,
-                                                                       int nh_alloc, const uint8_t *occ) {
+                                                                       int nh_alloc, const uint8_t *occ, const PcStreamEpi epi) {
     constexpr int NT = PC_STREAM_NT, CHUNK = PC_STREAM_CHUNK, STAGES = PC_STREAM_STAGES, SLOT = PC_STREAM_SLOT;
     extern __shared__ __align__(16) unsigned char smem[];
     uint64_t *bars = reinterpret_cast<uint64_t *>(smem + STAGES * SLOT);
@@ -131,9 +210,19 @@ __global__ void __launch_bounds__(PC_STREAM_NT) pc_large_stream_kernel(const PcS
     auto heavy_before = [&](int i) -> int {       // heavy ordinal of local atom i
         return (int)(__ldg(hpre + (i >> 5)) + __popc(__ldg(hmask + (i >> 5)) & ((1u << (i & 31)) - 1u)));
     };
+    // The heavy ordinals of the chunk boundaries are looked up by many threads at once BEFORE the loop: done by the
+    // producer as it went, their two dependent global loads sat in front of every bulk copy it issued, and the whole
+    // CTA waited for its warp at each chunk's barrier (1.3 us per 24 KB chunk and CTA).
+    __shared__ int s_hb[PC_STREAM_MAXCH + 1];
+    for (int q = tid; q <= min(nch, PC_STREAM_MAXCH); q += NT) {
+        const int k = q < nch ? pc_chunk_of<CHUNK>(seg, q).k0 : seg.natoms;
+        s_hb[q] = heavy_before(r0 + k);
+    }
+    __syncthreads();
     auto issue = [&](int q) {
         const PcChunk c = pc_chunk_of<CHUNK>(seg, q);
-        const int h0 = heavy_before(r0 + c.k0), h1 = heavy_before(r0 + c.k1);
+        const int h0 = q <= PC_STREAM_MAXCH ? s_hb[q] : heavy_before(r0 + c.k0);
+        const int h1 = q + 1 <= PC_STREAM_MAXCH ? s_hb[q + 1] : heavy_before(r0 + c.k1);
         const uintptr_t hs = (uintptr_t)(hinfo + h0), hs_al = hs & ~(uintptr_t)15;
         uintptr_t he = ((uintptr_t)(hinfo + h1) + 15) & ~(uintptr_t)15;
         if (he <= hs_al) he = hs_al + 16;
@@ -159,6 +248,15 @@ __global__ void __launch_bounds__(PC_STREAM_NT) pc_large_stream_kernel(const PcS
         cursor = side == 0 ? &fr[fb].nA_in : &fr[fb].nB_in;
     }
     float mn[3] = {INFINITY, INFINITY, INFINITY}, mx[3] = {-INFINITY, -INFINITY, -INFINITY};
+    // conservative box of the grid (BIN mode): cell coordinate u = (x - lo) * inv; x < lo - 0.01 gives u < 0, and
+    // x > lo + n * e * (1 + 1e-5) + 0.01 with e = 1 / inv (e * inv = 1 +- 2e-7) gives u > n
+    float plo[3] = {0.f, 0.f, 0.f}, phi[3] = {0.f, 0.f, 0.f};
+    if (MODE == PC_MODE_BIN) {
+        const float e = 1.0f / F.inv;
+        const int nn[3] = {F.nx, F.ny, F.nz};
+#pragma unroll
+        for (int k = 0; k < 3; k++) { plo[k] = F.lo[k] - 0.01f; phi[k] = F.lo[k] + (float)nn[k] * e * 1.00001f + 0.01f; }
+    }
 
     if (tid == 0)
         for (int q = 0; q < min(STAGES - 1, nch); q++) issue(q);
@@ -186,7 +284,11 @@ __global__ void __launch_bounds__(PC_STREAM_NT) pc_large_stream_kernel(const PcS
                     mx[0] = fmaxf(mx[0], x); mx[1] = fmaxf(mx[1], y); mx[2] = fmaxf(mx[2], z);
                 }
             } else {
-                int cell = heavy ? pc_large_cell_of(F, x, y, z) : -1;
+                // most atoms of a large selection are far outside the grid: a box test with a safety margin first (an
+                // atom it rejects has a cell coordinate < 0 or >= n for sure), the exact cell only for the few that pass
+                const bool maybe = heavy && x >= plo[0] && x <= phi[0] && y >= plo[1] && y <= phi[1] && z >= plo[2] && z <= phi[2];
+                if (!__any_sync(PC_FULL_MASK, maybe)) continue;
+                int cell = maybe ? pc_large_cell_of(F, x, y, z) : -1;
                 // an A atom whose 27-cell neighbourhood holds no B atom cannot have a partner
                 if (occ != nullptr && cell >= 0 && !occ[(size_t)fb * capCells + cell]) cell = -1;
                 const unsigned m = __ballot_sync(PC_FULL_MASK, cell >= 0);
@@ -220,41 +322,31 @@ __global__ void __launch_bounds__(PC_STREAM_NT) pc_large_stream_kernel(const PcS
         }
     }
     if (tid == 0 && s_bad) atomicOr(&a.counters[PC_CNT_STATUS], (unsigned long long)PC_ST_BAD_COORDS);
+    if (epi.what != PC_EPI_NONE) {
+        // every CTA of the frame arrives here (pc_stream_geom launches no CTA without atoms; frames without a grid left
+        // the bin pass above and need no occupancy); the last one does the epilogue
+        __shared__ int s_last, s_ncell;
+        __threadfence();
+        __syncthreads();
+        if (tid == 0) s_last = atomicAdd(&fr[fb].pad[epi.what - 1], 1u) == gridDim.x - 1u;
+        __syncthreads();
+        if (s_last) {
+            __threadfence();
+            if (epi.what == PC_EPI_GRID) {
+                pc_large_grid_frame(a, fr, fb, epi.capCells, epi.use_bboxB, epi.cellsA, epi.cellsB, &s_ncell);
+            } else {
+                pc_large_occ_frame(F.nx, F.ny, F.nz, epi.cellsB + (size_t)fb * (epi.capCells + 1),
+                                   epi.occ + (size_t)fb * epi.capCells, epi.occ2 + (size_t)fb * epi.capCells);
+            }
+        }
+    }
 }
 
-// ---- L2: grid geometry + zeroed cell counters (one CTA per frame) -----------------------------------
+// ---- L2: grid geometry + zeroed cell counters (one CTA per frame; pc_large_grid_frame above) ---------------
 __global__ void __launch_bounds__(256) pc_large_grid_kernel(const PcScanArgs a, PcLargeFrame *fr, int capCells, int use_bboxB,
                                                             uint32_t *cellsA, uint32_t *cellsB) {
-    const int fb = blockIdx.x;
     __shared__ int s_ncell;
-    if (threadIdx.x == 0) {
-        PcLargeFrame &F = fr[fb];
-        bool empty = false, bad = false;
-        float lo[3], ext[3];
-        for (int k = 0; k < 3; k++) {
-            const float minA = pc_dec_float(F.bbox[k]), maxA = pc_dec_float(F.bbox[3 + k]);
-            float l = minA - a.edge, h = maxA + a.edge;
-            if (!a.self_mode && use_bboxB) {
-                const float minB = pc_dec_float(F.bbox[6 + k]), maxB = pc_dec_float(F.bbox[9 + k]);
-                l = fmaxf(minA, minB) - a.edge; h = fminf(maxA, maxB) + a.edge;
-            }
-            if (!(l <= h)) empty = true;
-            else if (!isfinite(l) || !isfinite(h)) bad = true;
-            lo[k] = l; ext[k] = h - l;
-        }
-        if (bad && !empty) { atomicOr(&a.counters[PC_CNT_STATUS], PC_ST_BAD_COORDS); empty = true; }
-        int nx = 0, ny = 0, nz = 0;
-        float inv = 0.f;
-        if (!empty) pc_grid_dims(ext[0], ext[1], ext[2], a.edge, (long long)capCells, nx, ny, nz, inv);
-        F.lo[0] = lo[0]; F.lo[1] = lo[1]; F.lo[2] = lo[2]; F.inv = inv;
-        F.nx = nx; F.ny = ny; F.nz = nz; F.ncell = nx * ny * nz;
-        s_ncell = F.ncell;
-    }
-    __syncthreads();
-    const int ncell = s_ncell;
-    uint32_t *cA = cellsA + (size_t)fb * (capCells + 1);
-    uint32_t *cB = a.self_mode ? nullptr : cellsB + (size_t)fb * (capCells + 1);
-    for (int c = threadIdx.x; c <= ncell; c += blockDim.x) { cA[c] = 0; if (cB) cB[c] = 0; }
+    pc_large_grid_frame(a, fr, blockIdx.x, capCells, use_bboxB, cellsA, cellsB, &s_ncell);
 }
 
 // ---- L3b: dilated B occupancy (after B has been binned, before A is) -------------------------------------
