@@ -69,7 +69,8 @@ struct pc_ctx {
     // limits (0 = automatic)
     int lim_hits = 0, lim_hb = 0, lim_cells = 0, lim_table = 0;
     int force_path = 0;               // 0 = automatic, 1 = small-frame kernel, 2 = large-frame path
-    int tail_mode = 1;                // large-frame path: 2 = walk kernel (A from the frame), 1 = fused tail kernel on compacted A and B,
+    int tail_mode = 3;                // large-frame path: 3 = fused tail kernel, selection A read from the frame (default);
+                                      // 1 = fused tail kernel on the compacted atoms of both selections; 2 = walk kernel;
                                       // 0 = multi-kernel sequence
     int dense_mode = 0;               // multi-kernel sequence: pair kernel 0 = per frame on the device, 1 = thread per atom, 2 = warp per cell
     // batch outputs
@@ -158,7 +159,8 @@ extern "C" int pc_set_path(pc_ctx *c, int path) {
 
 extern "C" int pc_set_tail(pc_ctx *c, int on) {
     if (!c) return fail(PC_ERR_INVALID, "pc_set_tail: ctx is NULL");
-    if (on < 0 || on > 2) return fail(PC_ERR_INVALID, "pc_set_tail: 0 (multi-kernel sequence), 1 (fused tail kernel) or 2 (walk kernel)");
+    if (on < 0 || on > 3)
+        return fail(PC_ERR_INVALID, "pc_set_tail: 0 (multi-kernel sequence), 1 (fused tail kernel), 2 (walk kernel) or 3 (tail kernel, A from the frame)");
     c->tail_mode = on;
     return PC_OK;
 }

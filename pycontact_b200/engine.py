@@ -121,7 +121,7 @@ class ContactEngine:
         self.launches = 0
         self.forced_path = 0
         self.pack_bytes = 24
-        self.tail = 1
+        self.tail = 3
 
     # ------------------------------------------------------------------------------------------
     def close(self):
@@ -200,9 +200,9 @@ class ContactEngine:
         self.pack_bytes = int(bytes_per_row)
 
     def set_tail(self, mode):
-        """Large-frame path: 1 / True = fused tail kernel on the compacted atoms (default), 2 = walk kernel (A read
-        from the frame), 0 / False = multi-kernel sequence."""
-        self.tail = int(mode)
+        """Large-frame path: 3 / True = fused tail kernel that reads selection 1 from the frame (default), 1 = fused
+        tail kernel on the compacted atoms of both selections, 2 = walk kernel, 0 / False = multi-kernel sequence."""
+        self.tail = 3 if mode is True else int(mode)
         for s in self.slots:
             check(self.lib.pc_set_tail(s.ctx, self.tail))
 

@@ -8,6 +8,8 @@ results come back in frame order, like the concatenation at :447-451.
 """
 from __future__ import annotations
 
+import queue
+import threading
 from typing import Callable, List, Optional, Sequence
 
 import numpy as np
@@ -98,10 +100,53 @@ class DCDSource:
         return a, b
 
 
+def prefetched(gen, depth: int = 2):
+    """Run a frame-batch generator in a reader thread, up to ``depth`` batches ahead of its consumer.
+
+    The ingest step in front of the path: reading a batch (file I/O + the gather of the
+    selected atoms, numpy code that releases the GIL) overlaps the previous batches' H2D copies, kernels
+    and the processing of their results, instead of sitting between ``collect`` and the next ``submit``.
+    The reference holds the whole trajectory in RAM before it starts (core/multi_trajectory.py:401-417)."""
+    if depth <= 0:
+        yield from gen
+        return
+    q: "queue.Queue" = queue.Queue(maxsize=depth)
+    end = object()
+    stop = threading.Event()
+
+    def reader():
+        try:
+            for item in gen:
+                while not stop.is_set():
+                    try:
+                        q.put(item, timeout=0.1)
+                        break
+                    except queue.Full:
+                        continue
+                if stop.is_set():
+                    return
+            q.put(end)
+        except BaseException as exc:          # re-raised in the consumer
+            q.put(exc)
+
+    th = threading.Thread(target=reader, daemon=True, name="pycontact-frame-reader")
+    th.start()
+    try:
+        while True:
+            item = q.get()
+            if item is end:
+                return
+            if isinstance(item, BaseException):
+                raise item
+            yield item
+    finally:
+        stop.set()
+
+
 def run_scan(engines: Sequence[ContactEngine], source, *, batch_frames: Optional[int] = None,
              order_keys: bool = True, accumulate: bool = False, keep_contacts: bool = True,
              group_maps=None, frame_numbers: Optional[Sequence[int]] = None,
-             progress: Optional[Callable[[float], None]] = None):
+             progress: Optional[Callable[[float], None]] = None, prefetch: int = 2):
     """Scan every frame of ``source``.  Returns (TrajectoryContacts | None, AccumulationTable | None, stats)."""
     F = source.n_frames
     eng0 = engines[0]
@@ -118,7 +163,7 @@ def run_scan(engines: Sequence[ContactEngine], source, *, batch_frames: Optional
             a, b = source.read(lo, nf)
             yield lo, a, b
 
-    gens = [eng.scan_batches(batches(sl), order_keys=order_keys, accumulate=accumulate,
+    gens = [eng.scan_batches(prefetched(batches(sl), prefetch), order_keys=order_keys, accumulate=accumulate,
                              want_contacts=keep_contacts, want_hbonds=keep_contacts)
             for eng, sl in zip(engines, slices)]
     per_engine: List[list] = [[] for _ in gens]

@@ -90,8 +90,10 @@ def _run(s, coords, self_mode, maps, *, path=2, tail=True, table=0, dense=0, ord
 # tail: fused per-frame kernel or multi-kernel sequence; table: pc_set_limits' table_slots (0 = compact
 # shared-memory table, 16384 = global tile table)
 @pytest.mark.parametrize("name,self_mode,nframes,tail,table", [
-    ("c3_small", False, 5, True, 0),         # fused tail kernel on compacted atoms (tail mode 1) incl. pc_compact_frame
+    ("c3_small", False, 5, True, 0),         # fused tail kernel, A from the frame (tail mode 3, default) incl. pc_compact_frame
+    ("c3_small", False, 5, 1, 0),            # fused tail kernel on the compacted atoms of both selections (tail mode 1)
     ("c3_small", False, 5, 2, 0),            # walk kernel (tail mode 2)
+    ("small", False, 7, 1, 0), ("small_i", False, 4, 1, 0), ("tiny", False, 6, 1, 16384),
     ("c3_small", False, 5, False, 0),        # multi-kernel sequence + pc_accumulate_compact_kernel
     ("c3_small", False, 5, True, 16384),     # fused tail kernel, rows from the global tile table
     ("c3_small", False, 5, False, 16384),
@@ -107,7 +109,7 @@ def test_large_path_accumulation_without_order_keys(name, self_mode, nframes, ta
     traj, tab, ora, cells, c1, c2, final = _run(s, coords, self_mode, s.maps, tail=tail, table=table)
     assert final["path"] == 2
     if not self_mode:
-        assert final["tail"] == int(tail)     # a fused kernel did not silently hand the batch back
+        assert final["tail"] == (3 if tail is True else int(tail))     # a fused kernel did not silently hand the batch back
     _compare_unordered(traj, ora)
     _compare_cells(tab, cells, c1, c2)
 

@@ -16,7 +16,7 @@ from pycontact_b200.core.Biochemistry import AccumulatedContact, AtomContact, Hy
 from pycontact_b200.core.ContactAnalyzer import Analyzer
 from pycontact_b200.engine import BatchResult
 from pycontact_b200.results import AccumulationTable, LazyContactResults, TrajectoryContacts
-from pycontact_b200.scheduler import chunks, default_batch_frames, worker_slices
+from pycontact_b200.scheduler import chunks, default_batch_frames, prefetched, worker_slices
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
@@ -51,6 +51,30 @@ def test_worker_slices_assign_every_frame_exactly_once():
             ref = [c for c in chunks(list(range(F)), world) if len(c)]
             if len(ref) == world:              # where the reference's rule yields one slice per worker, it is kept
                 assert [(c[0], c[-1] + 1) for c in ref] == [x for x in sl if x[1] > x[0]]
+
+
+def test_prefetched_reader_thread_keeps_order_and_errors():
+    """scheduler.prefetched: batches come out in order, a reader's exception reaches the consumer, and a consumer
+    that stops early does not leave the reader blocked."""
+    import threading
+    import time
+
+    def gen(n, fail_at=None):
+        for i in range(n):
+            if i == fail_at:
+                raise ValueError("bad frame %d" % i)
+            time.sleep(0.002)
+            yield i, np.full(4, i)
+    for depth in (0, 1, 3):
+        got = list(prefetched(gen(17), depth))
+        assert [g[0] for g in got] == list(range(17)) and all((g[1] == g[0]).all() for g in got)
+        with pytest.raises(ValueError):
+            list(prefetched(gen(9, fail_at=5), depth))
+    g = prefetched(gen(1000), 2)
+    assert next(g)[0] == 0 and next(g)[0] == 1
+    g.close()
+    time.sleep(0.3)
+    assert not [t for t in threading.enumerate() if t.name == "pycontact-frame-reader" and t.is_alive()]
 
 
 def test_chunks_rule():
