@@ -166,6 +166,7 @@ enum { PC_MODE_BBOX = 0, PC_MODE_BIN = 1 };
 enum { PC_EPI_NONE = 0, PC_EPI_GRID = 1, PC_EPI_OCC = 2 };
 struct PcStreamEpi {
     int what, capCells, use_bboxB;
+    int l2;                           // L2 hint of the coordinate copies: 0 = none, 1 = evict_first, 2 = evict_last
     uint32_t *cellsA, *cellsB;
     uint8_t *occ, *occ2;
 };
@@ -234,7 +235,8 @@ __global__ void __launch_bounds__(PC_STREAM_NT) pc_large_stream_kernel(const PcS
         desc[st] = d;
         unsigned char *slot = smem + (size_t)st * SLOT;
         pc_mbar_expect_tx(bars + st, c.bytes + hbytes);          // release: desc is visible to whoever sees the phase flip
-        pc_bulk_g2s(slot, c.g0, c.bytes, bars + st);
+        if (epi.l2) pc_bulk_g2s_hint(slot, c.g0, c.bytes, bars + st, pc_l2_policy(epi.l2));
+        else pc_bulk_g2s(slot, c.g0, c.bytes, bars + st);
         pc_bulk_g2s(slot + CHUNK + 16, reinterpret_cast<const void *>(hs_al), hbytes, bars + st);
     };
 
@@ -406,7 +408,8 @@ __global__ void __launch_bounds__(PC_STREAM_NT) pc_large_binx_kernel(const PcSca
         d.cnt = c.k1 - c.k0; d.hoff = 0; d.off0 = c.off0; d.abase = r0 + c.k0;
         desc[st] = d;
         pc_mbar_expect_tx(bars + st, c.bytes);                   // release: desc is visible to whoever sees the phase flip
-        pc_bulk_g2s(smem + (size_t)st * SLOT, c.g0, c.bytes, bars + st);
+        if (epi.l2) pc_bulk_g2s_hint(smem + (size_t)st * SLOT, c.g0, c.bytes, bars + st, pc_l2_policy(epi.l2));
+        else pc_bulk_g2s(smem + (size_t)st * SLOT, c.g0, c.bytes, bars + st);
     };
     uint32_t *mycells = cells + (size_t)fb * (capCells + 1);
     float4 *mycand = cand + (size_t)fb * nh_alloc;

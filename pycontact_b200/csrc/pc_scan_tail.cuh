@@ -25,8 +25,14 @@
 #include "pc_accumulate.cuh"
 
 #define PC_TAIL_NT 1024
+#ifndef PC_TAIL_UNROLL
+#define PC_TAIL_UNROLL 4
+#endif
+constexpr int pc_tail_unroll = PC_TAIL_UNROLL;
 #define PC_TAIL_WQ 256                   // hits per warp queue
+#ifndef PC_TAIL_DRAIN_AT
 #define PC_TAIL_DRAIN_AT 96              // a warp drains its queue once this many hits wait (>= 3 full rounds of lanes)
+#endif
 #define PC_TAIL_GATE 4096                // N/O/S pairs per frame queued for the H-bond pass (more are tested in place)
 #define PC_TAIL_SMEM PC_COMPACT_SMEM     // dynamic shared memory: the accumulation table of T4 is the larger tenant
 #define PC_TAIL_POOL (PC_TAIL_SMEM - (PC_TAIL_NT / 32) * PC_TAIL_WQ * 4 - PC_TAIL_GATE * 4)   // cell offsets + sorted B
@@ -552,21 +558,22 @@ __global__ void __launch_bounds__(PC_TAIL_NT, 1) pc_large_tail_inl_kernel(const 
                     return ((occ[c >> 5] >> (c & 31)) & 1u) ? c : -1;
                 };
                 // pass 1 over the frame: kept atoms are compacted (arrival order, CTA-local cursor) and counted per cell;
-                // four atoms per thread and round: the index loads, then the coordinate loads, are issued back to back
+                // eight atoms per thread and round: the index loads, then the coordinate loads, are issued back to back (the
+                // pass is a chain of two dependent loads per atom, DRAM-cold: latency, not bandwidth)
                 float4 *cAw = const_cast<float4 *>(candA) + (size_t)fb * n1h_alloc;
                 uint32_t *ccAw = const_cast<uint32_t *>(ccellA) + (size_t)fb * n1h_alloc;
-                for (int k0 = tid; k0 < n1h; k0 += 4 * NT) {
-                    uint32_t info[4];
-                    float x[4], y[4], z[4];
+                for (int k0 = tid; k0 < n1h; k0 += 8 * NT) {
+                    uint32_t info[8];
+                    float x[8], y[8], z[8];
 #pragma unroll
-                    for (int u = 0; u < 4; u++) info[u] = __ldg(hinfo1 + min(k0 + u * NT, n1h - 1));
+                    for (int u = 0; u < 8; u++) info[u] = __ldg(hinfo1 + min(k0 + u * NT, n1h - 1));
 #pragma unroll
-                    for (int u = 0; u < 4; u++) {
+                    for (int u = 0; u < 8; u++) {
                         const float *p = fr1 + 3ll * PC_W_INDEX(info[u]);
                         x[u] = __ldg(p); y[u] = __ldg(p + 1); z[u] = __ldg(p + 2);
                     }
 #pragma unroll
-                    for (int u = 0; u < 4; u++) {
+                    for (int u = 0; u < 8; u++) {
                         const int c = k0 + u * NT < n1h ? cell_a(x[u], y[u], z[u]) : -1;
                         if (c < 0) continue;
                         const unsigned pos = atomicAdd(&s_next, 1u);          // (the search's item counter, not in use yet)
@@ -613,7 +620,7 @@ __global__ void __launch_bounds__(PC_TAIL_NT, 1) pc_large_tail_inl_kernel(const 
                         for (int kb = 0; kb < e2; kb += 32) {
                             const int cnt = min(32, e2 - kb);
                             unsigned m = 0;
-#pragma unroll 2
+#pragma unroll pc_tail_unroll
                             for (int k = 0; k < cnt; k++) {
                                 const int kk = kb + k;
                                 const int j = kk + (kk < e0 ? d0 : (kk < e1 ? d1 : d2));
@@ -1100,6 +1107,10 @@ static inline int pc_large_scan(PcLargeWork &W, const PcScanArgs &a, int num_sms
         PcStreamEpi grid_epi = none_epi, occ_epi = none_epi;
         grid_epi.what = PC_EPI_GRID; grid_epi.capCells = capCells; grid_epi.use_bboxB = 0; grid_epi.cellsA = W.cellA; grid_epi.cellsB = W.cellB;
         occ_epi.what = PC_EPI_OCC; occ_epi.capCells = capCells; occ_epi.cellsB = W.cellB; occ_epi.occ = W.occ; occ_epi.occ2 = W.occ2;
+        // L2 hints (tail mode 3 reads selection A again in the per-frame kernel): keep A's frames, do not keep B's stream
+        static const int l2hint = getenv("PC_L2HINT") ? atoi(getenv("PC_L2HINT")) : 1;           // experiments: 0 = off
+        PcStreamEpi b_epi = tail == 1 ? occ_epi : none_epi;
+        if (l2hint && tail == 3 && !self) { grid_epi.l2 = 2; none_epi.l2 = 0; b_epi.l2 = 1; }
         const bool epi = fused && !use_bboxB;
         pc_large_stream_kernel<PC_MODE_BBOX><<<dim3(ctasA, nfb), PC_STREAM_NT, PC_STREAM_SMEM, s>>>(
             a, W.frames, f0, 0, 0, perA, nullptr, 0, nullptr, nullptr, 0, nullptr, epi ? grid_epi : none_epi);
@@ -1118,10 +1129,10 @@ static inline int pc_large_scan(PcLargeWork &W, const PcScanArgs &a, int num_sms
             const bool binx = binx_env > 0;                  // measured on c3: no faster than the list walk (5.3 TB/s both), off
             if (binx)
                 pc_large_binx_kernel<<<dim3(ctasB, nfb), PC_STREAM_NT, PC_BINX_SMEM, s>>>(
-                    a, W.frames, f0, 1, perB, W.cellB, capCells, W.candB, W.ccellB, a2, tail == 1 ? occ_epi : none_epi);
+                    a, W.frames, f0, 1, perB, W.cellB, capCells, W.candB, W.ccellB, a2, b_epi);
             else
                 pc_large_stream_kernel<PC_MODE_BIN><<<dim3(ctasB, nfb), PC_STREAM_NT, PC_STREAM_SMEM, s>>>(
-                    a, W.frames, f0, 1, 0, perB, W.cellB, capCells, W.candB, W.ccellB, a2, nullptr, tail == 1 ? occ_epi : none_epi);
+                    a, W.frames, f0, 1, 0, perB, W.cellB, capCells, W.candB, W.ccellB, a2, nullptr, b_epi);
             if (probe1 && f0 == 0) cudaEventRecord(probe1, s);
             if (tail == 3) {
                 PcAccArgs none;

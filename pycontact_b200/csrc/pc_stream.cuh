@@ -54,6 +54,22 @@ __device__ __forceinline__ void pc_bulk_g2s(void *smem_dst, const void *gmem_src
                  : "memory");
 }
 
+// L2 eviction-priority hints for the bulk copies (createpolicy + .L2::cache_hint).  The 1 M-atom configuration streams
+// 11.4 MB of selection B per frame exactly once (evict_first: do not keep it), while selection A's 0.6 MB per frame is
+// read twice -- bounding boxes, then the per-frame kernel -- with B's stream in between (evict_last: keep it).
+__device__ __forceinline__ uint64_t pc_l2_policy(int kind) {          // 1 = evict_first, 2 = evict_last
+    uint64_t p;
+    if (kind == 2) asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+    else asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+__device__ __forceinline__ void pc_bulk_g2s_hint(void *smem_dst, const void *gmem_src, uint32_t bytes, uint64_t *bar, uint64_t policy) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(
+                     pc_smem_u32(smem_dst)),
+                 "l"(gmem_src), "r"(bytes), "r"(pc_smem_u32(bar)), "l"(policy)
+                 : "memory");
+}
+
 // One contiguous run of atoms (packed xyz) split into chunks.
 struct PcSegment {
     const unsigned char *sb;   // first byte of atom 0 of the segment
