@@ -445,12 +445,20 @@ def run_gpu(args):
     if os.environ.get("PC_TAIL"):                          # experiments: 0 = multi-kernel sequence, 1 = tail kernel v1, 2 = walk
         eng.set_tail(int(os.environ["PC_TAIL"]))
     n_keys = gm1.n_groups * gm2.n_groups
-    dense = n_keys <= (1 << 20) and not args.sparse_fold   # aggregated maps as a dense [n_keys][4] table (32 MB at most)
-    sparse = not dense                                     # ... or as a hash table keyed by the 64-bit key
+    # time-aggregated maps: a dense [n_keys][4] table (32 MB at most), else a hash table keyed by the 64-bit key; key spaces
+    # beyond 2^32 (3 M-atom residue-pair maps: 1.1 M cells per FRAME, as many rows as a hash table has room for) send the
+    # packed per-frame rows to the host instead
+    rows_to_host = args.rows_to_host or n_keys >= (1 << 32)
+    dense = n_keys <= (1 << 20) and not args.sparse_fold and not rows_to_host
+    sparse = not dense and not rows_to_host
     large_guess = max(s1.n, n2) > 200000
-    batch = args.batch or (148 if large_guess else int(max(1, min(F, 2048, (2 << 30) // in_bytes_frame))))
+    # large frames: 148 = one frame per SM for the per-frame tail kernel; 3 M-atom self contacts: the batch's accumulation
+    # table lives in global memory (1.1 M (frame, key) cells per frame), 16 frames per batch keep it at ~4 GB
+    batch = args.batch or ((16 if self_mode else 148) if large_guess else int(max(1, min(F, 2048, (2 << 30) // in_bytes_frame))))
     batch = min(batch, F)
     nb = (F + batch - 1) // batch
+    if not args.batch:
+        batch = (F + nb - 1) // nb                         # equal batches: no short last batch (1250 frames = 9 x 139, not 8 x 148 + 66)
     sparse_entries = [args.sparse_entries]
     totals = DeviceBuffer(max(1, n_keys if dense else 1) * 32, local)
     totals_t = None
@@ -508,17 +516,24 @@ def run_gpu(args):
         if sparse:
             eng.fold_sparse_init(sparse_entries[0])
         pending = []
+
+        def finish(sid):
+            nonlocal d_rows
+            tot[:] += eng.collect_device(sid)
+            if rows_to_host:
+                rows, _, _ = eng.fetch_rows(sid, packed=True)      # the per-frame maps of this rank's frames -> host
+                d_rows += rows.nbytes
         for b, f0 in enumerate(range(f_lo, f_hi, batch)):
             nf = min(batch, f_hi - f0)
             sid = b % len(eng.slots)
             if len(pending) == len(eng.slots):
-                tot[:] += eng.collect_device(pending.pop(0))
+                finish(pending.pop(0))
             eng.submit_device(sid, b1.at(f0 * n1 * 12), None if self_mode else b2.at(f0 * n2 * 12), nf,
-                              accumulate=True, events=ev[b] if events else None, pack_rows=False,
-                              fold=(totals_ptr(), n_keys) if dense else "sparse")
+                              accumulate=True, events=ev[b] if events else None, pack_rows=rows_to_host,
+                              fold=(totals_ptr(), n_keys) if dense else ("sparse" if sparse else None))
             pending.append(sid)
         while pending:
-            tot[:] += eng.collect_device(pending.pop(0))
+            finish(pending.pop(0))
         if dense:
             for sl in eng.slots:
                 check(lib.pc_stream_sync(sl.stream))
@@ -530,6 +545,8 @@ def run_gpu(args):
                 check(lib.pc_memcpy(local, host.ctypes.data, totals_ptr(), host.nbytes, 2, stream))
                 d_rows += host.nbytes
             check(lib.pc_stream_sync(stream))
+            device_step.last_entries = None
+        elif rows_to_host:
             device_step.last_entries = None
         else:
             if dist is not None:
@@ -556,8 +573,21 @@ def run_gpu(args):
         check(lib.pc_device_sync(local))
 
     n_warm = max(args.warmup, 3 if not args.quick else 1)
-    for _ in range(n_warm):
+    for k in range(n_warm):
         device_step()
+        if k == 0 and sparse and not args.sparse_entries_fixed:
+            # size the aggregated table from what the first pass found (x8, at least 64 k entries): clearing, compacting and
+            # exchanging a 2 M-entry table every step costs ~0.2 ms, which matters once 8 ranks share the trajectory
+            n_ent = int(eng.fold_sparse_fetch().size)
+            if dist is not None:
+                c = torch.tensor([n_ent], device="cuda")
+                dist.all_reduce(c, op=dist.ReduceOp.MAX)
+                n_ent = int(c.item()) * world              # rank 0 ends up with the union of all ranks' keys
+            want = 1 << 16
+            while want < 8 * n_ent:
+                want <<= 1
+            sparse_entries[0] = want
+            xchg["cap"] = 0
     launches0 = lib.pc_launch_count()
     sampler = ClockSampler(local)
     sampler.start()
@@ -749,7 +779,7 @@ def run_gpu(args):
     step_gbs = alg_bytes_step / step_s / 1e9
     k_s = kernel_ms / 1e3 / k_launches
     per_rank = dict(zip(("contacts", "hbonds", "rows", "evals"), (tot / args.steps).tolist()))
-    if large:
+    if large and max(n1, n2) >= 200000:
         n_dom = n1 if self_mode else n2
         k_bytes = 12.0 * n_dom * batch
         k_s_dom = probe_ms / 1e3 / k_launches
@@ -757,7 +787,8 @@ def run_gpu(args):
     else:
         k_bytes = batch * (in_bytes_frame + (16 * per_rank["contacts"] + 20 * per_rank["hbonds"]) / max(F, 1))
         k_s_dom = k_s
-        k_name = "pc_scan_small_kernel (whole per-frame analysis in one kernel)"
+        k_name = ("pc_scan_small_kernel (whole per-frame analysis in one kernel)" if not large else
+                  "large-frame launch sequence of one batch (no single kernel dominates at this size)")
     traffic = traffic_step = None
     try:
         with open(os.path.join(ROOT, "profiles", "traffic.json")) as fh:
@@ -769,8 +800,9 @@ def run_gpu(args):
     except Exception:
         pass
     e_alg_frame = float(np.mean(e_alg)) if len(e_alg) else None
-    roofline = {"bound": "hbm", "achieved": step_gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s",
-                "frac": step_gbs / peaks["hbm_gbs"], "traffic": traffic_step, "peak_source": peak_kind,
+    roofline = {"bound": "hbm", "achieved": step_gbs, "peak": peaks["hbm_gbs"] * world, "unit": "GB/s",
+                "frac": step_gbs / (peaks["hbm_gbs"] * world), "traffic": traffic_step,
+                "peak_source": peak_kind + (" x %d GPUs" % world if world > 1 else ""),
                 "what": "whole step: algorithmic bytes of all frames (12 B per selected atom + 16 B per contact + 20 B per H-bond "
                         "+ 16 B per (frame, key) cell) / ms_per_step",
                 "algorithmic_bytes_per_step": alg_bytes_step,
@@ -836,10 +868,11 @@ def run_gpu(args):
                        "kernel_path": "large-frame (streaming bin of the larger selection + fused per-frame kernel, tail mode %d)" % eng.tail if large and eng.tail else
                                       "large-frame (multi-kernel sequence)" if large else "small-frame (one CTA per frame)",
                        "l2": "inputs (%.1f GB per GPU and step, read once) exceed the 126 MB L2" % (F * in_bytes_frame / 1e9),
-                       "results": "per-frame records (contacts, H-bonds, (frame, key) cells) stay in HBM; time-aggregated maps ("
-                                  + ("dense table, one all-reduce over ranks" if dense else
-                                     "sparse table keyed by the 64-bit key, %s entries; ranks' tables meet in one all-gather" % entries_step)
-                                  + ") copied to the host every step",
+                       "results": ("contacts and H-bonds stay in HBM; packed per-frame (frame, key) cells -> host (24 B each)" if rows_to_host else
+                                   "per-frame records (contacts, H-bonds, (frame, key) cells) stay in HBM; time-aggregated maps ("
+                                   + ("dense table, one all-reduce over ranks" if dense else
+                                      "sparse table keyed by the 64-bit key, %s entries; ranks' tables meet in one all-gather" % entries_step)
+                                   + ") copied to the host every step"),
                        "parallelism": "one trajectory cut into %d contiguous frame slices (reference chunks rule), one exchange of the aggregated maps" % world
                                       if args.scaling == "strong" else "every rank its own %d frames" % F},
             "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu,
@@ -876,7 +909,9 @@ def main():
     ap.add_argument("--e2e-frames", type=int, default=0)
     ap.add_argument("--slots", type=int, default=3, help="frame batches in flight per GPU")
     ap.add_argument("--sparse-entries", type=int, default=1 << 21)
+    ap.add_argument("--sparse-entries-fixed", action="store_true", help="keep --sparse-entries instead of sizing the table from the first pass")
     ap.add_argument("--sparse-fold", action="store_true", help="aggregated maps in the sparse table even for small key spaces")
+    ap.add_argument("--rows-to-host", action="store_true", help="copy the packed per-frame rows to the host instead of aggregating on the device")
     ap.add_argument("--no-cpu", action="store_true", help="skip the CPU baseline leg")
     ap.add_argument("--no-port", action="store_true", help="--impl reference: skip the port's figure")
     ap.add_argument("--quick", action="store_true", help="profiling runs: 1 warm-up step")
