@@ -442,6 +442,8 @@ def run_gpu(args):
 
     eng = ContactEngine(s1, s2, CUTOFF, HB_CUTOFF, HB_ANGLE, device=local, slots=args.slots)
     eng.set_maps(gm1.gid, gm2.gid, gm2.n_groups)
+    if os.environ.get("PC_GROUP"):                         # experiments: 0 = multi-kernel sequence + global table instead of the group kernel
+        eng.set_group_mode(int(os.environ["PC_GROUP"]))
     if os.environ.get("PC_TAIL"):                          # experiments: 0 = multi-kernel sequence, 1 = tail kernel v1, 2 = walk
         eng.set_tail(int(os.environ["PC_TAIL"]))
     n_keys = gm1.n_groups * gm2.n_groups

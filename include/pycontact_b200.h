@@ -141,6 +141,16 @@ int pc_set_tail(pc_ctx *ctx, int mode);
  * by B atoms per cell, 1 = thread per (A atom, layer), 2 = warp per (A cell, layer) with the B runs in lanes. */
 int pc_set_dense_mode(pc_ctx *ctx, int mode);
 
+/* Large-frame path, frames the fused tail kernel does not take (self contacts, frames handed over with status bit
+ * 128): on = 1 (default) searches, records and accumulates in ONE kernel whose CTAs own whole accumulation groups of
+ * selection 1 (runs of consecutive atoms with one group id, e.g. residues) and emit their (frame, key) rows from a
+ * shared-memory table -- used when maps are set, no order keys are asked for and every group is one run of at most 256
+ * heavy atoms; on = 0 keeps the multi-kernel sequence + global table (analyze_contactResultsWithMaps,
+ * core/ContactAnalyzer.py:527-559, either way). */
+int pc_set_group_mode(pc_ctx *ctx, int on);
+/* 1 when the context's last scan ran the group kernel (tests). */
+int pc_last_group(const pc_ctx *ctx);
+
 /* Output capacities for one batch (totals over the batch, not per frame). */
 int pc_reserve(pc_ctx *ctx, int32_t max_frames, int64_t cap_contacts, int64_t cap_hbonds, int64_t cap_rows);
 

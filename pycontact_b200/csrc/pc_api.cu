@@ -13,6 +13,7 @@
 #include "pc_scan_small.cuh"
 #include "pc_scan_large.cuh"
 #include "pc_accumulate.cuh"
+#include "pc_scan_group.cuh"
 #include "pc_scan_tail.cuh"
 #include "pc_order.cuh"
 #include "pc_search.cuh"
@@ -111,6 +112,13 @@ struct pc_ctx {
     bool want_fused_acc = true;       // accumulate inside the small-frame scan kernel when possible
     bool last_fused = false;
     std::vector<uint32_t> h_meta;     // host copy of the scan's 4 frame arrays (large path: sliced outputs)
+    // group kernel of the large-frame path (pc_scan_group.cuh): units of whole accumulation groups of selection 1
+    std::vector<uint32_t> h_hinfo1;   // host copy of selection 1's heavy-atom list
+    DevBuf<uint32_t> group_units;     // n_units + 1 heavy ordinals
+    int n_units = 0;                  // 0: the maps' groups are not runs of the selection's order (or larger than a unit)
+    int group_mode = 1;               // 1 = use the group kernel when it applies (pc_set_group_mode)
+    DevBuf<pc_row> row_slices;        // nframes x (cap_rows / nframes), gathered into `rows`
+    bool last_group = false;
 };
 
 extern "C" const char *pc_last_error(void) { return g_err.c_str(); }
@@ -171,6 +179,14 @@ extern "C" int pc_set_dense_mode(pc_ctx *c, int mode) {
     return PC_OK;
 }
 
+extern "C" int pc_set_group_mode(pc_ctx *c, int on) {
+    if (!c) return fail(PC_ERR_INVALID, "pc_set_group_mode: ctx is NULL");
+    c->group_mode = on ? 1 : 0;
+    return PC_OK;
+}
+
+extern "C" int pc_last_group(const pc_ctx *c) { return c && c->last_group ? 1 : 0; }
+
 extern "C" int pc_set_probe(pc_ctx *c, void *start_event, void *end_event) {
     if (!c) return fail(PC_ERR_INVALID, "pc_set_probe: ctx is NULL");
     c->probe[0] = start_event; c->probe[1] = end_event;
@@ -199,7 +215,8 @@ struct SideBufs {
 };
 
 static cudaError_t upload_side(int n, const uint8_t *flags, const int32_t *resid, const int32_t *segid,
-                               const int32_t *hptr, const int32_t *hidx, SideBufs b, int &nheavy) {
+                               const int32_t *hptr, const int32_t *hidx, SideBufs b, int &nheavy,
+                               std::vector<uint32_t> *hinfo_out = nullptr) {
     std::vector<uint32_t> hinfo, linfo((size_t)n), hmask(((size_t)n + 31) / 32 + 4, 0u);
     std::vector<int> res((size_t)n, 0), seg((size_t)n, 0), ptr((size_t)n + 1, 0), idx;
     for (int i = 0; i < n; i++) {
@@ -228,7 +245,9 @@ static cudaError_t upload_side(int n, const uint8_t *flags, const int32_t *resid
     if ((e = b.lhidx->upload(idx)) != cudaSuccess) return e;
     const std::vector<uint8_t> fl(flags, flags + n);
     if ((e = b.lflag->upload(fl)) != cudaSuccess) return e;
-    return cudaDeviceSynchronize();      // every host vector above outlives this synchronisation
+    e = cudaDeviceSynchronize();         // every host vector above outlives this synchronisation
+    if (hinfo_out) hinfo_out->swap(hinfo);
+    return e;
 }
 
 extern "C" int pc_set_topology(pc_ctx *c, int32_t n1, int32_t n2, const uint8_t *f1, const uint8_t *f2,
@@ -243,7 +262,7 @@ extern "C" int pc_set_topology(pc_ctx *c, int32_t n1, int32_t n2, const uint8_t 
     c->n1 = n1;
     CUDA_TRY(upload_side(n1, f1, resid1, segid1, hptr1, hidx1,
                          SideBufs{&c->hinfo1, &c->hmask1, &c->hpre1, &c->linfo1, &c->lres1, &c->lseg1, &c->lhptr1, &c->lhidx1, &c->lflag1},
-                         c->n1h));
+                         c->n1h, &c->h_hinfo1));
     if (c->self_mode) {
         c->n2 = n1; c->n2h = c->n1h;
     } else {
@@ -274,6 +293,40 @@ extern "C" int pc_set_maps(pc_ctx *c, const int32_t *gid1, const int32_t *gid2, 
     int g1max = 0;
     for (int i = 0; i < c->n1; i++) g1max = std::max(g1max, gid1[i]);
     c->ngroups1 = (unsigned long long)g1max + 1;
+    // Units of the group kernel: selection 1's heavy atoms in index order, cut into runs of whole groups of at most
+    // PC_GROUP_NT atoms.  Only when every group is ONE run of consecutive heavy atoms (residue-level maps on any usual
+    // topology) does a unit see all contacts of its keys.
+    c->n_units = 0;
+    {
+        std::vector<uint32_t> units;
+        std::vector<uint8_t> seen((size_t)g1max + 1, 0);
+        bool ok = !c->h_hinfo1.empty() && (int)c->h_hinfo1.size() == c->n1h;
+        uint32_t unit_first = 0, run_first = 0;
+        units.push_back(0u);
+        for (uint32_t h = 0; ok && h <= (uint32_t)c->n1h; h++) {
+            const bool end = h == (uint32_t)c->n1h;
+            const int g = end ? -1 : gid1[PC_W_INDEX(c->h_hinfo1[h])];
+            if (!end && g < 0) { ok = false; break; }
+            const int gprev = h ? gid1[PC_W_INDEX(c->h_hinfo1[h - 1])] : -2;
+            if (h && g == gprev) continue;
+            // a run [run_first, h) of group gprev ends here
+            if (h) {
+                if (h - run_first > (uint32_t)PC_GROUP_NT) { ok = false; break; }
+                if (h - unit_first > (uint32_t)PC_GROUP_NT) { units.push_back(run_first); unit_first = run_first; }
+            }
+            if (!end) {
+                if (seen[g]) { ok = false; break; }
+                seen[g] = 1;
+                run_first = h;
+            }
+        }
+        if (ok) {
+            units.push_back((uint32_t)c->n1h);
+            CUDA_TRY(c->group_units.upload(units));
+            CUDA_TRY(cudaDeviceSynchronize());
+            c->n_units = (int)units.size() - 1;
+        }
+    }
     c->have_maps = true;
     return PC_OK;
 }
@@ -417,6 +470,7 @@ extern "C" int pc_scan_device(pc_ctx *c, const float *d_xyz1, const float *d_xyz
     const bool have_fast = small_ok && c->small_ctas != 1 && plan_small_cfg(c, fuse_acc, fast_ctas, cells2, hits2, hb2, L2);
     const bool fits_small = have_full || have_fast;
     c->last_fused = false;
+    c->last_group = false;
     c->packed_valid = false;
     if (c->force_path == 1 && !fits_small)
         return fail(PC_ERR_INVALID, "pc_scan_device: the frame does not fit the small-frame kernel");
@@ -456,13 +510,34 @@ extern "C" int pc_scan_device(pc_ctx *c, const float *d_xyz1, const float *d_xyz
         // the fused tail kernel also accumulates when the maps are known, no order keys are asked for and the
         // frame's keys are expected to fit its shared-memory table (pc_set_limits' table_slots <= 8192)
         const int tail = c->self_mode ? 0 : c->tail_mode;
-        const bool tail_acc = tail && c->want_fused_acc && c->have_maps && !order_keys && c->lim_table <= PC_COMPACT_SLOTS;
+        const bool can_acc = c->want_fused_acc && c->have_maps && !order_keys && c->lim_table <= PC_COMPACT_SLOTS;
+        const bool tail_acc = tail && can_acc;
+        // frames the tail kernel does not take (self contacts, or handed over after PC_ST_TAIL_OVERFLOW): the group kernel
+        // searches, records and accumulates unit by unit of whole groups (pc_scan_group.cuh) when the maps allow it
+        const bool group = !tail && can_acc && c->group_mode && c->n_units > 0 && c->n2h < (1 << 24) &&
+                           c->cap_rows / nframes >= 1;
         PcAccArgs acc = acc_args(c, false, nframes);
+        PcGroupArgs ga;
+        memset(&ga, 0, sizeof ga);
+        if (group) {
+            CUDA_TRY(c->row_slices.ensure((size_t)c->cap_rows));
+            ga.unit_start = c->group_units.p; ga.nunits = c->n_units;
+            ga.slices = c->row_slices.p; ga.cap_r_frame = c->cap_rows / nframes;
+            CUDA_TRY(cudaMemsetAsync(acc.frame_rcount, 0, (size_t)nframes * sizeof(uint32_t), s));
+        }
         int rc = pc_large_scan(c->large, a, c->num_sms, s, g_err, &g_launches, (cudaEvent_t)c->probe[0], (cudaEvent_t)c->probe[1],
-                               tail, tail_acc ? &acc : nullptr);
+                               tail, (tail_acc || group) ? &acc : nullptr, group ? &ga : nullptr);
         if (rc != PC_OK) return rc;
+        if (group) {
+            pc_group_offsets_kernel<<<1, 1024, 0, s>>>(acc, ga.cap_r_frame);
+            const int gb = std::max(1, std::min(64, 4 * c->num_sms / nframes + 1));
+            pc_group_gather_kernel<<<dim3(gb, nframes), 256, 0, s>>>(acc, ga.slices, ga.cap_r_frame);
+            CUDA_TRY(cudaGetLastError());
+            g_launches += 2;
+        }
         c->last_path = 2;
-        c->last_fused = tail_acc;
+        c->last_fused = tail_acc || group;
+        c->last_group = group;
     }
     if (order_keys) {
         if (c->n1 >= (1 << 27)) return fail(PC_ERR_INVALID, "pc_scan_device: order keys need n1 < 2^27");

@@ -1038,7 +1038,7 @@ static inline void pc_stream_geom(int n, int nfb, int num_sms, int waves, int &c
 // frame); two selections only.  acc != nullptr with a tail kernel: rows are produced too.
 static inline int pc_large_scan(PcLargeWork &W, const PcScanArgs &a, int num_sms, cudaStream_t s, std::string &err,
                                 unsigned long long *launches, cudaEvent_t probe0, cudaEvent_t probe1, int tail,
-                                const PcAccArgs *acc) {
+                                const PcAccArgs *acc, const PcGroupArgs *group = nullptr) {
     const int n1 = a.t.n1, n2 = a.self_mode ? a.t.n1 : a.t.n2;
     const int n1h = a.t.n1h, n2h = a.self_mode ? a.t.n1h : a.t.n2h;
     const bool self = a.self_mode != 0;
@@ -1079,6 +1079,7 @@ static inline int pc_large_scan(PcLargeWork &W, const PcScanArgs &a, int num_sms
         PCL_TRY(cudaFuncSetAttribute(pc_large_tail_kernel<768>, cudaFuncAttributeMaxDynamicSharedMemorySize, PC_TAIL_SMEM));
         PCL_TRY(cudaFuncSetAttribute(pc_large_tail_kernel<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, PC_TAIL_SMEM));
         PCL_TRY(cudaFuncSetAttribute(pc_large_walk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, PC_TAIL_SMEM));
+        PCL_TRY(cudaFuncSetAttribute(pc_large_group_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, PC_GROUP_SMEM));
         W.clean = false;
     }
     FB = W.FB;
@@ -1153,15 +1154,16 @@ static inline int pc_large_scan(PcLargeWork &W, const PcScanArgs &a, int num_sms
                 *launches += 3 + (use_bboxB ? 1 : 0);
                 continue;
             }
-            if (tail != 1) {
+            if (tail != 1 && !group) {
                 pc_large_occ_kernel<<<dim3(std::max(1, std::min((capCells + 255) / 256, 4 * num_sms / nfb + 1)), nfb), 256, 0, s>>>(
                     W.frames, W.cellB, capCells, W.occ);
                 *launches += 1;
             }
         }
         if (self && probe0 && f0 == 0) cudaEventRecord(probe0, s);
-        pc_large_stream_kernel<PC_MODE_BIN><<<dim3(ctasA, nfb), PC_STREAM_NT, PC_STREAM_SMEM, s>>>(
-            a, W.frames, f0, 0, 0, perA, W.cellA, capCells, W.candA, W.ccellA, a1, self ? nullptr : W.occ, none_epi);
+        if (self || !group)         // (the group kernel reads selection A from the frame: no bin pass for it)
+            pc_large_stream_kernel<PC_MODE_BIN><<<dim3(ctasA, nfb), PC_STREAM_NT, PC_STREAM_SMEM, s>>>(
+                a, W.frames, f0, 0, 0, perA, W.cellA, capCells, W.candA, W.ccellA, a1, self ? nullptr : W.occ, none_epi);
         if (self && probe1 && f0 == 0) cudaEventRecord(probe1, s);
         if (tail) {
             PcAccArgs none;
@@ -1191,6 +1193,15 @@ static inline int pc_large_scan(PcLargeWork &W, const PcScanArgs &a, int num_sms
         pc_large_scatter_kernel<<<dim3(blocksA, nfb), 256, 0, s>>>(W.frames, 0, W.cellA, capCells, W.candA, W.ccellA, W.sortA, a1);
         if (!self)
             pc_large_scatter_kernel<<<dim3(blocksB, nfb), 256, 0, s>>>(W.frames, 1, W.cellB, capCells, W.candB, W.ccellB, W.sortB, a2);
+        if (group) {
+            // search + records + H-bonds + rows of the units' keys in one kernel (pc_scan_group.cuh)
+            pc_large_group_kernel<<<dim3(group->nunits, nfb), PC_GROUP_NT, PC_GROUP_SMEM, s>>>(
+                a, W.frames, f0, self ? W.cellA : W.cellB, capCells, self ? W.sortA : W.sortB, self ? a1 : a2, o, *acc, *group);
+            pc_large_finish_kernel<<<(nfb + 63) / 64, 64, 0, s>>>(a, W.frames, f0, nfb, o);
+            PCL_TRY(cudaGetLastError());
+            *launches += 5 + (use_bboxB ? 1 : 0) + (self ? 0 : 2);
+            continue;
+        }
         // the number of in-grid A atoms is only known on the device: launch for the worst case, surplus CTAs exit
         const int pblocks = (int)std::max<long long>(1, std::min<long long>((3ll * n1h + 255) / 256, std::max(64, 2 * per_frame_blocks)));
         pc_large_pair_kernel<<<dim3(pblocks, nfb), 256, 0, s>>>(a, W.frames, f0, W.cellA, W.cellB, capCells, W.sortA, W.sortB,

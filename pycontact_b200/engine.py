@@ -211,6 +211,16 @@ class ContactEngine:
         for s in self.slots:
             check(self.lib.pc_set_dense_mode(s.ctx, int(mode)))
 
+    def set_group_mode(self, on):
+        """Large-frame path without the tail kernel: True (default) = group kernel (search + records + accumulation per
+        unit of whole groups) when the maps allow it, False = multi-kernel sequence + global table."""
+        for s in self.slots:
+            check(self.lib.pc_set_group_mode(s.ctx, int(bool(on))))
+
+    def last_group(self, slot_id=0) -> bool:
+        """True when the slot's last scan ran the group kernel."""
+        return bool(self.lib.pc_last_group(self.slots[slot_id].ctx))
+
     def set_path(self, path: int):
         """0 = automatic, 1 = small-frame kernel, 2 = large-frame path (tests cover both)."""
         self.forced_path = int(path)

@@ -58,7 +58,7 @@ def _compare_cells(table, oracle_cells, code1, code2):
 
 
 def _run(s, coords, self_mode, maps, *, path=2, tail=True, table=0, dense=0, order_keys=False, batch=3,
-         cutoff=5.0, search=None):
+         cutoff=5.0, search=None, group=False):
     """Scan + accumulate `coords` (all atoms of the system) on the device and through the oracle."""
     t = s.topology
     nf = coords.shape[0]
@@ -74,13 +74,14 @@ def _run(s, coords, self_mode, maps, *, path=2, tail=True, table=0, dense=0, ord
         eng.set_path(path)
         eng.set_tail(tail)
         eng.set_dense_mode(dense)
+        eng.set_group_mode(group)
         if table:
             eng.set_limits(table=table)
         eng.set_maps(gm1.gid, gm2.gid, gm2.n_groups)
         src = ArraySource(np.ascontiguousarray(coords[:, idx1]), None if self_mode else np.ascontiguousarray(coords[:, idx2]))
         traj, tab, stats = run_scan([eng], src, batch_frames=batch, order_keys=order_keys, accumulate=True,
                                     group_maps=(gm1, gm2))
-        final = dict(tail=eng.tail, lim=list(eng.lim), path=stats["path"])
+        final = dict(tail=eng.tail, lim=list(eng.lim), path=stats["path"], group=any(eng.last_group(k) for k in range(len(eng.slots))))
     c1 = frame_oracle.atom_key_codes(maps[0], t.n_atoms, t.names, t.resids, t.resnames, t.segids)
     c2 = frame_oracle.atom_key_codes(maps[1], t.n_atoms, t.names, t.resids, t.resnames, t.segids)
     cells = frame_oracle.accumulate_arrays(ora, c1, c2, s.backbone, t.n_atoms)
@@ -110,6 +111,45 @@ def test_large_path_accumulation_without_order_keys(name, self_mode, nframes, ta
     assert final["path"] == 2
     if not self_mode:
         assert final["tail"] == (3 if tail is True else int(tail))     # a fused kernel did not silently hand the batch back
+    _compare_unordered(traj, ora)
+    _compare_cells(tab, cells, c1, c2)
+
+
+# The group kernel (pc_scan_group.cuh): frames the tail kernel does not take -- self contacts, or tail mode 0 -- searched,
+# recorded and accumulated unit by unit of whole groups.  c4_small is the scaled capsid of the c4 bench line.
+@pytest.mark.parametrize("name,self_mode,nframes,batch", [
+    ("c4_small", True, 3, 2), ("tiny", True, 6, 3), ("small", True, 4, 3),
+    ("c3_small", False, 5, 3), ("small", False, 7, 3), ("small_i", False, 4, 4), ("tiny", False, 6, 1),
+])
+def test_group_kernel_matches_oracle(name, self_mode, nframes, batch):
+    s = synth.make_system(name)
+    coords = synth.frames_host(s, list(range(nframes)))
+    traj, tab, ora, cells, c1, c2, final = _run(s, coords, self_mode, s.maps, tail=False, group=True, batch=batch)
+    assert final["path"] == 2 and final["group"], "the group kernel did not run"
+    _compare_unordered(traj, ora)
+    _compare_cells(tab, cells, c1, c2)
+
+
+def test_group_kernel_is_skipped_when_groups_are_not_runs():
+    """Atom-name maps: a group's atoms are scattered over the selection, so no unit sees all contacts of a key --
+    the scan falls back to the multi-kernel sequence + table; results unchanged."""
+    s = synth.make_system("small")
+    coords = synth.frames_host(s, [0, 1, 2])
+    maps = ([0, 1, 0, 0, 0], [0, 1, 0, 0, 0])
+    traj, tab, ora, cells, c1, c2, final = _run(s, coords, False, maps, tail=False, group=True)
+    assert not final["group"]
+    _compare_unordered(traj, ora)
+    _compare_cells(tab, cells, c1, c2)
+
+
+def test_group_kernel_table_overflow_falls_back():
+    """Per-atom keys on selection 2: more than 1024 keys per unit -> PC_ST_TABLE_OVERFLOW -> the engine re-runs the
+    batch on the global table."""
+    s = synth.make_system("c4_small")
+    coords = synth.frames_host(s, [0])
+    maps = ([0, 0, 1, 1, 1], [1, 0, 0, 0, 0])
+    traj, tab, ora, cells, c1, c2, final = _run(s, coords, True, maps, tail=False, group=True, batch=1)
+    assert final["lim"][3] == 16384 and not final["group"]
     _compare_unordered(traj, ora)
     _compare_cells(tab, cells, c1, c2)
 
