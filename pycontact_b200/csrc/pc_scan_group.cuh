@@ -10,12 +10,14 @@
 // a CTA that searches a run of consecutive A atoms made of WHOLE groups sees every contact of its keys, and a
 // small table in shared memory is all the accumulation needs:
 //   G1  a thread per heavy A atom of the unit (read straight from the frame through the heavy-atom list, like the
-//       tail kernel's AFRAME mode); the unit's atoms and packed group words stay in shared memory
-//   G2  pair search of gridsearch.C:1111-1142 against the cell-sorted B atoms in global memory (L1 / L2: the atoms
-//       of a few consecutive residues share their neighbourhood), stencil layer by stencil layer, with the
-//       reference's exact float32 expression (pair_within_packed) and the self-interaction filter; hits go to
-//       per-warp queues in shared memory
-//   G3  a warp drains its queue whenever >= PC_GROUP_DRAIN_AT hits wait: float64 distance, weight, one coalesced run
+//       tail kernel's AFRAME mode); the unit's atoms are rank-sorted by cell inside the CTA (the table does not care
+//       in which order they are searched) and stay in shared memory with their packed group words
+//   G2  pair search of gridsearch.C:1111-1142, a warp per occupied cell of the unit: the B atoms of the cell's 27-cell
+//       neighbourhood are nine contiguous runs of the cell-sorted array; the warp walks them as ONE list, 32 at a time
+//       (one coalesced load each), against the cell's A atoms (broadcast from shared memory) with the reference's exact
+//       float32 expression (pair_within_packed) and the self-interaction filter (the B atoms' residue / segment come
+//       cell-sorted from the scatter kernel); ballot -> per-warp queues in shared memory.  Out of line, no calls inside
+//   G3  whenever a queue might not take the next round, its warp drains it: float64 distance, weight, one coalesced run
 //       of 16-byte contact records into the frame's slice, the donor-H...acceptor tests of N/O/S pairs
 //       (core/multi_trajectory.py:112-209), and the hit's weight into the unit's (key -> class sums) table
 //   G4  the table's rows go to the frame's slice of a row buffer; pc_group_offsets_kernel / pc_group_gather_kernel
@@ -29,11 +31,24 @@
 
 #define PC_GROUP_NT 256
 #define PC_GROUP_TAB 1024                 // table slots per unit (power of two)
-#define PC_GROUP_WQ 384                   // hits per warp queue (>= 32; its memory first stages the unit's atoms: 28 B each)
+#define PC_GROUP_WQ 384                   // hits per warp queue (>= 160; its memory first stages the unit's atoms: 32 B each)
 #ifndef PC_GROUP_MINB
 #define PC_GROUP_MINB 4                   // CTAs per SM the kernel is compiled for
 #endif
-#define PC_GROUP_SMEM (PC_GROUP_NT * 36 + 16 + PC_GROUP_TAB * 32 + (PC_GROUP_NT / 32) * PC_GROUP_WQ * 4)
+#define PC_GROUP_SMEM (PC_GROUP_NT * 36 + 16 + PC_GROUP_TAB * 32 + (PC_GROUP_NT / 32) * PC_GROUP_WQ * 4)   // == PC_GOFF_WQ + queues
+
+// Dynamic shared memory of the group kernel (byte offsets; the out-of-line device functions address it directly, so
+// that their loads and atomics are shared-memory instructions rather than generic ones)
+#define PC_GOFF_SA     0                                               // float4 [NT]  -x, -y, -z, atom word (cell order)
+#define PC_GOFF_TKEY   (PC_GOFF_SA + PC_GROUP_NT * 16)                 // u64 [TAB]
+#define PC_GOFF_TCLS   (PC_GOFF_TKEY + PC_GROUP_TAB * 8)               // float [4][TAB] class sums (pc_scan_small.cuh)
+#define PC_GOFF_TNCONT (PC_GOFF_TCLS + PC_GROUP_TAB * 16)              // u32 [TAB]
+#define PC_GOFF_TNHB   (PC_GOFF_TNCONT + PC_GROUP_TAB * 4)             // u32 [TAB]
+#define PC_GOFF_SRS    (PC_GOFF_TNHB + PC_GROUP_TAB * 4)               // int2 [NT] residue, segment (self filter)
+#define PC_GOFF_SG     (PC_GOFF_SRS + PC_GROUP_NT * 8)                 // u32 [NT] group id | backbone << 31
+#define PC_GOFF_SKEY   (PC_GOFF_SG + PC_GROUP_NT * 4)                  // u32 [NT] cell << 8 | thread, sorted
+#define PC_GOFF_CLIST  (PC_GOFF_SKEY + PC_GROUP_NT * 4)                // u32 [NT + 4] first atom of each occupied cell
+#define PC_GOFF_WQ     (PC_GOFF_CLIST + (PC_GROUP_NT + 4) * 4)         // u32 [NW][WQ] hit queues; before the search: staging
 
 struct PcGroupArgs {
     const uint32_t *unit_start;           // nunits + 1 heavy ordinals of selection A
@@ -51,17 +66,11 @@ struct PcGroupCtx {                       // per-CTA state of the out-of-line re
     unsigned int *hcursor;
     unsigned int status;
     // records + accumulation
-    const float4 *sA, *sB;                // the unit's A atoms (shared memory), the frame's cell-sorted B atoms (global)
-    const uint32_t *sG, *lgb2;            // group id | backbone << 31: of the unit's A atoms, per local index of selection 2
+    const float4 *sB;                     // the frame's cell-sorted B atoms (global)
+    const uint32_t *lgb2;                 // group id | backbone << 31 per local index of selection 2
     pc_contact *slice;
     long long cap_c;
     unsigned long long ngroups2;
-    unsigned long long *tkey;
-    float *tcls;
-    unsigned int *tncont, *tnhb;
-    // drain
-    const int2 *sRS;                      // residue, segment of the unit's A atoms (self-interaction filter)
-    const int *lres, *lseg;               // per local index of the (one) selection
     unsigned int *ccursor;
     int self;
 };
@@ -103,12 +112,17 @@ __device__ __noinline__ unsigned pc_group_hbond(PcGroupCtx *c, const float4 pa, 
 // H-bond tests of an N/O/S pair.  Out of line: the search loop keeps the kernel's registers to itself.
 __device__ __noinline__ void pc_group_emit(PcGroupCtx *c, const unsigned u, const long long slot) {
     constexpr int TAB = PC_GROUP_TAB;
-    float4 qa = c->sA[u >> 24];
+    extern __shared__ __align__(16) unsigned char pc_gsm[];
+    unsigned long long *tkey = reinterpret_cast<unsigned long long *>(pc_gsm + PC_GOFF_TKEY);
+    float *tcls = reinterpret_cast<float *>(pc_gsm + PC_GOFF_TCLS);
+    unsigned int *tncont = reinterpret_cast<unsigned int *>(pc_gsm + PC_GOFF_TNCONT);
+    unsigned int *tnhb = reinterpret_cast<unsigned int *>(pc_gsm + PC_GOFF_TNHB);
+    float4 qa = reinterpret_cast<const float4 *>(pc_gsm + PC_GOFF_SA)[u >> 24];
     qa.x = -qa.x; qa.y = -qa.y; qa.z = -qa.z;                          // (the search keeps the unit's atoms negated)
     const float4 qb = __ldg(c->sB + (u & 0xffffffu));
     const unsigned wa = __float_as_uint(qa.w), wb = __float_as_uint(qb.w);
     const int lj = PC_W_INDEX(wb);
-    const uint32_t g1 = c->sG[u >> 24], g2 = __ldg(c->lgb2 + lj);
+    const uint32_t g1 = reinterpret_cast<const uint32_t *>(pc_gsm + PC_GOFF_SG)[u >> 24], g2 = __ldg(c->lgb2 + lj);
     const double dx = (double)qa.x - (double)qb.x, dy = (double)qa.y - (double)qb.y, dz = (double)qa.z - (double)qb.z;
     const double dist = sqrt(dx * dx + dy * dy + dz * dz);
     const float wgt = contact_weight_f32(dist);
@@ -120,7 +134,6 @@ __device__ __noinline__ void pc_group_emit(PcGroupCtx *c, const unsigned u, cons
         atomicOr(&c->status, (unsigned)PC_ST_OUT_OVERFLOW);
     }
     const unsigned long long key = (unsigned long long)(g1 & 0x7fffffffu) * c->ngroups2 + (unsigned long long)(g2 & 0x7fffffffu);
-    unsigned long long *tkey = c->tkey;
     unsigned s = pc_hash_tab(key, 33 - __ffs(TAB));
     int probes = 0;
     for (;;) {
@@ -132,44 +145,22 @@ __device__ __noinline__ void pc_group_emit(PcGroupCtx *c, const unsigned u, cons
     if (s == 0xffffffffu) {
         atomicOr(&c->status, (unsigned)PC_ST_TABLE_OVERFLOW);
     } else {
-        atomicAdd(&c->tcls[((g1 >> 31) * 2 + (g2 >> 31)) * TAB + s], wgt);
-        if (atomicAdd(&c->tncont[s], 1u) == PC_FLOAT_SUM_MAX) atomicOr(&c->status, (unsigned)PC_ST_PRECISION);
+        atomicAdd(&tcls[((g1 >> 31) * 2 + (g2 >> 31)) * TAB + s], wgt);
+        if (atomicAdd(&tncont[s], 1u) == PC_FLOAT_SUM_MAX) atomicOr(&c->status, (unsigned)PC_ST_PRECISION);
     }
     if (wa & wb & PC_W_HBCLASS) {
         const unsigned nh = pc_group_hbond(c, qa, qb, 0) + pc_group_hbond(c, qa, qb, 1);
-        if (nh && s != 0xffffffffu) atomicAdd(&c->tnhb[s], nh);
+        if (nh && s != 0xffffffffu) atomicAdd(&tnhb[s], nh);
     }
 }
 
-// A warp's queued hits -> records + table; called by whole warps.  Self contacts: the self-interaction filter
-// (core/multi_trajectory.py:93-95: dropped when (resid1 - resid2) < 5, signed, in the same segment) runs here, on hits
-// only, and compacts the queue in place before the frame's cursor is claimed ONCE for what is left.  Out of line: its
-// state does not compete with the search loop's for registers.
-__device__ __noinline__ void pc_group_drain(PcGroupCtx *c, uint32_t *mywq, unsigned n) {
+// A warp's queued hits -> records + table; called by whole warps: lanes over hits, ONE claim of the frame's cursor per
+// call.  Out of line: its state does not compete with the search loop's for registers.
+__device__ __noinline__ void pc_group_drain(PcGroupCtx *c, const unsigned n) {
+    extern __shared__ __align__(16) unsigned char pc_gsm[];
     const int lane = threadIdx.x & 31;
-    const unsigned ltmask = (1u << lane) - 1u;
+    const uint32_t *mywq = reinterpret_cast<const uint32_t *>(pc_gsm + PC_GOFF_WQ) + (threadIdx.x >> 5) * PC_GROUP_WQ;
     __syncwarp();
-    if (c->self) {
-        const float4 *sB = c->sB;
-        unsigned kept = 0;
-        for (unsigned base = 0; base < n; base += 32) {
-            const unsigned k = base + lane;
-            unsigned u = 0;
-            bool keep = false;
-            if (k < n) {
-                u = mywq[k];
-                const int lj = PC_W_INDEX(__float_as_uint(__ldg(&sB[u & 0xffffffu].w)));
-                const int bres = __ldg(c->lres + lj), bseg = __ldg(c->lseg + lj);
-                const int2 rs = c->sRS[u >> 24];
-                keep = !((rs.x - bres) < 5 && rs.y == bseg);
-            }
-            const unsigned kb = __ballot_sync(PC_FULL_MASK, keep);         // (every lane has read its entry: writes may follow)
-            if (keep) mywq[kept + __popc(kb & ltmask)] = u;
-            kept += (unsigned)__popc(kb);
-        }
-        n = kept;
-        __syncwarp();
-    }
     if (n) {
         unsigned base = 0;
         if (lane == 0) base = atomicAdd(c->ccursor, n);
@@ -181,36 +172,60 @@ __device__ __noinline__ void pc_group_drain(PcGroupCtx *c, uint32_t *mywq, unsig
 
 // Per-CTA constants and per-warp resume state of the search (shared memory).
 struct PcGroupSearch {
-    const float4 *sA, *sB;                // the unit's A atoms (negated, cell order; shared memory), the frame's cell-sorted B atoms
+    const float4 *sB;                     // the frame's cell-sorted B atoms
+    const int2 *sBrs;                     // their (residue, segment), self contacts only
     const uint32_t *cB;                   // cB[c] == END of cell c in sB
-    const uint32_t *skey, *clist;         // sorted cell << 8 | thread keys, first atom of each occupied cell of the unit
     int nx, ny, nz, ncl;
-    float sqdist;
-    int ci[PC_GROUP_NT / 32], t0[PC_GROUP_NT / 32], k0[PC_GROUP_NT / 32];     // where each warp resumes
+    float inv_nx, inv_ny, sqdist;
+    int next;                             // next cell of the unit's cell list nobody has taken yet
+    int ci[PC_GROUP_NT / 32], t0[PC_GROUP_NT / 32], k0[PC_GROUP_NT / 32];     // where each warp resumes (ci < 0: take a cell)
     unsigned long long evals[PC_GROUP_NT / 32];
 };
 
-// G2: a warp per occupied cell of the unit.  The B atoms of the cell's 27-cell neighbourhood are nine contiguous runs of
-// the cell-sorted array (one per stencil row); the warp walks them as ONE list, 32 atoms at a time (lane -> list
-// position -> run by a four-step search over the runs' ends, held in lanes 0..8), one coalesced load each, and tests
-// them against the cell's A atoms (broadcast from shared memory) with the reference's exact float32 expression
-// (gridsearch.C:48-55, :1126); ballot -> the warp's queue.  Returns the queue's fill when the queue might not take the
-// next push (the caller drains it and calls again: the position is kept in S) or when the warp's cells are done
-// (S->ci[warp] >= S->ncl).  Out of line and free of calls: the loop nest has the register file to itself.
-__device__ __noinline__ unsigned pc_group_search(PcGroupSearch *S, uint32_t *mywq, unsigned wn) {
-    constexpr int NW = PC_GROUP_NT / 32, WQ = PC_GROUP_WQ;
+// n / d and n % d for 0 <= n < 2^22 through a float32 reciprocal (exact after one correction step)
+__device__ __forceinline__ void pc_divmod_small(const int n, const int d, const float inv_d, int &q, int &r) {
+    q = (int)((float)n * inv_d);
+    r = n - q * d;
+    if (r < 0) { q--; r += d; } else if (r >= d) { q++; r -= d; }
+}
+
+// G2: a warp per occupied cell of the unit (cells are handed out one at a time: the warps of a CTA finish together).  The B
+// atoms of the cell's 27-cell neighbourhood are nine contiguous runs of the cell-sorted array (one per stencil row); the
+// warp walks them as ONE list, 32 atoms at a time (lane -> list position -> run by a four-step search over the runs' ends,
+// held in lanes 0..8), one coalesced load each, and tests them against the cell's A atoms (broadcast from shared memory,
+// at most eight per round) with the reference's exact float32 expression (gridsearch.C:48-55, :1126); ballot -> the warp's queue.
+// Returns the queue's fill when the queue might not take the next round (the caller drains it and calls again: the
+// position is kept in S) or when no cell is left (S->ci[warp] >= S->ncl).  Out of line and free of calls: the loop
+// nest has the register file to itself.
+template <bool SELF>
+__device__ __noinline__ unsigned pc_group_search(PcGroupSearch *S) {
+    constexpr int WQ = PC_GROUP_WQ;
+    extern __shared__ __align__(16) unsigned char pc_gsm[];
+    const float4 *sA = reinterpret_cast<const float4 *>(pc_gsm + PC_GOFF_SA);
+    const uint32_t *skey = reinterpret_cast<const uint32_t *>(pc_gsm + PC_GOFF_SKEY);
+    const uint32_t *clist = reinterpret_cast<const uint32_t *>(pc_gsm + PC_GOFF_CLIST);
+    const int2 *sRS = reinterpret_cast<const int2 *>(pc_gsm + PC_GOFF_SRS);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    uint32_t *mywq = reinterpret_cast<uint32_t *>(pc_gsm + PC_GOFF_WQ) + warp * WQ;
     const unsigned ltmask = (1u << lane) - 1u;
-    const float4 *sA = S->sA, *sB = S->sB;
+    const float4 *sB = S->sB;
     const uint32_t *cB = S->cB;
     const int nx = S->nx, ny = S->ny, nz = S->nz, ncl = S->ncl;
     const float sqdist = S->sqdist;
     int ci = S->ci[warp], t0 = S->t0[warp], k0 = S->k0[warp];
     unsigned long long evals = 0;
-    for (; ci < ncl; ci += NW, t0 = 0, k0 = 0) {
-        const int a0 = (int)S->clist[ci], a1 = (int)S->clist[ci + 1];
-        const int c = (int)(S->skey[a0] >> 8);
-        const int cx = c % nx, cy = (c / nx) % ny, cz = c / (nx * ny);
+    unsigned wn = 0;
+    auto take = [&]() {
+        int v = 0;
+        if (lane == 0) v = atomicAdd(&S->next, 1);
+        return __shfl_sync(PC_FULL_MASK, v, 0);
+    };
+    if (ci < 0) ci = take();
+    while (ci < ncl) {
+        const int a0 = (int)clist[ci], a1 = (int)clist[ci + 1];
+        int cx, cy, cz, rowzy;
+        pc_divmod_small((int)(skey[a0] >> 8), nx, S->inv_nx, rowzy, cx);
+        pc_divmod_small(rowzy, ny, S->inv_ny, cz, cy);
         int b0 = 0, len = 0;
         if (lane < 9) {
             const int z = cz + lane / 3 - 1, y = cy + lane % 3 - 1;
@@ -223,7 +238,6 @@ __device__ __noinline__ unsigned pc_group_search(PcGroupSearch *S, uint32_t *myw
         const int end = (int)warp_incl_scan((uint32_t)len, lane);      // lanes 0..8: list position behind run `lane`; 9..31: nb
         const int nb = __shfl_sync(PC_FULL_MASK, end, 31);
         const int delta = b0 - (end - len);                            // list position t of run `lane` -> B position t + delta
-        if (lane == 0 && t0 == 0 && k0 == 0) evals += (unsigned long long)(a1 - a0) * (unsigned)nb;
         for (; t0 < nb; t0 += 32, k0 = 0) {
             const int t = t0 + lane;
             // first run whose end lies behind t (ends are non-decreasing; lanes >= 8 hold nb > t for every valid t)
@@ -236,18 +250,33 @@ __device__ __noinline__ unsigned pc_group_search(PcGroupSearch *S, uint32_t *myw
             const int j = t + __shfl_sync(PC_FULL_MASK, delta, min(r, 8));
             // lanes past the end test a point at infinity: never within the cutoff
             const float4 pb = t < nb ? __ldg(sB + j) : make_float4(INFINITY, 0.f, 0.f, 0.f);
-            for (int k = a0 + k0; k < a1; k++) {
-                if (wn + 32u > (unsigned)WQ) {                         // (warp-uniform) the next push might not fit: hand back
-                    if (lane == 0) { S->ci[warp] = ci; S->t0[warp] = t0; S->k0[warp] = k - a0; S->evals[warp] += evals; }
+            int2 brs = make_int2(0, 0);
+            if (SELF && t < nb) brs = __ldg(S->sBrs + j);
+            // the cell's A atoms, at most eight per round: a round's pushes (<= 32 per atom) must fit the queue
+            for (int ks = a0 + k0; ks < a1; ks += 8) {
+                const int ke = min(ks + 8, a1);
+                if (wn + 32u * (unsigned)(ke - ks) > (unsigned)WQ) {   // (warp-uniform) hand back: the caller drains and calls again
+                    if (lane == 0) { S->ci[warp] = ci; S->t0[warp] = t0; S->k0[warp] = ks - a0; S->evals[warp] += evals; }
                     return wn;
                 }
-                const float4 na = sA[k];
-                const bool hit = pair_within_packed(make_float2(na.x, na.y), na.z, pb, sqdist);
-                const unsigned m = __ballot_sync(PC_FULL_MASK, hit);
-                if (hit) mywq[wn + __popc(m & ltmask)] = ((unsigned)k << 24) | (unsigned)j;
-                wn += (unsigned)__popc(m);
+#pragma unroll 1
+                for (int k = ks; k < ke; k++) {
+                    const float4 na = sA[k];
+                    bool hit = pair_within_packed(make_float2(na.x, na.y), na.z, pb, sqdist);
+                    if (SELF) {
+                        // self-interaction filter (core/multi_trajectory.py:93-95): dropped when (resid1 - resid2) < 5,
+                        // signed, in the same segment
+                        const int2 ars = sRS[k];
+                        hit = hit && !((ars.x - brs.x) < 5 && ars.y == brs.y);
+                    }
+                    const unsigned m = __ballot_sync(PC_FULL_MASK, hit);
+                    if (hit) mywq[wn + __popc(m & ltmask)] = ((unsigned)k << 24) | (unsigned)j;
+                    wn += (unsigned)__popc(m);
+                }
             }
         }
+        if (lane == 0) evals += (unsigned long long)(a1 - a0) * (unsigned)nb;      // (counted once, when the cell is done)
+        ci = take(); t0 = 0; k0 = 0;
     }
     if (lane == 0) { S->ci[warp] = ci; S->evals[warp] += evals; }
     return wn;
@@ -255,21 +284,22 @@ __device__ __noinline__ unsigned pc_group_search(PcGroupSearch *S, uint32_t *myw
 
 __global__ void __launch_bounds__(PC_GROUP_NT, PC_GROUP_MINB) pc_large_group_kernel(const PcScanArgs a, PcLargeFrame *fr, const int f0,
                                                                                     const uint32_t *cellsB, const int capCells,
-                                                                                    const float4 *sortB, const int nBh_alloc,
-                                                                                    const PcLargeOut o, const PcAccArgs acc,
+                                                                                    const float4 *sortB, const int2 *sortRS,
+                                                                                    const int nBh_alloc, const PcLargeOut o,
+                                                                                    const PcAccArgs acc,
                                                                                     const PcGroupArgs g) {
     constexpr int NT = PC_GROUP_NT, NW = NT / 32, TAB = PC_GROUP_TAB, WQ = PC_GROUP_WQ;
     extern __shared__ __align__(16) unsigned char smem[];
-    float4 *sA = reinterpret_cast<float4 *>(smem);                                  // [NT] -x, -y, -z, atom word (cell order)
-    unsigned long long *tkey = reinterpret_cast<unsigned long long *>(sA + NT);     // [TAB]
-    float *tcls = reinterpret_cast<float *>(tkey + TAB);                            // [4][TAB] class sums (pc_scan_small.cuh)
-    unsigned int *tncont = reinterpret_cast<unsigned int *>(tcls + 4 * TAB);        // [TAB]
-    unsigned int *tnhb = tncont + TAB;                                              // [TAB]
-    int2 *sRS = reinterpret_cast<int2 *>(tnhb + TAB);                               // [NT] residue, segment (self filter)
-    uint32_t *sG = reinterpret_cast<uint32_t *>(sRS + NT);                          // [NT] group id | backbone << 31
-    uint32_t *skey = sG + NT;                                                       // [NT] cell << 8 | thread, sorted
-    uint32_t *clist = skey + NT;                                                    // [NT + 4] first atom of each occupied cell
-    uint32_t *wq = clist + NT + 4;                                                  // [NW][WQ] hit queues; before: staging
+    float4 *sA = reinterpret_cast<float4 *>(smem + PC_GOFF_SA);
+    unsigned long long *tkey = reinterpret_cast<unsigned long long *>(smem + PC_GOFF_TKEY);
+    float *tcls = reinterpret_cast<float *>(smem + PC_GOFF_TCLS);
+    unsigned int *tncont = reinterpret_cast<unsigned int *>(smem + PC_GOFF_TNCONT);
+    unsigned int *tnhb = reinterpret_cast<unsigned int *>(smem + PC_GOFF_TNHB);
+    int2 *sRS = reinterpret_cast<int2 *>(smem + PC_GOFF_SRS);
+    uint32_t *sG = reinterpret_cast<uint32_t *>(smem + PC_GOFF_SG);
+    uint32_t *skey = reinterpret_cast<uint32_t *>(smem + PC_GOFF_SKEY);
+    uint32_t *clist = reinterpret_cast<uint32_t *>(smem + PC_GOFF_CLIST);
+    uint32_t *wq = reinterpret_cast<uint32_t *>(smem + PC_GOFF_WQ);
     __shared__ PcLargeFrame F;
     __shared__ PcGroupCtx C;
     __shared__ PcGroupSearch S;
@@ -286,10 +316,9 @@ __global__ void __launch_bounds__(PC_GROUP_NT, PC_GROUP_MINB) pc_large_group_ker
         C.hb_cutoff = a.hb_cutoff; C.hb_angle = a.hb_angle;
         C.hslice = a.hbonds + (long long)f * o.cap_h_frame; C.cap_h = o.cap_h_frame;
         C.hcursor = &fr[fb].hcursor; C.status = 0;
-        C.sA = sA; C.sB = sortB + (size_t)fb * nBh_alloc; C.sG = sG; C.lgb2 = acc.lgb2;
+        C.sB = sortB + (size_t)fb * nBh_alloc; C.lgb2 = acc.lgb2;
         C.slice = a.contacts + (long long)f * o.cap_c_frame; C.cap_c = o.cap_c_frame; C.ngroups2 = acc.ngroups2;
-        C.tkey = tkey; C.tcls = tcls; C.tncont = tncont; C.tnhb = tnhb;
-        C.sRS = sRS; C.lres = a.t.lres1; C.lseg = a.t.lseg1; C.ccursor = &fr[fb].ccursor; C.self = a.self_mode;
+        C.ccursor = &fr[fb].ccursor; C.self = a.self_mode;
     }
     for (int s = tid; s < TAB; s += NT) {
         tkey[s] = PC_EMPTY_KEY; tcls[s] = 0.f; tcls[TAB + s] = 0.f; tcls[2 * TAB + s] = 0.f; tcls[3 * TAB + s] = 0.f;
@@ -302,7 +331,6 @@ __global__ void __launch_bounds__(PC_GROUP_NT, PC_GROUP_MINB) pc_large_group_ker
     const float *fr1 = a.xyz1 + (long long)f * a.pitch1;
     const uint32_t *cB = cellsB + (size_t)fb * (capCells + 1);  // after the scatter: cB[c] == END of cell c
     const float4 *sB = sortB + (size_t)fb * nBh_alloc;
-    uint32_t *mywq = wq + warp * WQ;
     const unsigned ltmask = (1u << lane) - 1u;
     unsigned long long evals = 0;
 
@@ -362,16 +390,16 @@ __global__ void __launch_bounds__(PC_GROUP_NT, PC_GROUP_MINB) pc_large_group_ker
 
     // ---- G2 / G3: search (pc_group_search) and drain (pc_group_drain) alternate until the warp's cells are done -----------
     if (tid == 0) {
-        S.sA = sA; S.sB = sB; S.cB = cB; S.skey = skey; S.clist = clist;
-        S.nx = nx; S.ny = ny; S.nz = nz; S.ncl = ncl; S.sqdist = a.sqdist;
+        S.sB = sB; S.sBrs = sortRS ? sortRS + (size_t)fb * nBh_alloc : nullptr; S.cB = cB; S.nx = nx; S.ny = ny; S.nz = nz; S.ncl = ncl; S.sqdist = a.sqdist;
+        S.inv_nx = 1.0f / (float)nx; S.inv_ny = 1.0f / (float)ny; S.next = 0;
     }
-    if (tid < NW) { S.ci[tid] = tid; S.t0[tid] = 0; S.k0[tid] = 0; S.evals[tid] = 0ull; }
+    if (tid < NW) { S.ci[tid] = -1; S.t0[tid] = 0; S.k0[tid] = 0; S.evals[tid] = 0ull; }
     __syncthreads();
     for (;;) {
-        const unsigned wn = pc_group_search(&S, mywq, 0u);
+        const unsigned wn = self ? pc_group_search<true>(&S) : pc_group_search<false>(&S);
         __syncwarp();
         const bool done = *(volatile int *)&S.ci[warp] >= ncl;
-        pc_group_drain(&C, mywq, wn);
+        pc_group_drain(&C, wn);
         if (done) break;
     }
     if (lane == 0) evals = S.evals[warp];

@@ -41,11 +41,12 @@ struct PcLargeWork {
     float4 *sortA = nullptr, *sortB = nullptr;        // FB x n_h   (cell order)
     uint8_t *occ = nullptr;                           // FB x capCells: cell has a B atom in its 27-cell neighbourhood
     uint8_t *occ2 = nullptr;                          // FB x capCells: scratch of the separable dilation
+    int2 *sortRS = nullptr;                           // FB x n_h  (self contacts: residue, segment in cell order)
     void release() {
-        void *ps[] = {frames, cellA, cellB, candA, candB, ccellA, ccellB, sortA, sortB, occ, occ2};
+        void *ps[] = {frames, cellA, cellB, candA, candB, ccellA, ccellB, sortA, sortB, occ, occ2, sortRS};
         for (void *p : ps) if (p) cudaFree(p);
         frames = nullptr; cellA = cellB = nullptr; candA = candB = sortA = sortB = nullptr;
-        ccellA = ccellB = nullptr; occ = occ2 = nullptr; FB = 0;
+        ccellA = ccellB = nullptr; occ = occ2 = nullptr; sortRS = nullptr; FB = 0;
     }
     ~PcLargeWork() { release(); }
 };
@@ -564,15 +565,25 @@ __global__ void __launch_bounds__(1024) pc_large_scan_kernel(PcLargeFrame *fr, u
 // ---- L5: scatter compacted atoms into cell order; afterwards cells[c] == END of cell c ---------
 __global__ void __launch_bounds__(256) pc_large_scatter_kernel(PcLargeFrame *fr, int side, uint32_t *cells, int capCells,
                                                                const float4 *cand, const uint32_t *ccell, float4 *sorted,
-                                                               int nh_alloc) {
+                                                               int nh_alloc, int2 *sorted_rs = nullptr, const int *lres = nullptr,
+                                                               const int *lseg = nullptr) {
     const int fb = blockIdx.y;
     const unsigned n = side == 0 ? fr[fb].nA_in : fr[fb].nB_in;
     uint32_t *mycells = cells + (size_t)fb * (capCells + 1);
     const float4 *mycand = cand + (size_t)fb * nh_alloc;
     const uint32_t *myccell = ccell + (size_t)fb * nh_alloc;
     float4 *mysorted = sorted + (size_t)fb * nh_alloc;
-    for (unsigned p = blockIdx.x * blockDim.x + threadIdx.x; p < n; p += gridDim.x * blockDim.x)
-        mysorted[atomicAdd(&mycells[myccell[p]], 1u)] = mycand[p];
+    for (unsigned p = blockIdx.x * blockDim.x + threadIdx.x; p < n; p += gridDim.x * blockDim.x) {
+        const float4 v = mycand[p];
+        const unsigned dst = atomicAdd(&mycells[myccell[p]], 1u);
+        mysorted[dst] = v;
+        // (residue, segment) of the atoms in the same order: the group kernel's self-interaction filter reads them
+        // coalesced, next to the coordinates
+        if (sorted_rs) {
+            const int l = PC_W_INDEX(__float_as_uint(v.w));
+            sorted_rs[(size_t)fb * nh_alloc + dst] = make_int2(__ldg(lres + l), __ldg(lseg + l));
+        }
+    }
 }
 
 // ---- L6: pair search ---------------------------------------------------------------------------------

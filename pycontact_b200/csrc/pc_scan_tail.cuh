@@ -1051,7 +1051,7 @@ static inline int pc_large_scan(PcLargeWork &W, const PcScanArgs &a, int num_sms
     const int capCells = (int)cc;
     const int a1 = std::max(n1h, 1), a2 = std::max(n2h, 1);
     // frames in flight: bound the work memory to ~6 GB
-    const size_t per_frame = (size_t)(capCells + 1) * 4 * (self ? 1 : 2) + (size_t)a1 * 36 + (self ? 0 : (size_t)a2 * 36);
+    const size_t per_frame = (size_t)(capCells + 1) * 4 * (self ? 1 : 2) + (size_t)a1 * (self ? 44 : 36) + (self ? 0 : (size_t)a2 * 36);
     int FB = (int)std::max<size_t>(1, std::min<size_t>(296, (6ull << 30) / std::max<size_t>(per_frame, 1)));
     FB = std::min(FB, a.nframes);
     if (W.FB < FB || W.capCells != capCells || W.n1h != n1h || W.n2h != n2h || W.self_mode != a.self_mode) {
@@ -1061,6 +1061,7 @@ static inline int pc_large_scan(PcLargeWork &W, const PcScanArgs &a, int num_sms
         PCL_TRY(cudaMalloc(&W.candA, (size_t)FB * a1 * sizeof(float4)));
         PCL_TRY(cudaMalloc(&W.ccellA, (size_t)FB * a1 * 4));
         PCL_TRY(cudaMalloc(&W.sortA, (size_t)FB * a1 * sizeof(float4)));
+        if (self) PCL_TRY(cudaMalloc(&W.sortRS, (size_t)FB * a1 * sizeof(int2)));
         if (!self) {
             PCL_TRY(cudaMalloc(&W.cellB, (size_t)FB * (capCells + 1) * 4));
             PCL_TRY(cudaMalloc(&W.candB, (size_t)FB * a2 * sizeof(float4)));
@@ -1190,13 +1191,15 @@ static inline int pc_large_scan(PcLargeWork &W, const PcScanArgs &a, int num_sms
         const int per_frame_blocks = std::max(1, 4 * num_sms / nfb);
         const int blocksA = std::max(1, std::min((n1h + 255) / 256, per_frame_blocks));
         const int blocksB = std::max(1, std::min((n2h + 255) / 256, per_frame_blocks));
-        pc_large_scatter_kernel<<<dim3(blocksA, nfb), 256, 0, s>>>(W.frames, 0, W.cellA, capCells, W.candA, W.ccellA, W.sortA, a1);
+        pc_large_scatter_kernel<<<dim3(blocksA, nfb), 256, 0, s>>>(W.frames, 0, W.cellA, capCells, W.candA, W.ccellA, W.sortA, a1,
+                                                                   self && group ? W.sortRS : nullptr, a.t.lres1, a.t.lseg1);
         if (!self)
             pc_large_scatter_kernel<<<dim3(blocksB, nfb), 256, 0, s>>>(W.frames, 1, W.cellB, capCells, W.candB, W.ccellB, W.sortB, a2);
         if (group) {
             // search + records + H-bonds + rows of the units' keys in one kernel (pc_scan_group.cuh)
             pc_large_group_kernel<<<dim3(group->nunits, nfb), PC_GROUP_NT, PC_GROUP_SMEM, s>>>(
-                a, W.frames, f0, self ? W.cellA : W.cellB, capCells, self ? W.sortA : W.sortB, self ? a1 : a2, o, *acc, *group);
+                a, W.frames, f0, self ? W.cellA : W.cellB, capCells, self ? W.sortA : W.sortB, self ? W.sortRS : nullptr,
+                self ? a1 : a2, o, *acc, *group);
             pc_large_finish_kernel<<<(nfb + 63) / 64, 64, 0, s>>>(a, W.frames, f0, nfb, o);
             PCL_TRY(cudaGetLastError());
             *launches += 5 + (use_bboxB ? 1 : 0) + (self ? 0 : 2);

@@ -143,12 +143,12 @@ def test_group_kernel_is_skipped_when_groups_are_not_runs():
 
 
 def test_group_kernel_table_overflow_falls_back():
-    """Per-atom keys on selection 2: more than 1024 keys per unit -> PC_ST_TABLE_OVERFLOW -> the engine re-runs the
-    batch on the global table."""
+    """Per-atom keys on selection 2 at a 6.5 A cutoff: more than 1024 keys per unit -> PC_ST_TABLE_OVERFLOW -> the engine
+    re-runs the batch on the global table."""
     s = synth.make_system("c4_small")
     coords = synth.frames_host(s, [0])
     maps = ([0, 0, 1, 1, 1], [1, 0, 0, 0, 0])
-    traj, tab, ora, cells, c1, c2, final = _run(s, coords, True, maps, tail=False, group=True, batch=1)
+    traj, tab, ora, cells, c1, c2, final = _run(s, coords, True, maps, tail=False, group=True, batch=1, cutoff=6.5)
     assert final["lim"][3] == 16384 and not final["group"]
     _compare_unordered(traj, ora)
     _compare_cells(tab, cells, c1, c2)
