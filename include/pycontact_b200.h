@@ -348,6 +348,20 @@ int pc_mem_info(int device, int64_t *free_bytes, int64_t *total_bytes);
 int pc_host_alloc(void **out, int64_t bytes);
 void pc_host_free(void *p);
 
+/* ---- XTC trajectories (ingest step in front of the path) --------------------------------------
+ * The reference reads trajectories through MDAnalysis (core/ContactAnalyzer.py:282, core/multi_trajectory.py:362; its
+ * tests open exampleData/md_noPBC.xtc, tests/test_basic.py:28-30).  Host code: GROMACS XTC frames (xdrfile's compressed
+ * integer coordinates) -> float32 positions in Angstrom (nm * 10, like MDAnalysis), optionally gathered through a
+ * selection's atom indices -- what sel.positions yields per frame (core/multi_trajectory.py:401-417). */
+typedef struct pc_xtc pc_xtc;
+int  pc_xtc_open(const char *path, pc_xtc **out);                       /* indexes the frames */
+int  pc_xtc_info(const pc_xtc *x, int32_t *natoms, int64_t *nframes);
+/* h_xyz: nframes x (nidx or natoms) x 3 floats; indices may be NULL (all atoms); h_step / h_time / h_box (nframes x 9,
+ * Angstrom) may be NULL */
+int  pc_xtc_read(pc_xtc *x, int64_t frame0, int32_t nframes, const int32_t *indices, int32_t nidx, float *h_xyz,
+                 int32_t *h_step, float *h_time, float *h_box);
+void pc_xtc_close(pc_xtc *x);
+
 #ifdef __cplusplus
 }
 #endif

@@ -59,7 +59,7 @@ class PcError(Exception):
 
 # every symbol include/pycontact_b200.h declares (tests check the library exports all of them)
 EXPORTS = [
-    "pc_last_error", "pc_version", "pc_device_count", "pc_create", "pc_destroy", "pc_set_topology", "pc_set_maps", "pc_set_limits", "pc_set_path", "pc_set_fused_accumulate", "pc_set_small_ctas", "pc_set_tail", "pc_set_dense_mode", "pc_set_group_mode", "pc_last_group",
+    "pc_last_error", "pc_version", "pc_device_count", "pc_create", "pc_destroy", "pc_set_topology", "pc_set_maps", "pc_set_limits", "pc_set_path", "pc_set_fused_accumulate", "pc_set_small_ctas", "pc_set_tail", "pc_set_dense_mode", "pc_set_group_mode", "pc_last_group", "pc_xtc_open", "pc_xtc_info", "pc_xtc_read", "pc_xtc_close",
     "pc_reserve", "pc_scan_device", "pc_accumulate", "pc_scan_host", "pc_batch_totals", "pc_last_status",
     "pc_device_outputs", "pc_fetch", "pc_find_contacts", "pc_free_host", "pc_synth_frames", "pc_host_alloc",
     "pc_host_free", "pc_load_records", "pc_stream_create", "pc_stream_sync", "pc_stream_destroy",
@@ -99,6 +99,11 @@ def load():
     lib.pc_set_dense_mode.argtypes = [vp, ctypes.c_int]
     lib.pc_set_group_mode.argtypes = [vp, ctypes.c_int]
     lib.pc_last_group.argtypes = [vp]
+    lib.pc_xtc_open.argtypes = [ctypes.c_char_p, ctypes.POINTER(vp)]
+    lib.pc_xtc_info.argtypes = [vp, ctypes.POINTER(i32), ctypes.POINTER(i64)]
+    lib.pc_xtc_read.argtypes = [vp, i64, i32, vp, i32, vp, vp, vp, vp]
+    lib.pc_xtc_close.argtypes = [vp]
+    lib.pc_xtc_close.restype = None
     lib.pc_reserve.argtypes = [vp, i32, i64, i64, i64]
     lib.pc_scan_device.argtypes = [vp, vp, vp, i32, i32, i64, i64, i32, vp]
     lib.pc_accumulate.argtypes = [vp, vp]

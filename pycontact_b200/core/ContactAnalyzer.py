@@ -212,10 +212,8 @@ class Analyzer(object):
             a = np.ascontiguousarray(arr[:, idx1], np.float32)
             b = None if idx2 is None else np.ascontiguousarray(arr[:, idx2], np.float32)
             return ArraySource(a, b)
-        from ..io.dcd import DCDReader
-        if not str(dcd).lower().endswith(".dcd"):
-            raise NotImplementedError("only DCD trajectories are read natively; pass frames= for other formats")
-        return DCDSource(DCDReader(dcd), idx1, idx2)
+        from ..io.xtc import open_trajectory
+        return DCDSource(open_trajectory(dcd), idx1, idx2)      # (.dcd or .xtc: the readers share one interface)
 
     def analyze_psf_dcd_grid(self, psf, dcd, cutoff, hbondcutoff, hbondcutangle, sel1text, sel2text, nproc=1):
         """Load topology + trajectory, scan all frames on the GPU(s) (:278-500)."""
@@ -267,10 +265,8 @@ class Analyzer(object):
             if arr.ndim != 3 or arr.shape[1] != natoms:
                 raise ValueError("selections with 'around' need frames= as (F, natoms, 3) over ALL atoms")
             return np.ascontiguousarray(arr, np.float32)
-        from ..io.dcd import DCDReader
-        if not str(dcd).lower().endswith(".dcd"):
-            raise NotImplementedError("only DCD trajectories are read natively; pass frames= for other formats")
-        rd = DCDReader(dcd)
+        from ..io.xtc import open_trajectory
+        rd = open_trajectory(dcd)
         out = np.empty((len(rd), natoms, 3), np.float32)
         for f in range(len(rd)):
             out[f] = rd.frame(f)

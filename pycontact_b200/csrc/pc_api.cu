@@ -21,6 +21,7 @@
 #include "pc_stats.cuh"
 #include "pc_sasa.cuh"
 #include "pc_peak.cuh"
+#include "pc_xtc.h"
 
 static thread_local std::string g_err;
 static unsigned long long g_launches = 0;      // kernels launched by this library (bench.py's gpu_launches)
@@ -1381,4 +1382,90 @@ extern "C" int pc_find_within(int device, const float *h_xyz, int32_t nframes, i
         CUDA_TRY(cudaStreamSynchronize(0));
     }
     return PC_OK;
+}
+
+// ---- XTC trajectory frames (decoder in pc_xtc.h, host code) -----------------------------------------
+extern "C" int pc_xtc_open(const char *path, pc_xtc **out) {
+    if (!path || !out) return fail(PC_ERR_INVALID, "pc_xtc_open: bad arguments");
+    FILE *fh = fopen(path, "rb");
+    if (!fh) return fail(PC_ERR_INVALID, std::string("pc_xtc_open: cannot open ") + path);
+    pc_xtc *x = new pc_xtc();
+    x->fh = fh;
+    // index the frames: every header tells how long its frame is
+    unsigned char hdr[92];
+    long long pos = 0;
+    for (;;) {
+        if (fseeko(fh, (off_t)pos, SEEK_SET) != 0) break;
+        memset(hdr, 0, sizeof hdr);
+        const size_t got = fread(hdr, 1, sizeof hdr, fh);
+        if (got < 56) break;
+        int natoms = 0;
+        const long long nb = pcxtc::frame_bytes(hdr, natoms);
+        if (nb == 0 || (natoms > 9 && got < 92)) {
+            if (x->offset.empty()) { fclose(fh); delete x; return fail(PC_ERR_INVALID, std::string("pc_xtc_open: not an XTC file: ") + path); }
+            break;                                   // trailing bytes of an interrupted write
+        }
+        if (x->offset.empty()) x->natoms = natoms;
+        else if (natoms != x->natoms) { fclose(fh); delete x; return fail(PC_ERR_INVALID, "pc_xtc_open: the number of atoms changes between frames"); }
+        x->offset.push_back(pos);
+        pos += nb;
+    }
+    fseeko(fh, 0, SEEK_END);
+    const long long fsize = (long long)ftello(fh);
+    if (!x->offset.empty() && pos > fsize) x->offset.pop_back();          // last frame cut short
+    if (x->offset.empty()) { fclose(fh); delete x; return fail(PC_ERR_INVALID, std::string("pc_xtc_open: no complete frame in ") + path); }
+    x->offset.push_back(std::min(pos, fsize));
+    x->xyz.resize((size_t)x->natoms * 3);
+    *out = x;
+    return PC_OK;
+}
+
+extern "C" int pc_xtc_info(const pc_xtc *x, int32_t *natoms, int64_t *nframes) {
+    if (!x) return fail(PC_ERR_INVALID, "pc_xtc_info: handle is NULL");
+    if (natoms) *natoms = x->natoms;
+    if (nframes) *nframes = (int64_t)x->offset.size() - 1;
+    return PC_OK;
+}
+
+extern "C" int pc_xtc_read(pc_xtc *x, int64_t frame0, int32_t nframes, const int32_t *indices, int32_t nidx, float *h_xyz,
+                           int32_t *h_step, float *h_time, float *h_box) {
+    if (!x || !h_xyz || nframes < 0 || frame0 < 0 || frame0 + nframes > (int64_t)x->offset.size() - 1)
+        return fail(PC_ERR_INVALID, "pc_xtc_read: bad frame range");
+    if (indices && nidx < 0) return fail(PC_ERR_INVALID, "pc_xtc_read: bad selection");
+    const int nout = indices ? nidx : x->natoms;
+    if (indices)
+        for (int k = 0; k < nidx; k++)
+            if (indices[k] < 0 || indices[k] >= x->natoms) return fail(PC_ERR_INVALID, "pc_xtc_read: atom index out of range");
+    for (int32_t f = 0; f < nframes; f++) {
+        const long long o0 = x->offset[(size_t)(frame0 + f)], o1 = x->offset[(size_t)(frame0 + f) + 1];
+        x->raw.resize((size_t)(o1 - o0));
+        if (fseeko(x->fh, (off_t)o0, SEEK_SET) != 0 || fread(x->raw.data(), 1, x->raw.size(), x->fh) != x->raw.size())
+            return fail(PC_ERR_INVALID, "pc_xtc_read: short read");
+        float box[9];
+        int step = 0;
+        float time = 0.f;
+        const std::string err = pcxtc::decode(x->raw.data(), x->raw.size(), x->natoms, x->xyz.data(), &step, &time, box);
+        if (!err.empty()) return fail(PC_ERR_INVALID, "pc_xtc_read: frame " + std::to_string(frame0 + f) + ": " + err);
+        // nm -> Angstrom in float32, like MDAnalysis' XTC reader hands positions to the reference
+        float *dst = h_xyz + (size_t)f * nout * 3;
+        const float *src = x->xyz.data();
+        if (indices) {
+            for (int k = 0; k < nidx; k++) {
+                const float *p = src + 3 * (size_t)indices[k];
+                dst[3 * k] = p[0] * 10.0f; dst[3 * k + 1] = p[1] * 10.0f; dst[3 * k + 2] = p[2] * 10.0f;
+            }
+        } else {
+            for (size_t k = 0; k < (size_t)x->natoms * 3; k++) dst[k] = src[k] * 10.0f;
+        }
+        if (h_step) h_step[f] = step;
+        if (h_time) h_time[f] = time;
+        if (h_box) for (int k = 0; k < 9; k++) h_box[(size_t)f * 9 + k] = box[k] * 10.0f;
+    }
+    return PC_OK;
+}
+
+extern "C" void pc_xtc_close(pc_xtc *x) {
+    if (!x) return;
+    if (x->fh) fclose(x->fh);
+    delete x;
 }

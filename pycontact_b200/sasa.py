@@ -56,8 +56,8 @@ def calculate_sasa(psf, dcd, seltext, resseltext="", seltext2="", contact_area=F
         from .io.psf import read_psf
         topology = read_psf(psf)
     if frames is None:
-        from .io.dcd import DCDReader
-        rd = DCDReader(dcd)
+        from .io.xtc import open_trajectory
+        rd = open_trajectory(dcd)
         frames = np.stack([rd.frame(f) for f in range(len(rd))]) if len(rd) else np.zeros((0, topology.n_atoms, 3), np.float32)
     frames = np.asarray(frames, np.float32)
     first = frames[0] if len(frames) else None

@@ -436,6 +436,29 @@ def test_analyzer_from_psf_dcd_files(tmp_path):
     assert an.getFilePaths() == (psf, dcd) and an.lastMap1 == s.maps[0]
 
 
+def test_analyzer_from_psf_xtc_files(tmp_path):
+    """The same constructor path on an XTC trajectory (the reference's tests open one, tests/test_basic.py:28-30): the
+    file's quantised coordinates (nm * 1000, rounded; back in Angstrom) are what the oracle gets."""
+    from tests.test_io_cpu import _write_psf, _write_xtc
+    from pycontact_b200.io.xtc import XTCReader
+    s = synth.make_system("tiny")
+    t = s.topology
+    psf, xtc = str(tmp_path / "tiny.psf"), str(tmp_path / "tiny.xtc")
+    _write_psf(psf, t)
+    _write_xtc(xtc, synth.frames_host(s, range(5)) / np.float32(10.0))
+    rd = XTCReader(xtc)
+    coords = np.stack([rd.frame(f) for f in range(len(rd))])
+    an = Analyzer(psf, xtc, 5.0, 2.5, 120, s.sel1text, s.sel2text, batch_frames=2)
+    an.runFrameScan(1)
+    acc = an.runContactAnalysis(s.maps[0], s.maps[1], 1)
+    ora = frame_oracle.scan_frames([coords[f, s.sel1] for f in range(5)], [coords[f, s.sel2] for f in range(5)],
+                                   s.sel1, s.sel2, 5.0, 2.5, 120, t.names, t.types, t.bonds)
+    _compare_traj(an.contactResults.traj, ora)
+    oacc = frame_oracle.accumulate(ora, s.maps[0], s.maps[1], t.names, t.resids, t.resnames, t.segids, s.backbone)
+    assert [a.key1 for a in acc] == oacc["key1"] and [a.key2 for a in acc] == oacc["key2"]
+    np.testing.assert_allclose(np.asarray([a.scoreArray for a in acc], float), oacc["score"], rtol=RTOL, atol=1e-12)
+
+
 @pytest.mark.parametrize("path", [1, 2])
 def test_edge_cases_empty_results_and_zero_distance(path):
     """Selections of hydrogens only, far-apart selections (empty grid), single atoms, coincident atoms."""

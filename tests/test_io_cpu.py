@@ -75,3 +75,115 @@ def test_selection_language(tmp_path):
         select_atoms(t, "segid")
     with pytest.raises(NotImplementedError):
         select_atoms(t, "around 5 segid PA0")
+
+
+# ---- XTC (csrc/pc_xtc.h through the C ABI; host code, no GPU needed) ------------------------------------------------
+XTC_REF = "/root/reference/PyContact/exampleData/md_noPBC.xtc"          # build container only
+
+
+class _Bits:
+    """MSB-first bit writer (the order xdrfile's receivebits reads)."""
+
+    def __init__(self):
+        self.acc, self.n, self.out = 0, 0, bytearray()
+
+    def put(self, value, nbits):
+        self.acc = (self.acc << nbits) | (value & ((1 << nbits) - 1))
+        self.n += nbits
+        while self.n >= 8:
+            self.n -= 8
+            self.out.append((self.acc >> self.n) & 0xff)
+        self.acc &= (1 << self.n) - 1
+
+    def bytes(self):
+        return bytes(self.out) + (bytes([(self.acc << (8 - self.n)) & 0xff]) if self.n else b"")
+
+
+def _write_xtc(path, frames_nm, precision=1000.0, cut=0):
+    """XTC writer for tests: every atom coded with the frame's full-range bits and flag bit 0 (no runs) -- a valid
+    stream for any xdrfile-compatible reader; <= 9 atoms are stored as plain floats like xdrfile does."""
+    with open(path, "wb") as fh:
+        for f, x in enumerate(np.asarray(frames_nm, np.float32)):
+            n = x.shape[0]
+            fh.write(struct.pack(">iiif", 1995, n, 10 * f, 2.5 * f) + np.diag([5.0, 6.0, 7.0]).astype(">f4").tobytes())
+            fh.write(struct.pack(">i", n))
+            if n <= 9:
+                fh.write(x.astype(">f4").tobytes())
+                continue
+            q = np.rint(x.astype(np.float64) * precision).astype(np.int64)
+            lo, hi = q.min(0), q.max(0)
+            size = (hi - lo + 1).tolist()
+            nbits = (size[0] * size[1] * size[2]).bit_length()                 # == xdrfile's sizeofints for these sizes
+            bw = _Bits()
+            for a in (q - lo).tolist():
+                total = (a[0] * size[1] + a[1]) * size[2] + a[2]
+                left = nbits
+                while left > 8:                                                # low bytes first, whole bytes
+                    bw.put(total & 0xff, 8)
+                    total >>= 8
+                    left -= 8
+                bw.put(total, left)
+                bw.put(0, 1)                                                   # flag: no run follows
+            data = bw.bytes()
+            fh.write(struct.pack(">f3i3iii", precision, *lo.tolist(), *hi.tolist(), 9, len(data)))
+            fh.write(data + b"\0" * (-len(data) % 4))
+        if cut:
+            fh.truncate(fh.tell() - cut)
+
+
+def test_xtc_reader_on_written_files(tmp_path):
+    from pycontact_b200.io.xtc import XTCReader, open_trajectory
+    rng = np.random.default_rng(5)
+    x = rng.uniform(-2.0, 9.0, (4, 300, 3)).astype(np.float32)                 # nm
+    p = str(tmp_path / "t.xtc")
+    _write_xtc(p, x)
+    rd = open_trajectory(p)
+    assert isinstance(rd, XTCReader) and rd.n_atoms == 300 and len(rd) == 4
+    want = (np.rint(x.astype(np.float64) * 1000.0).astype(np.int32).astype(np.float32) * np.float32(1.0 / np.float32(1000.0))) * np.float32(10.0)
+    got = np.empty((4, 300, 3), np.float32)
+    rd.read_into(got, 0, 4)
+    assert np.array_equal(got, want)                                           # bit-exact: int * (1 / precision) * 10 in float32
+    idx = np.array([7, 0, 299, 13], np.int32)
+    assert np.array_equal(rd.frame(2, idx), want[2, idx])
+    step, time, box = rd.header(3)
+    assert step == 30 and time == 7.5 and np.allclose(np.diag(box), [50.0, 60.0, 70.0])
+    with pytest.raises(IndexError):
+        rd.frame(4)
+    # <= 9 atoms: plain floats
+    p2 = str(tmp_path / "s.xtc")
+    _write_xtc(p2, x[:2, :5])
+    rd2 = XTCReader(p2)
+    assert rd2.n_atoms == 5 and len(rd2) == 2 and np.array_equal(rd2.frame(1), x[1, :5] * np.float32(10.0))
+    # a file cut inside its last frame (interrupted write) ends one frame earlier; garbage is refused
+    p3 = str(tmp_path / "c.xtc")
+    _write_xtc(p3, x, cut=40)
+    assert len(XTCReader(p3)) == 3
+    bad = tmp_path / "bad.xtc"
+    bad.write_bytes(b"not an xtc file" * 10)
+    from pycontact_b200._lib import PcError
+    with pytest.raises(PcError):
+        XTCReader(str(bad))
+
+
+@pytest.mark.skipif(not __import__("os").path.exists(XTC_REF), reason="reference fixture only exists in the build container")
+def test_xtc_reader_on_the_reference_fixture():
+    """exampleData/md_noPBC.xtc (tests/test_basic.py:28-30 opens it): written by GROMACS with runs and the water swap.
+    No MDAnalysis here to compare with, so the decode is pinned on physics: the file's 20 437 rigid SPC waters must come
+    back with O-H = 1.000 A and H-H = 1.633 A in every frame, to the file's 0.01 A quantisation."""
+    from pycontact_b200.io.xtc import XTCReader
+    rd = XTCReader(XTC_REF)
+    assert (rd.n_atoms, len(rd)) == (65765, 10)
+    steps = [rd.header(f)[0] for f in range(10)]
+    assert steps == [500000 * f for f in range(10)] and rd.header(9)[1] == 9000.0
+    assert abs(rd.header(0)[2][0, 0] - 86.9428) < 1e-3
+    w = np.arange(4330, 65641, 3)
+    for f in (0, 4, 9):
+        x = rd.frame(f).astype(np.float64)
+        oh = np.concatenate([np.linalg.norm(x[w + 1] - x[w], axis=1), np.linalg.norm(x[w + 2] - x[w], axis=1)])
+        hh = np.linalg.norm(x[w + 2] - x[w + 1], axis=1)
+        assert np.abs(oh - 1.0).max() < 0.02 and np.abs(hh - 1.633).max() < 0.02
+        assert abs(oh.mean() - 1.0) < 1e-3 and abs(hh.mean() - 1.633) < 1e-3
+        prot = np.linalg.norm(np.diff(x[:4330], axis=0), axis=1)
+        assert (prot > 10.0).sum() <= 2 and 1.0 < np.median(prot) < 2.6        # two folded chains, atom after atom
+    idx = np.arange(0, rd.n_atoms, 11, dtype=np.int32)
+    assert np.array_equal(rd.read_into(np.empty((2, idx.size, 3), np.float32), 3, 2, idx)[1], rd.frame(4)[idx])
