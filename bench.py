@@ -499,12 +499,12 @@ def run_gpu(args):
         eng.fold_sparse_export(ctypes.c_void_p(xchg["mine"].data_ptr()), cap)
         with torch.cuda.stream(ext0):
             dist.all_gather_into_tensor(xchg["big"], xchg["mine"])
-        if rank == 0:
-            for r in range(1, world):
-                eng.fold_sparse_import(ctypes.c_void_p(xchg["big"].data_ptr() + r * cap * ENT), cap)
+        if rank == 0:                                        # the other ranks' buffers are contiguous: one import launch
+            eng.fold_sparse_import(ctypes.c_void_p(xchg["big"].data_ptr() + cap * ENT), (world - 1) * cap)
 
-    def device_step(f_lo=0, f_hi=None, events=False, d_src=None):
-        """One pass over resident frames [f_lo, f_hi) of this rank.  Returns (counts, bytes copied to the host)."""
+    def device_step(f_lo=0, f_hi=None, events=False, d_src=None, sort_entries=False):
+        """One pass over resident frames [f_lo, f_hi) of this rank.  Returns (counts, bytes copied to the host).
+        The aggregated maps arrive on the host as (key, sums) entries in table order; sort_entries orders them by key."""
         f_hi = F if f_hi is None else f_hi
         b1, b2 = d_src if d_src is not None else (d1, d2)
         tot = np.zeros(4, np.int64)
@@ -555,12 +555,12 @@ def run_gpu(args):
                 exchange_sparse()
             if rank == 0 or dist is None:
                 try:
-                    ent = eng.fold_sparse_fetch()          # compacted entries -> host (pinned), synchronises
+                    ent = eng.fold_sparse_fetch(sort=sort_entries)   # compacted entries -> host (pinned), synchronises
                 except _lib.PcError:
                     sparse_entries[0] *= 4                 # table too small: grow and redo the pass
                     xchg["cap"] = 0
                     if dist is None:
-                        return device_step(f_lo, f_hi, events, d_src)
+                        return device_step(f_lo, f_hi, events, d_src, sort_entries)
                     raise
                 d_rows += ent.nbytes
                 device_step.last_entries = ent
@@ -610,6 +610,27 @@ def run_gpu(args):
     clocks = sampler.stop()
     launches = lib.pc_launch_count() - launches0
     entries_step = None if device_step.last_entries is None else int(device_step.last_entries.size)
+    if args.timeline:
+        # where one step's time goes: device timestamps of every batch's scan (events on the slots' streams) relative to
+        # the step's first event, host time beside them -- diagnostic only, printed to stderr
+        barrier()
+        check(lib.pc_event_record(e_all[0], stream))
+        th0 = time.perf_counter()
+        device_step(events=True)
+        check(lib.pc_event_record(e_all[1], stream))
+        check(lib.pc_device_sync(local))
+        th1 = time.perf_counter()
+        rel = ctypes.c_float()
+        out = []
+        for b in range(nb):
+            ts = []
+            for e in ev[b]:
+                check(lib.pc_event_elapsed_ms(e_all[0], e, ctypes.byref(rel)))
+                ts.append(rel.value)
+            out.append("%d: %.3f-%.3f" % (b, ts[0], ts[1]))
+        check(lib.pc_event_elapsed_ms(e_all[0], e_all[1], ctypes.byref(rel)))
+        print("timeline rank %d (ms from the step's start; scan of batch b): %s | step end %.3f, host %.3f"
+              % (rank, "  ".join(out), rel.value, (th1 - th0) * 1e3), file=sys.stderr)
 
     # ---- the dominant kernel alone: the same launches again, one batch at a time on one stream (in the step
     # above several batches are in flight, so an event pair around one launch also sees the other streams) ------
@@ -745,7 +766,7 @@ def run_gpu(args):
         dense, sparse = False, True                      # one code path for the comparison: the sparse maps
         xchg_saved = dict(xchg)
         xchg.update(cap=0, mine=None, big=None)
-        c_multi, _ = device_step(clo, chi, d_src=(c1b, c2b))
+        c_multi, _ = device_step(clo, chi, d_src=(c1b, c2b), sort_entries=True)
         ent_multi = None if rank != 0 else device_step.last_entries.copy()
         cm = torch.tensor(c_multi[:3], device="cuda")
         dist.all_reduce(cm)
@@ -753,7 +774,7 @@ def run_gpu(args):
             dist_save = dist
             dist = None                                  # rank 0 alone, no exchange
             try:
-                c_single, _ = device_step(0, Fc, d_src=(c1b, c2b))
+                c_single, _ = device_step(0, Fc, d_src=(c1b, c2b), sort_entries=True)
             finally:
                 dist = dist_save
             ent_single = device_step.last_entries
@@ -917,6 +938,7 @@ def main():
     ap.add_argument("--no-cpu", action="store_true", help="skip the CPU baseline leg")
     ap.add_argument("--no-port", action="store_true", help="--impl reference: skip the port's figure")
     ap.add_argument("--quick", action="store_true", help="profiling runs: 1 warm-up step")
+    ap.add_argument("--timeline", action="store_true", help="diagnostic: device timestamps of one step's batches on stderr")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

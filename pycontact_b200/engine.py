@@ -167,8 +167,9 @@ class ContactEngine:
         check(self.lib.pc_stream_sync(s0.stream))
         self.fold_entries = int(entries)
 
-    def fold_sparse_fetch(self) -> np.ndarray:
-        """Occupied entries of the table, sorted by key (_lib.fold_entry_dtype)."""
+    def fold_sparse_fetch(self, sort: bool = True) -> np.ndarray:
+        """Occupied entries of the table (_lib.fold_entry_dtype), sorted by key unless sort=False (then in table
+        order: a view of the slot's pinned buffer, valid until the next fetch)."""
         for s in self.slots[1:]:
             check(self.lib.pc_stream_sync(s.stream))
         s0 = self.slots[0]
@@ -176,7 +177,11 @@ class ContactEngine:
         n = ctypes.c_int64()
         check(self.lib.pc_fold_sparse_fetch(s0.ctx, s0.stream, ptr(buf), self.fold_entries, ctypes.byref(n)))
         ent = buf[:n.value]
-        return ent[np.argsort(ent["key"], kind="stable")]
+        if not sort:
+            return ent
+        # keys are unique; sorting a contiguous copy of the key column and gathering whole entries is 6x faster than
+        # argsort on the 40-byte-strided field (0.27 vs 1.6 ms for 13 k entries -- a third of a 1250-frame step)
+        return np.take(ent, np.argsort(np.ascontiguousarray(ent["key"])), axis=0)
 
     def fold_sparse_export(self, d_out, max_entries: int):
         """The table's occupied entries -> d_out[0 .. max_entries) on the device (compacted, padded with empty
