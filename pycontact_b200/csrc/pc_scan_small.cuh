@@ -29,6 +29,18 @@
 #pragma once
 #include "pc_common.cuh"
 
+// One pass over the frame instead of two when a CTA's previous frame predicts this one: the first pass (bounding
+// boxes) also keeps every heavy atom inside the previous frame's grid box grown by PC_SMALL_PRED_MARGIN on each side.
+// When this frame's exact box turns out to lie inside that box, the in-grid atoms are among the kept ones and are
+// filtered out of shared memory (phase 3'); otherwise the second pass over the frame runs as before.  The pair set does
+// not depend on which of the two happened: atoms outside the exact box cannot have a partner.
+#ifndef PC_SMALL_PRED
+#define PC_SMALL_PRED 1
+#endif
+#ifndef PC_SMALL_PRED_MARGIN
+#define PC_SMALL_PRED_MARGIN 1.0f
+#endif
+
 struct PcSmallSmem {
     // offsets (bytes) into dynamic shared memory, computed on the host
     int off_cand, off_ccell, off_hits, off_hb, off_tab, off_sort, off_cellA, off_cellB, total;
@@ -148,6 +160,10 @@ __global__ void __launch_bounds__(NT, NT >= 1024 ? 1 : NT >= 512 ? 2 : NT >= 384
     __shared__ unsigned int s_nhits, s_nhb, s_nA, s_nB, s_ngate, s_next;
     __shared__ long long s_cbase, s_hbase, s_rbase;
     __shared__ unsigned int s_status;
+    __shared__ float s_pbox[6];           // predicted box (lo xyz, hi xyz) from this CTA's previous frame
+    __shared__ int s_pred, s_usepred;     // s_pred: s_pbox is valid; s_usepred: this frame's exact box lies inside it
+    if (threadIdx.x == 0) { s_pred = 0; s_usepred = 0; s_nA = 0; s_nB = 0; }
+    __syncthreads();
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const bool self = a.self_mode != 0;
@@ -168,7 +184,9 @@ __global__ void __launch_bounds__(NT, NT >= 1024 ? 1 : NT >= 512 ? 2 : NT >= 384
 #pragma unroll
         for (int k = 0; k < 6; k++) { mn[k] = INFINITY; mx[k] = -INFINITY; }
         // four atoms per iteration: the index loads, then the coordinate loads, are issued back to back
-        auto bbox_pass = [&](const float *fr, const uint32_t *hinfo, int nh, float *lo3, float *hi3) {
+        const bool pred = PC_SMALL_PRED && s_pred != 0;
+        auto bbox_pass = [&](const float *fr, const uint32_t *hinfo, int nh, float *lo3, float *hi3, unsigned int *counter,
+                             const bool top) {
             for (int k0 = tid; k0 < nh; k0 += 4 * NT) {
                 uint32_t info[4];
                 float x[4], y[4], z[4];
@@ -180,18 +198,24 @@ __global__ void __launch_bounds__(NT, NT >= 1024 ? 1 : NT >= 512 ? 2 : NT >= 384
                 for (int u = 0; u < 4; u++) {       // a clamped duplicate of the last atom leaves min/max unchanged
                     lo3[0] = fminf(lo3[0], x[u]); lo3[1] = fminf(lo3[1], y[u]); lo3[2] = fminf(lo3[2], z[u]);
                     hi3[0] = fmaxf(hi3[0], x[u]); hi3[1] = fmaxf(hi3[1], y[u]); hi3[2] = fmaxf(hi3[2], z[u]);
+                    if (pred && k0 + u * NT < nh && x[u] >= s_pbox[0] && x[u] <= s_pbox[3] && y[u] >= s_pbox[1] &&
+                        y[u] <= s_pbox[4] && z[u] >= s_pbox[2] && z[u] <= s_pbox[5]) {
+                        const unsigned p = atomicAdd(counter, 1u);
+                        if (p < (unsigned)capCand)
+                            cand[top ? (unsigned)capCand - 1u - p : p] = make_float4(x[u], y[u], z[u], __uint_as_float(info[u]));
+                    }
                 }
             }
         };
-        bbox_pass(fr1, a.t.hinfo1, n1h, mn, mx);
-        if (!self) bbox_pass(fr2, a.t.hinfo2, n2h, mn + 3, mx + 3);
+        bbox_pass(fr1, a.t.hinfo1, n1h, mn, mx, &s_nA, false);
+        if (!self) bbox_pass(fr2, a.t.hinfo2, n2h, mn + 3, mx + 3, &s_nB, true);
 #pragma unroll
         for (int k = 0; k < 6; k++) { mn[k] = warp_min(mn[k]); mx[k] = warp_max(mx[k]); }
         if (lane == 0) {
 #pragma unroll
             for (int k = 0; k < 6; k++) { red[warp][k] = mn[k]; red[warp][6 + k] = mx[k]; }
         }
-        if (tid == 0) { s_nhits = 0; s_nhb = 0; s_status = 0; s_nA = 0; s_nB = 0; s_ngate = 0; s_next = 0; }
+        if (tid == 0) { s_nhits = 0; s_nhb = 0; s_status = 0; s_ngate = 0; s_next = 0; }     // (s_nA, s_nB: reset at the frame's end)
         __syncthreads();
         PC_PHASE_MARK(0);
 
@@ -215,6 +239,14 @@ __global__ void __launch_bounds__(NT, NT >= 1024 ? 1 : NT >= 512 ? 2 : NT >= 384
                         ez = __shfl_sync(PC_FULL_MASK, ext, 2);
             const float lx = __shfl_sync(PC_FULL_MASK, l, 0), ly = __shfl_sync(PC_FULL_MASK, l, 1),
                         lz = __shfl_sync(PC_FULL_MASK, l, 2);
+            {
+                // does the exact box lie inside the box the first pass kept atoms for?  Then: the next frame's prediction
+                const bool in_k = l >= s_pbox[lane % 3] && h <= s_pbox[3 + lane % 3];
+                const unsigned outm = __ballot_sync(PC_FULL_MASK, lane < 3 && !in_k);
+                const bool okbox = em == 0 && bm == 0 && n1h != 0 && n2h != 0;
+                if (lane < 3) { s_pbox[lane] = l - PC_SMALL_PRED_MARGIN; s_pbox[3 + lane] = h + PC_SMALL_PRED_MARGIN; }
+                if (lane == 0) { s_usepred = (pred && okbox && outm == 0) ? 1 : 0; s_pred = okbox ? 1 : 0; }
+            }
             if (lane == 0) {
                 bool empty = em != 0 || n1h == 0 || n2h == 0;
                 if (bm && !empty) { atomicOr(&s_status, (unsigned)PC_ST_BAD_COORDS); empty = true; }
@@ -249,7 +281,12 @@ __global__ void __launch_bounds__(NT, NT >= 1024 ? 1 : NT >= 512 ? 2 : NT >= 384
 
             // ---- phase 3: second pass over the frame (it is in L2 now): atoms inside the grid go to
             //      the candidate pool with their cell id; atoms per cell (shared atomics) -----------------
+            // (with the prediction's atoms in the pool: phase 3' below instead)
+            const int stA = (int)s_nA, stB = self ? 0 : (int)s_nB;            // kept by the first pass
+            const bool filt = s_usepred != 0 && stA + stB <= capCand;
+            __syncthreads();                                                  // everybody has read the counters
             for (int c = tid; c <= ncell; c += NT) { cellA[c] = 0; if (!self) cellB[c] = 0; }
+            if (!filt && tid == 0) { s_nA = 0; s_nB = 0; }
             __syncthreads();
             auto cell_of = [&](float x, float y, float z) -> int {
                 // atoms outside the grid box are farther than one cell edge (> cutoff) from the other
@@ -287,11 +324,27 @@ __global__ void __launch_bounds__(NT, NT >= 1024 ? 1 : NT >= 512 ? 2 : NT >= 384
                     }
                 }
             };
-            stage_pass(fr1, a.t.hinfo1, n1h, &s_nA, cellA, false);
-            if (!self) stage_pass(fr2, a.t.hinfo2, n2h, &s_nB, cellB, true);
+            if (filt) {
+                // ---- phase 3': the kept atoms' exact cells; atoms outside the exact grid are marked and left behind
+                for (int p = tid; p < stA; p += NT) {
+                    const float4 v = cand[p];
+                    const int c = cell_of(v.x, v.y, v.z);
+                    ccell[p] = (uint16_t)(c < 0 ? 0xffff : c);
+                    if (c >= 0) atomicAdd(&cellA[c], 1u);
+                }
+                for (int p = tid; p < stB; p += NT) {
+                    const float4 v = cand[capCand - 1 - p];
+                    const int c = cell_of(v.x, v.y, v.z);
+                    ccell[capCand - 1 - p] = (uint16_t)(c < 0 ? 0xffff : c);
+                    if (c >= 0) atomicAdd(&cellB[c], 1u);
+                }
+            } else {
+                stage_pass(fr1, a.t.hinfo1, n1h, &s_nA, cellA, false);
+                if (!self) stage_pass(fr2, a.t.hinfo2, n2h, &s_nB, cellB, true);
+            }
             __syncthreads();
             PC_PHASE_MARK(2);
-            nInA = (int)s_nA; nInB = self ? nInA : (int)s_nB;
+            nInA = (int)s_nA; nInB = self ? nInA : (int)s_nB;      // atoms in the pool
 #ifdef PC_PHASE_CLOCKS
             if (tid == 0) {
                 atomicAdd(&a.counters[PC_CNT_PHASE + 16], (unsigned long long)(nInA + (self ? 0 : nInB)));
@@ -307,11 +360,19 @@ __global__ void __launch_bounds__(NT, NT >= 1024 ? 1 : NT >= 512 ? 2 : NT >= 384
                 if (!self) block_excl_scan_inplace<NT>(cellB, ncell, wsum);
                 PC_PHASE_MARK(3);
                 // ---- phase 5: scatter into cell order; afterwards cell[c] == END of cell c -----------
-                sortA = sortp;
+                const int poolA = nInA, poolB = nInB;
+                nInA = (int)cellA[ncell]; nInB = self ? nInA : (int)cellB[ncell];     // atoms inside the grid (all of the pool
+                sortA = sortp;                                                        // unless phase 3' left some behind)
                 sortB = self ? sortp : sortp + (capCand - nInB);
-                for (int p = tid; p < nInA; p += NT) sortA[atomicAdd(&cellA[ccell[p]], 1u)] = cand[p];
+                for (int p = tid; p < poolA; p += NT) {
+                    const unsigned c = ccell[p];
+                    if (c != 0xffffu) sortA[atomicAdd(&cellA[c], 1u)] = cand[p];
+                }
                 if (!self)
-                    for (int p = tid; p < nInB; p += NT) sortB[atomicAdd(&cellB[ccell[capCand - 1 - p]], 1u)] = cand[capCand - 1 - p];
+                    for (int p = tid; p < poolB; p += NT) {
+                        const unsigned c = ccell[capCand - 1 - p];
+                        if (c != 0xffffu) sortB[atomicAdd(&cellB[c], 1u)] = cand[capCand - 1 - p];
+                    }
                 __syncthreads();
                 PC_PHASE_MARK(4);
 
@@ -608,6 +669,7 @@ __global__ void __launch_bounds__(NT, NT >= 1024 ? 1 : NT >= 512 ? 2 : NT >= 384
             }
         }
         if (tid == 0 && s_status) atomicOr(&a.counters[PC_CNT_STATUS], (unsigned long long)s_status);
+        if (tid == 0) { s_nA = 0; s_nB = 0; }          // the next frame's first pass appends kept atoms right away
         __syncthreads();
         PC_PHASE_MARK(10);
     }

@@ -265,6 +265,47 @@ def test_synthetic_matches_oracle(name, path, self_mode, nframes):
     np.testing.assert_allclose(table.sc2, acc["sc2"], rtol=RTOL, atol=1e-9)
 
 
+@pytest.mark.parametrize("self_mode", [False, True])
+def test_small_path_one_pass_prediction(self_mode):
+    """A CTA of the small-frame kernel keeps atoms for its NEXT frame's grid during the bounding-box pass (box of its
+    previous frame + a margin) and skips the second pass over the frame when the exact box lies inside it.  One launch
+    over more frames than there are CTAs (2 x 148), so that CTAs see a second and a third frame: contained boxes
+    (thermal jitter), boxes that jump (whole system translated: second pass), empty grids in between (selection 2 moved
+    away) -- every frame equals the oracle, with and without the fused accumulation."""
+    s = synth.make_system("small")
+    t = s.topology
+    nframes = 700
+    frames = list(range(nframes))
+    coords = synth.frames_host(s, frames).copy()
+    rng = np.random.default_rng(5)
+    jump = rng.random(nframes) < 0.3
+    coords[jump] += rng.uniform(-40, 40, (int(jump.sum()), 1, 3)).astype(np.float32)      # the box is somewhere else
+    idx1 = s.sel1
+    idx2 = s.sel1 if self_mode else s.sel2
+    if not self_mode:
+        far = np.nonzero(rng.random(nframes) < 0.05)[0]
+        coords[np.ix_(far, idx2)] += np.float32(500.0)                                    # no overlap: empty grid
+    ora = frame_oracle.scan_frames([coords[k, idx1] for k in range(nframes)], [coords[k, idx2] for k in range(nframes)],
+                                   idx1, idx2, 5.0, 2.5, 120, t.names, t.types, t.bonds, t.resids, t.segids, self_mode)
+    s1, s2 = _selections(t, idx1, None if self_mode else idx2, s.backbone)
+    gm1 = prepare.group_map(idx1, s.maps[0], t.names, t.resids, t.resnames, t.segids)
+    gm2 = prepare.group_map(idx2, s.maps[1], t.names, t.resids, t.resnames, t.segids)
+    with ContactEngine(s1, s2, 5.0, 2.5, 120) as eng:
+        eng.set_path(1)
+        eng.set_maps(gm1.gid, gm2.gid, gm2.n_groups)
+        src = ArraySource(np.ascontiguousarray(coords[:, idx1]), None if self_mode else np.ascontiguousarray(coords[:, idx2]))
+        traj, table, _ = run_scan([eng], src, batch_frames=nframes, order_keys=True, accumulate=True, group_maps=(gm1, gm2))
+        _compare_traj(traj, ora)
+        _, table2, _ = run_scan([eng], src, batch_frames=nframes, order_keys=False, accumulate=True, group_maps=(gm1, gm2))
+    acc = frame_oracle.accumulate(ora, s.maps[0], s.maps[1], t.names, t.resids, t.resnames, t.segids, s.backbone)
+    np.testing.assert_allclose(table.score_matrix(), acc["score"], rtol=RTOL, atol=1e-12)
+    # fused accumulation (no order keys): same keys in another order
+    o1, o2 = np.argsort(table.keys), np.argsort(table2.keys)
+    assert np.array_equal(table.keys[o1], table2.keys[o2])
+    np.testing.assert_allclose(table2.score_matrix()[o2], table.score_matrix()[o1], rtol=RTOL, atol=1e-9)
+    assert np.array_equal(table2.hbond_matrix()[o2], table.hbond_matrix()[o1])
+
+
 @pytest.mark.parametrize("cutoff", [3.0, 4.6, 8.0, 12.0])
 def test_cutoff_sweep_small_system(cutoff):
     """C5-style sweep on a small solvated system: pair sets exact at every cutoff."""
