@@ -184,6 +184,15 @@ int pc_fold_rows(pc_ctx *ctx, double *d_totals, int64_t n_keys, void *stream);
 int pc_key_stats(int device, const double *d_scores, const uint32_t *d_hbonds, int64_t n_keys, int32_t n_frames,
                  double ns_per_frame, double threshold, double *d_out, void *stream);
 
+/* The same statistics straight from the (frame, key) cells the accumulation emits, grouped by key (CSR): cells
+ * d_key_ptr[k] .. d_key_ptr[k + 1] belong to key k, each with its frame position (0 <= frame < n_frames), its score
+ * (AccumulatedContact.scoreArray[frame], core/ContactAnalyzer.py:561-577; frames without a cell score 0, :571-575) and its
+ * H-bond count (may be NULL).  The (keys x frames) matrix is assembled per key in shared memory and never exists in HBM or
+ * on the host.  Same output table and limits as pc_key_stats. */
+int pc_key_stats_rows(int device, const int64_t *d_key_ptr, const int32_t *d_row_frame, const double *d_row_score,
+                      const uint32_t *d_row_hbonds, int64_t n_keys, int32_t n_frames, double ns_per_frame, double threshold,
+                      double *d_out, void *stream);
+
 /* The same aggregation for key spaces too large for a dense table: a per-context open-addressing table
  * (key -> sum score, sum bb1, sum bb2, frames with an H-bond) that lives across batches.
  * pc_fold_sparse_init sizes it (entries, rounded up to a power of two) and clears it;

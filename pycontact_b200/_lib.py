@@ -64,7 +64,7 @@ EXPORTS = [
     "pc_device_outputs", "pc_fetch", "pc_find_contacts", "pc_free_host", "pc_synth_frames", "pc_host_alloc",
     "pc_host_free", "pc_load_records", "pc_stream_create", "pc_stream_sync", "pc_stream_destroy",
     "pc_device_alloc", "pc_device_free", "pc_memcpy", "pc_memset", "pc_device_sync",
-    "pc_launch_count", "pc_event_create", "pc_event_record", "pc_event_elapsed_ms", "pc_event_destroy", "pc_fold_rows", "pc_fetch_packed_rows", "pc_pack_rows", "pc_set_pack_format", "pc_fold_sparse_init", "pc_fold_rows_sparse", "pc_fold_sparse_fetch", "pc_fold_sparse_share", "pc_set_probe", "pc_key_stats", "pc_fold_sparse_export", "pc_fold_sparse_import", "pc_fp32_peak", "pc_mem_info",
+    "pc_launch_count", "pc_event_create", "pc_event_record", "pc_event_elapsed_ms", "pc_event_destroy", "pc_fold_rows", "pc_fetch_packed_rows", "pc_pack_rows", "pc_set_pack_format", "pc_fold_sparse_init", "pc_fold_rows_sparse", "pc_fold_sparse_fetch", "pc_fold_sparse_share", "pc_set_probe", "pc_key_stats", "pc_key_stats_rows", "pc_fold_sparse_export", "pc_fold_sparse_import", "pc_fp32_peak", "pc_mem_info",
     "pc_sasa_points", "pc_sasa", "pc_sasa_device", "pc_find_within", "pc_within_device",
 ]
 
@@ -130,6 +130,7 @@ def load():
     lib.pc_device_sync.argtypes = [ctypes.c_int]
     lib.pc_launch_count.restype = ctypes.c_int64
     lib.pc_key_stats.argtypes = [ctypes.c_int, vp, vp, i64, i32, f64, f64, vp, vp]
+    lib.pc_key_stats_rows.argtypes = [ctypes.c_int, vp, vp, vp, vp, i64, i32, f64, f64, vp, vp]
     lib.pc_event_create.argtypes = [ctypes.c_int, P(vp)]
     lib.pc_event_record.argtypes = [vp, vp]
     lib.pc_event_elapsed_ms.argtypes = [vp, vp, P(ctypes.c_float)]

@@ -655,27 +655,44 @@ extern "C" int pc_fold_rows(pc_ctx *c, double *d_totals, int64_t n_keys, void *s
     return PC_OK;
 }
 
+static int key_stats_launch(int device, const double *d_scores, const uint32_t *d_hbonds, const long long *d_key_ptr,
+                            const int *d_row_frame, int64_t n_keys, int32_t n_frames, double ns_per_frame, double threshold,
+                            double *d_out, void *stream) {
+    CUDA_TRY(cudaSetDevice(device));
+    const int fpad = (n_frames + 1) & ~1;
+    const size_t smem = sizeof(double) * (size_t)fpad + sizeof(unsigned int) * (size_t)(n_frames / 2 + 2);
+    auto kern = d_key_ptr ? pc_key_stats_kernel<true> : pc_key_stats_kernel<false>;
+    CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int sms = 0;
+    CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));
+    const int per_sm = std::max(1, std::min(4, (int)((size_t)(224 * 1024) / (smem + 4096))));
+    const int grid = (int)std::min<int64_t>(n_keys, (int64_t)per_sm * sms);
+    kern<<<grid, PC_STATS_NT, smem, (cudaStream_t)stream>>>(d_scores, d_hbonds, d_key_ptr, d_row_frame, (long long)n_keys, n_frames,
+                                                           fpad, ns_per_frame, threshold, d_out);
+    CUDA_TRY(cudaGetLastError());
+    g_launches += 1;
+    return PC_OK;
+}
+
 extern "C" int pc_key_stats(int device, const double *d_scores, const uint32_t *d_hbonds, int64_t n_keys, int32_t n_frames,
                             double ns_per_frame, double threshold, double *d_out, void *stream) {
     if (!d_scores || !d_out || n_keys < 0 || n_frames < 0) return fail(PC_ERR_INVALID, "pc_key_stats: bad arguments");
     if (n_frames > PC_STATS_MAX_FRAMES)
         return fail(PC_ERR_INVALID, "pc_key_stats: more than 16384 frames per call (split the frame range)");
     if (n_keys == 0) return PC_OK;
-    CUDA_TRY(cudaSetDevice(device));
-    int fpad = 2, rpad = 2;
-    while (fpad < n_frames) fpad <<= 1;
-    while (rpad < n_frames / 2 + 2) rpad <<= 1;
-    const size_t smem = sizeof(double) * (size_t)fpad + sizeof(unsigned int) * (size_t)rpad;
-    CUDA_TRY(cudaFuncSetAttribute(pc_key_stats_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    int sms = 0;
-    CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));
-    const int per_sm = smem > 100 * 1024 ? 1 : 2;
-    const int grid = (int)std::min<int64_t>(n_keys, (int64_t)per_sm * sms);
-    pc_key_stats_kernel<<<grid, PC_STATS_NT, smem, (cudaStream_t)stream>>>(d_scores, d_hbonds, (long long)n_keys, n_frames, fpad,
-                                                                        rpad, ns_per_frame, threshold, d_out);
-    CUDA_TRY(cudaGetLastError());
-    g_launches += 1;
-    return PC_OK;
+    return key_stats_launch(device, d_scores, d_hbonds, nullptr, nullptr, n_keys, n_frames, ns_per_frame, threshold, d_out, stream);
+}
+
+extern "C" int pc_key_stats_rows(int device, const int64_t *d_key_ptr, const int32_t *d_row_frame, const double *d_row_score,
+                                 const uint32_t *d_row_hbonds, int64_t n_keys, int32_t n_frames, double ns_per_frame,
+                                 double threshold, double *d_out, void *stream) {
+    if (!d_key_ptr || !d_out || n_keys < 0 || n_frames < 0) return fail(PC_ERR_INVALID, "pc_key_stats_rows: bad arguments");
+    if (n_frames > PC_STATS_MAX_FRAMES)
+        return fail(PC_ERR_INVALID, "pc_key_stats_rows: more than 16384 frames per call (split the frame range)");
+    if (n_keys == 0) return PC_OK;
+    static_assert(sizeof(long long) == sizeof(int64_t), "key_ptr is int64");
+    return key_stats_launch(device, d_row_score, d_row_hbonds, reinterpret_cast<const long long *>(d_key_ptr), d_row_frame, n_keys,
+                            n_frames, ns_per_frame, threshold, d_out, stream);
 }
 
 extern "C" int pc_fold_sparse_init(pc_ctx *c, int64_t entries, void *stream) {

@@ -277,6 +277,13 @@ class AccumulationTable:
         m[self.row_key, self.row_frames] = self.rows["nhbonds"]
         return m
 
+    def statistics(self, ns_per_frame: float = 1.0, threshold: float = 0.0, device: int = 0):
+        """mean / median score, hbond_percentage, total_time, mean / median life time of every key
+        (core/Biochemistry.py:150-213) from the table's cells, on the GPU (stats.key_statistics_rows)."""
+        from . import stats
+        return stats.key_statistics_rows(self.key_ptr, self.row_frames, self.rows["score"], self.rows["nhbonds"], self.n_frames,
+                                         ns_per_frame, threshold, device)
+
     def hbond_percentage(self) -> np.ndarray:
         """AccumulatedContact.hbond_percentage for every key (core/Biochemistry.py:150-158)."""
         hits = np.bincount(self.row_key, weights=(self.rows["nhbonds"] > 0), minlength=self.n_keys)

@@ -53,6 +53,40 @@ def key_statistics(score_matrix, hbond_matrix=None, ns_per_frame: float = 1.0, t
     return {c: out[:, i].copy() for i, c in enumerate(COLUMNS)}
 
 
+def key_statistics_rows(key_ptr, row_frames, row_scores, row_hbonds=None, n_frames: int = 0, ns_per_frame: float = 1.0,
+                        threshold: float = 0.0, device: int = 0) -> Dict[str, np.ndarray]:
+    """The same table from the (frame, key) cells themselves, grouped by key: cells ``key_ptr[k]:key_ptr[k+1]`` belong
+    to key k (``AccumulationTable.key_ptr / row_frames / rows["score"] / rows["nhbonds"]``).  The dense (keys x frames)
+    matrix is never built: every key's row is assembled in shared memory by ``pc_key_stats_rows``."""
+    lib = _lib.load()
+    kp = np.ascontiguousarray(key_ptr, dtype=np.int64)
+    K = kp.size - 1
+    F = int(n_frames)
+    if F > MAX_FRAMES:
+        raise ValueError("pc_key_stats_rows handles up to %d frames per call" % MAX_FRAMES)
+    out = np.zeros((max(K, 0), len(COLUMNS)))
+    if K <= 0:
+        return {c: out[:, i].copy() for i, c in enumerate(COLUMNS)}
+    fr = np.ascontiguousarray(row_frames, dtype=np.int32)
+    sc = np.ascontiguousarray(row_scores, dtype=np.float64)
+    if fr.size != sc.size or int(kp[-1]) != sc.size:
+        raise ValueError("key_ptr, row_frames and row_scores do not describe the same cells")
+    hb = None if row_hbonds is None else np.ascontiguousarray(row_hbonds, dtype=np.uint32)
+    bufs = [DeviceBuffer.from_array(kp, device), DeviceBuffer.from_array(fr if fr.size else np.zeros(1, np.int32), device),
+            DeviceBuffer.from_array(sc if sc.size else np.zeros(1), device),
+            DeviceBuffer.from_array(hb if hb.size else np.zeros(1, np.uint32), device) if hb is not None else None,
+            DeviceBuffer(out.nbytes, device)]
+    try:
+        check(lib.pc_key_stats_rows(device, bufs[0].ptr, bufs[1].ptr, bufs[2].ptr, bufs[3].ptr if bufs[3] is not None else None,
+                                    K, F, float(ns_per_frame), float(threshold), bufs[4].ptr, None))
+        out = bufs[4].download(np.float64, K * len(COLUMNS)).reshape(K, len(COLUMNS))
+    finally:
+        for b in bufs:
+            if b is not None:
+                b.free()
+    return {c: out[:, i].copy() for i, c in enumerate(COLUMNS)}
+
+
 def contact_statistics(contacts: Sequence, ns_per_frame: float = 1.0, threshold: float = 0.0, device: int = 0,
                        assign: bool = True) -> Dict[str, np.ndarray]:
     """Statistics of a list of AccumulatedContact (any object with ``scoreArray`` and ``hbondFramesScan``).

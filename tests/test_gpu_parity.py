@@ -696,6 +696,64 @@ def test_key_stats_full_size_and_limits():
     assert nohb["hbond_percentage"].tolist() == [0, 0, 0] and nohb["median_life_time"].tolist() == [5, 5, 5]
 
 
+def _cells_of(sc, hb, rng):
+    """(keys x frames) matrices -> CSR over keys of their non-zero cells (plus a few explicit zero cells), shuffled inside a key."""
+    kp, fr, val, hbv = [0], [], [], []
+    for k in range(sc.shape[0]):
+        f = np.nonzero((sc[k] != 0) | (hb[k] > 0) | (rng.random(sc.shape[1]) < 0.02))[0]
+        f = rng.permutation(f)
+        fr.append(f); val.append(sc[k, f]); hbv.append(hb[k, f])
+        kp.append(kp[-1] + f.size)
+    return np.asarray(kp), np.concatenate(fr), np.concatenate(val), np.concatenate(hbv)
+
+
+@pytest.mark.parametrize("F", [1, 2, 50, 777, 10000, 16384])
+def test_key_stats_from_cells_equals_dense_and_oracle(F):
+    """pc_key_stats_rows assembles every key's row in shared memory from the (frame, key) cells: same table as the dense
+    call (bit for bit: the medians are order statistics, the sums run over the same values) and as the oracle."""
+    from oracle import stats_oracle
+    from pycontact_b200 import stats
+    rng = np.random.default_rng(F)
+    K = 23
+    sc, hb = _random_scores(K, F, 300 + F)
+    if K > 3 and F > 2:
+        sc[2] = 0.7; sc[2, F // 2] = 0.0                  # two long runs
+        sc[3] = rng.normal(0, 1, F)                       # negative scores: the select's key order
+    kp, fr, val, hbv = _cells_of(sc, hb, rng)
+    for ns, thr in ((1, 0), (0.02, 0.5)):
+        rows = stats.key_statistics_rows(kp, fr, val, hbv, F, ns, thr)
+        dense = stats.key_statistics(sc, hb, ns, thr)
+        for k in rows:
+            if k == "mean":
+                np.testing.assert_allclose(rows[k], dense[k], rtol=STATS_RTOL, atol=1e-300)
+            else:
+                assert np.array_equal(rows[k], dense[k]), k
+        sample = np.arange(min(K, 6))
+        _check_stats({k: v[sample] for k, v in rows.items()}, stats_oracle.key_statistics(sc[sample], hb[sample], ns, thr))
+    assert np.array_equal(dense["median"], np.median(sc, axis=1))
+    empty = stats.key_statistics_rows(np.zeros(1, np.int64), np.zeros(0, np.int32), np.zeros(0), None, 10)
+    assert all(v.shape == (0,) for v in empty.values())
+    none = stats.key_statistics_rows(np.zeros(3, np.int64), np.zeros(0, np.int32), np.zeros(0), None, 10, 1, 0)   # keys without cells
+    assert none["mean"].tolist() == [0, 0] and none["life_entries"].tolist() == [1, 1]
+
+
+def test_accumulation_table_statistics_on_the_fixture(rpn11, golden_ab):
+    """AccumulationTable.statistics (cells -> pc_key_stats_rows) on the reference's fixture vs the values the reference's
+    AccumulatedContact methods give on its golden session."""
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "rpn11_ubq_stats_golden.npz"))
+    a = Analyzer("rpn11_ubq.psf", "rpn11_ubq.dcd", 5.0, 2.5, 120, "segid RN11", "segid UBQ",
+                 topology=rpn11.topology, frames=rpn11.coords)
+    a.runFrameScan(1)
+    a.runContactAnalysis([0, 0, 1, 1, 0], [0, 0, 1, 1, 0], 1)
+    ns, thr = g["params_a"]
+    st = a._table.statistics(ns, thr)
+    np.testing.assert_allclose(st["mean"], g["mean"], rtol=1e-6)
+    np.testing.assert_allclose(st["median"], g["median"], rtol=1e-6, atol=1e-12)
+    assert np.array_equal(st["hbond_percentage"], g["hbond_percentage"]) and st["hbond_percentage"].sum() == 676.0
+    np.testing.assert_allclose(st["total_time"], g["total_time_a"], rtol=1e-9)
+    assert np.array_equal(st["life_entries"], g["life_entries_a"])
+
+
 def test_filters_and_sorting_on_device():
     """core/ContactFilters.py:187-287: the criteria come from pc_key_stats; expectations from the oracle."""
     from oracle import stats_oracle
