@@ -444,7 +444,7 @@ def run_gpu(args):
     eng.set_maps(gm1.gid, gm2.gid, gm2.n_groups)
     if os.environ.get("PC_GROUP"):                         # experiments: 0 = multi-kernel sequence + global table instead of the group kernel
         eng.set_group_mode(int(os.environ["PC_GROUP"]))
-    if os.environ.get("PC_TAIL"):                          # experiments: 0 = multi-kernel sequence, 1 = tail kernel v1, 2 = walk
+    if os.environ.get("PC_TAIL"):                          # experiments: 0 = multi-kernel sequence, 1 = tail kernel on compacted atoms
         eng.set_tail(int(os.environ["PC_TAIL"]))
     n_keys = gm1.n_groups * gm2.n_groups
     # time-aggregated maps: a dense [n_keys][4] table (32 MB at most), else a hash table keyed by the 64-bit key; key spaces

@@ -128,9 +128,9 @@ int pc_set_path(pc_ctx *ctx, int path);
  * 3 x 384 / 4 x 256 threads per SM, then the full plan. */
 int pc_set_small_ctas(pc_ctx *ctx, int ctas);
 
-/* Large-frame path, what follows the streaming kernels.  mode 2 (default) and 1: ONE fused kernel, a CTA per frame
+/* Large-frame path, what follows the streaming kernels.  mode 3 (default) and 1: ONE fused kernel, a CTA per frame
  * (cell sort, pair search, records, H-bond test and -- with maps, without order keys -- the accumulation, all out of
- * shared memory); 2 reads selection 1 straight from the frame and balances the pair search inside the warp, 1 works on
+ * shared memory); 3 reads selection 1 straight from the frame (no bin pass for it), 1 works on
  * the compacted atoms of both selections.  0 = the multi-kernel sequence, which has no limit on a frame's in-grid
  * atoms.  A batch whose frames do not fit a fused kernel reports PC_ERR_CAPACITY with status bit 128; callers then
  * select 0 and re-run (ContactEngine does).  Same records either way (vmd_gridsearch3,

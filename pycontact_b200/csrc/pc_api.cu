@@ -168,8 +168,8 @@ extern "C" int pc_set_path(pc_ctx *c, int path) {
 
 extern "C" int pc_set_tail(pc_ctx *c, int on) {
     if (!c) return fail(PC_ERR_INVALID, "pc_set_tail: ctx is NULL");
-    if (on < 0 || on > 3)
-        return fail(PC_ERR_INVALID, "pc_set_tail: 0 (multi-kernel sequence), 1 (fused tail kernel), 2 (walk kernel) or 3 (tail kernel, A from the frame)");
+    if (on != 0 && on != 1 && on != 3)
+        return fail(PC_ERR_INVALID, "pc_set_tail: 0 (multi-kernel sequence), 1 (fused tail kernel on the compacted atoms) or 3 (tail kernel, A from the frame)");
     c->tail_mode = on;
     return PC_OK;
 }

@@ -360,138 +360,6 @@ __global__ void __launch_bounds__(PC_STREAM_NT) pc_large_stream_kernel(const PcS
     }
 }
 
-// ---- L3x: streaming bin of a selection that is mostly OUTSIDE the grid (1 M-atom frames: 950 k lipid + water atoms
-// around a protein) -------------------------------------------------------------------------------------------------
-// The bin mode above walks the chunk's slice of the heavy-atom list: per heavy atom an index load, three dependent
-// coordinate loads and the cell arithmetic, although 98 % of the atoms fall outside the grid.  Here every atom of the
-// chunk -- hydrogens too -- is tested against the grid's box first (three conflict-free loads at a 12-byte stride, six
-// compares); only atoms inside it (a few per warp and chunk) look up their heavy bit and packed word in global memory
-// and go through the exact cell test and the compaction.  No heavy-atom list in the ring: four stages of 24 KB per CTA
-// instead of three of 32 KB (50 % more bytes in flight with two CTAs per SM).
-#define PC_BINX_STAGES 4
-#define PC_BINX_SLOT (PC_STREAM_CHUNK + 16)
-#define PC_BINX_SMEM (PC_BINX_STAGES * PC_BINX_SLOT + PC_BINX_STAGES * 8 + 16)
-
-__global__ void __launch_bounds__(PC_STREAM_NT) pc_large_binx_kernel(const PcScanArgs a, PcLargeFrame *fr, int f0, int side,
-                                                                     int atoms_per_cta, uint32_t *cells, int capCells, float4 *cand,
-                                                                     uint32_t *ccell, int nh_alloc, const PcStreamEpi epi) {
-    constexpr int NT = PC_STREAM_NT, CHUNK = PC_STREAM_CHUNK, STAGES = PC_BINX_STAGES, SLOT = PC_BINX_SLOT;
-    extern __shared__ __align__(16) unsigned char smem[];
-    uint64_t *bars = reinterpret_cast<uint64_t *>(smem + STAGES * SLOT);
-    __shared__ PcLargeFrame F;
-    __shared__ PcStreamDesc desc[STAGES];
-    __shared__ unsigned int s_bad;
-    const int tid = threadIdx.x, lane = tid & 31;
-    const int fb = blockIdx.y, f = f0 + fb;
-    const int n = side == 0 ? a.t.n1 : a.t.n2;
-    const int r0 = blockIdx.x * atoms_per_cta;
-    if (r0 >= n) return;
-    if (tid == 0) {
-        F = fr[fb];
-        s_bad = 0;
-        for (int s = 0; s < STAGES; s++) pc_mbar_init(bars + s, 1);
-        pc_mbar_fence_init();
-    }
-    __syncthreads();
-    if (F.ncell == 0) return;
-    const float *frame = side == 0 ? a.xyz1 + (long long)f * a.pitch1 : a.xyz2 + (long long)f * a.pitch2;
-    const uint32_t *hmask = side == 0 ? a.t.hmask1 : a.t.hmask2;
-    const uint32_t *linfo = side == 0 ? a.t.linfo1 : a.t.linfo2;
-    PcSegment seg;
-    seg.sb = reinterpret_cast<const unsigned char *>(frame) + 12ll * r0;
-    seg.natoms = min(atoms_per_cta, n - r0);
-    seg.atom0 = r0;
-    const int nch = pc_seg_chunks<CHUNK>(seg);
-    auto issue = [&](int q) {
-        const PcChunk c = pc_chunk_of<CHUNK>(seg, q);
-        const int st = q % STAGES;
-        PcStreamDesc d;
-        d.cnt = c.k1 - c.k0; d.hoff = 0; d.off0 = c.off0; d.abase = r0 + c.k0;
-        desc[st] = d;
-        pc_mbar_expect_tx(bars + st, c.bytes);                   // release: desc is visible to whoever sees the phase flip
-        if (epi.l2) pc_bulk_g2s_hint(smem + (size_t)st * SLOT, c.g0, c.bytes, bars + st, pc_l2_policy(epi.l2));
-        else pc_bulk_g2s(smem + (size_t)st * SLOT, c.g0, c.bytes, bars + st);
-    };
-    uint32_t *mycells = cells + (size_t)fb * (capCells + 1);
-    float4 *mycand = cand + (size_t)fb * nh_alloc;
-    uint32_t *myccell = ccell + (size_t)fb * nh_alloc;
-    unsigned int *cursor = side == 0 ? &fr[fb].nA_in : &fr[fb].nB_in;
-    // conservative box of the grid: cell coordinate u = (x - lo) * inv; x < lo - 0.01 gives u < 0, and
-    // x > lo + n * e * (1 + 1e-5) + 0.01 with e = 1 / inv (e * inv = 1 +- 2e-7) gives u > n
-    float plo[3], phi[3];
-    {
-        const float e = 1.0f / F.inv;
-        const int nn[3] = {F.nx, F.ny, F.nz};
-#pragma unroll
-        for (int k = 0; k < 3; k++) { plo[k] = F.lo[k] - 0.01f; phi[k] = F.lo[k] + (float)nn[k] * e * 1.00001f + 0.01f; }
-    }
-    // an atom inside the box: heavy? -> exact cell -> compacted (x, y, z, packed word) + cell id; whole warps call this
-    auto keep = [&](const bool maybe, const int idx, const float x, const float y, const float z) {
-        int cell = -1;
-        uint32_t info = 0;
-        if (maybe && ((__ldg(hmask + (idx >> 5)) >> (idx & 31)) & 1u)) {
-            cell = pc_large_cell_of(F, x, y, z);
-            if (cell >= 0) info = __ldg(linfo + idx);
-        }
-        const unsigned m = __ballot_sync(PC_FULL_MASK, cell >= 0);
-        if (m) {
-            unsigned base = 0;
-            const int leader = __ffs(m) - 1;
-            if (lane == leader) base = atomicAdd(cursor, (unsigned)__popc(m));
-            base = __shfl_sync(PC_FULL_MASK, base, leader);
-            if (cell >= 0) {
-                const unsigned p = base + __popc(m & ((1u << lane) - 1u));
-                mycand[p] = make_float4(x, y, z, __uint_as_float(info));
-                myccell[p] = (uint32_t)cell;
-                atomicAdd(&mycells[cell], 1u);
-            }
-        }
-    };
-
-    if (tid == 0)
-        for (int q = 0; q < min(STAGES - 1, nch); q++) issue(q);
-    for (int q = 0; q < nch; q++) {
-        if (tid == 0 && q + STAGES - 1 < nch) issue(q + STAGES - 1);
-        const int st = q % STAGES;
-        if (!pc_mbar_wait(bars + st, (unsigned)(q / STAGES) & 1u)) { s_bad = 1; }
-        const PcStreamDesc d = desc[st];
-        const unsigned char *xyz = smem + (size_t)st * SLOT + d.off0;
-        const int na = d.cnt, abase = d.abase;
-        // two atoms per thread and round, NT apart: lane l reads words 3 l .. 3 l + 2 of its warp's 96 (no bank conflicts)
-        for (int i0 = 0; i0 < na; i0 += 2 * NT) {
-            const int i = i0 + tid, i2 = i + NT;
-            float x0 = 0.f, y0 = 0.f, z0 = 0.f, x1 = 0.f, y1 = 0.f, z1 = 0.f;
-            bool m0 = false, m1 = false;
-            if (i < na) {
-                const float *p = reinterpret_cast<const float *>(xyz + 12 * i);
-                x0 = p[0]; y0 = p[1]; z0 = p[2];
-            }
-            if (i2 < na) {
-                const float *p = reinterpret_cast<const float *>(xyz + 12 * i2);
-                x1 = p[0]; y1 = p[1]; z1 = p[2];
-            }
-            m0 = i < na && x0 >= plo[0] && x0 <= phi[0] && y0 >= plo[1] && y0 <= phi[1] && z0 >= plo[2] && z0 <= phi[2];
-            m1 = i2 < na && x1 >= plo[0] && x1 <= phi[0] && y1 >= plo[1] && y1 <= phi[1] && z1 >= plo[2] && z1 <= phi[2];
-            if (!__any_sync(PC_FULL_MASK, m0 || m1)) continue;
-            keep(m0, abase + i, x0, y0, z0);
-            keep(m1, abase + i2, x1, y1, z1);
-        }
-        __syncthreads();          // the slot (and its descriptor) may be refilled from here on
-    }
-    if (tid == 0 && s_bad) atomicOr(&a.counters[PC_CNT_STATUS], (unsigned long long)PC_ST_BAD_COORDS);
-    if (epi.what == PC_EPI_OCC) {
-        __shared__ int s_last;
-        __threadfence();
-        __syncthreads();
-        if (tid == 0) s_last = atomicAdd(&fr[fb].pad[1], 1u) == gridDim.x - 1u;
-        __syncthreads();
-        if (s_last) {
-            __threadfence();
-            pc_large_occ_frame(F.nx, F.ny, F.nz, epi.cellsB + (size_t)fb * (epi.capCells + 1), epi.occ + (size_t)fb * epi.capCells,
-                               epi.occ2 + (size_t)fb * epi.capCells);
-        }
-    }
-}
 
 // ---- L2: grid geometry + zeroed cell counters (one CTA per frame; pc_large_grid_frame above) ---------------
 __global__ void __launch_bounds__(256) pc_large_grid_kernel(const PcScanArgs a, PcLargeFrame *fr, int capCells, int use_bboxB,

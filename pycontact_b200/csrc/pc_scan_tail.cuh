@@ -37,332 +37,10 @@ constexpr int pc_tail_unroll = PC_TAIL_UNROLL;
 #define PC_TAIL_SMEM PC_COMPACT_SMEM     // dynamic shared memory: the accumulation table of T4 is the larger tenant
 #define PC_TAIL_POOL (PC_TAIL_SMEM - (PC_TAIL_NT / 32) * PC_TAIL_WQ * 4 - PC_TAIL_GATE * 4)   // cell offsets + sorted B
 
-// Per-frame state of the tail kernel, in shared memory: its rarely executed phases (records, H-bond tests, accumulation)
-// are compiled out of line and find their pointers here, so that their registers (float64 geometry, batched loads) do
-// not compete with the search loop's under the kernel's budget of 64 registers per thread (1024 threads per CTA) --
-// inlined, they pushed loop variables of the search into local memory (ncu: long-scoreboard stalls inside a loop that
-// only reads shared memory).
-#ifndef PC_TAIL_FN
-#define PC_TAIL_FN __noinline__
-#endif
-struct PcTailCtx {
-    const float4 *sA;                   // this frame's A atoms in cell order (global scratch)
-    const float4 *sortB;                // B atoms in cell order (shared memory)
-    pc_contact *slice;
-    pc_hbond *hslice;
-    long long cap_c, cap_h;
-    const float *fr1, *fr2;
-    const int *hptr1, *hidx1, *hptr2, *hidx2;
-    double hb_cutoff, hb_angle;
-    uint32_t *gateq;
-    unsigned int ngate, ccur, hcur, status, next;
-};
-
-// One donor-H...acceptor side of a gated pair (core/multi_trajectory.py:112-209).  side 0: donor = atom1, acceptor =
-// atom2; side 1: donor = atom2, acceptor = atom1.
-__device__ PC_TAIL_FN void pc_tail_hbond(PcTailCtx *c, const unsigned u, const int side) {
-    const float4 pa = c->sA[u >> 16], pb = c->sortB[u & 0xffffu];
-    const int li = PC_W_INDEX(__float_as_uint(pa.w)), lj = PC_W_INDEX(__float_as_uint(pb.w));
-    const int *hptr = side == 0 ? c->hptr1 : c->hptr2;
-    const int *hidx = side == 0 ? c->hidx1 : c->hidx2;
-    const float *frd = side == 0 ? c->fr1 : c->fr2;
-    const int heavy = side == 0 ? li : lj;
-    const int p0 = __ldg(hptr + heavy), p1 = __ldg(hptr + heavy + 1);
-    if (p0 == p1) return;
-    const double ax = pa.x, ay = pa.y, az = pa.z, bx = pb.x, by = pb.y, bz = pb.z;
-    const double hb_cutoff = c->hb_cutoff, hb_angle = c->hb_angle;
-    // up to four hydrogens per round: their indices, then their coordinates, are in flight together (a water oxygen has
-    // two, an amine three; one after the other they cost an L2 and a DRAM round trip each)
-    for (int pb0 = p0; pb0 < p1; pb0 += 4) {
-        int hl[4];
-        float hx[4], hy[4], hz[4];
-#pragma unroll
-        for (int q = 0; q < 4; q++) hl[q] = pb0 + q < p1 ? __ldg(hidx + pb0 + q) : -2;
-#pragma unroll
-        for (int q = 0; q < 4; q++) {
-            hx[q] = hy[q] = hz[q] = 0.f;
-            if (hl[q] >= 0) load_xyz(frd, hl[q], 3, hx[q], hy[q], hz[q]);       // the large-frame path reads packed xyz
-        }
-#pragma unroll
-        for (int q = 0; q < 4; q++) {
-            if (hl[q] == -2) break;
-            if (hl[q] < 0) { atomicOr(&c->status, (unsigned)PC_ST_MISSING_H); continue; }
-            double d = 0, ang = 0;
-            const bool ok = side == 0
-                ? hbond_test(hx[q], hy[q], hz[q], ax, ay, az, bx, by, bz, hb_cutoff, hb_angle, d, ang)
-                : hbond_test(hx[q], hy[q], hz[q], bx, by, bz, ax, ay, az, hb_cutoff, hb_angle, d, ang);
-            if (!ok) continue;
-            const unsigned hq = atomicAdd(&c->hcur, 1u);
-            if ((long long)hq < c->cap_h) {
-                pc_hbond r;
-                r.i = li; r.j = lj; r.hyd = (uint32_t)hl[q] | (side ? 0x80000000u : 0u);
-                r.distance = (float)d; r.angle = (float)ang;
-                c->hslice[hq] = r;
-            } else {
-                atomicOr(&c->status, (unsigned)PC_ST_OUT_OVERFLOW);
-            }
-        }
-    }
-}
-
-// one hit -> contact record `slot` of the frame's slice; N/O/S pairs are queued for the H-bond pass
-__device__ __forceinline__ void pc_tail_emit(PcTailCtx *c, const unsigned u, const long long slot) {
-    const float4 pa = c->sA[u >> 16], pb = c->sortB[u & 0xffffu];
-    const unsigned wa = __float_as_uint(pa.w), wb = __float_as_uint(pb.w);
-    const double dx = (double)pa.x - (double)pb.x, dy = (double)pa.y - (double)pb.y, dz = (double)pa.z - (double)pb.z;
-    const double dist = sqrt(dx * dx + dy * dy + dz * dz);
-    if (slot < c->cap_c) {
-        pc_contact rec;
-        rec.i = PC_W_INDEX(wa); rec.j = PC_W_INDEX(wb); rec.distance = (float)dist; rec.weight = contact_weight_f32(dist);
-        c->slice[slot] = rec;
-    } else {
-        atomicOr(&c->status, (unsigned)PC_ST_OUT_OVERFLOW);
-    }
-    if (wa & wb & PC_W_HBCLASS) {
-        const unsigned q = atomicAdd(&c->ngate, 1u);
-        if (q < (unsigned)PC_TAIL_GATE) c->gateq[q] = u;
-        else { pc_tail_hbond(c, u, 0); pc_tail_hbond(c, u, 1); }         // queue full: tested in place
-    }
-}
-// a hit that found its warp's queue full
-__device__ PC_TAIL_FN void pc_tail_emit_one(PcTailCtx *c, const unsigned u) {
-    pc_tail_emit(c, u, (long long)atomicAdd(&c->ccur, 1u));
-}
-// a warp's queued hits -> records (lanes over hits, one claim of the frame's cursor per call); called by whole warps
-__device__ PC_TAIL_FN void pc_tail_drain(PcTailCtx *c, const uint32_t *q, const unsigned n) {
-    const int lane = threadIdx.x & 31;
-    unsigned base = 0;
-    if (lane == 0) base = atomicAdd(&c->ccur, n);
-    base = __shfl_sync(PC_FULL_MASK, base, 0);
-    for (unsigned k = lane; k < n; k += 32) pc_tail_emit(c, q[k], (long long)base + k);
-}
-// T3 of the tail kernel: the pair search of one frame, called by every warp of the CTA.  Out of line, so that the loop has
-// the kernel's whole register budget to itself (what is live in the other phases is saved around ONE call per frame).
-// tri[c] = start | length << 16 of the B atoms in cells cx-1 .. cx+1 of c's row; items are (A atom, stencil layer), 32 per
-// warp and round, handed out by C->next.
-__device__ __noinline__ unsigned long long pc_tail_search(const PcLargeFrame *Fp, PcTailCtx *C, const uint32_t *tri, uint32_t *mywq,
-                                                          unsigned int *myqn, const float sqdist) {
-    const int lane = threadIdx.x & 31;
-    const int nx = Fp->nx, ny = Fp->ny, nz = Fp->nz, nA = (int)Fp->nA_in;
-    const float lox = Fp->lo[0], loy = Fp->lo[1], loz = Fp->lo[2], inv = Fp->inv;
-    const float4 *sA = C->sA, *sortB = C->sortB;
-    volatile unsigned int *vqn = myqn;
-    const int nitems = 3 * nA;
-    unsigned long long evals = 0;
-    for (;;) {
-        int w = 0;
-        if (lane == 0) w = (int)atomicAdd(&C->next, 32u);
-        w = __shfl_sync(PC_FULL_MASK, w, 0);
-        if (w >= nitems) break;
-        w += lane;
-        if (w < nitems) {
-            // layer-major items over the cell-sorted A atoms: the lanes of a warp hold the atoms of a few
-            // neighbouring cells on the same stencil layer
-            const int layer = (w >= nA) + (w >= 2 * nA), ia = w - layer * nA;
-            const float4 pa = sA[ia];
-            const int cx = (int)((pa.x - lox) * inv), cy = (int)((pa.y - loy) * inv), cz = (int)((pa.z - loz) * inv);
-            const int z = cz + layer - 1;
-            if (z >= 0 && z < nz) {
-                // the layer's three rows as ONE list of candidates: run r covers list positions [e_{r-1}, e_r)
-                const int row1 = (z * ny + cy) * nx + cx;
-                const unsigned t0 = cy > 0 ? tri[row1 - nx] : 0u, t1 = tri[row1], t2 = cy + 1 < ny ? tri[row1 + nx] : 0u;
-                const int e0 = (int)(t0 >> 16), e1 = e0 + (int)(t1 >> 16), e2 = e1 + (int)(t2 >> 16);
-                // list position k -> B position: k + (start of its run - list position of that start)
-                const int d0 = (int)(t0 & 0xffffu), d1 = (int)(t1 & 0xffffu) - e0, d2 = (int)(t2 & 0xffffu) - e1;
-                const float2 nxy = make_float2(-pa.x, -pa.y);
-                const float naz = -pa.z;
-                evals += (unsigned)e2;
-                for (int kb = 0; kb < e2; kb += 32) {
-                    const int cnt = min(32, e2 - kb);
-                    unsigned m = 0;
-#pragma unroll 2
-                    for (int k = 0; k < cnt; k++) {
-                        const int kk = kb + k;
-                        const int j = kk + (kk < e0 ? d0 : (kk < e1 ? d1 : d2));
-                        if (pair_within_packed(nxy, naz, sortB[j], sqdist)) m |= 1u << k;
-                    }
-                    if (!m) continue;
-                    unsigned p = atomicAdd(myqn, (unsigned)__popc(m));
-                    while (m) {
-                        const int kk = kb + __ffs(m) - 1;
-                        m &= m - 1;
-                        const unsigned u = ((unsigned)ia << 16) | (unsigned)(kk + (kk < e0 ? d0 : (kk < e1 ? d1 : d2)));
-                        if (p < (unsigned)PC_TAIL_WQ) mywq[p] = u;
-                        else pc_tail_emit_one(C, u);           // queue full: this lane drains its own hit
-                        p++;
-                    }
-                }
-            }
-        }
-        __syncwarp();
-        const unsigned nq = min(*vqn, (unsigned)PC_TAIL_WQ);
-        if (nq >= (unsigned)PC_TAIL_DRAIN_AT) {
-            pc_tail_drain(C, mywq, nq);
-            __syncwarp();
-            if (lane == 0) *myqn = 0;
-            __syncwarp();
-        }
-    }
-    __syncwarp();
-    const unsigned nq = min(*vqn, (unsigned)PC_TAIL_WQ);
-    if (nq) pc_tail_drain(C, mywq, nq);
-    return evals;
-}
-
-template <int NT>
-__device__ PC_TAIL_FN void pc_tail_compact(const PcAccArgs *acc, const int f, unsigned char *smem, uint32_t *wsum,
-                                           long long *s_base, unsigned int *s_status) {
-    pc_compact_frame<NT>(*acc, f, smem, wsum, s_base, s_status);
-}
-
-template <int NT>
-__global__ void __launch_bounds__(NT, 1) pc_large_tail_kernel(const PcScanArgs a, PcLargeFrame *fr, const int f0,
-                                                                      const int nfb, const uint32_t *cellsA, const uint32_t *cellsB,
-                                                                      const int capCells, const float4 *candA, const uint32_t *ccellA,
-                                                                      float4 *sortA_g, const float4 *candB, const uint32_t *ccellB,
-                                                                      const int n1h_alloc, const int n2h_alloc, const PcLargeOut o,
-                                                                      const PcAccArgs acc, const int fuse_acc) {
-    constexpr int NW = NT / 32;
-    constexpr int POOL = PC_TAIL_SMEM - NW * PC_TAIL_WQ * 4 - PC_TAIL_GATE * 4;      // cell offsets / x-triples + sorted B
-    extern __shared__ __align__(16) unsigned char smem[];
-    uint32_t *wq = reinterpret_cast<uint32_t *>(smem);                 // [NW][PC_TAIL_WQ]
-    uint32_t *gateq = wq + NW * PC_TAIL_WQ;                            // [PC_TAIL_GATE]
-    unsigned char *pool = reinterpret_cast<unsigned char *>(gateq + PC_TAIL_GATE);
-    __shared__ PcLargeFrame F;
-    __shared__ PcTailCtx C;
-    __shared__ PcAccArgs s_acc;
-    __shared__ uint32_t wsum[32];
-    __shared__ unsigned int wqn[NW];
-    __shared__ unsigned int s_keep[2];
-    __shared__ long long s_base;
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const float sqdist = a.sqdist;
-    unsigned long long evals = 0;
-    uint32_t *mywq = wq + warp * PC_TAIL_WQ;
-    if (tid == 0) s_acc = acc;
-
-    for (int fb = blockIdx.x; fb < nfb; fb += gridDim.x) {
-        const int f = f0 + fb;
-        if (tid == 0) {
-            F = fr[fb];
-            const size_t cb = ((size_t)(F.ncell + 1) * 4 + 15) & ~(size_t)15;
-            C.sA = sortA_g + (size_t)fb * n1h_alloc;
-            C.sortB = reinterpret_cast<const float4 *>(pool + cb);
-            C.slice = a.contacts + (long long)f * o.cap_c_frame;
-            C.hslice = a.hbonds + (long long)f * o.cap_h_frame;
-            C.cap_c = o.cap_c_frame; C.cap_h = o.cap_h_frame;
-            C.fr1 = a.xyz1 + (long long)f * a.pitch1; C.fr2 = a.xyz2 + (long long)f * a.pitch2;
-            C.hptr1 = a.t.lhptr1; C.hidx1 = a.t.lhidx1; C.hptr2 = a.t.lhptr2; C.hidx2 = a.t.lhidx2;
-            C.hb_cutoff = a.hb_cutoff; C.hb_angle = a.hb_angle;
-            C.gateq = gateq;
-            C.ngate = 0; C.ccur = 0; C.hcur = 0; C.status = 0; C.next = 0;
-        }
-        if (tid < NW) wqn[tid] = 0;
-        __syncthreads();
-        const int ncell = F.ncell, nA = (int)F.nA_in, nB = (int)F.nB_in;
-        const size_t cell_bytes = ((size_t)(ncell + 1) * 4 + 15) & ~(size_t)15;
-        const bool fits = nA <= 65535 && nB <= 65535 && cell_bytes + 16ull * (size_t)nB <= (size_t)POOL;
-        uint32_t *cellB_s = reinterpret_cast<uint32_t *>(pool);
-        float4 *sortB = reinterpret_cast<float4 *>(pool + cell_bytes);
-        float4 *sA = sortA_g + (size_t)fb * n1h_alloc;           // written in T0 by this CTA: plain loads
-
-        if (!fits) {
-            if (tid == 0) atomicOr(&C.status, (unsigned)PC_ST_TAIL_OVERFLOW);
-        } else if (ncell > 0 && nA > 0 && nB > 0) {
-            const int nx = F.nx, ny = F.ny, nz = F.nz;
-            const float lox = F.lo[0], loy = F.lo[1], loz = F.lo[2], inv = F.inv;
-            // ---- T0: selection A's compacted atoms -> cell order, in a global scratch array (L2): the lanes of a warp
-            //      then hold atoms of the same few cells, walk the same B runs and read the same shared-memory words
-            //      (broadcasts instead of the bank conflicts of selection-ordered atoms).  The cell offsets live where
-            //      B's will be in a moment.
-            {
-                const uint32_t *gA = cellsA + (size_t)fb * (capCells + 1);
-                for (int c = tid; c < ncell; c += NT) cellB_s[c] = __ldg(gA + c);
-                __syncthreads();
-                block_excl_scan_inplace<NT>(cellB_s, ncell, wsum);
-                const float4 *cA = candA + (size_t)fb * n1h_alloc;
-                const uint32_t *ccA = ccellA + (size_t)fb * n1h_alloc;
-                for (int p = tid; p < nA; p += NT) sA[atomicAdd(&cellB_s[__ldg(ccA + p)], 1u)] = __ldg(cA + p);
-                __syncthreads();
-            }
-            // ---- T1: B cell counts -> shared memory, exclusive scan -------------------------------------------
-            const uint32_t *gB = cellsB + (size_t)fb * (capCells + 1);
-            for (int c = tid; c < ncell; c += NT) cellB_s[c] = __ldg(gB + c);
-            __syncthreads();
-            block_excl_scan_inplace<NT>(cellB_s, ncell, wsum);
-            // ---- T2: compacted B atoms -> cell order; afterwards cellB_s[c] == END of cell c -----------------
-            const float4 *cB = candB + (size_t)fb * n2h_alloc;
-            const uint32_t *ccB = ccellB + (size_t)fb * n2h_alloc;
-            for (int p = tid; p < nB; p += NT) sortB[atomicAdd(&cellB_s[__ldg(ccB + p)], 1u)] = __ldg(cB + p);
-            __syncthreads();
-            // x-triples, in place: cell c's END becomes start | length << 16 of the B atoms in cells cx-1 .. cx+1 of c's
-            // row (ONE lookup per stencil row in the search).  NT cells at a time, lowest first; the two ends just below a
-            // chunk are kept aside, because the chunk before has already overwritten them (a triple reads the ends of
-            // cells c-2 .. c+1).
-            uint32_t *tri = cellB_s;
-            if (tid < 2) s_keep[tid] = 0u;
-            __syncthreads();
-            for (int lo = 0; lo < ncell; lo += NT) {
-                const int c = lo + tid;
-                unsigned j0 = 0, j1 = 0, mine = 0;
-                if (c < ncell) {
-                    const int cx = c % nx, row = c - cx;
-                    const int i0 = row + max(cx - 1, 0) - 1;
-                    j0 = i0 < 0 ? 0u : (i0 >= lo ? cellB_s[i0] : s_keep[i0 - (lo - 2)]);
-                    j1 = cellB_s[row + min(cx + 1, nx - 1)];
-                    mine = cellB_s[c];
-                }
-                __syncthreads();
-                if (c < ncell) {
-                    cellB_s[c] = j0 | ((j1 - j0) << 16);          // nB <= 65535: both halves fit
-                    if (tid >= NT - 2) s_keep[tid - (NT - 2)] = mine;
-                }
-                __syncthreads();
-            }
-            // ---- T3: pair search, warp-autonomous; hits go to the warp's queue, the queue to pc_tail_drain ------------
-            evals += pc_tail_search(&F, &C, cellB_s, mywq, wqn + warp, sqdist);
-            __syncthreads();
-            // ---- T3b: donor-H...acceptor tests, one thread per (gated pair, side) ------------------------------
-            const unsigned ngate = min(C.ngate, (unsigned)PC_TAIL_GATE);
-            for (unsigned it = tid; it < 2u * ngate; it += NT) pc_tail_hbond(&C, gateq[it >> 1], (int)(it & 1u));
-        }
-        __syncthreads();
-        // ---- per-frame counts and totals (what pc_large_finish_kernel does on the multi-kernel sequence) -----------
-        if (tid == 0) {
-            const unsigned cc = C.ccur, hc = C.hcur;
-            a.frame_cstart[f] = (uint32_t)((long long)f * o.cap_c_frame);
-            a.frame_ccount[f] = (uint32_t)min((long long)cc, o.cap_c_frame);
-            a.frame_hstart[f] = (uint32_t)((long long)f * o.cap_h_frame);
-            a.frame_hcount[f] = (uint32_t)min((long long)hc, o.cap_h_frame);
-            // the totals report what WOULD be needed so the host can re-reserve after an overflow
-            if (cc) atomicAdd(&a.counters[PC_CNT_CONTACTS], (unsigned long long)cc);
-            if (hc) atomicAdd(&a.counters[PC_CNT_HBONDS], (unsigned long long)hc);
-            atomicMax(&a.counters[6], (unsigned long long)cc);
-            atomicMax(&a.counters[7], (unsigned long long)hc);
-            if (C.status) atomicOr(&a.counters[PC_CNT_STATUS], (unsigned long long)C.status);
-            if (fuse_acc && cc == 0) { acc.frame_rstart[f] = 0; acc.frame_rcount[f] = 0; }
-            // the frame's work slot is left ready for the next batch (no reset launch in front of it)
-            PcLargeFrame &G = fr[fb];
-            for (int k = 0; k < 3; k++) { G.bbox[k] = 0xffffffffu; G.bbox[3 + k] = 0u; G.bbox[6 + k] = 0xffffffffu; G.bbox[9 + k] = 0u; }
-            G.nA_in = G.nB_in = 0; G.ccursor = G.hcursor = 0; G.ncell = 0; G.pad[0] = G.pad[1] = 0;
-        }
-        __syncthreads();
-        // ---- T4: per-frame accumulation of the records just written (they are in L2) -----------------------------
-        const bool have = fuse_acc && C.ccur != 0;
-        const bool do_acc = have && !(C.status & (unsigned)(PC_ST_OUT_OVERFLOW | PC_ST_TAIL_OVERFLOW));
-        __syncthreads();                   // the accumulation reuses C.status
-        if (do_acc) pc_tail_compact<NT>(&s_acc, f, smem, wsum, &s_base, &C.status);
-        else if (have && tid == 0) { acc.frame_rstart[f] = 0; acc.frame_rcount[f] = 0; }
-        __syncthreads();
-    }
-#pragma unroll
-    for (int s = 16; s > 0; s >>= 1) evals += __shfl_xor_sync(PC_FULL_MASK, evals, s);
-    if (lane == 0 && evals) atomicAdd(&a.counters[PC_CNT_EVALS], evals);
-}
-
-// The same kernel with every phase inlined (lambdas over the kernel's locals) -- the form measured fastest so far
-// (209 us per 148 frames of c3 against 225-290 us for the out-of-line phases above); kept selectable for A/B runs
-// (PC_TAIL_IMPL=1 inline, 0 out of line).
+// Every phase is a lambda over the kernel's locals.  (Measured against it and dropped: the rarely executed phases -- records,
+// H-bond tests, accumulation -- compiled out of line with their state in shared memory, 225-290 us per 148 frames of c3
+// against 209 us; and a "walk" kernel that balances the candidates of 32 A atoms over the lanes of a warp, 2.3x slower:
+// spills under the 64-register cap.  Both are in the repository's history, commits ac37fd8 and 8a0aded.)
 template <bool AFRAME>
 __global__ void __launch_bounds__(PC_TAIL_NT, 1) pc_large_tail_inl_kernel(const PcScanArgs a, PcLargeFrame *fr, const int f0,
                                                                           const int nfb, const uint32_t *cellsA, const uint32_t *cellsB,
@@ -682,338 +360,6 @@ __global__ void __launch_bounds__(PC_TAIL_NT, 1) pc_large_tail_inl_kernel(const 
     if (lane == 0 && evals) atomicAdd(&a.counters[PC_CNT_EVALS], evals);
 }
 
-// ---------------------------------------------------------------------------------------------------------------------
-// Tail kernel, second form ("walk"): same job, but selection A is read straight from the frame (no streaming bin, no
-// occupancy kernel for A) and the pair search is load-balanced inside the warp.
-//
-// In the kernel above a lane owns an (A atom, stencil layer) item and walks that item's three B runs; runs hold 0..8
-// atoms, so a warp spends its time on the longest run of its 32 lanes and on loop control (ncu: 80 % of the kernel's
-// instructions in the search, 15 of 32 lanes active).  Here a warp takes 32 consecutive heavy A atoms and
-//   setup  every lane looks its atom's (up to) nine rows up in a per-cell table of x-triples (start | length of the
-//          B atoms in cells cx-1..cx+1 of a row: ONE shared-memory load per row) -- atoms whose 27-cell neighbourhood is
-//          empty are skipped by a bit of the dilated occupancy map -- and the non-empty runs of all 32 atoms are
-//          written, compacted, to the warp's run list (warp prefix sums, no atomics);
-//   walk   the W candidates of the batch are cut into 32 equal ranges: a lane finds the start of its range (binary search
-//          over the lanes' prefix sums by shuffle, then over the owner's runs) and walks it -- one B atom from shared
-//          memory, the reference's float32 test, ballot-compacted append to the warp's hit queue -- moving to the next
-//          run / owner atom (coordinates parked in shared memory) as it goes.  Every lane does W / 32 evaluations.
-// Hits are drained like above, except that the A atom of a hit is re-read through the heavy-atom list (L1 / L2).
-// ---------------------------------------------------------------------------------------------------------------------
-#define PC_WALK_NT 1024
-#define PC_WALK_WQ 128
-#define PC_WALK_DRAIN_AT 96
-#define PC_WALK_GATE 1024
-#define PC_WALK_RUNS 160                      // run list of a round; 16 atoms x 9 rows always fit (rounds with more runs go in two halves)
-#define PC_WALK_FIXED ((PC_WALK_NT / 32) * (PC_WALK_WQ * 4 + PC_WALK_RUNS * 4 + 32 * 12) + PC_WALK_GATE * 4)
-#define PC_WALK_POOL (PC_TAIL_SMEM - PC_WALK_FIXED)     // occupancy bits + cell offsets / x-triples + sorted B
-#define PC_WALK_MAXRUN 2047u                  // a run's length has 11 bits in the run record
-
-__global__ void __launch_bounds__(PC_WALK_NT, 1) pc_large_walk_kernel(const PcScanArgs a, PcLargeFrame *fr, const int f0, const int nfb,
-                                                                      const uint32_t *cellsB, const int capCells,
-                                                                      const float4 *candB, const uint32_t *ccellB,
-                                                                      const int n2h_alloc, const PcLargeOut o, const PcAccArgs acc,
-                                                                      const int fuse_acc, const int reset_frames) {
-    constexpr int NT = PC_WALK_NT, NW = NT / 32;
-    extern __shared__ __align__(16) unsigned char smem[];
-    float *apos_all = reinterpret_cast<float *>(smem);                                     // [NW][3][32]: x, y, z of a round's atoms
-    uint32_t *wq = reinterpret_cast<uint32_t *>(apos_all + NW * 96);                       // [NW][PC_WALK_WQ]
-    uint32_t *runs_all = wq + NW * PC_WALK_WQ;                                             // [NW][PC_WALK_RUNS]
-    uint32_t *gateq = runs_all + NW * PC_WALK_RUNS;                                        // [PC_WALK_GATE]
-    unsigned char *pool = reinterpret_cast<unsigned char *>(gateq + PC_WALK_GATE);
-    __shared__ PcLargeFrame F;
-    __shared__ uint32_t wsum[32];
-    __shared__ unsigned int s_next, s_ccur, s_hcur, s_ngate, s_status;
-    __shared__ unsigned int s_keep[2];
-    __shared__ long long s_base;
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const unsigned lt_mask = (1u << lane) - 1u;
-    const float sqdist = a.sqdist;
-    unsigned long long evals = 0;
-    uint32_t *mywq = wq + warp * PC_WALK_WQ;
-    uint32_t *runs = runs_all + warp * PC_WALK_RUNS;
-    float *apos = apos_all + warp * 96;
-    const int n1h = a.t.n1h;
-    const uint32_t *hinfo1 = a.t.hinfo1;
-
-    for (int fb = blockIdx.x; fb < nfb; fb += gridDim.x) {
-        const int f = f0 + fb;
-        if (tid == 0) { F = fr[fb]; s_next = 0; s_ccur = 0; s_hcur = 0; s_ngate = 0; s_status = 0; }
-        __syncthreads();
-        const int ncell = F.ncell, nB = (int)F.nB_in;
-        const size_t occ_bytes = ((size_t)((ncell + 31) / 32) * 4 + 15) & ~(size_t)15;
-        const size_t cell_bytes = ((size_t)(ncell + 1) * 4 + 15) & ~(size_t)15;
-        const bool fits = n1h <= 65535 && nB <= 65535 && occ_bytes + cell_bytes + 16ull * (size_t)nB <= (size_t)PC_WALK_POOL;
-        uint32_t *occ = reinterpret_cast<uint32_t *>(pool);
-        uint32_t *cellB_s = reinterpret_cast<uint32_t *>(pool + occ_bytes);      // counts -> offsets -> ends -> x-triples
-        uint32_t *tri = cellB_s;
-        float4 *sortB = reinterpret_cast<float4 *>(pool + occ_bytes + cell_bytes);
-        pc_contact *slice = a.contacts + (long long)f * o.cap_c_frame;
-        pc_hbond *hslice = a.hbonds + (long long)f * o.cap_h_frame;
-        const float *fr1 = a.xyz1 + (long long)f * a.pitch1;
-        const float *fr2 = a.xyz2 + (long long)f * a.pitch2;
-
-        // A atom of a hit: heavy ordinal -> packed word -> coordinates (the warp read them a moment ago: L1 / L2)
-        auto load_a = [&](const unsigned ka) -> float4 {
-            const uint32_t info = __ldg(hinfo1 + ka);
-            const float *p = fr1 + 3ll * PC_W_INDEX(info);
-            return make_float4(__ldg(p), __ldg(p + 1), __ldg(p + 2), __uint_as_float(info));
-        };
-        auto hbond_side = [&](const unsigned u, const int side) {
-            const float4 pa = load_a(u >> 16), pb = sortB[u & 0xffffu];
-            const int li = PC_W_INDEX(__float_as_uint(pa.w)), lj = PC_W_INDEX(__float_as_uint(pb.w));
-            const int *hptr = side == 0 ? a.t.lhptr1 : a.t.lhptr2;
-            const int *hidx = side == 0 ? a.t.lhidx1 : a.t.lhidx2;
-            const int heavy = side == 0 ? li : lj;
-            const int p0 = __ldg(hptr + heavy), p1 = __ldg(hptr + heavy + 1);
-            if (p0 == p1) return;
-            const double ax = pa.x, ay = pa.y, az = pa.z, bx = pb.x, by = pb.y, bz = pb.z;
-            for (int p = p0; p < p1; p++) {
-                const int hl = __ldg(hidx + p);
-                if (hl < 0) { atomicOr(&s_status, (unsigned)PC_ST_MISSING_H); continue; }
-                float hxf, hyf, hzf;
-                load_xyz(side == 0 ? fr1 : fr2, hl, a.stride, hxf, hyf, hzf);
-                double d = 0, ang = 0;
-                const bool ok = side == 0
-                    ? hbond_test(hxf, hyf, hzf, ax, ay, az, bx, by, bz, a.hb_cutoff, a.hb_angle, d, ang)
-                    : hbond_test(hxf, hyf, hzf, bx, by, bz, ax, ay, az, a.hb_cutoff, a.hb_angle, d, ang);
-                if (!ok) continue;
-                const unsigned hq = atomicAdd(&s_hcur, 1u);
-                if ((long long)hq < o.cap_h_frame) {
-                    pc_hbond r;
-                    r.i = li; r.j = lj; r.hyd = (uint32_t)hl | (side ? 0x80000000u : 0u);
-                    r.distance = (float)d; r.angle = (float)ang;
-                    hslice[hq] = r;
-                } else {
-                    atomicOr(&s_status, (unsigned)PC_ST_OUT_OVERFLOW);
-                }
-            }
-        };
-        auto emit = [&](const unsigned u, const long long slot) {
-            const float4 pa = load_a(u >> 16), pb = sortB[u & 0xffffu];
-            const unsigned wa = __float_as_uint(pa.w), wb = __float_as_uint(pb.w);
-            const double dx = (double)pa.x - (double)pb.x, dy = (double)pa.y - (double)pb.y, dz = (double)pa.z - (double)pb.z;
-            const double dist = sqrt(dx * dx + dy * dy + dz * dz);
-            if (slot < o.cap_c_frame) {
-                pc_contact rec;
-                rec.i = PC_W_INDEX(wa); rec.j = PC_W_INDEX(wb); rec.distance = (float)dist; rec.weight = contact_weight_f32(dist);
-                slice[slot] = rec;
-            } else {
-                atomicOr(&s_status, (unsigned)PC_ST_OUT_OVERFLOW);
-            }
-            if (wa & wb & PC_W_HBCLASS) {
-                const unsigned q = atomicAdd(&s_ngate, 1u);
-                if (q < (unsigned)PC_WALK_GATE) gateq[q] = u;
-                else { hbond_side(u, 0); hbond_side(u, 1); }         // queue full: tested in place
-            }
-        };
-
-        if (!fits) {
-            if (tid == 0) {
-                atomicOr(&s_status, (unsigned)PC_ST_TAIL_OVERFLOW);
-                atomicMax(&a.counters[PC_CNT_WORK], (1ull << 56) | (unsigned long long)(occ_bytes + cell_bytes + 16ull * (size_t)nB));
-            }
-        } else if (ncell > 0 && n1h > 0 && nB > 0) {
-            const int nx = F.nx, ny = F.ny, nz = F.nz;
-            const float lox = F.lo[0], loy = F.lo[1], loz = F.lo[2], inv = F.inv;
-            // ---- T1: B cell counts -> shared memory, exclusive scan; T2: compacted B atoms -> cell order -----------
-            const uint32_t *gB = cellsB + (size_t)fb * (capCells + 1);
-            for (int c = tid; c < ncell; c += NT) cellB_s[c] = __ldg(gB + c);
-            __syncthreads();
-            block_excl_scan_inplace<NT>(cellB_s, ncell, wsum);
-            const float4 *cB = candB + (size_t)fb * n2h_alloc;
-            const uint32_t *ccB = ccellB + (size_t)fb * n2h_alloc;
-            for (int p = tid; p < nB; p += NT) sortB[atomicAdd(&cellB_s[__ldg(ccB + p)], 1u)] = __ldg(cB + p);
-            __syncthreads();                                        // cellB_s[c] == END of cell c from here on
-            // x-triples, in place: cell c's END becomes start | length << 16 of the B atoms in cells cx-1 .. cx+1 of c's
-            // row.  NT cells at a time, lowest first; the two ends just below a chunk are kept aside, because the chunk
-            // before has already overwritten them (a triple reads the ends of cells c-2 .. c+1).
-            if (tid < 2) s_keep[tid] = 0u;
-            __syncthreads();
-            for (int lo = 0; lo < ncell; lo += NT) {
-                const int c = lo + tid;
-                unsigned j0 = 0, j1 = 0, mine = 0;
-                if (c < ncell) {
-                    const int cx = c % nx, row = c - cx;
-                    const int i0 = row + max(cx - 1, 0) - 1;
-                    j0 = i0 < 0 ? 0u : (i0 >= lo ? cellB_s[i0] : s_keep[i0 - (lo - 2)]);
-                    j1 = cellB_s[row + min(cx + 1, nx - 1)];
-                    mine = cellB_s[c];
-                }
-                __syncthreads();
-                if (c < ncell) {
-                    if (j1 - j0 > PC_WALK_MAXRUN) {
-                        atomicOr(&s_status, (unsigned)PC_ST_TAIL_OVERFLOW);
-                        atomicMax(&a.counters[PC_CNT_WORK], (2ull << 56) | ((unsigned long long)(unsigned)c << 32) | (unsigned long long)(j1 - j0));
-                    }
-                    cellB_s[c] = j0 | ((j1 - j0) << 16);
-                    if (tid >= NT - 2) s_keep[tid - (NT - 2)] = mine;
-                }
-                __syncthreads();
-            }
-            // dilated occupancy: bit c = some B atom in the 27 cells around c (nine x-triples)
-            for (int c0 = warp * 32; c0 < ncell; c0 += NT) {
-                const int c = c0 + lane;
-                bool any = false;
-                if (c < ncell) {
-                    const int cx = c % nx, cy = (c / nx) % ny, cz = c / (nx * ny);
-                    for (int z = max(cz - 1, 0); z <= min(cz + 1, nz - 1); z++)
-                        for (int y = max(cy - 1, 0); y <= min(cy + 1, ny - 1); y++)
-                            any |= (tri[(z * ny + y) * nx + cx] >> 16) != 0u;
-                }
-                const unsigned bal = __ballot_sync(PC_FULL_MASK, any);
-                if (lane == 0) occ[c0 >> 5] = bal;
-            }
-            __syncthreads();
-            if (!(s_status & (unsigned)PC_ST_TAIL_OVERFLOW)) {
-            // ---- T3: pair search, 32 heavy A atoms per warp and round ---------------------------------------------
-            unsigned wn = 0;                                        // hits in this warp's queue (uniform)
-            auto drain_queue = [&]() {
-                __syncwarp();
-                unsigned base = 0;
-                if (lane == 0) base = atomicAdd(&s_ccur, wn);
-                base = __shfl_sync(PC_FULL_MASK, base, 0);
-                for (unsigned k = lane; k < wn; k += 32) emit(mywq[k], (long long)base + k);
-                wn = 0;
-                __syncwarp();
-            };
-            for (;;) {
-                int k0 = 0;
-                if (lane == 0) k0 = (int)atomicAdd(&s_next, 32u);
-                k0 = __shfl_sync(PC_FULL_MASK, k0, 0);
-                if (k0 >= n1h) break;
-                const int k = k0 + lane;
-                // -- setup: this lane's atom, its cell, its non-empty rows
-                float x = 0.f, y = 0.f, z = 0.f;
-                int cx = 0, cy = 0, cz = 0;
-                bool has = false;
-                if (k < n1h) {
-                    const uint32_t info = __ldg(hinfo1 + k);
-                    const float *p = fr1 + 3ll * PC_W_INDEX(info);
-                    x = __ldg(p); y = __ldg(p + 1); z = __ldg(p + 2);
-                    const float ux = (x - lox) * inv, uy = (y - loy) * inv, uz = (z - loz) * inv;
-                    if (ux >= 0.f && uy >= 0.f && uz >= 0.f) {
-                        cx = (int)ux; cy = (int)uy; cz = (int)uz;
-                        if (cx < nx && cy < ny && cz < nz) {
-                            const int c = (cz * ny + cy) * nx + cx;
-                            has = (occ[c >> 5] >> (c & 31)) & 1u;
-                        }
-                    }
-                }
-                if (!__ballot_sync(PC_FULL_MASK, has)) continue;    // 32 atoms without any B atom around them
-                unsigned nr = 0, T = 0;
-                if (has) {
-                    for (int zz = max(cz - 1, 0); zz <= min(cz + 1, nz - 1); zz++)
-                        for (int yy = max(cy - 1, 0); yy <= min(cy + 1, ny - 1); yy++) {
-                            const unsigned len = tri[(zz * ny + yy) * nx + cx] >> 16;
-                            nr += len != 0u; T += len;
-                        }
-                }
-                apos[lane] = x; apos[32 + lane] = y; apos[64 + lane] = z;
-                const unsigned nr_all = __reduce_add_sync(PC_FULL_MASK, nr);
-                const int nparts = nr_all > (unsigned)PC_WALK_RUNS ? 2 : 1;        // 16 atoms have at most 144 runs
-                for (int part = 0; part < nparts; part++) {
-                const bool mine = has && (nparts == 1 || (lane >> 4) == part);
-                const unsigned nrp = mine ? nr : 0u, Tp = mine ? T : 0u;
-                const unsigned rincl = warp_incl_scan(nrp, lane), tincl = warp_incl_scan(Tp, lane);
-                const unsigned W = __shfl_sync(PC_FULL_MASK, tincl, 31);
-                const unsigned off = tincl - Tp;                    // candidates of the lanes before this one
-                unsigned rpos = rincl - nrp;
-                const unsigned roff = rpos;
-                __syncwarp();                                       // the previous part's walk has left the run list
-                if (mine) {
-                    for (int zz = max(cz - 1, 0); zz <= min(cz + 1, nz - 1); zz++)
-                        for (int yy = max(cy - 1, 0); yy <= min(cy + 1, ny - 1); yy++) {
-                            const unsigned t3 = tri[(zz * ny + yy) * nx + cx];
-                            if (t3 >> 16) runs[rpos++] = t3 | ((unsigned)lane << 27);     // start 16 | length 11 | owner 5
-                        }
-                }
-                __syncwarp();
-                // -- walk: lane l evaluates candidates [l * per, (l + 1) * per) of the W candidates
-                const unsigned per = (W + 31u) >> 5;
-                const unsigned lo = min((unsigned)lane * per, W), hi = min(lo + per, W);
-                evals += hi - lo;
-                unsigned L = 0;
-#pragma unroll
-                for (int sft = 16; sft > 0; sft >>= 1) {
-                    const unsigned cand = L + (unsigned)sft;
-                    const unsigned v = __shfl_sync(PC_FULL_MASK, off, cand & 31u);
-                    if (cand < 32u && v <= lo) L = cand;
-                }
-                unsigned ri = __shfl_sync(PC_FULL_MASK, roff, L);
-                unsigned rem = lo - __shfl_sync(PC_FULL_MASK, off, L);
-                unsigned j = 0, jend = 0, ka = 0;
-                float2 nxy = make_float2(0.f, 0.f);
-                float naz = 0.f;
-                if (lo < hi) {
-                    unsigned rec = runs[ri], len = (rec >> 16) & 0x7ffu;
-                    while (rem >= len) { rem -= len; rec = runs[++ri]; len = (rec >> 16) & 0x7ffu; }
-                    j = (rec & 0xffffu) + rem; jend = (rec & 0xffffu) + len; L = rec >> 27;
-                    nxy = make_float2(-apos[L], -apos[32 + L]); naz = -apos[64 + L]; ka = (unsigned)k0 + L;
-                }
-                for (unsigned it = 0; it < per; it++) {
-                    const bool act = lo + it < hi;
-                    bool hit = false;
-                    if (act) hit = pair_within_packed(nxy, naz, sortB[j], sqdist);
-                    const unsigned bal = __ballot_sync(PC_FULL_MASK, hit);
-                    if (bal) {
-                        if (hit) mywq[wn + __popc(bal & lt_mask)] = (ka << 16) | j;
-                        wn += __popc(bal);
-                    }
-                    if (act && ++j == jend && lo + it + 1 < hi) {
-                        const unsigned rec = runs[++ri];
-                        j = rec & 0xffffu; jend = j + ((rec >> 16) & 0x7ffu);
-                        if ((rec >> 27) != L) {
-                            L = rec >> 27;
-                            nxy = make_float2(-apos[L], -apos[32 + L]); naz = -apos[64 + L]; ka = (unsigned)k0 + L;
-                        }
-                    }
-                    if (wn > (unsigned)(PC_WALK_WQ - 32)) drain_queue();
-                }
-                }
-                if (wn >= (unsigned)PC_WALK_DRAIN_AT) drain_queue();
-                __syncwarp();
-            }
-            drain_queue();
-            }
-            __syncthreads();
-            // ---- T3b: donor-H...acceptor tests, one thread per (gated pair, side) ------------------------------
-            const unsigned ngate = min(s_ngate, (unsigned)PC_WALK_GATE);
-            for (unsigned it = tid; it < 2u * ngate; it += NT) hbond_side(gateq[it >> 1], (int)(it & 1u));
-        }
-        __syncthreads();
-        // ---- per-frame counts and totals; the frame's work slot is made ready for the next batch -----------------
-        if (tid == 0) {
-            const unsigned cc = s_ccur, hc = s_hcur;
-            a.frame_cstart[f] = (uint32_t)((long long)f * o.cap_c_frame);
-            a.frame_ccount[f] = (uint32_t)min((long long)cc, o.cap_c_frame);
-            a.frame_hstart[f] = (uint32_t)((long long)f * o.cap_h_frame);
-            a.frame_hcount[f] = (uint32_t)min((long long)hc, o.cap_h_frame);
-            if (cc) atomicAdd(&a.counters[PC_CNT_CONTACTS], (unsigned long long)cc);
-            if (hc) atomicAdd(&a.counters[PC_CNT_HBONDS], (unsigned long long)hc);
-            atomicMax(&a.counters[6], (unsigned long long)cc);
-            atomicMax(&a.counters[7], (unsigned long long)hc);
-            if (s_status) atomicOr(&a.counters[PC_CNT_STATUS], (unsigned long long)s_status);
-            if (fuse_acc && cc == 0) { acc.frame_rstart[f] = 0; acc.frame_rcount[f] = 0; }
-            if (reset_frames) {
-                PcLargeFrame &G = fr[fb];
-                for (int k = 0; k < 3; k++) { G.bbox[k] = 0xffffffffu; G.bbox[3 + k] = 0u; G.bbox[6 + k] = 0xffffffffu; G.bbox[9 + k] = 0u; }
-                G.nA_in = G.nB_in = 0; G.ccursor = G.hcursor = 0; G.ncell = 0; G.pad[0] = G.pad[1] = 0;
-            }
-        }
-        __syncthreads();
-        // ---- T4: per-frame accumulation of the records just written (they are in L2) -----------------------------
-        const bool have = fuse_acc && s_ccur != 0;
-        const bool do_acc = have && !(s_status & (unsigned)(PC_ST_OUT_OVERFLOW | PC_ST_TAIL_OVERFLOW));
-        __syncthreads();                   // pc_compact_frame reuses s_status
-        if (do_acc) pc_compact_frame<NT>(acc, f, smem, wsum, &s_base, &s_status);
-        else if (have && tid == 0) { acc.frame_rstart[f] = 0; acc.frame_rcount[f] = 0; }
-        __syncthreads();
-    }
-#pragma unroll
-    for (int sft = 16; sft > 0; sft >>= 1) evals += __shfl_xor_sync(PC_FULL_MASK, evals, sft);
-    if (lane == 0 && evals) atomicAdd(&a.counters[PC_CNT_EVALS], evals);
-}
-
 // ---- host side of the large-frame path --------------------------------------------------------------------------
 static inline int pc_large_fail(std::string &err, const char *what, cudaError_t e) {
     err = std::string(what) + ": " + cudaGetErrorString(e);
@@ -1034,8 +380,8 @@ static inline void pc_stream_geom(int n, int nfb, int num_sms, int waves, int &c
     ctas = (n + per - 1) / per;
 }
 
-// tail: 0 = multi-kernel sequence, 1 = fused tail kernel on the compacted A and B atoms, 2 = walk kernel (A read from the
-// frame); two selections only.  acc != nullptr with a tail kernel: rows are produced too.
+// tail: 0 = multi-kernel sequence, 1 = fused tail kernel on the compacted A and B atoms, 3 = fused tail kernel that reads
+// selection A from the frame (default); two selections only.  acc != nullptr with a tail kernel: rows are produced too.
 static inline int pc_large_scan(PcLargeWork &W, const PcScanArgs &a, int num_sms, cudaStream_t s, std::string &err,
                                 unsigned long long *launches, cudaEvent_t probe0, cudaEvent_t probe1, int tail,
                                 const PcAccArgs *acc, const PcGroupArgs *group = nullptr) {
@@ -1073,13 +419,8 @@ static inline int pc_large_scan(PcLargeWork &W, const PcScanArgs &a, int num_sms
         W.FB = FB; W.capCells = capCells; W.n1h = n1h; W.n2h = n2h; W.self_mode = a.self_mode;
         PCL_TRY(cudaFuncSetAttribute(pc_large_stream_kernel<PC_MODE_BBOX>, cudaFuncAttributeMaxDynamicSharedMemorySize, PC_STREAM_SMEM));
         PCL_TRY(cudaFuncSetAttribute(pc_large_stream_kernel<PC_MODE_BIN>, cudaFuncAttributeMaxDynamicSharedMemorySize, PC_STREAM_SMEM));
-        PCL_TRY(cudaFuncSetAttribute(pc_large_binx_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, PC_BINX_SMEM));
-        PCL_TRY(cudaFuncSetAttribute(pc_large_tail_kernel<1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, PC_TAIL_SMEM));
         PCL_TRY(cudaFuncSetAttribute(pc_large_tail_inl_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, PC_TAIL_SMEM));
         PCL_TRY(cudaFuncSetAttribute(pc_large_tail_inl_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, PC_TAIL_SMEM));
-        PCL_TRY(cudaFuncSetAttribute(pc_large_tail_kernel<768>, cudaFuncAttributeMaxDynamicSharedMemorySize, PC_TAIL_SMEM));
-        PCL_TRY(cudaFuncSetAttribute(pc_large_tail_kernel<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, PC_TAIL_SMEM));
-        PCL_TRY(cudaFuncSetAttribute(pc_large_walk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, PC_TAIL_SMEM));
         PCL_TRY(cudaFuncSetAttribute(pc_large_group_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, PC_GROUP_SMEM));
         W.clean = false;
     }
@@ -1126,15 +467,10 @@ static inline int pc_large_scan(PcLargeWork &W, const PcScanArgs &a, int num_sms
         if (!self) {
             // B first: its cell counts tell which A atoms can have a partner at all
             if (probe0 && f0 == 0) cudaEventRecord(probe0, s);
-            // a B selection much larger than A lies mostly outside the grid around A: box test first (pc_large_binx_kernel)
-            static const int binx_env = getenv("PC_BINX") ? atoi(getenv("PC_BINX")) : -1;          // experiments: 0 / 1 force
-            const bool binx = binx_env > 0;                  // measured on c3: no faster than the list walk (5.3 TB/s both), off
-            if (binx)
-                pc_large_binx_kernel<<<dim3(ctasB, nfb), PC_STREAM_NT, PC_BINX_SMEM, s>>>(
-                    a, W.frames, f0, 1, perB, W.cellB, capCells, W.candB, W.ccellB, a2, b_epi);
-            else
-                pc_large_stream_kernel<PC_MODE_BIN><<<dim3(ctasB, nfb), PC_STREAM_NT, PC_STREAM_SMEM, s>>>(
-                    a, W.frames, f0, 1, 0, perB, W.cellB, capCells, W.candB, W.ccellB, a2, nullptr, b_epi);
+            // (measured and dropped: a bin kernel that box-tests whole coordinates before it looks an atom up in the heavy-atom
+            // list -- 5.3 TB/s like the list walk)
+            pc_large_stream_kernel<PC_MODE_BIN><<<dim3(ctasB, nfb), PC_STREAM_NT, PC_STREAM_SMEM, s>>>(
+                a, W.frames, f0, 1, 0, perB, W.cellB, capCells, W.candB, W.ccellB, a2, nullptr, b_epi);
             if (probe1 && f0 == 0) cudaEventRecord(probe1, s);
             if (tail == 3) {
                 PcAccArgs none;
@@ -1142,15 +478,6 @@ static inline int pc_large_scan(PcLargeWork &W, const PcScanArgs &a, int num_sms
                 pc_large_tail_inl_kernel<true><<<std::min(nfb, num_sms), PC_TAIL_NT, PC_TAIL_SMEM, s>>>(
                     a, W.frames, f0, nfb, W.cellA, W.cellB, capCells, W.candA, W.ccellA, W.sortA, W.candB, W.ccellB, a1, a2, o,
                     acc ? *acc : none, acc ? 1 : 0);
-                PCL_TRY(cudaGetLastError());
-                *launches += 3 + (use_bboxB ? 1 : 0);
-                continue;
-            }
-            if (tail == 2) {
-                PcAccArgs none;
-                memset(&none, 0, sizeof none);
-                pc_large_walk_kernel<<<std::min(nfb, num_sms), PC_WALK_NT, PC_TAIL_SMEM, s>>>(
-                    a, W.frames, f0, nfb, W.cellB, capCells, W.candB, W.ccellB, a2, o, acc ? *acc : none, acc ? 1 : 0, 1);
                 PCL_TRY(cudaGetLastError());
                 *launches += 3 + (use_bboxB ? 1 : 0);
                 continue;
@@ -1169,18 +496,7 @@ static inline int pc_large_scan(PcLargeWork &W, const PcScanArgs &a, int num_sms
         if (tail) {
             PcAccArgs none;
             memset(&none, 0, sizeof none);
-            static const int tail_nt = getenv("PC_TAIL_NT") ? atoi(getenv("PC_TAIL_NT")) : PC_TAIL_NT;     // experiments
-            static const int tail_impl = getenv("PC_TAIL_IMPL") ? atoi(getenv("PC_TAIL_IMPL")) : 1;
-            if (tail_impl == 1) {
-                pc_large_tail_inl_kernel<false><<<std::min(nfb, num_sms), PC_TAIL_NT, PC_TAIL_SMEM, s>>>(
-                    a, W.frames, f0, nfb, W.cellA, W.cellB, capCells, W.candA, W.ccellA, W.sortA, W.candB, W.ccellB, a1, a2, o,
-                    acc ? *acc : none, acc ? 1 : 0);
-                PCL_TRY(cudaGetLastError());
-                *launches += 4 + (use_bboxB ? 1 : 0);
-                continue;
-            }
-            auto kern = tail_nt == 512 ? pc_large_tail_kernel<512> : tail_nt == 768 ? pc_large_tail_kernel<768> : pc_large_tail_kernel<1024>;
-            kern<<<std::min(nfb, num_sms), tail_nt == 512 ? 512 : tail_nt == 768 ? 768 : 1024, PC_TAIL_SMEM, s>>>(
+            pc_large_tail_inl_kernel<false><<<std::min(nfb, num_sms), PC_TAIL_NT, PC_TAIL_SMEM, s>>>(
                 a, W.frames, f0, nfb, W.cellA, W.cellB, capCells, W.candA, W.ccellA, W.sortA, W.candB, W.ccellB, a1, a2, o,
                 acc ? *acc : none, acc ? 1 : 0);
             PCL_TRY(cudaGetLastError());

@@ -206,7 +206,7 @@ class ContactEngine:
 
     def set_tail(self, mode):
         """Large-frame path: 3 / True = fused tail kernel that reads selection 1 from the frame (default), 1 = fused
-        tail kernel on the compacted atoms of both selections, 2 = walk kernel, 0 / False = multi-kernel sequence."""
+        tail kernel on the compacted atoms of both selections, 0 / False = multi-kernel sequence."""
         self.tail = 3 if mode is True else int(mode)
         for s in self.slots:
             check(self.lib.pc_set_tail(s.ctx, self.tail))

@@ -93,13 +93,13 @@ def _run(s, coords, self_mode, maps, *, path=2, tail=True, table=0, dense=0, ord
 @pytest.mark.parametrize("name,self_mode,nframes,tail,table", [
     ("c3_small", False, 5, True, 0),         # fused tail kernel, A from the frame (tail mode 3, default) incl. pc_compact_frame
     ("c3_small", False, 5, 1, 0),            # fused tail kernel on the compacted atoms of both selections (tail mode 1)
-    ("c3_small", False, 5, 2, 0),            # walk kernel (tail mode 2)
+    ("c3_small", False, 5, 1, 0),            # tail kernel on the compacted atoms of both selections (tail mode 1)
     ("small", False, 7, 1, 0), ("small_i", False, 4, 1, 0), ("tiny", False, 6, 1, 16384),
     ("c3_small", False, 5, False, 0),        # multi-kernel sequence + pc_accumulate_compact_kernel
     ("c3_small", False, 5, True, 16384),     # fused tail kernel, rows from the global tile table
     ("c3_small", False, 5, False, 16384),
-    ("small", False, 7, True, 0), ("small", False, 7, 2, 0), ("small", False, 7, False, 0), ("small", False, 7, False, 16384),
-    ("small_i", False, 4, True, 0), ("small_i", False, 4, 2, 16384), ("small_i", False, 4, False, 0),   # interdigitated chains
+    ("small", False, 7, True, 0), ("small", False, 7, False, 0), ("small", False, 7, False, 16384),
+    ("small_i", False, 4, True, 0), ("small_i", False, 4, 1, 16384), ("small_i", False, 4, False, 0),   # interdigitated chains
     ("tiny", False, 6, True, 0), ("tiny", True, 6, False, 0), ("tiny", True, 6, False, 16384),
     ("c4_small", True, 2, False, 0),         # more keys per frame than the compact table: overflow -> global table
     ("c4_small", True, 2, False, 16384),
