@@ -444,6 +444,9 @@ def run_gpu(args):
     eng.set_maps(gm1.gid, gm2.gid, gm2.n_groups)
     if os.environ.get("PC_GROUP"):                         # experiments: 0 = multi-kernel sequence + global table instead of the group kernel
         eng.set_group_mode(int(os.environ["PC_GROUP"]))
+    if os.environ.get("PC_SMALL_CTAS"):                    # experiments: CTA plan of the small-frame kernel (pc_set_small_ctas)
+        for sl in eng.slots:
+            check(lib.pc_set_small_ctas(sl.ctx, int(os.environ["PC_SMALL_CTAS"])))
     if os.environ.get("PC_TAIL"):                          # experiments: 0 = multi-kernel sequence, 1 = tail kernel on compacted atoms
         eng.set_tail(int(os.environ["PC_TAIL"]))
     n_keys = gm1.n_groups * gm2.n_groups

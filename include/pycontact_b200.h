@@ -122,7 +122,8 @@ int pc_set_limits(pc_ctx *ctx, int32_t hits_per_frame, int32_t hbonds_per_frame,
  * 2 = tiled large-frame path.  Both give the same records; tests use this to cover both. */
 int pc_set_path(pc_ctx *ctx, int path);
 
-/* Small-frame kernel: CTAs per SM.  0 = automatic (a "fast" plan of two 512-thread CTAs per SM; frames whose
+/* Small-frame kernel: CTAs per SM.  0 = automatic (a "fast" plan of two 512-thread CTAs per SM -- three of 384 threads
+ * for selections of at most 3000 heavy atoms together; frames whose
  * in-grid atoms or hits do not fit it are redone by the "full" plan, one 1024-thread CTA), 1 = full plan
  * only, 2 = fast plan only (PC_ST_STAGE_OVERFLOW when a frame does not fit), 3 / 4 = fast plan with
  * 3 x 384 / 4 x 256 threads per SM, then the full plan. */

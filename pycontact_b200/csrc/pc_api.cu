@@ -467,7 +467,12 @@ extern "C" int pc_scan_device(pc_ctx *c, const float *d_xyz1, const float *d_xyz
     int cells1 = 0, hits1 = 0, hb1 = 0, cells2 = 0, hits2 = 0, hb2 = 0;
     const bool small_ok = c->force_path != 2 && c->n1h <= 65535 && c->n2h <= 65535;
     const bool have_full = small_ok && c->small_ctas != 2 && plan_small_cfg(c, fuse_acc, 1, cells1, hits1, hb1, L);
-    const int fast_ctas = c->small_ctas >= 3 ? c->small_ctas : 2;     // CTAs per SM of the fast plan
+    // CTAs per SM of the fast plan: two of 512 threads; selections of a few thousand heavy atoms (the reference's own fixture:
+    // 2.2 k) run three of 384 -- their phases are short and latency-bound, a third frame in flight hides more of it (c1
+    // kernel 0.216 -> 0.192 ms per 1600 frames, the 1920-atom synthetic system 0.386 -> 0.329 ms per 4096), while at C2's
+    // 6000 heavy atoms the search and the drain are bound by the SM's shared-memory pipe and three CTAs are slower (0.49 vs 0.36)
+    const int small_sel = (c->self_mode ? c->n1h : c->n1h + c->n2h) <= 3000;
+    const int fast_ctas = c->small_ctas >= 3 ? c->small_ctas : (c->small_ctas == 0 && small_sel ? 3 : 2);
     const bool have_fast = small_ok && c->small_ctas != 1 && plan_small_cfg(c, fuse_acc, fast_ctas, cells2, hits2, hb2, L2);
     const bool fits_small = have_full || have_fast;
     c->last_fused = false;

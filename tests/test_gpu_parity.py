@@ -116,7 +116,7 @@ def test_cy_find_contacts_self_keeps_ii_pairs():
 # ---------------------------------------------------------------------------------------------------
 # B2 / B3: frame scan + accumulation on the reference's fixture (golden session)
 # ---------------------------------------------------------------------------------------------------
-@pytest.mark.parametrize("path,ctas", [(1, 1), (1, 2), (2, 0)])
+@pytest.mark.parametrize("path,ctas", [(1, 0), (1, 1), (1, 2), (1, 3), (1, 4), (2, 0)])
 def test_scan_fixture_matches_golden_session(rpn11, golden_ab, path, ctas):
     idx1, idx2 = golden_ab["sel1"].astype(np.int64), golden_ab["sel2"].astype(np.int64)
     s1, s2 = _selections(rpn11.topology, idx1, idx2, rpn11.backbone)
