@@ -152,10 +152,10 @@ __device__ __forceinline__ void pc_large_occ_frame(const int nx, const int ny, c
 #define PC_STREAM_STAGES 3
 #endif
 #define PC_STREAM_OCCW 1024                                  // words of the occupancy bitmap in shared memory (32768 cells)
-#define PC_STREAM_MAXCH 256                                  // chunk boundaries whose heavy ordinals are looked up ahead of the loop
+#define PC_STREAM_MAXCH 512                                  // chunk boundaries whose heavy ordinals are looked up ahead of the loop
 #define PC_STREAM_HINFO (PC_STREAM_CHUNK / 12 * 4 + 32)      // a chunk's slice of the heavy-atom list
 #define PC_STREAM_SLOT (PC_STREAM_CHUNK + 16 + PC_STREAM_HINFO)
-#define PC_STREAM_SMEM (PC_STREAM_STAGES * PC_STREAM_SLOT + PC_STREAM_STAGES * 8 + 16)
+#define PC_STREAM_SMEM (PC_STREAM_STAGES * PC_STREAM_SLOT + PC_STREAM_STAGES * 16 + 16)      // ring + full / empty barriers
 
 struct PcStreamDesc { int cnt, hoff, off0, abase; };          // per ring slot, written by the issuing thread
 
@@ -192,7 +192,8 @@ __global__ void __launch_bounds__(PC_STREAM_NT) pc_large_stream_kernel(const PcS
     if (tid == 0) {
         F = fr[fb];
         s_bad = 0;
-        for (int s = 0; s < STAGES; s++) pc_mbar_init(bars + s, 1);
+        // full[s]: the producer's expect_tx + the copies' bytes; empty[s]: one arrival per consumer warp
+        for (int s = 0; s < STAGES; s++) { pc_mbar_init(bars + s, 1); pc_mbar_init(bars + STAGES + s, NT / 32 - 1); }
         pc_mbar_fence_init();
     }
     __syncthreads();
@@ -275,18 +276,27 @@ __global__ void __launch_bounds__(PC_STREAM_NT) pc_large_stream_kernel(const PcS
         for (int k = 0; k < 3; k++) { plo[k] = F.lo[k] - 0.01f; phi[k] = F.lo[k] + (float)nn[k] * e * 1.00001f + 0.01f; }
     }
 
-    if (tid == 0)
-        for (int q = 0; q < min(STAGES - 1, nch); q++) issue(q);
+    // The last warp only issues copies (lane 0), as far ahead as the ring allows: it refills a slot as soon as every
+    // consumer warp has arrived on the slot's empty barrier.  The other warps consume: no CTA barrier per chunk, and the
+    // issue of a chunk (64-bit divisions of pc_chunk_of, two bulk copies) is off their critical path -- done by thread 0
+    // between two barriers it bounded a CTA at 22 GB/s.
+    constexpr int CNT = NT - 32;                      // consumer threads
+    if (warp == NT / 32 - 1) {
+        if (lane == 0)
+            for (int q = 0; q < nch; q++) {
+                if (q >= STAGES && !pc_mbar_wait(bars + STAGES + q % STAGES, (unsigned)(q / STAGES - 1) & 1u)) { s_bad = 1; break; }
+                issue(q);
+            }
+    } else
     for (int q = 0; q < nch; q++) {
-        if (tid == 0 && q + STAGES - 1 < nch) issue(q + STAGES - 1);
         const int st = q % STAGES;
-        if (!pc_mbar_wait(bars + st, (unsigned)(q / STAGES) & 1u)) { s_bad = 1; }
+        if (!pc_mbar_wait(bars + st, (unsigned)(q / STAGES) & 1u)) { s_bad = 1; break; }      // (a bug, not a data condition)
         const PcStreamDesc d = desc[st];
         const unsigned char *slot = smem + (size_t)st * SLOT;
         const unsigned char *xyz = slot + d.off0;
         const uint32_t *hin = reinterpret_cast<const uint32_t *>(slot + CHUNK + 16 + d.hoff);
         const int cnt = d.cnt, abase = d.abase;
-        for (int kk = tid; kk < ((cnt + 31) & ~31); kk += NT) {
+        for (int kk = tid; kk < ((cnt + 31) & ~31); kk += CNT) {
             const bool heavy = kk < cnt;
             uint32_t info = 0;
             float x = 0.f, y = 0.f, z = 0.f;
@@ -324,7 +334,8 @@ __global__ void __launch_bounds__(PC_STREAM_NT) pc_large_stream_kernel(const PcS
                 }
             }
         }
-        __syncthreads();          // the slot (and its descriptor) may be refilled from here on
+        __syncwarp();
+        if (lane == 0) pc_mbar_arrive(bars + STAGES + st);        // the slot (and its descriptor) may be refilled once every warp is here
     }
     if (MODE == PC_MODE_BBOX) {
 #pragma unroll
