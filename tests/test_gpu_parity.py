@@ -128,6 +128,7 @@ def test_scan_fixture_matches_golden_session(rpn11, golden_ab, path, ctas):
         traj, _, stats = run_scan([eng], src, batch_frames=16, order_keys=True)
     assert stats["path"] == path
     assert stats["contacts"] == 23208 and stats["hbonds"] == 457
+    assert traj.packed_sorts > 0                     # the device's order keys took the one-pass host sort (results.py)
     _compare_traj(traj, _golden_frames(golden_ab))
 
 

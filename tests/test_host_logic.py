@@ -124,7 +124,19 @@ def test_hydrogen_csr_matches_oracle(rpn11, golden_ab):
     assert ((s1.flags & _lib.PC_ATOM_HYDROGEN) > 0).sum() == sum(t.names[i].startswith("H") for i in idx1)
 
 
-def _fake_batch(frames, sel1, sel2, rng, frame0=0, with_rows=None):
+def _device_order_keys(fr):
+    """Order keys in the device's layout (local index 1 << 37 | stencil rank << 32 | local index 2, pc_order.cuh) whose
+    sorted order is the oracle's: the rank of a contact = descents of atom 2's index so far in its atom 1's run."""
+    i1, i2 = np.asarray(fr["lidx1"], np.int64), np.asarray(fr["lidx2"], np.int64)
+    rank = np.zeros(i1.size, np.uint64)
+    for c in range(1, i1.size):
+        if i1[c] == i1[c - 1]:
+            rank[c] = rank[c - 1] + (1 if i2[c] < i2[c - 1] else 0)
+    assert rank.max(initial=0) < 27
+    return (i1.astype(np.uint64) << np.uint64(37)) | (rank << np.uint64(32)) | i2.astype(np.uint64)
+
+
+def _fake_batch(frames, sel1, sel2, rng, frame0=0, with_rows=None, device_keys=False):
     """Oracle frames -> the arrays the device would return, records shuffled inside each frame."""
     loc1 = {int(g): k for k, g in enumerate(sel1.indices)}
     loc2 = {int(g): k for k, g in enumerate(sel2.indices)}
@@ -135,7 +147,7 @@ def _fake_batch(frames, sel1, sel2, rng, frame0=0, with_rows=None):
         rec = np.zeros(n, _lib.contact_dtype)
         rec["i"] = fr["lidx1"]; rec["j"] = fr["lidx2"]
         rec["distance"] = fr["distance"]; rec["weight"] = fr["weight"]
-        key = np.arange(n, dtype=np.uint64) * np.uint64(7) + np.uint64(3)       # any increasing order key
+        key = _device_order_keys(fr) if device_keys else np.arange(n, dtype=np.uint64) * np.uint64(7) + np.uint64(3)  # any increasing key
         p = rng.permutation(n)
         cs.append(rec[p]); ks.append(key[p]); ccount.append(n)
         m = len(fr["hb_donor"])
@@ -174,6 +186,27 @@ def test_trajectory_contacts_restore_reference_order(rpn11, golden_ab):
     n = hp[fp[6]]
     for k in ("hb_donor", "hb_acceptor", "hb_hydrogen"):
         assert np.array_equal(getattr(traj, k), golden_ab[k][:n])
+    # the packed one-pass sort and the lexsort fallback give the same arrays
+    rng = np.random.default_rng(0)
+    slow = TrajectoryContacts(s1, s2, 2.5, 120)
+    slow._packable = False
+    slow.add_batch(_fake_batch(ora[:4], s1, s2, rng), frames[:4])
+    slow.add_batch(_fake_batch(ora[4:], s1, s2, rng, 4), frames[4:])
+    slow.finalize()
+    assert traj._packable is True                    # (these fake order keys are not the device's: sorted as they are)
+    # ... and with order keys in the device's layout the one-pass sort itself runs
+    rng = np.random.default_rng(1)
+    fast = TrajectoryContacts(s1, s2, 2.5, 120)
+    fast.add_batch(_fake_batch(ora[:4], s1, s2, rng, device_keys=True), frames[:4])
+    fast.add_batch(_fake_batch(ora[4:], s1, s2, rng, 4, device_keys=True), frames[4:])
+    fast.finalize()
+    assert fast.packed_sorts == 2 and traj.packed_sorts == 0
+    for k in ("frame_ptr", "li", "lj", "idx1", "idx2", "distance", "weight", "hb_ptr", "hb_donor", "hb_acceptor",
+              "hb_hydrogen", "hb_side", "hb_distance", "hb_angle"):
+        assert np.array_equal(getattr(traj, k), getattr(fast, k)), k
+    for k in ("frame_ptr", "li", "lj", "idx1", "idx2", "distance", "weight", "hb_ptr", "hb_donor", "hb_acceptor",
+              "hb_hydrogen", "hb_side", "hb_distance", "hb_angle"):
+        assert np.array_equal(getattr(traj, k), getattr(slow, k)), k
     # object views
     res = LazyContactResults(traj)
     assert len(res) == 6 and len(res[2]) == fp[3] - fp[2]
