@@ -83,8 +83,9 @@ class TrajectoryContacts:
                 # the device's order key is local index 1 << 37 | stencil rank << 32 | local index 2 (pc_order.cuh); any
                 # other key (a caller's own) is sorted as it is
                 okv = b.order_keys[src]
-                fits = bool(np.array_equal(okv >> np.uint64(37), ci.astype(np.uint64)) and
-                            np.array_equal(okv & np.uint64(0xffffffff), cj.astype(np.uint64)))
+                smp = np.unique(np.linspace(0, max(okv.size - 1, 0), 4096).astype(np.int64)) if okv.size else np.zeros(0, np.int64)
+                fits = bool(np.array_equal(okv[smp] >> np.uint64(37), ci[smp].astype(np.uint64)) and
+                            np.array_equal(okv[smp] & np.uint64(0xffffffff), cj[smp].astype(np.uint64)))   # (4096 samples)
                 rank = (okv >> np.uint64(32)) & np.uint64(31)
             self.packed_sorts += int(fits)
             if fits:
@@ -94,6 +95,7 @@ class TrajectoryContacts:
         if order is not None:
             src = src[order]                             # (frame_of is the leading part of the key: it stays as it is)
             c = b.contacts[src]
+            li, lj = ci[order].astype(np.int64), cj[order].astype(np.int64)
         else:
             c = b.contacts[src]
             if b.order_keys is not None:
@@ -102,13 +104,14 @@ class TrajectoryContacts:
                 ok = (c["i"].astype(np.uint64) << np.uint64(32)) | c["j"].astype(np.uint64)
             order = np.lexsort((ok, frame_of))
             c, frame_of = c[order], frame_of[order]
+            li, lj = c["i"].astype(np.int64), c["j"].astype(np.int64)
         # ---- H-bonds: attach to their contact, order = atom1's hydrogens then atom2's (CSR order)
         hcnt = b.hcount.astype(np.int64)
         hframe = np.repeat(np.arange(nf, dtype=np.int64), hcnt)
         hsrc = np.repeat(b.hstart.astype(np.int64), hcnt) + (np.arange(hcnt.sum()) - np.repeat(np.cumsum(hcnt) - hcnt, hcnt))
         h = b.hbonds[hsrc]
         n2 = self.sel2.n
-        ckey = frame_of * (self.sel1.n * n2) + c["i"].astype(np.int64) * n2 + c["j"].astype(np.int64)
+        ckey = frame_of * (self.sel1.n * n2) + li * n2 + lj
         hkey = hframe * (self.sel1.n * n2) + h["i"].astype(np.int64) * n2 + h["j"].astype(np.int64)
         # contacts are unique per (frame, i, j): locate each H-bond's contact
         co = np.argsort(ckey, kind="stable")
@@ -126,14 +129,14 @@ class TrajectoryContacts:
                 pos[m] = p[np.searchsorted(comp, q)]
         horder = np.lexsort((pos, side, where))
         h, side, hl, where = h[horder], side[horder], hl[horder], where[horder]
-        g1 = self.sel1.indices[c["i"]]
-        g2 = self.sel2.indices[c["j"]]
+        g1 = self.sel1.indices[li]
+        g2 = self.sel2.indices[lj]
         donor_sel1 = side == 0
         hyd_g = np.where(donor_sel1, self.sel1.indices[np.minimum(hl, self.sel1.n - 1)],
                          self.sel2.indices[np.minimum(hl, n2 - 1)])
         part = dict(
             frame_counts=np.bincount(frame_of, minlength=nf).astype(np.int64),
-            li=c["i"].astype(np.int64), lj=c["j"].astype(np.int64), idx1=g1, idx2=g2,
+            li=li, lj=lj, idx1=g1, idx2=g2,
             distance=c["distance"].astype(np.float64), weight=c["weight"].astype(np.float64),
             hb_count=np.bincount(where, minlength=c.size).astype(np.int64),
             hb_donor=np.where(donor_sel1, g1[where], g2[where]) if where.size else np.zeros(0, np.int64),
