@@ -94,7 +94,7 @@ class TrajectoryContacts:
                 order = np.argsort(comp)
         if order is not None:
             src = src[order]                             # (frame_of is the leading part of the key: it stays as it is)
-            c = b.contacts[src]
+            c = np.take(b.contacts, src)
             li, lj = ci[order].astype(np.int64), cj[order].astype(np.int64)
         else:
             c = b.contacts[src]
@@ -220,7 +220,7 @@ class AccumulationTable:
             raise ValueError("batch was not accumulated")
         cnt = b.rcount.astype(np.int64)
         src = np.repeat(b.rstart.astype(np.int64), cnt) + (np.arange(cnt.sum()) - np.repeat(np.cumsum(cnt) - cnt, cnt))
-        self._rows.append(b.rows[src])
+        self._rows.append(np.take(b.rows, src))
         self._frames.append(np.repeat(np.arange(b.nframes, dtype=np.int64) + frame_pos0, cnt))
 
     def add_packed(self, rows: np.ndarray, rstart, rcount, frame_pos0: int):
@@ -246,19 +246,40 @@ class AccumulationTable:
         from ._lib import row_dtype
         rows = np.concatenate(self._rows) if self._rows else np.zeros(0, row_dtype)
         frames = np.concatenate(self._frames) if self._frames else np.zeros(0, np.int64)
-        keys, kid = np.unique(rows["key"], return_inverse=True)
+        # dense key ids, each key's first appearance (smallest frame, then smallest order key in that frame) and the final
+        # (output position, frame) order with two argsorts of contiguous 64-bit keys and segment reductions -- np.unique
+        # with inverse plus two two-key lexsorts over all rows cost 1 us per row (2 s for a C2-sized trajectory)
+        N = rows.size
+        kc = np.ascontiguousarray(rows["key"])
+        o = np.argsort(kc)
+        ks = kc[o]
+        newk = np.ones(N, bool)
+        if N:
+            newk[1:] = ks[1:] != ks[:-1]
+        starts = np.flatnonzero(newk)
+        keys = ks[starts]
         K = keys.size
-        # first appearance over the trajectory: smallest (frame, in-frame order key)
-        o = np.lexsort((rows["first"], frames))
-        first_row = np.full(K, -1, np.int64)
-        seen_order = kid[o]
-        _, first_pos = np.unique(seen_order, return_index=True)     # index into o of each key's first row
-        first_row[:] = first_pos
-        rank_of_key = np.argsort(np.argsort(first_row, kind="stable"), kind="stable")   # key -> output position
+        kid_sorted = np.cumsum(newk) - 1
+        kid = np.empty(N, np.int64)
+        kid[o] = kid_sorted
+        if K:
+            fs = frames[o]
+            minf = np.minimum.reduceat(fs, starts)
+            firsts = np.ascontiguousarray(rows["first"])[o]
+            firsts[fs != minf[kid_sorted]] = np.iinfo(np.uint64).max
+            minfirst = np.minimum.reduceat(firsts, starts)
+            appear = np.lexsort((minfirst, minf))                   # keys in first-appearance order
+        else:
+            appear = np.zeros(0, np.int64)
+        rank_of_key = np.empty(K, np.int64)                          # key -> output position
+        rank_of_key[appear] = np.arange(K)
         kpos = rank_of_key[kid]
         # rows sorted by (output position, frame)
-        o2 = np.lexsort((frames, kpos))
-        self.rows = rows[o2]
+        if N and int(frames.max()) < (1 << 32) and int(frames.min()) >= 0:
+            o2 = np.argsort((kpos.astype(np.uint64) << np.uint64(32)) | frames.astype(np.uint64))
+        else:
+            o2 = np.lexsort((frames, kpos))
+        self.rows = np.take(rows, o2)                # (np.take on a structured array: 4x faster than fancy indexing)
         self.row_frames = frames[o2]
         self.row_key = kpos[o2]
         self.key_ptr = np.zeros(K + 1, np.int64)
