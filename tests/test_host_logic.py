@@ -270,6 +270,51 @@ def test_accumulation_table_matches_golden(rpn11, golden_ab):
     assert o2.scoreArray == objs[3].scoreArray and o2.key1 == objs[3].key1 and o2.hbondFrames == objs[3].hbondFramesScan()
 
 
+def _finalize_reference(rows, frames):
+    """AccumulationTable.finalize, the plain way: np.unique + lexsorts (what the vectorised version replaced)."""
+    keys, kid = np.unique(rows["key"], return_inverse=True)
+    K = keys.size
+    o = np.lexsort((rows["first"], frames))
+    _, first_pos = np.unique(kid[o], return_index=True)
+    rank_of_key = np.argsort(np.argsort(first_pos, kind="stable"), kind="stable")
+    kpos = rank_of_key[kid]
+    o2 = np.lexsort((frames, kpos))
+    out_keys = np.empty(K, np.uint64)
+    out_keys[rank_of_key] = keys
+    key_ptr = np.zeros(K + 1, np.int64)
+    np.cumsum(np.bincount(kpos, minlength=K), out=key_ptr[1:])
+    return out_keys, key_ptr, rows[o2], frames[o2]
+
+
+@pytest.mark.parametrize("n_rows,n_keys,n_frames,seed", [(0, 0, 5, 0), (1, 1, 1, 1), (50, 1, 50, 2), (400, 37, 60, 3),
+                                                         (5000, 300, 700, 4), (3000, 3000, 1, 5)])
+def test_accumulation_table_finalize_equals_plain_version(n_rows, n_keys, n_frames, seed):
+    """Keys in first-appearance order (smallest frame, then smallest order key), cells by (key, frame): the two-argsort
+    finalize against np.unique + lexsort on random cells -- one cell per (frame, key), frames in any order over batches."""
+    rng = np.random.default_rng(seed)
+
+    class GM:
+        n_groups = 1 << 20
+    cells = rng.choice(max(n_keys * n_frames, 1), n_rows, replace=False) if n_rows else np.zeros(0, np.int64)
+    key_values = rng.choice(1 << 40, max(n_keys, 1), replace=False).astype(np.uint64)
+    rows = np.zeros(n_rows, _lib.row_dtype)
+    rows["key"] = key_values[cells % max(n_keys, 1)] if n_rows else 0
+    frames = (cells // max(n_keys, 1)).astype(np.int64) + 3            # frame positions need not start at 0
+    rows["score"] = rng.random(n_rows); rows["bb1"] = rows["score"] * 0.25; rows["bb2"] = rows["score"] * 0.5
+    rows["ncontacts"] = rng.integers(1, 9, n_rows); rows["nhbonds"] = rng.integers(0, 3, n_rows)
+    rows["first"] = rng.choice(1 << 50, max(n_rows, 1), replace=False).astype(np.uint64)[:n_rows]
+    perm = rng.permutation(n_rows)
+    t = AccumulationTable(n_frames + 3, GM(), GM())
+    for part in np.array_split(perm, 3):
+        t.add_rows(rows[part], frames[part])
+    t.finalize()
+    keys, key_ptr, srows, sframes = _finalize_reference(rows[perm], frames[perm])
+    assert np.array_equal(t.keys, keys) and np.array_equal(t.key_ptr, key_ptr)
+    assert np.array_equal(t.row_frames, sframes) and np.array_equal(t.rows, srows)
+    assert np.array_equal(t.row_key, np.repeat(np.arange(keys.size), np.diff(key_ptr)))
+    np.testing.assert_allclose(t.total_score, [srows["score"][a:b].sum() for a, b in zip(key_ptr[:-1], key_ptr[1:])], rtol=1e-12)
+
+
 def test_key_helpers_round_trip():
     an = Analyzer("a.psf", "a.dcd", 5.0, 2.5, 120, "segid A", "segid B")
     an.setTrajectoryData(["ASP", "LYS"], [21, 11], ["OD1", "NZ"], ["RN11", "UBQ"], [], "segid A", "segid B")
