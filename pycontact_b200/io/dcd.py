@@ -66,13 +66,44 @@ class DCDReader:
             out[:, ax] = a if indices is None else a[indices]
         return out
 
+    def _frames_view(self):
+        """The whole file as a (frames, 3, atoms) float32 array: the X, Y, Z records of every frame sit at fixed offsets,
+        so this is a strided view of the memory map (None when the records are not 4-byte aligned in the file)."""
+        if not hasattr(self, "_v"):
+            start = self._first + self._cell_bytes + 4
+            self._v = None
+            if self.n_frames > 0 and start % 4 == 0 and self._frame_bytes % 4 == 0:
+                self._v = np.ndarray((self.n_frames, 3, self.n_atoms), dtype=self._endian + "f4", buffer=self._raw, offset=start,
+                                     strides=(self._frame_bytes, self._rec, 4))
+        return self._v
+
     def read_into(self, out: np.ndarray, frame0: int, nframes: int, indices=None):
         """Fill ``out[k] = positions(frame0 + k)[indices]`` for a frame batch;
-        ``out`` is float32 (nframes, n, 3), typically a pinned staging buffer."""
-        for k in range(nframes):
-            for ax in range(3):
-                a = self._axis(frame0 + k, ax)
-                out[k, :, ax] = a if indices is None else a[indices]
+        ``out`` is float32 (nframes, n, 3), typically a pinned staging buffer.  One gather per run of consecutive atom
+        indices over all frames and axes of the batch (a segment selection is one run): per frame and axis -- 6 numpy
+        calls of ~12 us each -- the Python overhead was most of a C2 frame's 74 us."""
+        if not (0 <= frame0 and frame0 + nframes <= self.n_frames):
+            raise IndexError((frame0, nframes))
+        v = self._frames_view()
+        if v is None:
+            for k in range(nframes):
+                for ax in range(3):
+                    a = self._axis(frame0 + k, ax)
+                    out[k, :, ax] = a if indices is None else a[indices]
+            return out
+        blk = v[frame0:frame0 + nframes]                     # (nframes, 3, atoms)
+        if indices is None:
+            out[...] = blk.transpose(0, 2, 1)
+            return out
+        idx = np.asarray(indices, np.int64)
+        cuts = np.flatnonzero(np.diff(idx) != 1) + 1         # runs of consecutive indices
+        if cuts.size + 1 <= 64:
+            lo = 0
+            for hi in list(cuts) + [idx.size]:
+                out[:, lo:hi, :] = blk[:, :, int(idx[lo]):int(idx[hi - 1]) + 1].transpose(0, 2, 1)
+                lo = hi
+        else:
+            out[...] = blk[:, :, idx].transpose(0, 2, 1)
         return out
 
     def __iter__(self):
