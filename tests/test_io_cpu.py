@@ -59,6 +59,16 @@ def test_psf_dcd_round_trip(tmp_path, with_cell):
     buf = np.empty((2, len(sel), 3), np.float32)
     r.read_into(buf, 1, 2, sel)
     assert np.array_equal(buf, coords[1:3][:, sel])
+    # batch reads: all atoms, many short runs of indices (one gather per run), scattered indices (one fancy gather)
+    allbuf = np.empty((4, t.n_atoms, 3), np.float32)
+    assert np.array_equal(r.read_into(allbuf, 0, 4), coords)
+    rng = np.random.default_rng(3)
+    for pick in (np.sort(rng.choice(t.n_atoms, 40, replace=False)), np.sort(rng.choice(t.n_atoms, 400, replace=False)),
+                 np.r_[5:9, 100:180, 300:301]):
+        out = np.empty((3, len(pick), 3), np.float32)
+        assert np.array_equal(r.read_into(out, 1, 3, pick), coords[1:4][:, pick])
+    with pytest.raises(IndexError):
+        r.read_into(buf, 3, 2, sel)
 
 
 def test_selection_language(tmp_path):
