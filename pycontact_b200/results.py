@@ -61,6 +61,18 @@ class TrajectoryContacts:
 
     def add_batch(self, b: BatchResult, frame_numbers):
         """Sort one batch's records into the reference's order and keep them."""
+        self.append_part(self.make_part(b), frame_numbers)
+
+    def append_part(self, part, frame_numbers):
+        """Keep a batch prepared by make_part; batches are appended in trajectory order."""
+        self.packed_sorts += int(part.pop("packed"))
+        self._parts.append(part)
+        self.frame_numbers.extend(int(f) for f in frame_numbers)
+
+    def make_part(self, b: BatchResult):
+        """One batch's records in the reference's order, as the arrays finalize() concatenates.  Does not touch the
+        container (apart from two lazily built, idempotent lookup tables), so batches can be prepared by worker threads
+        while the scan goes on -- numpy's sorts and gathers release the GIL (scheduler.run_scan)."""
         if b.contacts is None or b.hbonds is None:
             raise ValueError("batch was fetched without its contact / H-bond records")
         nf = b.nframes
@@ -87,11 +99,11 @@ class TrajectoryContacts:
                 fits = bool(np.array_equal(okv[smp] >> np.uint64(37), ci[smp].astype(np.uint64)) and
                             np.array_equal(okv[smp] & np.uint64(0xffffffff), cj[smp].astype(np.uint64)))   # (4096 samples)
                 rank = (okv >> np.uint64(32)) & np.uint64(31)
-            self.packed_sorts += int(fits)
             if fits:
                 comp = ((frame_of.astype(np.uint64) << np.uint64(45)) | (ci.astype(np.uint64) << np.uint64(25)) |
                         (rank << np.uint64(20)) | cj.astype(np.uint64))
                 order = np.argsort(comp)
+        packed = order is not None
         if order is not None:
             src = src[order]                             # (frame_of is the leading part of the key: it stays as it is)
             c = np.take(b.contacts, src)
@@ -142,9 +154,9 @@ class TrajectoryContacts:
             hb_donor=np.where(donor_sel1, g1[where], g2[where]) if where.size else np.zeros(0, np.int64),
             hb_acceptor=np.where(donor_sel1, g2[where], g1[where]) if where.size else np.zeros(0, np.int64),
             hb_hydrogen=hyd_g.astype(np.int64), hb_side=side,
-            hb_distance=h["distance"].astype(np.float64), hb_angle=h["angle"].astype(np.float64))
-        self._parts.append(part)
-        self.frame_numbers.extend(int(f) for f in frame_numbers)
+            hb_distance=h["distance"].astype(np.float64), hb_angle=h["angle"].astype(np.float64),
+            packed=packed)
+        return part
 
     def finalize(self):
         if not self._parts:
